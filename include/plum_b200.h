@@ -1,0 +1,249 @@
+/* plum_b200 — C ABI of the B200-native energy engine for Plum's per-trial-move
+ * energy path.
+ *
+ * This header is the drop-in boundary.  Everything above it (the MC driver,
+ * run.in parsing, move generators, Metropolis test) is Plum's own C++ and stays
+ * as it is; everything below it is hand-written sm_100a CUDA.  The host façade
+ * `plum_b200/host/force_field.{h,cc}` has the public signature of the
+ * reference's `class ForceField` (src/force_field/force_field.h:207-294) and
+ * forwards to these entry points; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C types only: pointers and sizes, no C++/torch types;
+ *  - every entry point returns 0 on success, a negative pg_status on failure;
+ *    `pg_last_error(h)` gives a message (CUDA error strings included);
+ *  - all pointers are HOST pointers owned by the caller unless the name ends
+ *    in `_dev`;
+ *  - beads are indexed densely in molecule order (the iteration order of every
+ *    reference loop, e.g. src/force_field/potential_pair.cc:181-197); a
+ *    molecule is a contiguous bead range;
+ *  - all arithmetic is FP64.  Energies are in kBT, lengths in "ul".
+ *  - one handle = one system replica on one GPU; a handle is not thread safe.
+ *  - there is no CPU fallback: if no CUDA device is usable pg_create fails.
+ */
+#ifndef PLUM_B200_H_
+#define PLUM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+/* The reference's sentinel for "infinite" energy (src/utilities/constants.h:16). */
+#define PG_VERY_LARGE_ENERGY 1.0e8
+
+typedef enum pg_status {
+  PG_OK = 0,
+  PG_ERR_INVALID = -1,   /* bad argument */
+  PG_ERR_CUDA = -2,      /* CUDA runtime error, see pg_last_error */
+  PG_ERR_NO_DEVICE = -3, /* no usable sm_100 device: there is no CPU fallback */
+  PG_ERR_STATE = -4,     /* call out of order (e.g. commit without a trial) */
+  PG_ERR_CAPACITY = -5,  /* exceeds a compiled-in or allocated capacity */
+  PG_ERR_TIMEOUT = -6    /* device did not answer within the watchdog time */
+} pg_status;
+
+/* pair_kind: which PotentialPair subclass (src/force_field/force_field.cc:123-139) */
+enum { PG_PAIR_NONE = 0, PG_PAIR_TRUNCATED_LJ = 1, PG_PAIR_HARD_SPHERE = 2 };
+/* bond_kind (src/force_field/force_field.cc:154-165) */
+enum { PG_BOND_NONE = 0, PG_BOND_SPRING = 1 };
+/* ext_kind (src/force_field/force_field.cc:174-195) */
+enum { PG_EXT_NONE = 0, PG_EXT_TRUNCATED_LJ_WALL = 1, PG_EXT_HARD_WALL = 2, PG_EXT_WELL_WALL = 3 };
+/* graft_kind per bead type: symbol "L" / "R" select the tethered branch of the
+ * LJ wall (src/force_field/potential_truncated_lj_wall.cc:82-115). */
+enum { PG_GRAFT_NONE = 0, PG_GRAFT_LEFT = 1, PG_GRAFT_RIGHT = 2 };
+
+/* Force-field parameters.  Bead "symbols" (strings in the reference) are mapped
+ * by the caller to dense int type ids 0..n_types-1; a symbol missing from a
+ * reference std::map reads as 0 there (operator[]), so absent entries are 0 here. */
+typedef struct pg_params {
+  double box[3];            /* ForceField::box_l, the unpadded box             */
+  int32_t npbc;             /* 2 or 3 (src/simulation/simulation.cc:152)       */
+  int32_t n_types;
+  double beta;
+
+  int32_t pair_kind;        /* PG_PAIR_*                                       */
+  int32_t _pad0;
+  double lj_cutoff;         /* <0: WCA (potential_truncated_lj.cc:69-76)       */
+  const double* lj_sigma;   /* [n_types]                                       */
+  const double* lj_epsilon; /* [n_types]                                       */
+  const double* hs_radius;  /* [n_types] (potential_hard_sphere.cc:38-49)      */
+
+  int32_t use_ewald;        /* PotentialEwaldCoul                              */
+  int32_t dipole_correction;
+  double lB;                /* Bjerrum length                                  */
+  double alpha;             /* Ewald alpha, ul^-2 (it is kappa^2)              */
+
+  int32_t bond_kind;        /* PG_BOND_*                                       */
+  int32_t _pad1;
+  double bond_k;            /* potential_spring.cc:15-20                       */
+  double bond_r0;
+
+  int32_t ext_kind;         /* PG_EXT_*                                        */
+  int32_t _pad2;
+  double wall_cut;          /* m_cut (potential_truncated_lj_wall.cc:23)       */
+  const double* wall_sigma;   /* [n_types] LJ wall sigma, or radius for hard/well walls */
+  const double* wall_epsilon; /* [n_types]                                     */
+  const int32_t* graft_kind;  /* [n_types] PG_GRAFT_*                          */
+  double well_width;        /* potential_well_wall.cc:41-55                    */
+  double well_depth;
+} pg_params;
+
+/* Derived Ewald set-up (src/force_field/potential_ewald_coul.cc:29-132). */
+typedef struct pg_ewald_info {
+  double ewald_box[3];   /* padded in z when dipole correction is on           */
+  double box_vol;
+  double real_cutoff;
+  int32_t real_cell[3];
+  int32_t n_k;           /* k vectors with 0 < k2 <= repl_cutoff in the cube   */
+  double repl_cutoff;
+  int32_t repl_cell[3];
+  int32_t n_k_half;      /* the half-space actually stored on the device       */
+} pg_ewald_info;
+
+/* Components of one trial move's energy change, and the orchestrated total the
+ * driver compares with kVeryLargeEnergy (src/force_field/force_field.cc:407-434). */
+typedef struct pg_delta {
+  double dE;          /* what ForceField::EnergyDifference returns               */
+  double pair;        /* PotentialPair::EnergyDifference                         */
+  double ext;         /* PotentialExternal::EnergyDifference (exactly 1e8 if out)*/
+  double ewald;       /* real + recip (+ dipole term supplied by the caller)     */
+  double bond;        /* PotentialBond::EnergyDifference                         */
+  double real;        /* Ewald real-space part                                   */
+  double recip;       /* Ewald reciprocal part via dS(k)                         */
+  double mz_current;  /* sum q*z over all beads, current coordinates             */
+  int32_t stage;      /* 0 full; 1 returned after pair; 2 returned after ext     */
+  int32_t n_overlap;  /* pairs that hit the r<=0 / hard-core sentinel            */
+} pg_delta;
+
+/* Running totals as the reference accumulates them (E_tot of each potential). */
+typedef struct pg_totals {
+  double pair, ewald, bond, ext;
+  double real, recip, self, dipole;   /* Ewald split; dipole = current_dipl_E   */
+} pg_totals;
+
+typedef struct pg_engine pg_engine;
+
+/* ---- life cycle --------------------------------------------------------- */
+/* Replaces ForceField::Initialize's potential construction
+ * (src/force_field/force_field.cc:118-195).  `device` is a CUDA ordinal.
+ * `capacity_beads` sizes the resident arrays (>= n ever present; GC grows). */
+int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine** out);
+int pg_destroy(pg_engine* h);
+const char* pg_last_error(const pg_engine* h);
+int pg_abi_version(void);
+int pg_get_ewald_info(const pg_engine* h, pg_ewald_info* out);
+
+/* ---- state --------------------------------------------------------------- */
+/* Uploads the whole system (replaces the map fills of
+ * PotentialPair::EnergyInitialization potential_pair.cc:55-100 and
+ * PotentialEwald::EnergyInitialization potential_ewald.cc:176-230):
+ * xyz is [n][3]; mol_first has n_mol+1 entries (bead range of each molecule). */
+int pg_upload_system(pg_engine* h, int n_beads, const double* xyz, const double* q,
+                     const int32_t* type, int n_mol, const int32_t* mol_first);
+/* Full recompute of every total from resident coordinates, including the full
+ * S(k) (ForceField::InitializeEnergy force_field.cc:365-381).  Resets the
+ * running totals to the recomputed values. */
+int pg_init_energy(pg_engine* h, pg_totals* out);
+/* Recompute totals WITHOUT touching the running totals or S(k) (drift check). */
+int pg_recompute_totals(pg_engine* h, pg_totals* out);
+int pg_get_totals(const pg_engine* h, pg_totals* out);
+int pg_download_positions(pg_engine* h, double* xyz /* [n][3] */);
+int pg_num_beads(const pg_engine* h);
+
+/* ---- the per-move hot path ------------------------------------------------ */
+/* ForceField::EnergyDifference (force_field.cc:407-434).  `mol` is the moved
+ * molecule; trial_xyz is [len][3] for ALL its beads (trial == current for the
+ * unmoved ones); moved is [len] 0/1 (Bead::GetMoved).  Synchronous: returns when
+ * the result is on the host.  `dipole_lag` is added to the Ewald term: the
+ * reference's trial_dipl_E - current_dipl_E quirk is a host-side state machine
+ * (potential_ewald.cc:527-531) fed from out->mz_current. */
+int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* moved,
+               pg_delta* out);
+/* ForceField::FinalizeEnergies (force_field.cc:436-451): accept applies the
+ * position deltas and S(k) += dS(k) on the device and adds the components to
+ * the running totals; reject drops the trial.  Asynchronous on the device. */
+int pg_commit(pg_engine* h, int accept);
+
+/* ---- device-resident replay (bench `value` leg; inputs already in HBM) ---- */
+/* A packed list of proposals is uploaded once; pg_replay runs them back to
+ * back with the Metropolis decision taken on the device from the recorded
+ * uniform variate (u < exp(-beta dE), skipped when dE >= 1e8 exactly like
+ * src/simulation/simulation.cc:327-332).  No host round trip per move. */
+typedef struct pg_proposal {
+  int32_t mol;        /* moved molecule                                        */
+  int32_t xyz_offset; /* offset (in beads) of its trial coordinates in xyz     */
+  double u;           /* uniform variate for the acceptance test               */
+} pg_proposal;
+int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves,
+                     int n_xyz_beads, const double* trial_xyz, const uint8_t* moved);
+/* Runs moves [first, first+count); dE_out/accept_out (host, may be NULL) are
+ * filled after the batch.  elapsed_ms is CUDA-event time on the engine stream. */
+int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out,
+                  float* elapsed_ms);
+
+/* ---- configurational-bias trial energies (ForceField::BeadsEnergy) ------- */
+/* One launch evaluates n_trials candidate (monomer, counter-ion) pairs against
+ * every resident bead except molecules [skip_mol_first, skip_mol_last] (the
+ * chain being retraced, cbmc.cc:22-23; pass -1,-1 for insertion) and against
+ * the partial chain grown so far (cbmc.cc:54-90).
+ *   bead1_xyz [n_trials][3], bead2_xyz [n_trials][3] (ignored if !use_bead2)
+ *   chain_xyz/chain_q: current_len monomers followed by current_len ions
+ *   out_energy[n_trials]: what BeadsEnergy returns (1e8 sentinel included)
+ *   out_pair / out_ewald (may be NULL): its pair_e and ewald_e partial sums.
+ * dipole: the caller passes mz_base = sum q z over the partners the reference
+ * includes (cbmc DipoleEDiff, potential_ewald_coul.cc:473-530) or NaN to have
+ * the device compute it. */
+typedef struct pg_trial_set {
+  int32_t n_trials;
+  int32_t use_bead2;
+  int32_t type1, type2;
+  double q1, q2;
+  int32_t current_len;     /* beads already grown                              */
+  int32_t skip_mol_first;  /* -1: nothing skipped                              */
+  int32_t skip_mol_last;
+  int32_t _pad;
+} pg_trial_set;
+int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1_xyz,
+                      const double* bead2_xyz, const double* chain_xyz, const double* chain_q,
+                      const int32_t* chain_type, double* out_energy, double* out_pair,
+                      double* out_ewald);
+
+/* ---- grand-canonical bookkeeping ------------------------------------------ */
+/* Append n_new_mol molecules at the end (accepted insertion: cbmc.cc:306-320 +
+ * ForceField::EnergyInitForAddedMolecule force_field.cc:1088-1105).  Adds their
+ * energy with everything (and among themselves) to the running totals and
+ * updates S(k).  `added` returns the energy components that were added. */
+int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, const double* xyz,
+                        const double* q, const int32_t* type, pg_totals* added);
+/* Remove molecules [mol_first, mol_last] (accepted deletion: the four
+ * AdjustEnergyUponMolDeletion, cbmc.cc:422-436), compacting the arrays. */
+int pg_delete_molecules(pg_engine* h, int mol_first, int mol_last, pg_totals* removed);
+
+/* ---- reciprocal space, shardable ------------------------------------------ */
+/* Full S(k) over all charged beads for the k slice [k_first, k_first+k_count)
+ * of the half-space list; writes interleaved (re,im) to sk_dev (device pointer,
+ * may alias a torch tensor) or, if NULL, into the engine's own S(k).  Used by
+ * the k-sharded recompute: each rank fills its slice, NCCL all-gathers. */
+int pg_sk_compute_slice(pg_engine* h, int k_first, int k_count, double* sk_dev);
+/* Adopt a full S(k) (n_k_half complex numbers, device pointer) as the engine's. */
+int pg_sk_set(pg_engine* h, const double* sk_dev);
+/* Reciprocal energy of the k slice from the engine's S(k). */
+int pg_sk_energy(pg_engine* h, int k_first, int k_count, double* e_out);
+int pg_sk_download(pg_engine* h, double* sk_host /* [n_k_half][2] */);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* Number of kernels this engine has launched since creation. */
+uint64_t pg_launch_count(const pg_engine* h);
+/* The CUDA stream the engine launches on (cudaStream_t as void*). */
+void* pg_stream(const pg_engine* h);
+/* FP64 FMA throughput microbenchmark (GFLOP/s, FMA = 2 flop) used as the
+ * roofline denominator the driver's MEASURED_PEAKS.json does not carry. */
+int pg_measure_fp64_peak(pg_engine* h, double* gflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLUM_B200_H_ */

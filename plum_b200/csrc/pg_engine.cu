@@ -1,0 +1,998 @@
+// plum_b200 — host side of the engine and the C ABI (include/plum_b200.h).
+//
+// One pg_engine = one system replica resident on one GPU.  The host keeps only
+// small mirrors (molecule table, per-bead charge/type) so it can describe a bead
+// group to the kernels without reading the device back; coordinates, S(k) and
+// the running energy totals are device-authoritative.
+//
+// Reference behaviour replaced (file:line relative to /root/reference):
+//   ForceField::Initialize / InitializeEnergy   src/force_field/force_field.cc:46-405
+//   ForceField::EnergyDifference                src/force_field/force_field.cc:407-434
+//   ForceField::FinalizeEnergies                src/force_field/force_field.cc:436-451
+//   ForceField::BeadsEnergy                     src/force_field/cbmc.cc:5-151
+//   ForceField::EnergyInitForAddedMolecule      src/force_field/force_field.cc:1088-1105
+//   *::AdjustEnergyUponMolDeletion              src/force_field/cbmc.cc:422-436
+//   PotentialEwaldCoul::ReadParameters          src/force_field/potential_ewald_coul.cc:29-132
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/plum_b200.h"
+#include "pg_kernels.cu"
+
+namespace {
+
+// src/utilities/constants.h:5-62 (truncated on purpose: parity with the reference)
+const double kPi = 3.14159265359;
+const double kEwaldCutoff = 1E-7;
+const int kDiCorrection = 3;
+const double k213 = 1.25992104989;
+const double k216 = 1.12246204831;
+
+struct ReplayMove {
+  int mol, g0, glen, off;  // off: bead offset into the packed proposal buffers
+  double u;
+};
+
+}  // namespace
+
+struct pg_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  PgDev P;
+  pg_ewald_info info;
+  std::string err;
+  uint64_t launches = 0;
+
+  // resident system
+  int cap = 0, n = 0, n_mol = 0;
+  double2 *xy = nullptr, *zq = nullptr;
+  int *type = nullptr, *mol = nullptr;
+  double2 *t_xy = nullptr, *t_zq = nullptr;   // compaction scratch
+  int *t_type = nullptr, *t_mol = nullptr;
+  std::vector<int> mol_first;   // host mirror [n_mol+1]
+  std::vector<double> h_q;      // host mirror of charges
+  std::vector<int> h_type;      // host mirror of types
+
+  // reciprocal space
+  int nk = 0;
+  std::vector<int> h_kl;        // [nk][4]
+  std::vector<double> h_ek2;
+  int* d_kl = nullptr;
+  double* d_ek2 = nullptr;
+  double2 *d_S = nullptr, *d_dS = nullptr, *d_Sp = nullptr, *d_Stmp = nullptr;
+
+  // group staging: one pinned block + one device block with the same layout
+  int gcap = 0;
+  char* h_stage = nullptr;
+  char* d_stage = nullptr;
+  size_t stage_bytes = 0;
+
+  // scratch
+  int partial_cap = 0;
+  double* d_partial = nullptr;
+  int* d_partial_i = nullptr;
+  double* d_out8 = nullptr;     // 8 doubles
+  double* h_out8 = nullptr;     // pinned
+  PgState* d_state = nullptr;
+  PgResult* h_result = nullptr; // mapped pinned
+  PgResult* d_result = nullptr; // device alias of h_result
+  unsigned int seq = 0;
+  bool use_mailbox = true;
+
+  // pending trial
+  bool pending = false;
+  int pend_mode = 0, pend_g0 = 0, pend_glen = 0;
+
+  // CBMC staging
+  int tcap = 0;       // trials capacity
+  int ccap = 0;       // chain capacity
+  double *h_trial_in = nullptr, *d_trial_in = nullptr;    // b1 | b2 | chain_xyz | chain_q
+  int *h_trial_ct = nullptr, *d_trial_ct = nullptr;
+  double *h_trial_out = nullptr, *d_trial_out = nullptr;  // energy | pair | ewald
+
+  // replay
+  std::vector<ReplayMove> rp_moves;
+  char* d_rp = nullptr;
+  size_t rp_beads = 0;
+  double* d_rp_dE = nullptr;
+  uint8_t* d_rp_acc = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define PG_CUDA(h, call)                                                                     \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+      return PG_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+namespace {
+
+static std::string g_create_err;
+
+// Stage layout for a group of `cap` beads.
+struct StageView {
+  double* trial;   // [cap][3]
+  double* gq;      // [cap]
+  int* gtype;      // [cap]
+  uint8_t* moved;  // [cap]
+};
+size_t stage_size(int cap) { return sizeof(double) * 4 * (size_t)cap + sizeof(int) * (size_t)cap + (size_t)cap + 64; }
+StageView stage_view(char* base, int cap) {
+  StageView v;
+  v.trial = reinterpret_cast<double*>(base);
+  v.gq = v.trial + 3 * (size_t)cap;
+  v.gtype = reinterpret_cast<int*>(v.gq + cap);
+  v.moved = reinterpret_cast<uint8_t*>(v.gtype + cap);
+  return v;
+}
+
+// PotentialEwaldCoul::ReadParameters, potential_ewald_coul.cc:29-132.
+void ewald_setup(pg_engine* h, const pg_params* p) {
+  PgDev& P = h->P;
+  pg_ewald_info& I = h->info;
+  memset(&I, 0, sizeof(I));
+  double box_l[3] = {p->box[0], p->box[1], p->box[2]};
+  if (p->dipole_correction) {
+    double min_padding = 150;
+    if (box_l[2] * kDiCorrection > min_padding)
+      box_l[2] = box_l[2] * kDiCorrection;
+    else
+      box_l[2] += min_padding;
+  }
+  double box_vol = box_l[0] * box_l[1] * box_l[2];
+  double lB = p->lB, alpha = p->alpha;
+  double real_cutoff = 1;
+  while (0.5 * lB * 1 * 1 * erfc(sqrt(alpha) * real_cutoff) / real_cutoff > kEwaldCutoff) real_cutoff += 1;
+  int real_cell[3], repl_cell[3], ceto[3];
+  for (int i = 0; i < 3; i++) real_cell[i] = (int)ceil(real_cutoff / box_l[i]);
+  double repl_cutoff = alpha;
+  double min_box_vol = pow(box_l[0], 3);
+  while (lB * 1 * 1 / (2 * kPi * min_box_vol) * (4 * kPi * kPi) * exp(-repl_cutoff / (4 * alpha)) / repl_cutoff >
+         kEwaldCutoff)
+    repl_cutoff += alpha;
+  for (int i = 0; i < 3; i++) repl_cell[i] = (int)ceil(sqrt(repl_cutoff) * box_l[i] / (2 * kPi));
+  for (int i = 0; i < 3; i++) ceto[i] = 2 * repl_cell[i] + 1;
+  std::vector<double> kx(ceto[0]), ky(ceto[1]), kz(ceto[2]);
+  for (int l = -repl_cell[0]; l <= repl_cell[0]; l++) kx[l + repl_cell[0]] = l * 2 * kPi / box_l[0];
+  for (int l = -repl_cell[1]; l <= repl_cell[1]; l++) ky[l + repl_cell[1]] = l * 2 * kPi / box_l[1];
+  for (int l = -repl_cell[2]; l <= repl_cell[2]; l++) kz[l + repl_cell[2]] = l * 2 * kPi / box_l[2];
+  h->h_kl.clear();
+  h->h_ek2.clear();
+  int n_k = 0;
+  for (int ix = 0; ix < ceto[0]; ix++)
+    for (int iy = 0; iy < ceto[1]; iy++)
+      for (int iz = 0; iz < ceto[2]; iz++) {
+        double k2 = kx[ix] * kx[ix] + ky[iy] * ky[iy] + kz[iz] * kz[iz];
+        double ek2 = exp(-k2 / (4 * alpha)) / k2;
+        if (!(k2 > 0 && k2 <= repl_cutoff)) continue;
+        n_k++;
+        int ax = ix - repl_cell[0], ay = iy - repl_cell[1], az = iz - repl_cell[2];
+        // S(-k) = conj(S(k)) and ek2(-k) == ek2(k) bit for bit: keep the half space, weight 2
+        bool pos = (ax > 0) || (ax == 0 && ay > 0) || (ax == 0 && ay == 0 && az > 0);
+        if (!pos) continue;
+        h->h_kl.push_back(ax); h->h_kl.push_back(ay); h->h_kl.push_back(az); h->h_kl.push_back(0);
+        h->h_ek2.push_back(ek2);
+      }
+  h->nk = (int)h->h_ek2.size();
+  for (int i = 0; i < 3; i++) {
+    I.ewald_box[i] = box_l[i];
+    I.real_cell[i] = real_cell[i];
+    I.repl_cell[i] = repl_cell[i];
+    P.ebox[i] = box_l[i];
+    P.inv_ebox[i] = 1.0 / box_l[i];
+    P.real_cell[i] = real_cell[i];
+  }
+  I.box_vol = box_vol;
+  I.real_cutoff = real_cutoff;
+  I.repl_cutoff = repl_cutoff;
+  I.n_k = n_k;
+  I.n_k_half = h->nk;
+  P.lB = lB;
+  P.sqrt_alpha = sqrt(alpha);
+  P.real_cutoff = real_cutoff;
+  P.rc_relaxed = real_cutoff * (1.0 + 1e-9);
+  P.rc2_relaxed = P.rc_relaxed * P.rc_relaxed;
+  P.recip_pref = 2 * kPi * lB / box_vol;
+  P.self_pref = -lB * sqrt(alpha / kPi);
+  P.dipole_pref = lB * 2 * kPi / (box_vol / 1.0);
+  // only the central image can pass r <= real_cutoff when every axis is periodic and
+  // the relaxed cutoff stays below half the shortest cell edge
+  bool single = (p->npbc == 3);
+  for (int i = 0; i < 3; i++)
+    if (!(P.rc_relaxed < 0.5 * box_l[i] * (1.0 - 1e-9))) single = false;
+  P.single_image = single ? 1 : 0;
+}
+
+int build_params(pg_engine* h, const pg_params* p) {
+  PgDev& P = h->P;
+  memset(&P, 0, sizeof(P));
+  if (p->n_types < 1 || p->n_types > PG_MAX_TYPES) {
+    g_create_err = "n_types out of range (1.." + std::to_string(PG_MAX_TYPES) + ")";
+    return PG_ERR_CAPACITY;
+  }
+  if (p->npbc < 2 || p->npbc > 3) {
+    g_create_err = "npbc must be 2 or 3";
+    return PG_ERR_INVALID;
+  }
+  for (int i = 0; i < 3; i++) {
+    if (!(p->box[i] > 0)) { g_create_err = "box lengths must be positive"; return PG_ERR_INVALID; }
+    P.box[i] = p->box[i];
+    P.inv_box[i] = 1.0 / p->box[i];
+    P.half_box[i] = 0.5 * p->box[i];
+    P.pbc[i] = (i < p->npbc) ? 1 : 0;
+    P.ebox[i] = p->box[i];
+    P.inv_ebox[i] = 1.0 / p->box[i];
+  }
+  P.n_types = p->n_types;
+  P.beta = p->beta;
+  P.pair_kind = p->pair_kind;
+  P.lj_cutoff = p->lj_cutoff;
+  for (int a = 0; a < p->n_types; a++)
+    for (int b = 0; b < p->n_types; b++) {
+      int tp = a * PG_MAX_TYPES + b;
+      if (p->pair_kind == PG_PAIR_TRUNCATED_LJ) {
+        // potential_truncated_lj.cc:55-82
+        double sigma = (p->lj_sigma[a] + p->lj_sigma[b]) / 2;
+        double epsilon = sqrt((p->lj_epsilon[a] * p->lj_epsilon[b]));
+        double r6_ref, rcut;
+        if (p->lj_cutoff < 0) {
+          r6_ref = pow((1.0 / k216), 6);
+          rcut = k216 * sigma;
+        } else {
+          r6_ref = pow((sigma / p->lj_cutoff), 6);
+          rcut = p->lj_cutoff;
+        }
+        P.lj_sigma[tp] = sigma;
+        P.lj_eps4[tp] = 4 * epsilon;
+        P.lj_eref[tp] = 4 * epsilon * (r6_ref * r6_ref - r6_ref);
+        P.lj_rcut[tp] = rcut;
+        double rr = rcut * (1.0 + 1e-9);
+        P.lj_rcut2_relaxed[tp] = rr * rr;
+      } else if (p->pair_kind == PG_PAIR_HARD_SPHERE) {
+        P.hs_allowed[tp] = p->hs_radius[a] + p->hs_radius[b];
+      }
+    }
+  P.use_ewald = p->use_ewald ? 1 : 0;
+  P.dipole = (p->use_ewald && p->dipole_correction) ? 1 : 0;
+  h->nk = 0;
+  memset(&h->info, 0, sizeof(h->info));
+  if (p->use_ewald) {
+    if (!(p->alpha > 0) || !(p->lB >= 0)) { g_create_err = "Ewald alpha must be > 0"; return PG_ERR_INVALID; }
+    ewald_setup(h, p);
+  }
+  for (int i = 0; i < 3; i++) P.same_box[i] = (P.ebox[i] == P.box[i]) ? 1 : 0;
+  P.bond_kind = p->bond_kind;
+  P.bond_k = p->bond_k;
+  P.bond_r0 = p->bond_r0;
+  P.ext_kind = p->ext_kind;
+  P.wall_cut = p->wall_cut;
+  P.well_width = p->well_width;
+  P.well_depth = p->well_depth;
+  for (int t = 0; t < p->n_types; t++) {
+    P.wall_sigma[t] = p->wall_sigma ? p->wall_sigma[t] : 0.0;
+    P.wall_eps[t] = p->wall_epsilon ? p->wall_epsilon[t] : 0.0;
+    P.graft[t] = p->graft_kind ? p->graft_kind[t] : 0;
+    if (p->ext_kind == PG_EXT_TRUNCATED_LJ_WALL) {
+      // potential_truncated_lj_wall.cc:69-70,117-118: reference energy of the branch in use
+      double r3_ref = (p->wall_cut < 0 || P.graft[t] != 0) ? pow((1.0 / k213), 3) : pow((1.0 / p->wall_cut), 3);
+      P.wall_r3ref_e[t] = 2.59807621135 * P.wall_eps[t] * (r3_ref * r3_ref - r3_ref);
+    }
+  }
+  return PG_OK;
+}
+
+int ensure_group(pg_engine* h, int glen) {
+  if (glen <= h->gcap) return PG_OK;
+  int cap = std::max(256, glen * 2);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->h_stage = nullptr; h->d_stage = nullptr;
+  h->stage_bytes = stage_size(cap);
+  PG_CUDA(h, cudaHostAlloc((void**)&h->h_stage, h->stage_bytes, cudaHostAllocDefault));
+  PG_CUDA(h, cudaMalloc((void**)&h->d_stage, h->stage_bytes));
+  h->gcap = cap;
+  return PG_OK;
+}
+
+int ensure_partials(pg_engine* h, int n_ctas) {
+  if (n_ctas <= h->partial_cap) return PG_OK;
+  int cap = std::max(4096, n_ctas * 2);
+  if (h->d_partial) cudaFree(h->d_partial);
+  if (h->d_partial_i) cudaFree(h->d_partial_i);
+  h->d_partial = nullptr; h->d_partial_i = nullptr;
+  PG_CUDA(h, cudaMalloc((void**)&h->d_partial, sizeof(double) * 4 * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&h->d_partial_i, sizeof(int) * (size_t)cap));
+  h->partial_cap = cap;
+  return PG_OK;
+}
+
+int ensure_capacity(pg_engine* h, int n_need) {
+  if (n_need <= h->cap) return PG_OK;
+  int cap = std::max(n_need * 2, 1024);
+  double2 *xy, *zq, *txy, *tzq;
+  int *type, *mol, *ttype, *tmol;
+  PG_CUDA(h, cudaMalloc((void**)&xy, sizeof(double2) * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&zq, sizeof(double2) * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&type, sizeof(int) * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&mol, sizeof(int) * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&txy, sizeof(double2) * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&tzq, sizeof(double2) * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&ttype, sizeof(int) * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&tmol, sizeof(int) * (size_t)cap));
+  if (h->n > 0) {
+    PG_CUDA(h, cudaMemcpyAsync(xy, h->xy, sizeof(double2) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(zq, h->zq, sizeof(double2) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(type, h->type, sizeof(int) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(mol, h->mol, sizeof(int) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  cudaFree(h->xy); cudaFree(h->zq); cudaFree(h->type); cudaFree(h->mol);
+  cudaFree(h->t_xy); cudaFree(h->t_zq); cudaFree(h->t_type); cudaFree(h->t_mol);
+  h->xy = xy; h->zq = zq; h->type = type; h->mol = mol;
+  h->t_xy = txy; h->t_zq = tzq; h->t_type = ttype; h->t_mol = tmol;
+  h->cap = cap;
+  return PG_OK;
+}
+
+// Wait for the result mailbox (or the stream) — the driver's call is synchronous.
+int wait_result(pg_engine* h, unsigned int seq) {
+  if (h->use_mailbox) {
+    auto t0 = std::chrono::steady_clock::now();
+    unsigned long spins = 0;
+    while (h->h_result->seq != seq) {
+      if ((++spins & 0xfffff) == 0) {
+        cudaError_t q = cudaStreamQuery(h->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) {
+          h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
+          return PG_ERR_CUDA;
+        }
+        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (dt > 30.0) {
+          h->err = "device did not answer within 30 s";
+          return PG_ERR_TIMEOUT;
+        }
+      }
+    }
+    return PG_OK;
+  }
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->h_result->seq != seq) { h->err = "result sequence mismatch"; return PG_ERR_STATE; }
+  return PG_OK;
+}
+
+// Launch k_delta for the group currently described in h_stage (already filled).
+int launch_delta(pg_engine* h, int mode, int g0, int glen, int chain_len_first, int bond_first, int bond_len,
+                 const char* d_group, int group_cap, bool decide_on_device, double u, int replay_index,
+                 bool want_result) {
+  PgDeltaArgs A;
+  memset(&A, 0, sizeof(A));
+  A.xy = h->xy; A.zq = h->zq; A.type = h->type;
+  A.n_partners = h->n;
+  A.g0 = g0; A.glen = glen; A.mode = mode;
+  A.has_old = (mode != PG_MODE_INSERT);
+  A.has_new = (mode != PG_MODE_DELETE);
+  StageView dv = stage_view(const_cast<char*>(d_group), group_cap);
+  A.trial = dv.trial; A.gq = dv.gq; A.gtype = dv.gtype; A.moved = dv.moved;
+  A.chain_len_first = chain_len_first;
+  A.bond_first = bond_first; A.bond_len = bond_len;
+  A.kl = h->d_kl; A.ek2 = h->d_ek2; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->nk;
+  A.n_tiles = std::max(1, (h->n + PG_TILE - 1) / PG_TILE);
+  A.n_chunks = std::max(1, (glen + PG_GCHUNK - 1) / PG_GCHUNK);
+  A.chunk_size = std::max(1, (glen + A.n_chunks - 1) / A.n_chunks);
+  A.n_pair_ctas = A.n_tiles * A.n_chunks;
+  A.n_k_ctas = h->P.use_ewald ? (h->nk + PG_KTILE - 1) / PG_KTILE : 0;
+  int n_ctas = A.n_pair_ctas + A.n_k_ctas;
+  int rc = ensure_partials(h, n_ctas);
+  if (rc) return rc;
+  A.partial = h->d_partial; A.partial_i = h->d_partial_i;
+  A.state = h->d_state;
+  A.result = want_result ? h->d_result : nullptr;
+  A.decide_on_device = decide_on_device ? 1 : 0;
+  A.u = u;
+  A.replay_dE = decide_on_device ? h->d_rp_dE : nullptr;
+  A.replay_acc = decide_on_device ? h->d_rp_acc : nullptr;
+  A.replay_index = replay_index;
+  A.seq = ++h->seq;
+  k_delta<<<n_ctas, PG_TILE, 0, h->stream>>>(h->P, A);
+  h->launches++;
+  PG_CUDA(h, cudaGetLastError());
+  return PG_OK;
+}
+
+int launch_commit(pg_engine* h, int accept_flag, int mode, int g0, int glen, const char* d_group, int group_cap) {
+  StageView dv = stage_view(const_cast<char*>(d_group), group_cap);
+  int nthreads = std::max(std::max(glen, h->nk), 1);
+  int nb = (nthreads + 255) / 256;
+  k_commit<<<nb, 256, 0, h->stream>>>(h->P, accept_flag, mode, g0, glen, dv.trial, dv.gq, dv.gtype, h->xy, h->zq,
+                                      h->type, h->d_S, h->d_dS, h->P.use_ewald ? h->nk : 0, h->d_state);
+  h->launches++;
+  PG_CUDA(h, cudaGetLastError());
+  return PG_OK;
+}
+
+void fill_delta(const PgResult* r, pg_delta* o) {
+  o->dE = r->dE; o->pair = r->pair; o->ext = r->ext; o->ewald = r->ewald; o->bond = r->bond;
+  o->real = r->real; o->recip = r->recip; o->mz_current = r->mz_current;
+  o->stage = r->stage; o->n_overlap = r->n_overlap;
+}
+
+int compute_totals(pg_engine* h, bool set_state, pg_totals* out) {
+  double2* S = set_state ? h->d_S : h->d_Stmp;
+  if (h->P.use_ewald && h->nk > 0) {
+    int nb = (h->nk + PG_TILE - 1) / PG_TILE;
+    k_sk_slice<<<nb, PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->n, h->d_kl, 0, h->nk, S);
+    h->launches++;
+    PG_CUDA(h, cudaGetLastError());
+  }
+  int n_tiles = (h->n + PG_TILE - 1) / PG_TILE;
+  int rc = ensure_partials(h, n_tiles);
+  if (rc) return rc;
+  if (n_tiles > 0) {
+    k_tot_pairs<<<n_tiles, PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->type, h->mol, h->n, h->d_partial);
+    h->launches++;
+    PG_CUDA(h, cudaGetLastError());
+  }
+  k_tot_final<<<1, 256, 0, h->stream>>>(h->P, h->xy, h->zq, h->type, h->mol, h->n, h->d_partial, n_tiles, S,
+                                        h->d_ek2, h->nk, h->d_out8, h->d_state, set_state ? 1 : 0);
+  h->launches++;
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaMemcpyAsync(h->h_out8, h->d_out8, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (out) {
+    out->pair = h->h_out8[0]; out->ewald = h->h_out8[1]; out->bond = h->h_out8[2]; out->ext = h->h_out8[3];
+    out->real = h->h_out8[4]; out->recip = h->h_out8[5]; out->self = h->h_out8[6]; out->dipole = h->h_out8[7];
+  }
+  return PG_OK;
+}
+
+void free_all(pg_engine* h) {
+  cudaFree(h->xy); cudaFree(h->zq); cudaFree(h->type); cudaFree(h->mol);
+  cudaFree(h->t_xy); cudaFree(h->t_zq); cudaFree(h->t_type); cudaFree(h->t_mol);
+  cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_S); cudaFree(h->d_dS); cudaFree(h->d_Sp); cudaFree(h->d_Stmp);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  cudaFree(h->d_stage);
+  cudaFree(h->d_partial); cudaFree(h->d_partial_i); cudaFree(h->d_out8);
+  if (h->h_out8) cudaFreeHost(h->h_out8);
+  cudaFree(h->d_state);
+  if (h->h_result) cudaFreeHost(h->h_result);
+  if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
+  if (h->h_trial_ct) cudaFreeHost(h->h_trial_ct);
+  if (h->h_trial_out) cudaFreeHost(h->h_trial_out);
+  cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_trial_out);
+  cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+}  // namespace
+
+// =============================================================== C ABI ====
+extern "C" {
+
+int pg_abi_version(void) { return PG_ABI_VERSION; }
+
+const char* pg_last_error(const pg_engine* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine** out) {
+  if (!params || !out) { g_create_err = "null argument"; return PG_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    g_create_err = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+    return PG_ERR_NO_DEVICE;
+  }
+  pg_engine* h = new pg_engine();
+  h->device = device;
+  int rc = build_params(h, params);
+  if (rc) { delete h; return rc; }
+#define PG_CREATE_CUDA(call)                                                    \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      g_create_err = std::string(#call) + ": " + cudaGetErrorString(e_);        \
+      free_all(h); delete h; return PG_ERR_CUDA;                                \
+    }                                                                           \
+  } while (0)
+  PG_CREATE_CUDA(cudaSetDevice(device));
+  PG_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  PG_CREATE_CUDA(cudaEventCreate(&h->ev0));
+  PG_CREATE_CUDA(cudaEventCreate(&h->ev1));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_state, sizeof(PgState)));
+  PG_CREATE_CUDA(cudaMemset(h->d_state, 0, sizeof(PgState)));
+  PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_result, sizeof(PgResult), cudaHostAllocMapped));
+  memset((void*)h->h_result, 0, sizeof(PgResult));
+  PG_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_result, (void*)h->h_result, 0));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_out8, sizeof(double) * 8));
+  PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_out8, sizeof(double) * 8, cudaHostAllocDefault));
+  int nk_alloc = std::max(h->nk, 1);
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_kl, sizeof(int) * 4 * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_ek2, sizeof(double) * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_S, sizeof(double2) * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_dS, sizeof(double2) * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_Sp, sizeof(double2) * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_Stmp, sizeof(double2) * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMemset(h->d_S, 0, sizeof(double2) * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMemset(h->d_dS, 0, sizeof(double2) * (size_t)nk_alloc));
+  if (h->nk > 0) {
+    PG_CREATE_CUDA(cudaMemcpy(h->d_kl, h->h_kl.data(), sizeof(int) * 4 * (size_t)h->nk, cudaMemcpyHostToDevice));
+    PG_CREATE_CUDA(cudaMemcpy(h->d_ek2, h->h_ek2.data(), sizeof(double) * (size_t)h->nk, cudaMemcpyHostToDevice));
+  }
+#undef PG_CREATE_CUDA
+  const char* mb = getenv("PLUM_B200_NO_MAILBOX");
+  h->use_mailbox = !(mb && mb[0] == '1');
+  h->mol_first.assign(1, 0);
+  rc = ensure_capacity(h, std::max(capacity_beads, 1));
+  if (!rc) rc = ensure_group(h, 256);
+  if (!rc) rc = ensure_partials(h, 4096);
+  if (rc) { g_create_err = h->err; free_all(h); delete h; return rc; }
+  *out = h;
+  return PG_OK;
+}
+
+int pg_destroy(pg_engine* h) {
+  if (!h) return PG_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_all(h);
+  delete h;
+  return PG_OK;
+}
+
+int pg_get_ewald_info(const pg_engine* h, pg_ewald_info* out) {
+  if (!h || !out) return PG_ERR_INVALID;
+  *out = h->info;
+  return PG_OK;
+}
+
+int pg_num_beads(const pg_engine* h) { return h ? h->n : PG_ERR_INVALID; }
+uint64_t pg_launch_count(const pg_engine* h) { return h ? h->launches : 0; }
+void* pg_stream(const pg_engine* h) { return h ? (void*)h->stream : nullptr; }
+
+int pg_upload_system(pg_engine* h, int n_beads, const double* xyz, const double* q, const int32_t* type, int n_mol,
+                     const int32_t* mol_first) {
+  if (!h || n_beads < 0 || n_mol < 0 || !mol_first) return PG_ERR_INVALID;
+  if (n_beads > 0 && (!xyz || !q || !type)) { h->err = "null bead arrays"; return PG_ERR_INVALID; }
+  if (mol_first[0] != 0 || mol_first[n_mol] != n_beads) { h->err = "mol_first must span [0, n_beads]"; return PG_ERR_INVALID; }
+  for (int i = 0; i < n_beads; i++)
+    if (type[i] < 0 || type[i] >= h->P.n_types) { h->err = "bead type id out of range"; return PG_ERR_INVALID; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_capacity(h, std::max(n_beads, 1));
+  if (rc) return rc;
+  std::vector<double2> hxy(std::max(n_beads, 1)), hzq(std::max(n_beads, 1));
+  std::vector<int> hmol(std::max(n_beads, 1));
+  h->h_q.assign(q, q + n_beads);
+  h->h_type.assign(type, type + n_beads);
+  h->mol_first.assign(mol_first, mol_first + n_mol + 1);
+  for (int m = 0; m < n_mol; m++) {
+    if (mol_first[m + 1] < mol_first[m]) { h->err = "mol_first must be non-decreasing"; return PG_ERR_INVALID; }
+    for (int i = mol_first[m]; i < mol_first[m + 1]; i++) hmol[i] = m;
+  }
+  for (int i = 0; i < n_beads; i++) {
+    hxy[i] = make_double2(xyz[3 * i], xyz[3 * i + 1]);
+    hzq[i] = make_double2(xyz[3 * i + 2], q[i]);
+  }
+  if (n_beads > 0) {
+    PG_CUDA(h, cudaMemcpyAsync(h->xy, hxy.data(), sizeof(double2) * (size_t)n_beads, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(h->zq, hzq.data(), sizeof(double2) * (size_t)n_beads, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(h->type, type, sizeof(int) * (size_t)n_beads, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(h->mol, hmol.data(), sizeof(int) * (size_t)n_beads, cudaMemcpyHostToDevice, h->stream));
+  }
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n = n_beads;
+  h->n_mol = n_mol;
+  h->pending = false;
+  return PG_OK;
+}
+
+int pg_init_energy(pg_engine* h, pg_totals* out) {
+  if (!h) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->pending = false;
+  return compute_totals(h, true, out);
+}
+
+int pg_recompute_totals(pg_engine* h, pg_totals* out) {
+  if (!h) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  return compute_totals(h, false, out);
+}
+
+int pg_get_totals(const pg_engine* hc, pg_totals* out) {
+  pg_engine* h = const_cast<pg_engine*>(hc);
+  if (!h || !out) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PgState st;
+  PG_CUDA(h, cudaMemcpyAsync(&st, h->d_state, sizeof(PgState), cudaMemcpyDeviceToHost, h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  out->pair = st.E_pair; out->ewald = st.E_ewald; out->bond = st.E_bond; out->ext = st.E_ext;
+  out->real = st.E_real; out->recip = st.E_recip; out->self = st.E_self; out->dipole = st.cur_dipl;
+  return PG_OK;
+}
+
+int pg_download_positions(pg_engine* h, double* xyz) {
+  if (!h || (!xyz && h->n > 0)) return PG_ERR_INVALID;
+  if (h->n == 0) return PG_OK;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  std::vector<double2> hxy(h->n), hzq(h->n);
+  PG_CUDA(h, cudaMemcpyAsync(hxy.data(), h->xy, sizeof(double2) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  PG_CUDA(h, cudaMemcpyAsync(hzq.data(), h->zq, sizeof(double2) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->n; i++) { xyz[3 * i] = hxy[i].x; xyz[3 * i + 1] = hxy[i].y; xyz[3 * i + 2] = hzq[i].x; }
+  return PG_OK;
+}
+
+// ------------------------------------------------------------ per-move path
+int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* moved, pg_delta* out) {
+  if (!h || !trial_xyz || !moved || !out) return PG_ERR_INVALID;
+  if (mol < 0 || mol >= h->n_mol) { h->err = "molecule index out of range"; return PG_ERR_INVALID; }
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  const int g0 = h->mol_first[mol], glen = h->mol_first[mol + 1] - g0;
+  int rc = ensure_group(h, glen);
+  if (rc) return rc;
+  StageView sv = stage_view(h->h_stage, h->gcap);
+  memcpy(sv.trial, trial_xyz, sizeof(double) * 3 * (size_t)glen);
+  for (int i = 0; i < glen; i++) {
+    sv.gq[i] = h->h_q[g0 + i];
+    sv.gtype[i] = h->h_type[g0 + i];
+    sv.moved[i] = moved[i] ? 1 : 0;
+  }
+  PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, h->stage_bytes, cudaMemcpyHostToDevice, h->stream));
+  rc = launch_delta(h, PG_MODE_MOVE, g0, glen, glen, 0, glen, h->d_stage, h->gcap, false, 0.0, 0, true);
+  if (rc) return rc;
+  rc = wait_result(h, h->seq);
+  if (rc) return rc;
+  fill_delta(h->h_result, out);
+  h->pending = true;
+  h->pend_mode = PG_MODE_MOVE; h->pend_g0 = g0; h->pend_glen = glen;
+  return PG_OK;
+}
+
+int pg_commit(pg_engine* h, int accept) {
+  if (!h) return PG_ERR_INVALID;
+  if (!h->pending) { h->err = "no pending trial"; return PG_ERR_STATE; }
+  h->pending = false;
+  return launch_commit(h, accept ? 1 : 0, h->pend_mode, h->pend_g0, h->pend_glen, h->d_stage, h->gcap);
+}
+
+// ------------------------------------------------------------------ replay
+int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_xyz_beads, const double* trial_xyz,
+                     const uint8_t* moved) {
+  if (!h || n_moves < 0 || (n_moves > 0 && (!moves || !trial_xyz || !moved))) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->rp_moves.clear();
+  cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
+  h->d_rp = nullptr; h->d_rp_dE = nullptr; h->d_rp_acc = nullptr;
+  h->rp_beads = (size_t)std::max(n_xyz_beads, 1);
+  std::vector<char> host(stage_size((int)h->rp_beads));
+  StageView sv = stage_view(host.data(), (int)h->rp_beads);
+  memcpy(sv.trial, trial_xyz, sizeof(double) * 3 * (size_t)n_xyz_beads);
+  for (int i = 0; i < n_xyz_beads; i++) sv.moved[i] = moved[i] ? 1 : 0;
+  for (int m = 0; m < n_moves; m++) {
+    int mol = moves[m].mol;
+    if (mol < 0 || mol >= h->n_mol) { h->err = "replay: molecule index out of range"; return PG_ERR_INVALID; }
+    ReplayMove r;
+    r.mol = mol; r.g0 = h->mol_first[mol]; r.glen = h->mol_first[mol + 1] - r.g0; r.off = moves[m].xyz_offset;
+    r.u = moves[m].u;
+    if (r.off < 0 || r.off + r.glen > n_xyz_beads) { h->err = "replay: xyz_offset out of range"; return PG_ERR_INVALID; }
+    for (int i = 0; i < r.glen; i++) { sv.gq[r.off + i] = h->h_q[r.g0 + i]; sv.gtype[r.off + i] = h->h_type[r.g0 + i]; }
+    h->rp_moves.push_back(r);
+  }
+  PG_CUDA(h, cudaMalloc((void**)&h->d_rp, host.size()));
+  PG_CUDA(h, cudaMemcpy(h->d_rp, host.data(), host.size(), cudaMemcpyHostToDevice));
+  PG_CUDA(h, cudaMalloc((void**)&h->d_rp_dE, sizeof(double) * (size_t)std::max(n_moves, 1)));
+  PG_CUDA(h, cudaMalloc((void**)&h->d_rp_acc, (size_t)std::max(n_moves, 1)));
+  return PG_OK;
+}
+
+int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, float* elapsed_ms) {
+  if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  // The packed buffer has the StageView layout with capacity rp_beads; a group at bead
+  // offset `off` is the same view shifted by `off` elements of each sub-array, so pass
+  // shifted pointers through a per-move StageView computed here.
+  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  StageView base = stage_view(h->d_rp, (int)h->rp_beads);
+  for (int m = first; m < first + count; m++) {
+    const ReplayMove& r = h->rp_moves[m];
+    PgDeltaArgs A;
+    memset(&A, 0, sizeof(A));
+    A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n_partners = h->n;
+    A.g0 = r.g0; A.glen = r.glen; A.mode = PG_MODE_MOVE; A.has_old = 1; A.has_new = 1;
+    A.trial = base.trial + 3 * (size_t)r.off; A.gq = base.gq + r.off; A.gtype = base.gtype + r.off;
+    A.moved = base.moved + r.off;
+    A.chain_len_first = r.glen; A.bond_first = 0; A.bond_len = r.glen;
+    A.kl = h->d_kl; A.ek2 = h->d_ek2; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->nk;
+    A.n_tiles = std::max(1, (h->n + PG_TILE - 1) / PG_TILE);
+    A.n_chunks = std::max(1, (r.glen + PG_GCHUNK - 1) / PG_GCHUNK);
+    A.chunk_size = std::max(1, (r.glen + A.n_chunks - 1) / A.n_chunks);
+    A.n_pair_ctas = A.n_tiles * A.n_chunks;
+    A.n_k_ctas = h->P.use_ewald ? (h->nk + PG_KTILE - 1) / PG_KTILE : 0;
+    int n_ctas = A.n_pair_ctas + A.n_k_ctas;
+    int rc = ensure_partials(h, n_ctas);
+    if (rc) return rc;
+    A.partial = h->d_partial; A.partial_i = h->d_partial_i; A.state = h->d_state; A.result = nullptr;
+    A.decide_on_device = 1; A.u = r.u; A.replay_dE = h->d_rp_dE; A.replay_acc = h->d_rp_acc; A.replay_index = m;
+    A.seq = ++h->seq;
+    k_delta<<<n_ctas, PG_TILE, 0, h->stream>>>(h->P, A);
+    int nthreads = std::max(std::max(r.glen, h->nk), 1);
+    k_commit<<<(nthreads + 255) / 256, 256, 0, h->stream>>>(h->P, -1, PG_MODE_MOVE, r.g0, r.glen, A.trial, A.gq,
+                                                            A.gtype, h->xy, h->zq, h->type, h->d_S, h->d_dS,
+                                                            h->P.use_ewald ? h->nk : 0, h->d_state);
+    h->launches += 2;
+  }
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  PG_CUDA(h, cudaEventSynchronize(h->ev1));
+  if (elapsed_ms) PG_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  if (dE_out && count > 0)
+    PG_CUDA(h, cudaMemcpy(dE_out, h->d_rp_dE + first, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost));
+  if (accept_out && count > 0)
+    PG_CUDA(h, cudaMemcpy(accept_out, h->d_rp_acc + first, (size_t)count, cudaMemcpyDeviceToHost));
+  return PG_OK;
+}
+
+// -------------------------------------------------------------------- CBMC
+int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1_xyz, const double* bead2_xyz,
+                      const double* chain_xyz, const double* chain_q, const int32_t* chain_type, double* out_energy,
+                      double* out_pair, double* out_ewald) {
+  if (!h || !set || !bead1_xyz || !out_energy) return PG_ERR_INVALID;
+  const int nt = set->n_trials, cl = set->current_len, use2 = set->use_bead2 ? 1 : 0;
+  if (nt <= 0 || cl < 0) return PG_ERR_INVALID;
+  if (use2 && !bead2_xyz) return PG_ERR_INVALID;
+  const int n_chain = cl * (use2 ? 2 : 1);
+  if (n_chain > 0 && (!chain_xyz || !chain_q || !chain_type)) return PG_ERR_INVALID;
+  if (set->type1 < 0 || set->type1 >= h->P.n_types || set->type2 < 0 || set->type2 >= h->P.n_types) {
+    h->err = "trial bead type id out of range";
+    return PG_ERR_INVALID;
+  }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  if (nt > h->tcap || n_chain > h->ccap) {
+    int tcap = std::max(64, nt * 2), ccap = std::max(64, n_chain * 2);
+    if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
+    if (h->h_trial_ct) cudaFreeHost(h->h_trial_ct);
+    if (h->h_trial_out) cudaFreeHost(h->h_trial_out);
+    cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_trial_out);
+    h->h_trial_in = nullptr; h->h_trial_ct = nullptr; h->h_trial_out = nullptr;
+    h->d_trial_in = nullptr; h->d_trial_ct = nullptr; h->d_trial_out = nullptr;
+    size_t in_d = (size_t)tcap * 6 + (size_t)ccap * 4;
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_in, sizeof(double) * in_d, cudaHostAllocDefault));
+    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_in, sizeof(double) * in_d));
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_ct, sizeof(int) * (size_t)ccap, cudaHostAllocDefault));
+    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_ct, sizeof(int) * (size_t)ccap));
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_out, sizeof(double) * 3 * (size_t)tcap, cudaHostAllocDefault));
+    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_out, sizeof(double) * 3 * (size_t)tcap));
+    h->tcap = tcap; h->ccap = ccap;
+  }
+  const int tcap = h->tcap, ccap = h->ccap;
+  double* hb1 = h->h_trial_in;
+  double* hb2 = hb1 + 3 * (size_t)tcap;
+  double* hcx = hb2 + 3 * (size_t)tcap;
+  double* hcq = hcx + 3 * (size_t)ccap;
+  memcpy(hb1, bead1_xyz, sizeof(double) * 3 * (size_t)nt);
+  if (use2) memcpy(hb2, bead2_xyz, sizeof(double) * 3 * (size_t)nt);
+  for (int i = 0; i < n_chain; i++) {
+    hcx[3 * i] = chain_xyz[3 * i]; hcx[3 * i + 1] = chain_xyz[3 * i + 1]; hcx[3 * i + 2] = chain_xyz[3 * i + 2];
+    hcq[i] = chain_q[i];
+    if (chain_type[i] < 0 || chain_type[i] >= h->P.n_types) { h->err = "chain type id out of range"; return PG_ERR_INVALID; }
+    h->h_trial_ct[i] = chain_type[i];
+  }
+  size_t in_d = (size_t)tcap * 6 + (size_t)ccap * 4;
+  PG_CUDA(h, cudaMemcpyAsync(h->d_trial_in, h->h_trial_in, sizeof(double) * in_d, cudaMemcpyHostToDevice, h->stream));
+  if (n_chain > 0)
+    PG_CUDA(h, cudaMemcpyAsync(h->d_trial_ct, h->h_trial_ct, sizeof(int) * (size_t)n_chain, cudaMemcpyHostToDevice,
+                               h->stream));
+  int skip_b0 = 0, skip_b1 = 0;
+  if (set->skip_mol_first >= 0) {
+    if (set->skip_mol_last < set->skip_mol_first || set->skip_mol_last >= h->n_mol) {
+      h->err = "skip molecule range out of bounds";
+      return PG_ERR_INVALID;
+    }
+    skip_b0 = h->mol_first[set->skip_mol_first];
+    skip_b1 = h->mol_first[set->skip_mol_last + 1];
+  }
+  double* db1 = h->d_trial_in;
+  double* db2 = db1 + 3 * (size_t)tcap;
+  double* dcx = db2 + 3 * (size_t)tcap;
+  double* dcq = dcx + 3 * (size_t)ccap;
+  if (h->P.use_ewald && h->nk > 0) {
+    k_sprime<<<(h->nk + PG_TILE - 1) / PG_TILE, PG_TILE, 0, h->stream>>>(h->P, h->d_S, h->d_kl, h->nk, h->xy, h->zq,
+                                                                        skip_b0, skip_b1, dcx, dcq, n_chain, h->d_Sp);
+    h->launches++;
+  }
+  PgTrialArgs A;
+  memset(&A, 0, sizeof(A));
+  A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n = h->n;
+  A.skip_b0 = skip_b0; A.skip_b1 = skip_b1;
+  A.b1 = db1; A.b2 = db2; A.use_b2 = use2; A.t1 = set->type1; A.t2 = set->type2; A.q1 = set->q1; A.q2 = use2 ? set->q2 : 0.0;
+  A.chain_xyz = dcx; A.chain_q = dcq; A.chain_type = h->d_trial_ct; A.current_len = cl;
+  A.kl = h->d_kl; A.ek2 = h->d_ek2; A.Sp = h->d_Sp; A.nk = h->P.use_ewald ? h->nk : 0;
+  A.out_energy = h->d_trial_out; A.out_pair = h->d_trial_out + tcap; A.out_ewald = h->d_trial_out + 2 * (size_t)tcap;
+  k_trials<<<nt, PG_TILE, 0, h->stream>>>(h->P, A);
+  h->launches++;
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaMemcpyAsync(h->h_trial_out, h->d_trial_out, sizeof(double) * 3 * (size_t)tcap, cudaMemcpyDeviceToHost,
+                             h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  memcpy(out_energy, h->h_trial_out, sizeof(double) * (size_t)nt);
+  if (out_pair) memcpy(out_pair, h->h_trial_out + tcap, sizeof(double) * (size_t)nt);
+  if (out_ewald) memcpy(out_ewald, h->h_trial_out + 2 * (size_t)tcap, sizeof(double) * (size_t)nt);
+  return PG_OK;
+}
+
+// ------------------------------------------------------------ GC bookkeeping
+static void result_to_totals(const PgResult* r, double sign, pg_totals* t) {
+  t->pair = sign * r->pair; t->ewald = sign * r->ewald; t->bond = sign * r->bond; t->ext = sign * r->ext;
+  t->real = sign * r->real; t->recip = sign * r->recip; t->self = r->self_e; t->dipole = sign * r->dipole;
+}
+
+int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, const double* xyz, const double* q,
+                        const int32_t* type, pg_totals* added) {
+  if (!h || n_new_mol <= 0 || !mol_len || !xyz || !q || !type) return PG_ERR_INVALID;
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  int n_add = 0;
+  for (int m = 0; m < n_new_mol; m++) {
+    if (mol_len[m] <= 0) { h->err = "molecule length must be positive"; return PG_ERR_INVALID; }
+    n_add += mol_len[m];
+  }
+  for (int i = 0; i < n_add; i++)
+    if (type[i] < 0 || type[i] >= h->P.n_types) { h->err = "bead type id out of range"; return PG_ERR_INVALID; }
+  int rc = ensure_capacity(h, h->n + n_add);
+  if (!rc) rc = ensure_group(h, n_add);
+  if (rc) return rc;
+  StageView sv = stage_view(h->h_stage, h->gcap);
+  memcpy(sv.trial, xyz, sizeof(double) * 3 * (size_t)n_add);
+  for (int i = 0; i < n_add; i++) { sv.gq[i] = q[i]; sv.gtype[i] = type[i]; sv.moved[i] = 1; }
+  PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, h->stage_bytes, cudaMemcpyHostToDevice, h->stream));
+  // potential_bond.cc:29-34: only the LAST appended molecule's bond energy is added
+  const int last_len = mol_len[n_new_mol - 1];
+  rc = launch_delta(h, PG_MODE_INSERT, h->n, n_add, mol_len[0], n_add - last_len, last_len, h->d_stage, h->gcap, false,
+                    0.0, 0, true);
+  if (rc) return rc;
+  rc = wait_result(h, h->seq);
+  if (rc) return rc;
+  if (added) result_to_totals(h->h_result, 1.0, added);
+  rc = launch_commit(h, 1, PG_MODE_INSERT, h->n, n_add, h->d_stage, h->gcap);
+  if (rc) return rc;
+  std::vector<int> hmol(n_add);
+  int b = 0;
+  for (int m = 0; m < n_new_mol; m++) {
+    for (int i = 0; i < mol_len[m]; i++) hmol[b++] = h->n_mol + m;
+    h->mol_first.push_back(h->mol_first.back() + mol_len[m]);
+  }
+  PG_CUDA(h, cudaMemcpyAsync(h->mol + h->n, hmol.data(), sizeof(int) * (size_t)n_add, cudaMemcpyHostToDevice, h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->h_q.insert(h->h_q.end(), q, q + n_add);
+  h->h_type.insert(h->h_type.end(), type, type + n_add);
+  h->n += n_add;
+  h->n_mol += n_new_mol;
+  return PG_OK;
+}
+
+int pg_delete_molecules(pg_engine* h, int mf, int ml, pg_totals* removed) {
+  if (!h || mf < 0 || ml < mf || ml >= h->n_mol) return PG_ERR_INVALID;
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  const int b0 = h->mol_first[mf], b1 = h->mol_first[ml + 1], glen = b1 - b0;
+  int rc = ensure_group(h, glen);
+  if (rc) return rc;
+  StageView sv = stage_view(h->h_stage, h->gcap);
+  for (int i = 0; i < glen; i++) {
+    sv.trial[3 * i] = sv.trial[3 * i + 1] = sv.trial[3 * i + 2] = 0.0;
+    sv.gq[i] = h->h_q[b0 + i]; sv.gtype[i] = h->h_type[b0 + i]; sv.moved[i] = 1;
+  }
+  PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, h->stage_bytes, cudaMemcpyHostToDevice, h->stream));
+  const int first_len = h->mol_first[mf + 1] - b0;
+  rc = launch_delta(h, PG_MODE_DELETE, b0, glen, first_len, 0, first_len, h->d_stage, h->gcap, false, 0.0, 0, true);
+  if (rc) return rc;
+  rc = wait_result(h, h->seq);
+  if (rc) return rc;
+  if (removed) result_to_totals(h->h_result, -1.0, removed);
+  rc = launch_commit(h, 1, PG_MODE_DELETE, b0, glen, h->d_stage, h->gcap);
+  if (rc) return rc;
+  const int tail = h->n - b1, nm = ml - mf + 1;
+  const int nb = std::max(1, (tail + 255) / 256);
+  if (tail > 0) {
+    k_gather_tail<<<nb, 256, 0, h->stream>>>(h->xy, h->zq, h->type, h->mol, b1, h->n, h->t_xy, h->t_zq, h->t_type,
+                                             h->t_mol);
+    h->launches++;
+  }
+  k_scatter_tail<<<nb, 256, 0, h->stream>>>(h->xy, h->zq, h->type, h->mol, b0, tail, nm, h->t_xy, h->t_zq, h->t_type,
+                                            h->t_mol, h->d_state, h->n - glen);
+  h->launches++;
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->h_q.erase(h->h_q.begin() + b0, h->h_q.begin() + b1);
+  h->h_type.erase(h->h_type.begin() + b0, h->h_type.begin() + b1);
+  std::vector<int> mfirst;
+  for (int m = 0; m <= mf; m++) mfirst.push_back(h->mol_first[m]);
+  for (int m = ml + 2; m <= h->n_mol; m++) mfirst.push_back(h->mol_first[m] - glen);
+  h->mol_first.swap(mfirst);
+  h->n -= glen;
+  h->n_mol -= nm;
+  return PG_OK;
+}
+
+// ------------------------------------------------------- reciprocal space
+int pg_sk_compute_slice(pg_engine* h, int k_first, int k_count, double* sk_dev) {
+  if (!h || k_first < 0 || k_count < 0 || k_first + k_count > h->nk) return PG_ERR_INVALID;
+  if (k_count == 0) return PG_OK;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  double2* out = sk_dev ? reinterpret_cast<double2*>(sk_dev) : (h->d_S + k_first);
+  k_sk_slice<<<(k_count + PG_TILE - 1) / PG_TILE, PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->n, h->d_kl, k_first,
+                                                                          k_count, out);
+  h->launches++;
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return PG_OK;
+}
+
+int pg_sk_set(pg_engine* h, const double* sk_dev) {
+  if (!h || !sk_dev) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  if (h->nk > 0)
+    PG_CUDA(h, cudaMemcpyAsync(h->d_S, sk_dev, sizeof(double2) * (size_t)h->nk, cudaMemcpyDeviceToDevice, h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return PG_OK;
+}
+
+int pg_sk_energy(pg_engine* h, int k_first, int k_count, double* e_out) {
+  if (!h || !e_out || k_first < 0 || k_count < 0 || k_first + k_count > h->nk) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  k_sk_energy<<<1, 256, 0, h->stream>>>(h->P, h->d_S, h->d_ek2, k_first, k_count, h->d_out8);
+  h->launches++;
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaMemcpyAsync(h->h_out8, h->d_out8, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  *e_out = h->h_out8[0];
+  return PG_OK;
+}
+
+int pg_sk_download(pg_engine* h, double* sk_host) {
+  if (!h || (!sk_host && h->nk > 0)) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  if (h->nk > 0)
+    PG_CUDA(h, cudaMemcpyAsync(sk_host, h->d_S, sizeof(double2) * (size_t)h->nk, cudaMemcpyDeviceToHost, h->stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return PG_OK;
+}
+
+// --------------------------------------------------------- instrumentation
+int pg_measure_fp64_peak(pg_engine* h, double* gflops) {
+  if (!h || !gflops) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  PG_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    k_fp64_peak<<<blocks, threads, 0, h->stream>>>(h->d_out8, iters, 1.0000001, 1e-9);
+    h->launches++;
+    PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    PG_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    PG_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    double fl = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e9);
+  }
+  *gflops = best;
+  return PG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+"""ctypes binding of libplum_b200.so (the C ABI in include/plum_b200.h).
+
+This is the Python harness over the boundary — used by tests and bench.py.  The
+per-move product path is C++ (plum_b200/host/force_field.cc) over the same ABI.
+There is no fallback: if the shared library or a CUDA device is missing, every
+entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import (ParamBlock, PgDelta, PgEwaldInfo, PgParams, PgProposal, PgTotals, PgTrialSet, bptr, c_double_p,
+                   c_int32_p, c_uint8_p, dptr, iptr)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libplum_b200.so")
+
+# Every symbol include/plum_b200.h declares (tests check the library exports them all).
+ABI_SYMBOLS = [
+    "pg_create", "pg_destroy", "pg_last_error", "pg_abi_version", "pg_get_ewald_info", "pg_upload_system",
+    "pg_init_energy", "pg_recompute_totals", "pg_get_totals", "pg_download_positions", "pg_num_beads", "pg_delta_e",
+    "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_trial_energies", "pg_insert_molecules",
+    "pg_delete_molecules", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
+    "pg_stream", "pg_measure_fp64_peak",
+]
+
+_LIB = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                              f"g.build()'` — there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.pg_create.argtypes = [C.POINTER(PgParams), C.c_int, C.c_int, C.POINTER(vp)]
+        L.pg_destroy.argtypes = [vp]
+        L.pg_last_error.restype = C.c_char_p
+        L.pg_last_error.argtypes = [vp]
+        L.pg_get_ewald_info.argtypes = [vp, C.POINTER(PgEwaldInfo)]
+        L.pg_upload_system.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_int32_p, C.c_int, c_int32_p]
+        L.pg_init_energy.argtypes = [vp, C.POINTER(PgTotals)]
+        L.pg_recompute_totals.argtypes = [vp, C.POINTER(PgTotals)]
+        L.pg_get_totals.argtypes = [vp, C.POINTER(PgTotals)]
+        L.pg_download_positions.argtypes = [vp, c_double_p]
+        L.pg_num_beads.argtypes = [vp]
+        L.pg_delta_e.argtypes = [vp, C.c_int, c_double_p, c_uint8_p, C.POINTER(PgDelta)]
+        L.pg_commit.argtypes = [vp, C.c_int]
+        L.pg_replay_upload.argtypes = [vp, C.c_int, C.POINTER(PgProposal), C.c_int, c_double_p, c_uint8_p]
+        L.pg_replay_run.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_uint8_p, C.POINTER(C.c_float)]
+        L.pg_trial_energies.argtypes = [vp, C.POINTER(PgTrialSet), c_double_p, c_double_p, c_double_p, c_double_p,
+                                        c_int32_p, c_double_p, c_double_p, c_double_p]
+        L.pg_insert_molecules.argtypes = [vp, C.c_int, c_int32_p, c_double_p, c_double_p, c_int32_p,
+                                          C.POINTER(PgTotals)]
+        L.pg_delete_molecules.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PgTotals)]
+        L.pg_sk_compute_slice.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+        L.pg_sk_set.argtypes = [vp, C.c_void_p]
+        L.pg_sk_energy.argtypes = [vp, C.c_int, C.c_int, c_double_p]
+        L.pg_sk_download.argtypes = [vp, c_double_p]
+        L.pg_launch_count.restype = C.c_uint64
+        L.pg_launch_count.argtypes = [vp]
+        L.pg_stream.restype = C.c_void_p
+        L.pg_stream.argtypes = [vp]
+        L.pg_measure_fp64_peak.argtypes = [vp, c_double_p]
+        _LIB = L
+    return _LIB
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """One system replica resident on one GPU."""
+
+    def __init__(self, params: dict, device: int = 0, capacity_beads: int = 1024):
+        self.L = lib()
+        self.pb = ParamBlock(params)
+        h = C.c_void_p()
+        rc = self.L.pg_create(C.byref(self.pb.struct), int(device), int(capacity_beads), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"pg_create failed ({rc}): {self.L.pg_last_error(None).decode()}")
+        self.h = h
+        self.mol_first = np.zeros(1, dtype=np.int32)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self.L.pg_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- set-up ------------------------------------------------------------
+    def ewald_info(self) -> PgEwaldInfo:
+        o = PgEwaldInfo()
+        self._check(self.L.pg_get_ewald_info(self.h, C.byref(o)), "pg_get_ewald_info")
+        return o
+
+    def upload(self, xyz, q, type_ids, mol_first):
+        xyz = _f64(xyz).reshape(-1, 3)
+        q = _f64(q)
+        t = np.ascontiguousarray(type_ids, dtype=np.int32)
+        mf = np.ascontiguousarray(mol_first, dtype=np.int32)
+        self.mol_first = mf.copy()
+        self._check(self.L.pg_upload_system(self.h, xyz.shape[0], dptr(xyz), dptr(q), iptr(t), mf.shape[0] - 1,
+                                            iptr(mf)), "pg_upload_system")
+
+    @property
+    def n(self) -> int:
+        return self.L.pg_num_beads(self.h)
+
+    def positions(self) -> np.ndarray:
+        out = np.zeros((max(self.n, 1), 3), dtype=np.float64)
+        self._check(self.L.pg_download_positions(self.h, dptr(out)), "pg_download_positions")
+        return out[:self.n]
+
+    def init_energy(self) -> dict:
+        t = PgTotals()
+        self._check(self.L.pg_init_energy(self.h, C.byref(t)), "pg_init_energy")
+        return t.as_dict()
+
+    def recompute_totals(self) -> dict:
+        t = PgTotals()
+        self._check(self.L.pg_recompute_totals(self.h, C.byref(t)), "pg_recompute_totals")
+        return t.as_dict()
+
+    def totals(self) -> dict:
+        t = PgTotals()
+        self._check(self.L.pg_get_totals(self.h, C.byref(t)), "pg_get_totals")
+        return t.as_dict()
+
+    # -- per-move ----------------------------------------------------------
+    def delta_e(self, mol: int, trial_xyz, moved) -> dict:
+        xyz = _f64(trial_xyz).reshape(-1, 3)
+        mv = np.ascontiguousarray(moved, dtype=np.uint8)
+        d = PgDelta()
+        self._check(self.L.pg_delta_e(self.h, int(mol), dptr(xyz), bptr(mv), C.byref(d)), "pg_delta_e")
+        return d.as_dict()
+
+    def delta_e_raw(self, mol: int, xyz: np.ndarray, mv: np.ndarray, out: PgDelta):
+        """No-allocation variant for timing loops (arrays must be contiguous f64 / u8)."""
+        return self.L.pg_delta_e(self.h, mol, dptr(xyz), bptr(mv), C.byref(out))
+
+    def commit(self, accept: bool):
+        self._check(self.L.pg_commit(self.h, int(bool(accept))), "pg_commit")
+
+    # -- replay ------------------------------------------------------------
+    def replay_upload(self, mols, offsets, us, trial_xyz, moved):
+        n = len(mols)
+        arr = (PgProposal * max(n, 1))()
+        for i in range(n):
+            arr[i].mol = int(mols[i])
+            arr[i].xyz_offset = int(offsets[i])
+            arr[i].u = float(us[i])
+        xyz = _f64(trial_xyz).reshape(-1, 3)
+        mv = np.ascontiguousarray(moved, dtype=np.uint8)
+        self._check(self.L.pg_replay_upload(self.h, n, arr, xyz.shape[0], dptr(xyz), bptr(mv)), "pg_replay_upload")
+
+    def replay_run(self, first: int, count: int):
+        dE = np.zeros(max(count, 1), dtype=np.float64)
+        acc = np.zeros(max(count, 1), dtype=np.uint8)
+        ms = C.c_float()
+        self._check(self.L.pg_replay_run(self.h, first, count, dptr(dE), bptr(acc), C.byref(ms)), "pg_replay_run")
+        return dE[:count], acc[:count], ms.value
+
+    # -- CBMC --------------------------------------------------------------
+    def trial_energies(self, b1, b2, t1, q1, t2, q2, use_bead2, chain_xyz, chain_q, chain_type, current_len,
+                       skip_first=-1, skip_last=-1):
+        b1 = _f64(b1).reshape(-1, 3)
+        nt = b1.shape[0]
+        b2 = _f64(b2).reshape(-1, 3) if use_bead2 else np.zeros((nt, 3))
+        n_chain = current_len * (2 if use_bead2 else 1)
+        cx = _f64(chain_xyz).reshape(-1, 3) if n_chain else np.zeros((1, 3))
+        cq = _f64(chain_q) if n_chain else np.zeros(1)
+        ct = np.ascontiguousarray(chain_type, dtype=np.int32) if n_chain else np.zeros(1, dtype=np.int32)
+        s = PgTrialSet(n_trials=nt, use_bead2=int(use_bead2), type1=int(t1), type2=int(t2), q1=float(q1), q2=float(q2),
+                       current_len=int(current_len), skip_mol_first=int(skip_first), skip_mol_last=int(skip_last))
+        e = np.zeros(nt)
+        pe = np.zeros(nt)
+        ee = np.zeros(nt)
+        self._check(self.L.pg_trial_energies(self.h, C.byref(s), dptr(b1), dptr(b2), dptr(cx), dptr(cq), iptr(ct),
+                                             dptr(e), dptr(pe), dptr(ee)), "pg_trial_energies")
+        return e, pe, ee
+
+    def beads_energy(self, b1, t1, q1, b2, t2, q2, use_bead2, chain_xyz, chain_q, chain_type, current_len,
+                     skip_first=-1, skip_last=-1):
+        """Single-trial form with the oracle's signature (tests/replay.py)."""
+        e, pe, ee = self.trial_energies(np.asarray(b1).reshape(1, 3), np.asarray(b2).reshape(1, 3), t1, q1, t2, q2,
+                                        use_bead2, chain_xyz, chain_q, chain_type, current_len, skip_first, skip_last)
+        return float(e[0]), float(pe[0]), float(ee[0])
+
+    # -- GC ----------------------------------------------------------------
+    def insert_molecules(self, mol_len, xyz, q, type_ids) -> dict:
+        ml = np.ascontiguousarray(mol_len, dtype=np.int32)
+        xyz = _f64(xyz).reshape(-1, 3)
+        q = _f64(q)
+        t = np.ascontiguousarray(type_ids, dtype=np.int32)
+        a = PgTotals()
+        self._check(self.L.pg_insert_molecules(self.h, ml.shape[0], iptr(ml), dptr(xyz), dptr(q), iptr(t),
+                                               C.byref(a)), "pg_insert_molecules")
+        last = int(self.mol_first[-1])
+        self.mol_first = np.concatenate([self.mol_first, last + np.cumsum(ml)]).astype(np.int32)
+        return a.as_dict()
+
+    def delete_molecules(self, mf: int, ml: int) -> dict:
+        r = PgTotals()
+        self._check(self.L.pg_delete_molecules(self.h, int(mf), int(ml), C.byref(r)), "pg_delete_molecules")
+        first = self.mol_first
+        nrem = int(first[ml + 1] - first[mf])
+        self.mol_first = np.concatenate([first[:mf + 1], first[ml + 2:] - nrem]).astype(np.int32)
+        return r.as_dict()
+
+    # -- reciprocal space --------------------------------------------------
+    def sk_compute_slice(self, k_first: int, k_count: int, dev_ptr: int = 0):
+        self._check(self.L.pg_sk_compute_slice(self.h, k_first, k_count, C.c_void_p(dev_ptr or None)),
+                    "pg_sk_compute_slice")
+
+    def sk_set(self, dev_ptr: int):
+        self._check(self.L.pg_sk_set(self.h, C.c_void_p(dev_ptr)), "pg_sk_set")
+
+    def sk_energy(self, k_first: int, k_count: int) -> float:
+        e = C.c_double()
+        self._check(self.L.pg_sk_energy(self.h, k_first, k_count, C.cast(C.byref(e), c_double_p)), "pg_sk_energy")
+        return e.value
+
+    def sk_download(self) -> np.ndarray:
+        nk = self.ewald_info().n_k_half
+        out = np.zeros((max(nk, 1), 2))
+        self._check(self.L.pg_sk_download(self.h, dptr(out)), "pg_sk_download")
+        return out[:nk]
+
+    # -- instrumentation ---------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.L.pg_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(self.L.pg_stream(self.h) or 0)
+
+    def measure_fp64_peak(self) -> float:
+        g = C.c_double()
+        self._check(self.L.pg_measure_fp64_peak(self.h, C.cast(C.byref(g), c_double_p)), "pg_measure_fp64_peak")
+        return g.value

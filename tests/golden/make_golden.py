@@ -1,0 +1,120 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures from the REAL reference.
+
+Runs only where /root/reference and oracle/_ref/plum_ref exist (the build
+container).  For each example of BASELINE.json's configs it
+  1. copies the three input files (run.in, input_crd.dat, input_top.dat) next to
+     this script — they are the reference's example *inputs*, needed on the GPU
+     box where /root/reference does not exist;
+  2. runs plum_ref (unmodified reference arithmetic + seed/trace hooks, see
+     oracle/build_ref.py) with PLUM_SEED and writes
+       short/<example>_seed<k>.trace.gz   full replayable trace (coordinates of every
+                                          trial, every CBMC BeadsEnergy call) of the
+                                          first SHORT_STEPS steps;
+       long/<example>_seed1.npz           the first 10^5 steps: accept/reject bits and
+                                          move kinds for every step, dE for the first
+                                          2000 steps and every 25th step after, the
+                                          four running totals every 1000 steps.
+Usage: python tests/golden/make_golden.py [--long-from DIR]
+  --long-from DIR : reuse existing <DIR>/<example>/trace_seed1.txt instead of re-running
+"""
+import argparse
+import gzip
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import replay  # noqa: E402
+
+EXAMPLES = ["bulk_nvt", "confined_nvt", "bulk_muvt", "confined_muvt"]
+SHORT_STEPS = {"bulk_nvt": 250, "confined_nvt": 500, "bulk_muvt": 400, "confined_muvt": 400}
+SHORT_SEEDS = [1, 2]
+LONG_STEPS = 100000
+REF_EXAMPLES = "/root/reference/examples"
+
+
+def compact_long(lines, path, n_steps):
+    """Arrays are indexed by step-1; steps that attempted no move (empty system) keep kind 3."""
+    kind = np.full(n_steps, 3, dtype=np.uint8)      # 0 translational, 1 GC insert, 2 GC delete, 3 none
+    accept = np.zeros(n_steps, dtype=np.uint8)
+    mtype = np.full(n_steps, -1, dtype=np.int8)
+    mol = np.full(n_steps, -1, dtype=np.int32)
+    dE_idx, dE_val = [], []
+    tot_idx, tot_val = [], []
+    init = None
+    for ln in lines:
+        f = ln.split()
+        if not f:
+            continue
+        if f[0] == "I":
+            init = [replay.hx(x) for x in f[2:6]]
+            continue
+        if f[0] not in ("T", "G"):
+            continue
+        step = int(f[1])
+        i = step - 1
+        if f[0] == "T":
+            kind[i] = 0
+            mtype[i] = int(f[2])
+            mol[i] = int(f[3])
+            accept[i] = int(f[5])
+            val = replay.hx(f[4])                      # dE
+            tots = [replay.hx(x) for x in f[6:10]]
+        else:
+            kind[i] = 1 if f[2] == "I" else 2
+            mol[i] = int(f[3])                         # insertion 0/1, deletion: molecule id or -1
+            accept[i] = 1 if ((f[2] == "I" and int(f[3]) == 1) or (f[2] == "D" and int(f[3]) >= 0)) else 0
+            val = replay.hx(f[4])                      # Rosenbluth weight at the acceptance test (-1: not reached)
+            tots = [replay.hx(x) for x in f[6:10]]
+        if step <= 2000 or step % 25 == 0:
+            dE_idx.append(step)
+            dE_val.append(val)
+        if step % 500 == 0:
+            tot_idx.append(step)
+            tot_val.append(tots)
+    np.savez_compressed(
+        path, init=np.array(init), kind=kind, accept=np.packbits(accept), n_steps=n_steps, move_type=mtype, mol=mol,
+        dE_step=np.array(dE_idx, dtype=np.int32), dE=np.array(dE_val), tot_step=np.array(tot_idx, dtype=np.int32),
+        tot=np.array(tot_val))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--long-from", default=None)
+    ap.add_argument("--skip-long", action="store_true")
+    a = ap.parse_args()
+    if not replay.have_plum_ref():
+        raise SystemExit("oracle/_ref/plum_ref missing: run python oracle/build_ref.py")
+    os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, "long"), exist_ok=True)
+    for ex in EXAMPLES:
+        src = os.path.join(REF_EXAMPLES, ex)
+        dst = os.path.join(HERE, "examples", ex)
+        os.makedirs(dst, exist_ok=True)
+        for fn in ("run.in", "input_crd.dat", "input_top.dat"):
+            shutil.copyfile(os.path.join(src, fn), os.path.join(dst, fn))
+        for seed in SHORT_SEEDS:
+            lines = replay.run_plum_ref(src, SHORT_STEPS[ex], seed, xyz=True)
+            with gzip.open(os.path.join(HERE, "short", f"{ex}_seed{seed}.trace.gz"), "wt") as f:
+                f.write("\n".join(lines))
+            print("short", ex, seed, len(lines), "lines")
+        if a.skip_long:
+            continue
+        if a.long_from:
+            with open(os.path.join(a.long_from, ex, "trace_seed1.txt")) as f:
+                lines = f.read().split("\n")
+        else:
+            lines = replay.run_plum_ref(src, LONG_STEPS, 1, xyz=False)
+        compact_long(lines, os.path.join(HERE, "long", f"{ex}_seed1.npz"), LONG_STEPS)
+        print("long", ex, len(lines), "lines")
+
+
+if __name__ == "__main__":
+    main()

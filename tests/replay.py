@@ -1,0 +1,196 @@
+"""Replay a trace written by the real reference (oracle/_ref/plum_ref, format in
+oracle/build_ref.py) through an engine-like object — the CPU oracle or the CUDA
+engine — and report the worst disagreement.  Test helper, not product code."""
+from __future__ import annotations
+
+import dataclasses
+import os
+import subprocess
+import tempfile
+from typing import List, Optional
+
+import numpy as np
+
+from plum_b200 import runin
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUM_REF = os.path.join(REPO, "oracle", "_ref", "plum_ref")
+GOLDEN = os.path.join(REPO, "tests", "golden")
+VLE = 1.0e8
+
+
+def hx(s: str) -> float:
+    return float.fromhex(s)
+
+
+def have_plum_ref() -> bool:
+    return os.path.exists(PLUM_REF) and os.access(PLUM_REF, os.X_OK)
+
+
+def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, extra_sed=None) -> List[str]:
+    """Run the reference binary on an example (inputs copied to a temp dir) and return trace lines."""
+    with tempfile.TemporaryDirectory(prefix="plum_ref_run_") as tmp:
+        with open(os.path.join(example_dir, "run.in")) as f:
+            text = f.read()
+        out = []
+        for ln in text.split("\n"):
+            if ln.startswith("s1_total_simulation_steps"):
+                ln = f"s1_total_simulation_steps {steps}"
+            out.append(ln)
+        with open(os.path.join(tmp, "run.in"), "w") as f:
+            f.write("\n".join(out))
+        for fn in ("input_crd.dat", "input_top.dat"):
+            with open(os.path.join(example_dir, fn)) as fi, open(os.path.join(tmp, fn), "w") as fo:
+                fo.write(fi.read())
+        env = dict(os.environ, PLUM_SEED=str(seed), PLUM_TRACE=os.path.join(tmp, "trace.txt"))
+        if xyz:
+            env["PLUM_TRACE_XYZ"] = "1"
+        with open(os.path.join(tmp, "run.in")) as fin, open(os.path.join(tmp, "run.log"), "w") as fout:
+            subprocess.check_call([PLUM_REF], stdin=fin, stdout=fout, cwd=tmp, env=env)
+        with open(os.path.join(tmp, "trace.txt")) as f:
+            return f.read().split("\n")
+
+
+@dataclasses.dataclass
+class ReplayReport:
+    n_moves: int = 0
+    n_accept: int = 0
+    n_gc: int = 0
+    n_beads_energy: int = 0
+    max_rel_dE: float = 0.0         # |dE - ref| / max(|ref|, scale)
+    max_abs_dE: float = 0.0
+    max_rel_tot: float = 0.0
+    max_rel_beads: float = 0.0
+    sentinel_mismatch: int = 0      # dE >= 1e8 on one side only
+    worst: Optional[str] = None
+
+
+def rel(a: float, b: float, floor: float = 1.0) -> float:
+    return abs(a - b) / max(abs(b), floor)
+
+
+def replay(engine, r: runin.RunIn, sysm: runin.System, types: runin.TypeTable, lines: List[str],
+           max_steps: Optional[int] = None, check_totals_every: int = 1, beads_energy=True) -> ReplayReport:
+    """`engine` needs: upload, init_energy, delta_e, commit, totals, insert_molecules,
+    delete_molecules, and (optionally) beads_energy."""
+    rep = ReplayReport()
+    engine.upload(sysm.xyz, sysm.q, types.ids(sysm.symbol), sysm.mol_first)
+    tot = engine.init_energy()
+    mol_first = sysm.mol_first.copy()
+    q = sysm.q.copy()
+    gc_type = types.index.get(r.gc_bead_symbol, 0)
+    pending = None
+    step_count = 0
+    for ln in lines:
+        if not ln:
+            continue
+        f = ln.split()
+        tag = f[0]
+        if tag == "I":
+            ref = dict(pair=hx(f[2]), ewald=hx(f[3]), bond=hx(f[4]), ext=hx(f[5]))
+            for k in ref:
+                e = rel(tot[k], ref[k])
+                if e > rep.max_rel_tot:
+                    rep.max_rel_tot = e
+                    rep.worst = f"init {k}: {tot[k]!r} vs {ref[k]!r}"
+        elif tag == "T":
+            pending = f
+        elif tag == "X":
+            assert pending is not None
+            t = pending
+            pending = None
+            step, mol, dE_ref, acc = int(t[1]), int(t[3]), hx(t[4]), int(t[5])
+            if max_steps is not None and step > max_steps:
+                break
+            n = int(f[1])
+            vals = f[2:]
+            moved = np.array([int(vals[4 * i]) for i in range(n)], dtype=np.uint8)
+            xyz = np.array([[hx(vals[4 * i + 1]), hx(vals[4 * i + 2]), hx(vals[4 * i + 3])] for i in range(n)])
+            d = engine.delta_e(mol, xyz, moved)
+            rep.n_moves += 1
+            rep.n_accept += acc
+            if (d["dE"] >= VLE) != (dE_ref >= VLE):
+                rep.sentinel_mismatch += 1
+                rep.worst = f"step {step}: sentinel mismatch {d['dE']!r} vs {dE_ref!r}"
+            elif dE_ref < VLE:
+                e = rel(d["dE"], dE_ref)
+                rep.max_abs_dE = max(rep.max_abs_dE, abs(d["dE"] - dE_ref))
+                if e > rep.max_rel_dE:
+                    rep.max_rel_dE = e
+                    rep.worst = f"step {step} mol {mol}: dE {d['dE']!r} vs {dE_ref!r}"
+            engine.commit(bool(acc))
+            step_count += 1
+            if check_totals_every and step_count % check_totals_every == 0:
+                tot = engine.totals()
+                ref = dict(pair=hx(t[6]), ewald=hx(t[7]), bond=hx(t[8]), ext=hx(t[9]))
+                for k in ref:
+                    e = rel(tot[k], ref[k])
+                    if e > rep.max_rel_tot:
+                        rep.max_rel_tot = e
+                        rep.worst = f"step {step} total {k}: {tot[k]!r} vs {ref[k]!r}"
+        elif tag == "B" and beads_energy and hasattr(engine, "beads_energy"):
+            cur_len, delete_id = int(f[1]), int(f[2])
+            b1 = [hx(f[3]), hx(f[4]), hx(f[5])]
+            q1 = hx(f[6])
+            b2 = [hx(f[7]), hx(f[8]), hx(f[9])]
+            q2 = hx(f[10])
+            e_ref = hx(f[13])
+            nch = int(f[14])
+            ch = np.array([hx(v) for v in f[15:15 + 4 * nch]]).reshape(-1, 4) if nch else np.zeros((0, 4))
+            use2 = int(r.gc_bead_charge != 0)
+            skip_first, skip_last = -1, -1
+            if delete_id >= 0:
+                skip_first = delete_id
+                skip_last = delete_id + (r.gc_chain_len if r.gc_bead_charge != 0 else 0)
+            e, pe, ee = engine.beads_energy(b1, gc_type, q1, b2, gc_type, q2, use2, ch[:, :3], ch[:, 3],
+                                            np.full(max(nch, 1), gc_type, dtype=np.int32), cur_len,
+                                            skip_first, skip_last)
+            rep.n_beads_energy += 1
+            if (e >= VLE) != (e_ref >= VLE):
+                rep.sentinel_mismatch += 1
+                rep.worst = f"BeadsEnergy sentinel mismatch {e!r} vs {e_ref!r}"
+            elif e_ref < VLE:
+                er = rel(e, e_ref)
+                if er > rep.max_rel_beads:
+                    rep.max_rel_beads = er
+                    rep.worst = f"BeadsEnergy {e!r} vs {e_ref!r} (len {cur_len}, del {delete_id})"
+        elif tag == "A":
+            nb = int(f[1])
+            vals = f[2:]
+            mols, syms, qs, xyz = [], [], [], []
+            for i in range(nb):
+                mols.append(int(vals[6 * i]))
+                syms.append(vals[6 * i + 1])
+                qs.append(hx(vals[6 * i + 2]))
+                xyz.append([hx(vals[6 * i + 3]), hx(vals[6 * i + 4]), hx(vals[6 * i + 5])])
+            lens = []
+            for m in mols:
+                if not lens or m != last_m:
+                    lens.append(0)
+                lens[-1] += 1
+                last_m = m
+            engine.insert_molecules(lens, np.array(xyz), np.array(qs), types.ids(syms))
+            q = np.concatenate([q, np.array(qs)])
+            mol_first = np.concatenate([mol_first, mol_first[-1] + np.cumsum(lens)]).astype(np.int32)
+        elif tag == "G":
+            step = int(f[1])
+            if max_steps is not None and step > max_steps:
+                break
+            rep.n_gc += 1
+            kind, result = f[2], int(f[3])
+            if kind == "D" and result >= 0:
+                b0, b1_ = mol_first[result], mol_first[result + 1]
+                ions = int(sum(abs(round(x)) for x in q[b0:b1_]))
+                ml = result + ions
+                nrem = int(mol_first[ml + 1] - mol_first[result])
+                engine.delete_molecules(result, ml)
+                q = np.concatenate([q[:b0], q[b0 + nrem:]])
+                mol_first = np.concatenate([mol_first[:result + 1], mol_first[ml + 2:] - nrem]).astype(np.int32)
+            tot = engine.totals()
+            ref = dict(pair=hx(f[6]), ewald=hx(f[7]), bond=hx(f[8]), ext=hx(f[9]))
+            for k in ref:
+                e = rel(tot[k], ref[k])
+                if e > rep.max_rel_tot:
+                    rep.max_rel_tot = e
+                    rep.worst = f"GC step {step} total {k}: {tot[k]!r} vs {ref[k]!r}"
+    return rep
