@@ -199,7 +199,7 @@ int po_get_ewald_info(const po_system *s, pg_ewald_info *o) {
 }
 
 static void reserve(po_system *s, int n, int n_mol) {
-  if (n > s->cap) {
+  if (n > s->cap || s->cur == NULL) {
     int c = n * 2 + 64;
     s->cur = (double *)realloc(s->cur, sizeof(double) * 3 * (size_t)c);
     s->tri = (double *)realloc(s->tri, sizeof(double) * 3 * (size_t)c);
@@ -225,7 +225,7 @@ int po_upload_system(po_system *s, int n, const double *xyz, const double *q, co
   memcpy(s->q, q, sizeof(double) * (size_t)n);
   for (int i = 0; i < n; i++) s->type[i] = type[i];
   for (int i = 0; i <= n_mol; i++) s->mol_first[i] = mol_first[i];
-  memset(s->moved, 0, (size_t)(n > 0 ? n : 1));
+  if (n > 0) memset(s->moved, 0, (size_t)n);
   s->pending_mol = -1;
   return 0;
 }

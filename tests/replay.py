@@ -194,3 +194,25 @@ def replay(engine, r: runin.RunIn, sysm: runin.System, types: runin.TypeTable, l
                     rep.max_rel_tot = e
                     rep.worst = f"GC step {step} total {k}: {tot[k]!r} vs {ref[k]!r}"
     return rep
+
+
+# ---------------------------------------------------------------- golden data
+def golden_example_dir(name: str) -> str:
+    return os.path.join(GOLDEN, "examples", name)
+
+
+def load_golden(name: str):
+    """(RunIn, System, TypeTable, params dict) of a committed example input."""
+    r, s = runin.load_example(golden_example_dir(name))
+    types = runin.TypeTable(r, s.symbol)
+    return r, s, types, runin.params_dict(r, s.box, types)
+
+
+def golden_short_trace(name: str, seed: int) -> List[str]:
+    import gzip
+    with gzip.open(os.path.join(GOLDEN, "short", f"{name}_seed{seed}.trace.gz"), "rt") as f:
+        return f.read().split("\n")
+
+
+def golden_long(name: str):
+    return np.load(os.path.join(GOLDEN, "long", f"{name}_seed1.npz"))

@@ -1,0 +1,71 @@
+"""Pins the CPU oracle (oracle/plum_oracle.c) against the REAL reference.
+
+The committed traces under tests/golden/short were written by the reference
+itself (oracle/_ref/plum_ref = /root/reference/src compiled with seed + trace
+hooks, tests/golden/make_golden.py).  Replaying them through the oracle must
+reproduce every per-move dE, every CBMC BeadsEnergy value and the four running
+energy totals.  Tolerance: 1e-12 relative (floor 1.0) for the pairwise
+reciprocal form, which follows the reference's loop order; 1e-11 for the S(k)
+form the CUDA path uses (truncated kPi makes the two forms differ by O(1e-13)).
+"""
+import pytest
+
+import replay
+from oracle.oracle_py import Oracle
+
+EXAMPLES = ["bulk_nvt", "confined_nvt", "bulk_muvt", "confined_muvt"]
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_replays_reference_trace_pairwise(name, seed):
+    r, s, types, params = replay.load_golden(name)
+    o = Oracle(params, repl_mode=0)
+    rep = replay.replay(o, r, s, types, replay.golden_short_trace(name, seed))
+    assert rep.n_moves > 100
+    assert rep.sentinel_mismatch == 0, rep.worst
+    assert rep.max_rel_dE < 1e-12, rep.worst
+    assert rep.max_rel_tot < 1e-11, rep.worst
+    assert rep.max_rel_beads < 1e-12, rep.worst
+    if "muvt" in name:
+        assert rep.n_gc > 10 and rep.n_beads_energy > 1000
+
+
+@pytest.mark.parametrize("name", ["bulk_nvt", "confined_nvt"])
+def test_oracle_structure_factor_form_matches_reference(name):
+    r, s, types, params = replay.load_golden(name)
+    o = Oracle(params, repl_mode=1)
+    rep = replay.replay(o, r, s, types, replay.golden_short_trace(name, 1), max_steps=150)
+    assert rep.sentinel_mismatch == 0, rep.worst
+    assert rep.max_rel_dE < 1e-11, rep.worst
+    assert rep.max_rel_tot < 1e-10, rep.worst
+
+
+def test_ewald_setup_matches_reference_logs():
+    """Cutoffs / k tables as echoed by the reference."""
+    expect = {
+        "bulk_nvt": (100.0, [2, 2, 2], [2, 2, 2], 26),
+        "confined_nvt": (100.0, [3, 3, 1], [2, 2, 7], 40),
+        "bulk_muvt": (100.0, [1, 1, 1], [3, 3, 3], 92),
+    }
+    for name, (rc, real_cell, repl_cell, nk) in expect.items():
+        _, _, _, params = replay.load_golden(name)
+        info = Oracle(params).ewald_info()
+        assert info.real_cutoff == rc
+        assert list(info.real_cell) == real_cell
+        assert list(info.repl_cell) == repl_cell
+        assert info.n_k == nk and info.n_k_half * 2 == nk
+
+
+@pytest.mark.skipif(not replay.have_plum_ref(), reason="oracle/_ref/plum_ref not built here")
+def test_fresh_reference_run_agrees_with_oracle():
+    """A trace generated now by the reference binary (different seed from the fixtures)."""
+    import os
+    d = "/root/reference/examples/confined_nvt"
+    if not os.path.isdir(d):
+        d = replay.golden_example_dir("confined_nvt")
+    r, s, types, params = replay.load_golden("confined_nvt")
+    lines = replay.run_plum_ref(d, 200, 7)
+    rep = replay.replay(Oracle(params), r, s, types, lines)
+    assert rep.n_moves == 200 and rep.sentinel_mismatch == 0
+    assert rep.max_rel_dE < 1e-12, rep.worst
