@@ -1,0 +1,737 @@
+// B200 façade behind Plum's ForceField interface — see force_field.h.
+//
+// What each member replaces in the reference (file:line relative to /root/reference):
+//   Initialize            src/force_field/force_field.cc:46-363 (+ the potentials' ReadParameters)
+//   EnergyDifference      src/force_field/force_field.cc:407-434   -> pg_delta_e
+//   FinalizeEnergies      src/force_field/force_field.cc:436-451   -> pg_commit
+//   CBMCFGenTrialBeads    src/force_field/cbmc.cc:161-212          -> pg_trial_energies (batched)
+//   CBMCFChainInsertion   src/force_field/cbmc.cc:214-328
+//   CBMCFChainDeletion    src/force_field/cbmc.cc:330-442          -> pg_delete_molecules
+//   EnergyInitForAddedMolecule  src/force_field/force_field.cc:1088-1105 -> pg_insert_molecules
+//   UpdateMolCounts       src/force_field/force_field.cc:1258-1277
+// The random-number draws are made in exactly the reference's order: a trajectory is
+// identical as long as every accept/reject and roulette decision agrees.
+#include "force_field.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#include "../utilities/constants.h"
+#include "../utilities/misc.h"
+#include "plum_b200.h"
+
+using namespace std;
+
+// Set by the driver's trace hook build (plum_b200/host/driver_hooks.py); harmless otherwise.
+double plum_trace_weight __attribute__((weak)) = -1;
+
+namespace {
+double Uniform(mt19937& g) { return (double)g() / g.max(); }
+}  // namespace
+
+ForceField::ForceField() : engine(NULL), pending_mol(-1) {}
+
+ForceField::~ForceField() {
+  if (engine) pg_destroy(engine);
+}
+
+void ForceField::Fail(const char* what, int rc) {
+  cout << "  plum_b200: " << what << " failed (" << rc << "): " << pg_last_error(engine) << endl;
+  cout << "  There is no CPU fallback. Exiting! Program complete." << endl;
+  exit(1);
+}
+
+int ForceField::TypeId(const string& symbol) {
+  map<string, int>::iterator it = type_of.find(symbol);
+  if (it != type_of.end()) return it->second;
+  if (engine) {
+    cout << "  plum_b200: bead type \"" << symbol << "\" appeared after the engine was created."
+         << " Exiting! Program complete." << endl;
+    exit(1);
+  }
+  int id = (int)type_symbols.size();
+  type_of[symbol] = id;
+  type_symbols.push_back(symbol);
+  return id;
+}
+
+// The s2/s3 part of run.in: same tokens, same order, flag names discarded.
+void ForceField::ReadPotentialParameters(vector<Molecule>& mols) {
+  string flag, symbol;
+  cin >> flag >> vp_el_res;
+  cin >> flag >> vp_bead_size;
+  cin >> flag >> use_pair_pot;
+  cin >> flag >> use_ewald_pot;
+  cin >> flag >> use_bond_pot;
+  cin >> flag >> use_bond_rigid;
+  cin >> flag >> use_angle_pot;
+  cin >> flag >> use_dihed_pot;
+  cin >> flag >> use_ext_pot;
+  cout << "  Force field parameters (B200 engine)." << endl;
+  cout << setw(35) << "[P] g(r) bin resolution (ul): " << vp_el_res << endl;
+  cout << setw(35) << "[P] Hard sphere size (ul)   : " << vp_bead_size << endl;
+  cout << setw(35) << "Use pair potential?         : " << YesOrNo(use_pair_pot) << endl;
+  cout << setw(35) << "Use Ewald sum potential?    : " << YesOrNo(use_ewald_pot) << endl;
+  cout << setw(35) << "Use bond potential?         : " << YesOrNo(use_bond_pot) << endl;
+  cout << setw(35) << "Use rigid bond?             : " << YesOrNo(use_bond_rigid) << endl;
+  cout << setw(35) << "Use angle potential?        : " << YesOrNo(use_angle_pot) << endl;
+  cout << setw(35) << "Use dihedral potential?     : " << YesOrNo(use_dihed_pot) << endl;
+  cout << setw(35) << "Use external potential?     : " << YesOrNo(use_ext_pot) << endl;
+  cin >> flag >> use_gc;
+  cout << setw(35) << "Use grand canonical MC?     : " << YesOrNo(use_gc) << endl;
+  if (use_gc) {
+    cin >> flag >> chem_pot >> flag >> gc_deBroglie_prefactor >> flag >> gc_freq >> flag >> gc_chain_len >> flag >>
+        gc_bead_charge >> flag >> gc_bead_symbol >> flag >> cbmc_no_of_trials;
+    cout << setw(35) << "[GC] Chemical pot (kBT)     : " << chem_pot << endl;
+    cout << setw(35) << "[GC] de Broglie wavelength^3: " << gc_deBroglie_prefactor << endl;
+    cout << setw(35) << "[GC] GCMC move frequency    : " << gc_freq << endl;
+    cout << setw(35) << "[GC] CBMC chain length      : " << gc_chain_len << endl;
+    cout << setw(35) << "[GC] CBMC bead charge (e)   : " << gc_bead_charge << endl;
+    cout << setw(35) << "[GC] CBMC bead type         : " << gc_bead_symbol << endl;
+    cout << setw(35) << "[GC] CBMC trials            : " << cbmc_no_of_trials << endl;
+  }
+
+  if (use_pair_pot) {
+    cin >> flag >> pair_name;
+    if (pair_name == "TruncatedLJ") {
+      cout << setw(35) << "[PP] Pair potential type    : " << "Truncated LJ" << endl;
+      cin >> flag >> lj_cutoff;
+      cout << setw(35) << "[PP] Pair potential cutoff  : " << lj_cutoff << endl;
+      while (true) {
+        cin >> flag >> symbol;
+        if (symbol == "end") break;
+        double sigma, epsilon;
+        cin >> flag >> sigma >> flag >> epsilon;
+        lj_sigmas[symbol] = sigma;
+        lj_epsilons[symbol] = epsilon;
+        TypeId(symbol);
+        cout << setw(35) << "[PP] Sigma for bead type    : " << symbol << " - " << sigma << endl;
+        cout << setw(35) << "[PP] Epsilon for bead type  : " << symbol << " - " << epsilon << endl;
+      }
+    } else if (pair_name == "HardSphere") {
+      cout << setw(35) << "[PP] Pair potential type    : " << "Hard sphere" << endl;
+      while (true) {
+        cin >> flag >> symbol;
+        if (symbol == "end") break;
+        double radius;
+        cin >> flag >> radius;
+        hs_radii[symbol] = radius;
+        TypeId(symbol);
+        cout << setw(35) << "[PP] Bead type and r (ul)   : " << symbol << " - " << radius << endl;
+      }
+    } else {
+      cout << "ForceField::ReadParameters: " << endl;
+      cout << "  Undefined pair potential! Exiting." << endl;
+      exit(1);
+    }
+  }
+  if (use_ewald_pot) {
+    cin >> flag >> ewald_name;
+    if (ewald_name != "Coul") {
+      cout << "ForceField::ReadParameters: " << endl;
+      cout << "  Undefined Ewald potential! Exiting." << endl;
+      exit(1);
+    }
+    cout << setw(35) << "[EP] Ewald potential type   : " << "Coul" << endl;
+    cin >> flag >> lB >> flag >> dielectric >> flag >> alpha >> flag >> dipole_correction;
+  }
+  if (use_bond_pot) {
+    cin >> flag >> bond_name;
+    if (bond_name != "Spring") {
+      cout << "ForceField::ReadParameters: " << endl;
+      cout << "  Undefined bonded potential! Exiting." << endl;
+      exit(1);
+    }
+    cout << setw(35) << "Bond potential type         : " << "Harmonic spring" << endl;
+    cin >> flag >> bond_k >> flag >> bond_r0;
+    cout << setw(37) << "Bond strength in eV/ul^2    = " << bond_k << endl;
+    cout << setw(37) << "Resting bond length in ul   = " << bond_r0 << endl;
+  }
+  if (use_bond_rigid) {
+    cin >> flag >> rigid_bond;
+    cout << setw(35) << "[RB] Rigid bond length      : " << rigid_bond << "A" << endl;
+  }
+  if (use_ext_pot) {
+    cin >> flag >> ext_name;
+    if (ext_name == "TruncatedLJWall") {
+      cout << setw(35) << "[eP] External potential type: " << "Truncated LJ wall" << endl;
+      cin >> flag >> wall_cut >> flag >> wall_sig >> flag >> wall_eps;
+      cout << setw(35) << "[eP] LJ cutoff              : " << wall_cut << endl;
+      cout << setw(35) << "[eP] Sigma for wall         : " << wall_sig << endl;
+      cout << setw(35) << "[eP] Epsilon for wall       : " << wall_eps << endl;
+      while (true) {
+        cin >> flag >> symbol;
+        if (symbol == "end") break;
+        double sigma, epsilon;
+        cin >> flag >> sigma >> flag >> epsilon;
+        wall_sigmas[symbol] = sigma;
+        wall_epsilons[symbol] = epsilon;
+        TypeId(symbol);
+        cout << setw(35) << "[eP] Sigma for bead type    : " << symbol << " - " << sigma << endl;
+        cout << setw(35) << "[eP] Epsilon for bead type  : " << symbol << " - " << epsilon << endl;
+      }
+    } else if (ext_name == "HardWall" || ext_name == "WellWall") {
+      if (ext_name == "WellWall") {
+        cout << "  Note: Currently, no correct pressure calculation" << endl;
+        cout << "        routine exists for well wall potential." << endl;
+        cin >> flag >> well_width;
+        cin >> flag >> well_depth;
+        cout << setw(31) << "Well witdh in unit length   = " << well_width << endl;
+        cout << setw(31) << "Well depth in kT            = " << well_depth << endl;
+      }
+      while (true) {
+        cin >> flag >> symbol;
+        if (symbol == "end") break;
+        double radius;
+        cin >> flag >> radius;
+        wall_sigmas[symbol] = radius;
+        TypeId(symbol);
+        cout << setw(35) << "[eP] Radius for bead type   : " << symbol << " - " << radius << endl;
+      }
+    } else {
+      cout << "ForceField::ReadParameters: " << endl;
+      cout << "  Undefined external potential! Exiting." << endl;
+      exit(1);
+    }
+  }
+  if (vp_bead_size < 0) {
+    cout << "  Virial bead size has to be bigger than zero!" << "Exiting! Program complete." << endl;
+    exit(1);
+  }
+  if (use_ext_pot) {
+    cout << "  Note: [!!!] If a wall confining potential is used, the" << endl;
+    cout << "        z-length of the simulation box needs to be 3 to" << endl;
+    cout << "        5 times wider than the confinement for the" << endl;
+    cout << "        electrostatics calculation to be correct!" << endl;
+  }
+  // Every symbol present in the coordinates gets a type id too (absent table entries read as 0,
+  // like operator[] on the reference's std::map).
+  for (int i = 0; i < (int)mols.size(); i++)
+    for (int j = 0; j < mols[i].Size(); j++) TypeId(mols[i].bds[j].Symbol());
+}
+
+void ForceField::CreateEngine(vector<Molecule>& mols) {
+  TypeId(gc_bead_symbol);
+  const int nt = (int)type_symbols.size();
+  vector<double> ljs(nt, 0.0), lje(nt, 0.0), hsr(nt, 0.0), ws(nt, 0.0), we(nt, 0.0);
+  vector<int32_t> graft(nt, PG_GRAFT_NONE);
+  for (int t = 0; t < nt; t++) {
+    const string& s = type_symbols[t];
+    if (lj_sigmas.count(s)) ljs[t] = lj_sigmas[s];
+    if (lj_epsilons.count(s)) lje[t] = lj_epsilons[s];
+    if (hs_radii.count(s)) hsr[t] = hs_radii[s];
+    if (wall_sigmas.count(s)) ws[t] = wall_sigmas[s];
+    if (wall_epsilons.count(s)) we[t] = wall_epsilons[s];
+    if (s == "L") graft[t] = PG_GRAFT_LEFT;
+    if (s == "R") graft[t] = PG_GRAFT_RIGHT;
+  }
+  pg_params p;
+  for (int i = 0; i < 3; i++) p.box[i] = box_l[i];
+  p.npbc = npbc;
+  p.n_types = nt;
+  p.beta = beta;
+  p.pair_kind = !use_pair_pot ? PG_PAIR_NONE : (pair_name == "HardSphere" ? PG_PAIR_HARD_SPHERE : PG_PAIR_TRUNCATED_LJ);
+  p._pad0 = 0;
+  p.lj_cutoff = lj_cutoff;
+  p.lj_sigma = ljs.data();
+  p.lj_epsilon = lje.data();
+  p.hs_radius = hsr.data();
+  p.use_ewald = use_ewald_pot ? 1 : 0;
+  p.dipole_correction = (use_ewald_pot && dipole_correction) ? 1 : 0;
+  p.lB = lB;
+  p.alpha = alpha;
+  p.bond_kind = use_bond_pot ? PG_BOND_SPRING : PG_BOND_NONE;
+  p._pad1 = 0;
+  p.bond_k = bond_k;
+  p.bond_r0 = bond_r0;
+  p.ext_kind = !use_ext_pot ? PG_EXT_NONE
+                            : (ext_name == "HardWall" ? PG_EXT_HARD_WALL
+                                                      : (ext_name == "WellWall" ? PG_EXT_WELL_WALL : PG_EXT_TRUNCATED_LJ_WALL));
+  p._pad2 = 0;
+  p.wall_cut = wall_cut;
+  p.wall_sigma = ws.data();
+  p.wall_epsilon = we.data();
+  p.graft_kind = graft.data();
+  p.well_width = well_width;
+  p.well_depth = well_depth;
+  int device = 0;
+  if (getenv("PLUM_B200_DEVICE")) device = atoi(getenv("PLUM_B200_DEVICE"));
+  int n_beads = 0;
+  for (int i = 0; i < (int)mols.size(); i++) n_beads += mols[i].Size();
+  int rc = pg_create(&p, device, n_beads + 4096, &engine);
+  if (rc) Fail("pg_create", rc);
+  if (use_ewald_pot) {
+    pg_ewald_info info;
+    pg_get_ewald_info(engine, &info);
+    cout << setw(35) << "[EP] Bjerrum length (ul)    : " << lB << endl;
+    cout << setw(35) << "[EP] Dielectric constant    : " << dielectric << endl;
+    cout << setw(35) << "[EP] Ewald alpha (ul^-2)    : " << alpha << endl;
+    cout << setw(35) << "[EP] Real space cutoff (ul) : " << info.real_cutoff << endl;
+    cout << setw(35) << "[EP] (cell sum number)      : "
+         << ceil((info.real_cell[0] + info.real_cell[1] + info.real_cell[2]) / 3.0) << endl;
+    cout << setw(35) << "[EP] k space cutoff (ul^-2) : " << info.repl_cutoff << endl;
+    cout << setw(35) << "[EP] (k sum number)         : "
+         << ceil((info.repl_cell[0] + info.repl_cell[1] + info.repl_cell[2]) / 3.0) << endl;
+    cout << setw(35) << "[EP] k vectors on device    : " << info.n_k_half << " (half space of " << info.n_k << ")"
+         << endl;
+    cout << setw(35) << "[EP] Use dipole correction? : " << YesOrNo(dipole_correction) << endl;
+  }
+}
+
+void ForceField::UploadSystem(vector<Molecule>& mols) {
+  vector<double> xyz, q;
+  vector<int32_t> type, first;
+  first.push_back(0);
+  for (int i = 0; i < (int)mols.size(); i++) {
+    for (int j = 0; j < mols[i].Size(); j++) {
+      Bead& b = mols[i].bds[j];
+      xyz.push_back(b.GetCrd(0, 0));
+      xyz.push_back(b.GetCrd(0, 1));
+      xyz.push_back(b.GetCrd(0, 2));
+      q.push_back(b.Charge());
+      type.push_back(TypeId(b.Symbol()));
+    }
+    first.push_back((int32_t)q.size());
+  }
+  int rc = pg_upload_system(engine, (int)q.size(), xyz.data(), q.data(), type.data(), (int)mols.size(), first.data());
+  if (rc) Fail("pg_upload_system", rc);
+}
+
+void ForceField::Initialize(double beta_in, int npbc_in, double box_l_in[3], vector<Molecule>& mols, int phantom_in,
+                            int coion_in, int grafted_in, int grafted_counterion_in) {
+  beta = beta_in;
+  npbc = npbc_in;
+  rigid_bond = -1;
+  for (int i = 0; i < 3; i++) box_l[i] = box_l_in[i];
+  vol = box_l[0] * box_l[1] * box_l[2];
+  phantom = phantom_in;
+  coion = coion_in;
+  grafted = grafted_in;
+  grafted_counterion = grafted_counterion_in;
+  use_gc = false;
+  chem_pot = 0; gc_freq = 1; gc_bead_charge = 0; gc_chain_len = 1;
+  lj_cutoff = -1; lB = 0; dielectric = 0; alpha = 0; dipole_correction = false;
+  bond_k = 0; bond_r0 = 0; wall_cut = -1; wall_sig = 0; wall_eps = 0; well_width = 0; well_depth = 0;
+
+  ReadPotentialParameters(mols);
+
+  // Chain bookkeeping, force_field.cc:236-284.
+  mu_tot_ins = 50;
+  chain_len = -1;
+  if (use_gc) {
+    chain_len = gc_chain_len;
+  } else {
+    for (int i = phantom; i < (int)mols.size(); i++) {
+      chain_len = mols[i].Size();
+      gc_bead_charge = mols[i].bds[0].Charge();
+      if (chain_len > 1) break;
+    }
+    gc_deBroglie_prefactor = 1;
+    gc_chain_len = chain_len;
+    gc_bead_symbol = "P";
+    cbmc_no_of_trials = 30;
+  }
+  UpdateMolCounts(mols);
+  n_chain += grafted;   // the start-up count of force_field.cc:260-278 does not subtract grafted chains
+  if (gc_chain_len < 0) gc_chain_len = 0;
+  gc_chain_chg.assign(gc_chain_len, (double)gc_bead_charge);
+
+  CreateEngine(mols);
+  InitializeEnergy(mols);
+}
+
+void ForceField::InitializeEnergy(vector<Molecule>& mols) {
+  UploadSystem(mols);
+  pg_totals t;
+  int rc = pg_init_energy(engine, &t);
+  if (rc) Fail("pg_init_energy", rc);
+  if (use_pair_pot) cout << "  Initialized pair potential." << endl;
+  if (use_ewald_pot) cout << "  Initialized Ewald potential." << endl;
+  if (use_bond_pot) cout << "  Initialized bond potential." << endl;
+  if (use_ext_pot) cout << "  Initialized external potential." << endl;
+
+  // CBMC scratch beads, force_field.cc:383-403: chain monomers then their counter-ions.
+  cbmc_chain.clear();
+  cbmc_trial_beads.clear();
+  for (int i = 0; i < gc_chain_len; i++) cbmc_chain.push_back(Bead(gc_bead_symbol, -1, -1, gc_chain_chg[i], 0, 0, 0));
+  for (int i = 0; i < cbmc_no_of_trials; i++)
+    cbmc_trial_beads.push_back(Bead(gc_bead_symbol, -1, -1, gc_chain_len ? gc_chain_chg[0] : 0.0, 0, 0, 0));
+  for (int i = 0; i < gc_chain_len; i++) cbmc_chain.push_back(Bead(gc_bead_symbol, -1, -1, -gc_chain_chg[i], 0, 0, 0));
+  for (int i = 0; i < cbmc_no_of_trials; i++)
+    cbmc_trial_beads.push_back(Bead(gc_bead_symbol, -1, -1, gc_chain_len ? -gc_chain_chg[0] : 0.0, 0, 0, 0));
+  cbmc_trial_weights.assign(cbmc_no_of_trials, 0.0);
+}
+
+// ------------------------------------------------------------------ per move
+double ForceField::EnergyDifference(vector<Molecule>& mols, int moved_mol) {
+  Molecule& m = mols[moved_mol];
+  const int len = m.Size();
+  vector<double> trial(3 * len);
+  vector<uint8_t> moved(len);
+  for (int i = 0; i < len; i++) {
+    trial[3 * i] = m.bds[i].GetCrd(1, 0);
+    trial[3 * i + 1] = m.bds[i].GetCrd(1, 1);
+    trial[3 * i + 2] = m.bds[i].GetCrd(1, 2);
+    moved[i] = m.bds[i].GetMoved() ? 1 : 0;
+  }
+  pg_delta d;
+  int rc = pg_delta_e(engine, moved_mol, trial.data(), moved.data(), &d);
+  if (rc) Fail("pg_delta_e", rc);
+  pending_mol = moved_mol;
+  return d.dE;
+}
+
+void ForceField::FinalizeEnergies(vector<Molecule>& mols, bool accept, int moved_mol) {
+  (void)mols;
+  if (pending_mol != moved_mol) return;   // EnergyDifference was skipped by the driver
+  int rc = pg_commit(engine, accept ? 1 : 0);
+  if (rc) Fail("pg_commit", rc);
+  pending_mol = -1;
+}
+
+// ---------------------------------------------------------------------- CBMC
+void ForceField::TrialEnergies(int n_trials, const double* b1, const double* b2, int current_len, int delete_id,
+                               double* energy_out) {
+  const bool charged = (gc_bead_charge != 0);
+  pg_trial_set set;
+  set.n_trials = n_trials;
+  set.use_bead2 = charged ? 1 : 0;
+  set.type1 = TypeId(gc_bead_symbol);
+  set.type2 = set.type1;
+  set.q1 = gc_chain_len ? gc_chain_chg[0] : 0.0;
+  set.q2 = -set.q1;
+  set.current_len = current_len;
+  set.skip_mol_first = -1;
+  set.skip_mol_last = -1;
+  set._pad = 0;
+  if (delete_id >= 0) {
+    set.skip_mol_first = delete_id;
+    set.skip_mol_last = delete_id + (charged ? gc_chain_len : 0);
+  }
+  // Partial chain: current_len monomers followed by their current_len ions.
+  const int n_chain_beads = current_len * (charged ? 2 : 1);
+  vector<double> cx(3 * (n_chain_beads > 0 ? n_chain_beads : 1)), cq(n_chain_beads > 0 ? n_chain_beads : 1);
+  vector<int32_t> ct(n_chain_beads > 0 ? n_chain_beads : 1, set.type1);
+  for (int i = 0; i < n_chain_beads; i++) {
+    Bead& b = (i < current_len) ? cbmc_chain[i] : cbmc_chain[gc_chain_len + (i - current_len)];
+    cx[3 * i] = b.GetCrd(1, 0);
+    cx[3 * i + 1] = b.GetCrd(1, 1);
+    cx[3 * i + 2] = b.GetCrd(1, 2);
+    cq[i] = b.Charge();
+  }
+  int rc = pg_trial_energies(engine, &set, b1, b2, cx.data(), cq.data(), ct.data(), energy_out, NULL, NULL);
+  if (rc) Fail("pg_trial_energies", rc);
+}
+
+// potential_spring.cc:50-61 (host RNG logic only; consumes the same variates).
+double ForceField::RandomBondLen(mt19937& rand_gen) {
+  double len = 0;
+  double sigma = sqrt(1 / (beta * bond_k));
+  double a = (bond_r0 + 3 * sigma) * (bond_r0 + 3 * sigma);
+  bool ready = false;
+  while (!ready) {
+    len = gasdev(bond_r0, sigma, rand_gen);
+    ready = (Uniform(rand_gen) < (len * len / a));
+  }
+  return len;
+}
+
+// Generates the k candidates of one growth step (all random draws first, in the reference's
+// order — BeadsEnergy itself draws nothing), then evaluates them in ONE batched launch.
+double ForceField::CBMCFGenTrialBeads(Bead& end_bead, vector<Molecule>& mols, int current_len, mt19937& rand_gen,
+                                      int delete_id) {
+  (void)mols;
+  const int k = cbmc_no_of_trials;
+  const bool charged = (gc_bead_charge != 0);
+  vector<double> b1(3 * k), b2(3 * k, 0.0), e(k);
+  for (int i = 0; i < k; i++) {
+    double bond_len = 0;
+    if (use_bond_pot)
+      bond_len = RandomBondLen(rand_gen);
+    else if (use_bond_rigid)
+      bond_len = rigid_bond;
+    double c[3];
+    randSphere(c, rand_gen);
+    for (int j = 0; j < 3; j++) {
+      c[j] *= bond_len;
+      c[j] += end_bead.GetCrd(0, j);
+    }
+    cbmc_trial_beads[i].SetAllCrd(c);
+    for (int j = 0; j < 3; j++) b1[3 * i + j] = c[j];
+    if (charged) {
+      c[0] = Uniform(rand_gen) * box_l[0];
+      c[1] = Uniform(rand_gen) * box_l[1];
+      c[2] = Uniform(rand_gen) * box_l[2];
+      cbmc_trial_beads[i + k].SetAllCrd(c);
+      for (int j = 0; j < 3; j++) b2[3 * i + j] = c[j];
+    }
+  }
+  TrialEnergies(k, b1.data(), b2.data(), current_len, delete_id, e.data());
+  double Wi = 0;
+  for (int i = 0; i < k; i++) {
+    cbmc_trial_weights[i] = exp(-beta * e[i]);
+    Wi += cbmc_trial_weights[i];
+  }
+  return Wi;
+}
+
+bool ForceField::CBMCFChainInsertion(vector<Molecule>& mols, mt19937& rand_gen) {
+  bool accept = false;
+  double weight = 1.0;
+  const bool charged = (gc_bead_charge != 0);
+  const int k = cbmc_no_of_trials;
+  plum_trace_weight = -1;
+
+  // First monomer (+ its ion) uniformly in the box.
+  double xyz[3];
+  const int initial_beads = charged ? 2 : 1;
+  for (int i = 0; i < initial_beads; i++) {
+    for (int j = 0; j < 3; j++) xyz[j] = Uniform(rand_gen) * box_l[j];
+    cbmc_chain[i * gc_chain_len].SetAllCrd(xyz);
+  }
+  {
+    double b1[3], b2[3] = {0, 0, 0}, e;
+    for (int j = 0; j < 3; j++) b1[j] = cbmc_chain[0].GetCrd(1, j);
+    if (charged)
+      for (int j = 0; j < 3; j++) b2[j] = cbmc_chain[gc_chain_len].GetCrd(1, j);
+    TrialEnergies(1, b1, b2, 0, -1, &e);
+    weight *= exp(-beta * e);
+  }
+  if (weight <= 0) return false;
+
+  for (int i = 1; i < gc_chain_len; i++) {
+    double Wi = CBMCFGenTrialBeads(cbmc_chain[i - 1], mols, i, rand_gen, -1);
+    weight *= Wi / k;
+    if (weight <= 0) return accept;
+    // Roulette selection on the cumulative weights.
+    double rand_num = Uniform(rand_gen) * Wi;
+    int current_bead = 0;
+    double cumulate_weight = cbmc_trial_weights[0];
+    while (cumulate_weight < rand_num && current_bead < k - 1) {
+      current_bead++;
+      cumulate_weight += cbmc_trial_weights[current_bead];
+    }
+    for (int j = 0; j < 3; j++) xyz[j] = cbmc_trial_beads[current_bead].GetCrd(0, j);
+    cbmc_chain[i].SetAllCrd(xyz);
+    if (charged) {
+      for (int j = 0; j < 3; j++) xyz[j] = cbmc_trial_beads[current_bead + k].GetCrd(0, j);
+      cbmc_chain[i + gc_chain_len].SetAllCrd(xyz);
+    }
+  }
+
+  // Acceptance rule, cbmc.cc:273-300.
+  UpdateMolCounts(mols);
+  int spc1;
+  if (gc_chain_len > 1) spc1 = n_chain;
+  else if (gc_bead_charge >= 0) spc1 = n_cion - coion;
+  else spc1 = n_aion - coion;
+  int spc2;
+  if (gc_bead_charge == 0) spc2 = 0;
+  else if (gc_bead_charge > 0) spc2 = n_aion;
+  else spc2 = n_cion;
+  int spc1_add = 1;
+  int spc2_add = charged ? gc_chain_len : 0;
+  double factorial = 1;
+  double m1 = gc_chain_len, m2 = 1;
+  double vol_over_lam = 1;
+  for (int i = spc1 + 1; i <= spc1 + spc1_add; i++) factorial *= i;
+  for (int i = spc2 + 1; i <= spc2 + spc2_add; i++) factorial *= i;
+  vol_over_lam *= pow(vol / (gc_deBroglie_prefactor / pow(m1, 1.5)), spc1_add);
+  vol_over_lam *= pow(vol / (gc_deBroglie_prefactor / pow(m2, 1.5)), spc2_add);
+  double C = vol_over_lam * (1.0 / (double)factorial);
+  double rand_num = Uniform(rand_gen);
+  plum_trace_weight = weight;
+  if (rand_num < (exp(beta * chem_pot) * weight) * C) {
+    accept = true;
+    mols.push_back(Molecule());
+    for (int i = 0; i < gc_chain_len; i++) mols[(int)mols.size() - 1].AddBead(cbmc_chain[i]);
+    for (int i = 0; i < mols[(int)mols.size() - 1].Size() - 1; i++) mols[(int)mols.size() - 1].AddBond(i, i + 1);
+    if (charged) {
+      for (int i = gc_chain_len; i < gc_chain_len * 2; i++) {
+        mols.push_back(Molecule());
+        mols[(int)mols.size() - 1].AddBead(cbmc_chain[i]);
+      }
+    }
+  }
+  return accept;
+}
+
+void ForceField::EnergyInitForAddedMolecule(vector<Molecule>& mols) {
+  int added = 1;
+  if (gc_bead_charge != 0) added += gc_chain_len;
+  vector<int32_t> lens, type;
+  vector<double> xyz, q;
+  for (int i = (int)mols.size() - added; i < (int)mols.size(); i++) {
+    lens.push_back(mols[i].Size());
+    for (int j = 0; j < mols[i].Size(); j++) {
+      Bead& b = mols[i].bds[j];
+      for (int a = 0; a < 3; a++) xyz.push_back(b.GetCrd(0, a));
+      q.push_back(b.Charge());
+      type.push_back(TypeId(b.Symbol()));
+    }
+  }
+  int rc = pg_insert_molecules(engine, added, lens.data(), xyz.data(), q.data(), type.data(), NULL);
+  if (rc) Fail("pg_insert_molecules", rc);
+}
+
+int ForceField::CBMCFChainDeletion(vector<Molecule>& mols, mt19937& rand_gen) {
+  UpdateMolCounts(mols);
+  const bool charged = (gc_bead_charge != 0);
+  const int k = cbmc_no_of_trials;
+  plum_trace_weight = -1;
+  int spc1;
+  if (gc_chain_len > 1) spc1 = n_chain;
+  else if (gc_bead_charge >= 0) spc1 = n_cion - coion;
+  else spc1 = n_aion - coion;
+
+  int delete_id = floor(Uniform(rand_gen) * spc1);
+  if (delete_id >= spc1) delete_id = spc1 - 1;
+  if (charged)
+    delete_id = phantom + coion + grafted + grafted_counterion + delete_id * (1 + gc_chain_len);
+  else
+    delete_id = phantom + coion + grafted + grafted_counterion + delete_id;
+  if (delete_id < 0 || delete_id >= (int)mols.size()) return -1;   // nothing of the GC species to delete
+
+  // Retrace the chain: first monomer (+ion) against everything but the chain itself.
+  double weight = 1.0;
+  const int second_mol = charged ? delete_id + 1 : delete_id;
+  double b1[3], b2[3] = {0, 0, 0}, e;
+  for (int j = 0; j < 3; j++) b1[j] = mols[delete_id].bds[0].GetCrd(0, j);
+  if (charged)
+    for (int j = 0; j < 3; j++) b2[j] = mols[second_mol].bds[0].GetCrd(0, j);
+  TrialEnergies(1, b1, b2, 0, delete_id, &e);
+  weight *= exp(-beta * e);
+  cbmc_chain[0].SetAllCrd(b1);
+  if (charged) cbmc_chain[gc_chain_len].SetAllCrd(b2);
+
+  for (int i = 1; i < gc_chain_len; i++) {
+    double xyz[3];
+    for (int j = 0; j < 3; j++) xyz[j] = mols[delete_id].bds[i].GetCrd(0, j);
+    cbmc_chain[i].SetAllCrd(xyz);
+    if (charged) {
+      for (int j = 0; j < 3; j++) xyz[j] = mols[delete_id + i + 1].bds[0].GetCrd(0, j);
+      cbmc_chain[i + gc_chain_len].SetAllCrd(xyz);
+    }
+    // k fresh candidates (their draws are consumed), slot 0 replaced by the real bead.
+    CBMCFGenTrialBeads(cbmc_chain[i - 1], mols, i, rand_gen, delete_id);
+    for (int j = 0; j < 3; j++) b1[j] = cbmc_chain[i].GetCrd(1, j);
+    if (charged)
+      for (int j = 0; j < 3; j++) b2[j] = cbmc_chain[i + gc_chain_len].GetCrd(1, j);
+    TrialEnergies(1, b1, b2, i, delete_id, &e);
+    cbmc_trial_weights[0] = exp(-beta * e);
+    double Wi = 0;
+    for (int j = 0; j < k; j++) Wi += cbmc_trial_weights[j];
+    weight *= Wi / k;
+  }
+
+  int spc2;
+  if (gc_bead_charge == 0) spc2 = 0;
+  else if (gc_bead_charge > 0) spc2 = n_aion;
+  else spc2 = n_cion;
+  int spc1_del = 1;
+  int spc2_del = charged ? gc_chain_len : 0;
+  double factorial = 1;
+  double m1 = gc_chain_len, m2 = 1;
+  double lam_over_vol = 1;
+  for (int i = spc1; i > spc1 - spc1_del; i--) factorial *= i;
+  for (int i = spc2; i > spc2 - spc2_del; i--) factorial *= i;
+  lam_over_vol *= pow((gc_deBroglie_prefactor / pow(m1, 1.5)) / vol, spc1_del);
+  lam_over_vol *= pow((gc_deBroglie_prefactor / pow(m2, 1.5)) / vol, spc2_del);
+  double C = lam_over_vol * (double)factorial;
+  double rand_num = Uniform(rand_gen);
+  plum_trace_weight = weight;
+  if (rand_num < C / (exp(beta * chem_pot) * weight)) {
+    // Monovalent counter-ions, as the reference assumes (potential_pair.cc:251-255).
+    int counterion = 0;
+    for (int i = 0; i < mols[delete_id].Size(); i++) counterion += (int)abs(round(mols[delete_id].bds[i].Charge()));
+    int rc = pg_delete_molecules(engine, delete_id, delete_id + counterion, NULL);
+    if (rc) Fail("pg_delete_molecules", rc);
+    return delete_id;
+  }
+  return -1;
+}
+
+double ForceField::CalcChemicalPotentialF(vector<Molecule>& mols, mt19937& rand_gen) {
+  (void)mols; (void)rand_gen;
+  cout << "  plum_b200: the Widom chemical-potential sampler (cbmc.cc:444-531) is not part of the" << endl;
+  cout << "  per-move energy path yet (SURVEY.md 8(f) #3); set s1_calc_chem_pot 0. Exiting! Program complete." << endl;
+  exit(1);
+  return 0;
+}
+
+// ------------------------------------------------------------------ samplers
+void ForceField::CalcPressureVolScalingHSELSlit(vector<Molecule>& mols) { (void)mols; }
+void ForceField::CalcPressureForceLJELSlit(vector<Molecule>& mols) { (void)mols; }
+
+string ForceField::GetPressure() {
+  // Pressure sampling is "next" (SURVEY.md 8(f) #1): columns are kept so output_stat.dat parses.
+  if (use_ext_pot) return "0 0 0 0 0 0";
+  return "nan";
+}
+
+// ----------------------------------------------------------------- utilities
+int ForceField::GCFrequency() { return gc_freq; }
+bool ForceField::UseGC() { return use_gc; }
+bool ForceField::UsePairPot() { return use_pair_pot; }
+bool ForceField::UseEwaldPot() { return use_ewald_pot; }
+bool ForceField::UseBondPot() { return use_bond_pot; }
+bool ForceField::UseBondRigid() { return use_bond_rigid; }
+bool ForceField::UseAnglePot() { return use_angle_pot; }
+bool ForceField::UseDihedPot() { return use_dihed_pot; }
+bool ForceField::UseExtPot() { return use_ext_pot; }
+
+double ForceField::TotPairEnergy() {
+  pg_totals t;
+  int rc = pg_get_totals(engine, &t);
+  if (rc) Fail("pg_get_totals", rc);
+  return t.pair;
+}
+double ForceField::TotEwaldEnergy() {
+  pg_totals t;
+  int rc = pg_get_totals(engine, &t);
+  if (rc) Fail("pg_get_totals", rc);
+  return t.ewald;
+}
+double ForceField::TotBondEnergy() {
+  pg_totals t;
+  int rc = pg_get_totals(engine, &t);
+  if (rc) Fail("pg_get_totals", rc);
+  return t.bond;
+}
+double ForceField::TotExtEnergy() {
+  pg_totals t;
+  int rc = pg_get_totals(engine, &t);
+  if (rc) Fail("pg_get_totals", rc);
+  return t.ext;
+}
+
+double ForceField::RigidBondLen() { return rigid_bond; }
+
+void ForceField::SetBoxLen(double box_l_in[3]) {
+  box_l[0] = box_l_in[0];
+  box_l[1] = box_l_in[1];
+  box_l[2] = box_l_in[2];
+}
+
+void ForceField::UpdateMolCounts(vector<Molecule>& mols) {
+  n_mol = (int)mols.size();
+  n_chain = 0;
+  n_cion = 0;
+  n_aion = 0;
+  for (int i = phantom; i < n_mol; i++) {
+    if (mols[i].Size() > 1) n_chain++;
+    else if (mols[i].bds[0].Charge() >= 0) n_cion++;
+    else if (mols[i].bds[0].Charge() < 0) n_aion++;
+  }
+  n_chain -= grafted;
+}
+
+double ForceField::EqBondLen() {
+  if (use_bond_pot) return bond_r0;
+  cout << "  Illegal request of bond length! Exiting. Program complete." << endl;
+  exit(1);
+  return 0;
+}

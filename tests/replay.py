@@ -27,15 +27,28 @@ def have_plum_ref() -> bool:
     return os.path.exists(PLUM_REF) and os.access(PLUM_REF, os.X_OK)
 
 
-def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, extra_sed=None) -> List[str]:
-    """Run the reference binary on an example (inputs copied to a temp dir) and return trace lines."""
+PLUM_GPU = os.path.join(REPO, "bin", "plum_gpu")
+
+
+def have_plum_gpu() -> bool:
+    return os.path.exists(PLUM_GPU) and os.access(PLUM_GPU, os.X_OK)
+
+
+def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, binary: str = None,
+                 overrides: dict = None) -> List[str]:
+    """Run a driver binary (default: the reference, oracle/_ref/plum_ref; or bin/plum_gpu) on an example
+    (inputs copied to a temp dir) and return its trace lines.  `overrides` replaces run.in values by key."""
+    binary = binary or PLUM_REF
+    overrides = dict(overrides or {})
+    overrides["s1_total_simulation_steps"] = steps
     with tempfile.TemporaryDirectory(prefix="plum_ref_run_") as tmp:
         with open(os.path.join(example_dir, "run.in")) as f:
             text = f.read()
         out = []
         for ln in text.split("\n"):
-            if ln.startswith("s1_total_simulation_steps"):
-                ln = f"s1_total_simulation_steps {steps}"
+            key = ln.split()[0] if ln.split() else ""
+            if key in overrides:
+                ln = f"{key} {overrides[key]}"
             out.append(ln)
         with open(os.path.join(tmp, "run.in"), "w") as f:
             f.write("\n".join(out))
@@ -46,7 +59,7 @@ def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, extr
         if xyz:
             env["PLUM_TRACE_XYZ"] = "1"
         with open(os.path.join(tmp, "run.in")) as fin, open(os.path.join(tmp, "run.log"), "w") as fout:
-            subprocess.check_call([PLUM_REF], stdin=fin, stdout=fout, cwd=tmp, env=env)
+            subprocess.check_call([binary], stdin=fin, stdout=fout, cwd=tmp, env=env)
         with open(os.path.join(tmp, "trace.txt")) as f:
             return f.read().split("\n")
 
