@@ -183,6 +183,10 @@ int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves,
  * filled after the batch.  elapsed_ms is CUDA-event time on the engine stream. */
 int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out,
                   float* elapsed_ms);
+/* Same proposals, energy kernel only (no commit: the state does not advance): the
+ * CUDA-event time of `count` back-to-back launches of the dominant kernel, for the
+ * roofline figure. */
+int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms);
 
 /* ---- configurational-bias trial energies (ForceField::BeadsEnergy) ------- */
 /* One launch evaluates n_trials candidate (monomer, counter-ion) pairs against

@@ -698,42 +698,53 @@ int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_
   return PG_OK;
 }
 
-int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, float* elapsed_ms) {
-  if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
-  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
-  PG_CUDA(h, cudaSetDevice(h->device));
-  // The packed buffer has the StageView layout with capacity rp_beads; a group at bead
-  // offset `off` is the same view shifted by `off` elements of each sub-array, so pass
-  // shifted pointers through a per-move StageView computed here.
-  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+static int replay_launch(pg_engine* h, int m, bool commit) {
+  const ReplayMove& r = h->rp_moves[m];
+  // The packed buffer has the StageView layout with capacity rp_beads; the group at bead offset
+  // `off` is that view with every sub-array shifted by `off` elements.
   StageView base = stage_view(h->d_rp, (int)h->rp_beads);
-  for (int m = first; m < first + count; m++) {
-    const ReplayMove& r = h->rp_moves[m];
-    PgDeltaArgs A;
-    memset(&A, 0, sizeof(A));
-    A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n_partners = h->n;
-    A.g0 = r.g0; A.glen = r.glen; A.mode = PG_MODE_MOVE; A.has_old = 1; A.has_new = 1;
-    A.trial = base.trial + 3 * (size_t)r.off; A.gq = base.gq + r.off; A.gtype = base.gtype + r.off;
-    A.moved = base.moved + r.off;
-    A.chain_len_first = r.glen; A.bond_first = 0; A.bond_len = r.glen;
-    A.kl = h->d_kl; A.ek2 = h->d_ek2; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->nk;
-    A.n_tiles = std::max(1, (h->n + PG_TILE - 1) / PG_TILE);
-    A.n_chunks = std::max(1, (r.glen + PG_GCHUNK - 1) / PG_GCHUNK);
-    A.chunk_size = std::max(1, (r.glen + A.n_chunks - 1) / A.n_chunks);
-    A.n_pair_ctas = A.n_tiles * A.n_chunks;
-    A.n_k_ctas = h->P.use_ewald ? (h->nk + PG_KTILE - 1) / PG_KTILE : 0;
-    int n_ctas = A.n_pair_ctas + A.n_k_ctas;
-    int rc = ensure_partials(h, n_ctas);
-    if (rc) return rc;
-    A.partial = h->d_partial; A.partial_i = h->d_partial_i; A.state = h->d_state; A.result = nullptr;
-    A.decide_on_device = 1; A.u = r.u; A.replay_dE = h->d_rp_dE; A.replay_acc = h->d_rp_acc; A.replay_index = m;
-    A.seq = ++h->seq;
-    k_delta<<<n_ctas, PG_TILE, 0, h->stream>>>(h->P, A);
+  PgDeltaArgs A;
+  memset(&A, 0, sizeof(A));
+  A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n_partners = h->n;
+  A.g0 = r.g0; A.glen = r.glen; A.mode = PG_MODE_MOVE; A.has_old = 1; A.has_new = 1;
+  A.trial = base.trial + 3 * (size_t)r.off; A.gq = base.gq + r.off; A.gtype = base.gtype + r.off;
+  A.moved = base.moved + r.off;
+  A.chain_len_first = r.glen; A.bond_first = 0; A.bond_len = r.glen;
+  A.kl = h->d_kl; A.ek2 = h->d_ek2; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->nk;
+  A.n_tiles = std::max(1, (h->n + PG_TILE - 1) / PG_TILE);
+  A.n_chunks = std::max(1, (r.glen + PG_GCHUNK - 1) / PG_GCHUNK);
+  A.chunk_size = std::max(1, (r.glen + A.n_chunks - 1) / A.n_chunks);
+  A.n_pair_ctas = A.n_tiles * A.n_chunks;
+  A.n_k_ctas = h->P.use_ewald ? (h->nk + PG_KTILE - 1) / PG_KTILE : 0;
+  int n_ctas = A.n_pair_ctas + A.n_k_ctas;
+  int rc = ensure_partials(h, n_ctas);
+  if (rc) return rc;
+  A.partial = h->d_partial; A.partial_i = h->d_partial_i; A.state = h->d_state; A.result = nullptr;
+  A.decide_on_device = 1; A.u = r.u;
+  A.replay_dE = commit ? h->d_rp_dE : nullptr;
+  A.replay_acc = commit ? h->d_rp_acc : nullptr;
+  A.replay_index = m;
+  A.seq = ++h->seq;
+  k_delta<<<n_ctas, PG_TILE, 0, h->stream>>>(h->P, A);
+  h->launches++;
+  if (commit) {
     int nthreads = std::max(std::max(r.glen, h->nk), 1);
     k_commit<<<(nthreads + 255) / 256, 256, 0, h->stream>>>(h->P, -1, PG_MODE_MOVE, r.g0, r.glen, A.trial, A.gq,
                                                             A.gtype, h->xy, h->zq, h->type, h->d_S, h->d_dS,
                                                             h->P.use_ewald ? h->nk : 0, h->d_state);
-    h->launches += 2;
+    h->launches++;
+  }
+  return PG_OK;
+}
+
+int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, float* elapsed_ms) {
+  if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (int m = first; m < first + count; m++) {
+    int rc = replay_launch(h, m, true);
+    if (rc) return rc;
   }
   PG_CUDA(h, cudaGetLastError());
   PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -743,6 +754,27 @@ int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* a
     PG_CUDA(h, cudaMemcpy(dE_out, h->d_rp_dE + first, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost));
   if (accept_out && count > 0)
     PG_CUDA(h, cudaMemcpy(accept_out, h->d_rp_acc + first, (size_t)count, cudaMemcpyDeviceToHost));
+  return PG_OK;
+}
+
+int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms) {
+  if (!h || !elapsed_ms || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (int m = first; m < first + count; m++) {
+    int rc = replay_launch(h, m, false);
+    if (rc) return rc;
+  }
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  PG_CUDA(h, cudaEventSynchronize(h->ev1));
+  PG_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  // a trial evaluated without commit leaves trial_dipl touched: restore the lag state
+  k_commit<<<1, 32, 0, h->stream>>>(h->P, 0, PG_MODE_MOVE, 0, 0, nullptr, nullptr, nullptr, h->xy, h->zq, h->type,
+                                    h->d_S, h->d_dS, 0, h->d_state);
+  h->launches++;
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
   return PG_OK;
 }
 
