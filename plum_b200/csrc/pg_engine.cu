@@ -26,6 +26,7 @@
 
 #include "../../include/plum_b200.h"
 #include "pg_kernels.cu"
+#include "pg_move.cu"
 
 namespace {
 
@@ -65,15 +66,25 @@ struct pg_engine {
   int nk = 0;
   std::vector<int> h_kl;        // [nk][4]
   std::vector<double> h_ek2;
+  std::vector<double> h_kvec;   // [nk][4] (kx, ky, kz, ek2)
+  double4* d_kvec = nullptr;
   int* d_kl = nullptr;
   double* d_ek2 = nullptr;
   double2 *d_S = nullptr, *d_dS = nullptr, *d_Sp = nullptr, *d_Stmp = nullptr;
 
-  // group staging: one pinned block + one device block with the same layout
+  // group staging: two pinned + two device blocks (ping-pong: the previous trial's block must
+  // stay intact until its deferred commit has been applied by the next k_move launch)
   int gcap = 0;
-  char* h_stage = nullptr;
+  char* h_stage2[2] = {nullptr, nullptr};
+  char* d_stage2[2] = {nullptr, nullptr};
+  char* h_stage = nullptr;      // current slot (aliases h_stage2[slot])
   char* d_stage = nullptr;
+  int slot = 0;
   size_t stage_bytes = 0;
+  bool fast = false;            // k_move<true> hot loop is valid for this force field
+
+  // deferred commit of the last trial (applied by the next k_move or by flush_commit)
+  struct { bool valid; int accept; int g0, glen; const char* d_group; int cap; } pc = {false, 0, 0, 0, nullptr, 0};
 
   // scratch
   int partial_cap = 0;
@@ -82,14 +93,21 @@ struct pg_engine {
   double* d_out8 = nullptr;     // 8 doubles
   double* h_out8 = nullptr;     // pinned
   PgState* d_state = nullptr;
+  unsigned long long* d_timing = nullptr;   // debug stamps (PLUM_B200_TIMING=1)
+  int timing_ctas = 0;
+  PgDev* d_P = nullptr;          // device copy of P for non-inlined device functions
   PgResult* h_result = nullptr; // mapped pinned
   PgResult* d_result = nullptr; // device alias of h_result
+  PgMailRec* h_mail = nullptr;  // mapped pinned: k_move's self-validating result records
+  PgMailRec* d_mail = nullptr;
+  int move_slots = 0;           // resident k_move CTAs on the device (one wave)
   unsigned int seq = 0;
   bool use_mailbox = true;
 
   // pending trial
   bool pending = false;
-  int pend_mode = 0, pend_g0 = 0, pend_glen = 0;
+  int pend_mode = 0, pend_g0 = 0, pend_glen = 0, pend_cap = 0;
+  const char* pend_group = nullptr;
 
   // CBMC staging
   int tcap = 0;       // trials capacity
@@ -169,6 +187,7 @@ void ewald_setup(pg_engine* h, const pg_params* p) {
   for (int l = -repl_cell[2]; l <= repl_cell[2]; l++) kz[l + repl_cell[2]] = l * 2 * kPi / box_l[2];
   h->h_kl.clear();
   h->h_ek2.clear();
+  h->h_kvec.clear();
   int n_k = 0;
   for (int ix = 0; ix < ceto[0]; ix++)
     for (int iy = 0; iy < ceto[1]; iy++)
@@ -183,6 +202,7 @@ void ewald_setup(pg_engine* h, const pg_params* p) {
         if (!pos) continue;
         h->h_kl.push_back(ax); h->h_kl.push_back(ay); h->h_kl.push_back(az); h->h_kl.push_back(0);
         h->h_ek2.push_back(ek2);
+        h->h_kvec.push_back(kx[ix]); h->h_kvec.push_back(ky[iy]); h->h_kvec.push_back(kz[iz]); h->h_kvec.push_back(ek2);
       }
   h->nk = (int)h->h_ek2.size();
   for (int i = 0; i < 3; i++) {
@@ -292,17 +312,33 @@ int build_params(pg_engine* h, const pg_params* p) {
   return PG_OK;
 }
 
+int flush_commit(pg_engine* h);
+
 int ensure_group(pg_engine* h, int glen) {
   if (glen <= h->gcap) return PG_OK;
+  int rc = flush_commit(h);   // the pending trial's block is about to be freed
+  if (rc) return rc;
   int cap = std::max(256, glen * 2);
-  if (h->h_stage) cudaFreeHost(h->h_stage);
-  if (h->d_stage) cudaFree(h->d_stage);
-  h->h_stage = nullptr; h->d_stage = nullptr;
   h->stage_bytes = stage_size(cap);
-  PG_CUDA(h, cudaHostAlloc((void**)&h->h_stage, h->stage_bytes, cudaHostAllocDefault));
-  PG_CUDA(h, cudaMalloc((void**)&h->d_stage, h->stage_bytes));
+  for (int s = 0; s < 2; s++) {
+    if (h->h_stage2[s]) cudaFreeHost(h->h_stage2[s]);
+    if (h->d_stage2[s]) cudaFree(h->d_stage2[s]);
+    h->h_stage2[s] = nullptr; h->d_stage2[s] = nullptr;
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_stage2[s], h->stage_bytes, cudaHostAllocDefault));
+    PG_CUDA(h, cudaMalloc((void**)&h->d_stage2[s], h->stage_bytes));
+  }
+  h->slot = 0;
+  h->h_stage = h->h_stage2[0];
+  h->d_stage = h->d_stage2[0];
   h->gcap = cap;
   return PG_OK;
+}
+
+// Next staging slot (the other one keeps the previous trial until its commit is applied).
+void next_slot(pg_engine* h) {
+  h->slot ^= 1;
+  h->h_stage = h->h_stage2[h->slot];
+  h->d_stage = h->d_stage2[h->slot];
 }
 
 int ensure_partials(pg_engine* h, int n_ctas) {
@@ -311,7 +347,7 @@ int ensure_partials(pg_engine* h, int n_ctas) {
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_partial_i) cudaFree(h->d_partial_i);
   h->d_partial = nullptr; h->d_partial_i = nullptr;
-  PG_CUDA(h, cudaMalloc((void**)&h->d_partial, sizeof(double) * 4 * (size_t)cap));
+  PG_CUDA(h, cudaMalloc((void**)&h->d_partial, sizeof(double) * 8 * (size_t)cap));
   PG_CUDA(h, cudaMalloc((void**)&h->d_partial_i, sizeof(int) * (size_t)cap));
   h->partial_cap = cap;
   return PG_OK;
@@ -421,13 +457,107 @@ int launch_commit(pg_engine* h, int accept_flag, int mode, int g0, int glen, con
   return PG_OK;
 }
 
-void fill_delta(const PgResult* r, pg_delta* o) {
-  o->dE = r->dE; o->pair = r->pair; o->ext = r->ext; o->ewald = r->ewald; o->bond = r->bond;
-  o->real = r->real; o->recip = r->recip; o->mz_current = r->mz_current;
-  o->stage = r->stage; o->n_overlap = r->n_overlap;
+// Fills the tiling of a k_move launch: (partner tile x group chunk) CTAs + k CTAs sized so the
+// whole grid is resident at once (one wave on the 148 SMs) whenever the chunk fits shared memory.
+void move_tiling(pg_engine* h, int glen, PgMoveArgs& A) {
+  A.n_tiles = std::max(1, (h->n + MV_THREADS - 1) / MV_THREADS);
+  A.n_k_ctas = h->P.use_ewald ? (h->nk + MV_THREADS - 1) / MV_THREADS : 0;
+  int min_chunks = std::max(1, (glen + MV_GCHUNK - 1) / MV_GCHUNK);
+  const int n_intra = (glen * (glen - 1) / 2 + MV_THREADS - 1) / MV_THREADS;
+  int fit = std::max(1, (h->move_slots - A.n_k_ctas - n_intra) / A.n_tiles);
+  A.n_chunks = std::max(min_chunks, std::min(fit, std::max(glen, 1)));
+  A.chunk_size = std::max(1, (glen + A.n_chunks - 1) / A.n_chunks);
+  A.n_chunks = std::max(1, (glen + A.chunk_size - 1) / A.chunk_size);
+  A.n_pair_ctas = A.n_tiles * A.n_chunks;
+  A.n_intra_ctas = (glen * (glen - 1) / 2 + MV_THREADS - 1) / MV_THREADS;
 }
 
+// One launch per move: energy change of the trial in `d_group` + deferred commit of h->pc.
+int launch_move(pg_engine* h, int g0, int glen, const char* d_group, int group_cap, bool decide_on_device, double u,
+                int replay_index, bool want_result, bool log_replay) {
+  PgMoveArgs A;
+  memset(&A, 0, sizeof(A));
+  A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n = h->n;
+  A.g0 = g0; A.glen = glen;
+  StageView dv = stage_view(const_cast<char*>(d_group), group_cap);
+  A.trial = dv.trial; A.gq = dv.gq; A.gtype = dv.gtype; A.moved = dv.moved;
+  if (h->pc.valid) {
+    StageView pv = stage_view(const_cast<char*>(h->pc.d_group), h->pc.cap);
+    A.prev_valid = 1; A.prev_accept = h->pc.accept; A.pg0 = h->pc.g0; A.pglen = h->pc.glen; A.ptrial = pv.trial;
+  }
+  A.kvec = h->d_kvec; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->P.use_ewald ? h->nk : 0;
+  move_tiling(h, glen, A);
+  const int n_ctas = A.n_pair_ctas + A.n_k_ctas + A.n_intra_ctas;
+  int rc = ensure_partials(h, n_ctas);
+  if (rc) return rc;
+  A.partial = h->d_partial;
+  A.state = h->d_state;
+  A.mail = want_result ? h->d_mail : nullptr;
+  A.decide_on_device = decide_on_device ? 1 : 0;
+  A.u = u;
+  A.replay_dE = log_replay ? h->d_rp_dE : nullptr;
+  A.replay_acc = log_replay ? h->d_rp_acc : nullptr;
+  A.replay_index = replay_index;
+  A.seq = ++h->seq;
+  A.Pg = h->d_P;
+  A.timing = (h->d_timing && n_ctas <= 8192) ? h->d_timing : nullptr;
+  h->timing_ctas = n_ctas;
+  if (h->fast)
+    k_move<true><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
+  else
+    k_move<false><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
+  h->launches++;
+  h->pc.valid = false;   // the launch applies it
+  PG_CUDA(h, cudaGetLastError());
+  return PG_OK;
+}
+
+// Apply a commit that no k_move launch has picked up yet (needed before anything else reads
+// positions, S(k) or the totals).
+int flush_commit(pg_engine* h) {
+  if (!h->pc.valid) return PG_OK;
+  h->pc.valid = false;
+  return launch_commit(h, h->pc.accept, PG_MODE_MOVE, h->pc.g0, h->pc.glen, h->pc.d_group, h->pc.cap);
+}
+
+// Spin on k_move's mailbox: every 16-byte record carries the launch's sequence number, so a
+// record whose seq matches is complete (no device-side system fence on the critical path).
+int wait_mail(pg_engine* h, unsigned int seq, pg_delta* o) {
+  volatile PgMailRec* m = h->h_mail;
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned long spins = 0;
+  double val[MV_NSLOT];
+  int aux[MV_NSLOT];
+  for (int s = 0; s < MV_NSLOT; s++) {
+    for (;;) {
+      if (m[s].seq == seq) {
+        val[s] = m[s].value;
+        aux[s] = m[s].aux;
+        if (m[s].seq == seq) break;
+      }
+      if ((++spins & 0xfffff) == 0) {
+        cudaError_t q = cudaStreamQuery(h->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) {
+          h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
+          return PG_ERR_CUDA;
+        }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) {
+          h->err = "device did not answer within 30 s";
+          return PG_ERR_TIMEOUT;
+        }
+      }
+    }
+  }
+  o->dE = val[0]; o->pair = val[1]; o->ext = val[2]; o->ewald = val[3]; o->bond = val[4];
+  o->real = val[5]; o->recip = val[6]; o->mz_current = val[7];
+  o->stage = aux[0] & 0xff; o->n_overlap = aux[1];
+  return PG_OK;
+}
+
+
 int compute_totals(pg_engine* h, bool set_state, pg_totals* out) {
+  int frc = flush_commit(h);
+  if (frc) return frc;
   double2* S = set_state ? h->d_S : h->d_Stmp;
   if (h->P.use_ewald && h->nk > 0) {
     int nb = (h->nk + PG_TILE - 1) / PG_TILE;
@@ -459,13 +589,17 @@ int compute_totals(pg_engine* h, bool set_state, pg_totals* out) {
 void free_all(pg_engine* h) {
   cudaFree(h->xy); cudaFree(h->zq); cudaFree(h->type); cudaFree(h->mol);
   cudaFree(h->t_xy); cudaFree(h->t_zq); cudaFree(h->t_type); cudaFree(h->t_mol);
-  cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_S); cudaFree(h->d_dS); cudaFree(h->d_Sp); cudaFree(h->d_Stmp);
-  if (h->h_stage) cudaFreeHost(h->h_stage);
-  cudaFree(h->d_stage);
+  cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_kvec); cudaFree(h->d_S); cudaFree(h->d_dS); cudaFree(h->d_Sp); cudaFree(h->d_Stmp);
+  for (int s = 0; s < 2; s++) {
+    if (h->h_stage2[s]) cudaFreeHost(h->h_stage2[s]);
+    cudaFree(h->d_stage2[s]);
+  }
   cudaFree(h->d_partial); cudaFree(h->d_partial_i); cudaFree(h->d_out8);
   if (h->h_out8) cudaFreeHost(h->h_out8);
   cudaFree(h->d_state);
+  cudaFree(h->d_P);
   if (h->h_result) cudaFreeHost(h->h_result);
+  if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
   if (h->h_trial_ct) cudaFreeHost(h->h_trial_ct);
   if (h->h_trial_out) cudaFreeHost(h->h_trial_out);
@@ -499,6 +633,21 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   h->device = device;
   int rc = build_params(h, params);
   if (rc) { delete h; return rc; }
+  {
+    // k_move<true>: central image only, one box for LJ and Ewald, three periodic axes, and every
+    // LJ cutoff well inside half the cell so BBDist's fold can only act beyond it.
+    const PgDev& P = h->P;
+    double lmin = std::min(P.box[0], std::min(P.box[1], P.box[2]));
+    bool lj_ok = true;
+    if (P.pair_kind == PG_PAIR_TRUNCATED_LJ)
+      for (int a = 0; a < P.n_types; a++)
+        for (int b = 0; b < P.n_types; b++)
+          if (!(P.lj_rcut[a * PG_MAX_TYPES + b] < 0.49 * lmin)) lj_ok = false;
+    h->fast = (params->npbc == 3) && P.pair_kind != PG_PAIR_HARD_SPHERE && lj_ok && P.same_box[0] && P.same_box[1] &&
+              P.same_box[2] && (!P.use_ewald || P.single_image);
+    const char* nf = getenv("PLUM_B200_NO_FAST");
+    if (nf && nf[0] == '1') h->fast = false;
+  }
 #define PG_CREATE_CUDA(call)                                                    \
   do {                                                                          \
     cudaError_t e_ = (call);                                                    \
@@ -513,14 +662,26 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   PG_CREATE_CUDA(cudaEventCreate(&h->ev1));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_state, sizeof(PgState)));
   PG_CREATE_CUDA(cudaMemset(h->d_state, 0, sizeof(PgState)));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_P, sizeof(PgDev)));
+  PG_CREATE_CUDA(cudaMemcpy(h->d_P, &h->P, sizeof(PgDev), cudaMemcpyHostToDevice));
   PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_result, sizeof(PgResult), cudaHostAllocMapped));
   memset((void*)h->h_result, 0, sizeof(PgResult));
   PG_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_result, (void*)h->h_result, 0));
+  PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_mail, sizeof(PgMailRec) * MV_NSLOT, cudaHostAllocMapped));
+  memset((void*)h->h_mail, 0, sizeof(PgMailRec) * MV_NSLOT);
+  PG_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_mail, (void*)h->h_mail, 0));
+  {
+    int per_sm = 0, n_sm = 0;
+    PG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move<true>, MV_THREADS, 0));
+    PG_CREATE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    h->move_slots = std::max(1, per_sm * n_sm);
+  }
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_out8, sizeof(double) * 8));
   PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_out8, sizeof(double) * 8, cudaHostAllocDefault));
   int nk_alloc = std::max(h->nk, 1);
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_kl, sizeof(int) * 4 * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_ek2, sizeof(double) * (size_t)nk_alloc));
+  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_kvec, sizeof(double4) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_S, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_dS, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_Sp, sizeof(double2) * (size_t)nk_alloc));
@@ -530,8 +691,15 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   if (h->nk > 0) {
     PG_CREATE_CUDA(cudaMemcpy(h->d_kl, h->h_kl.data(), sizeof(int) * 4 * (size_t)h->nk, cudaMemcpyHostToDevice));
     PG_CREATE_CUDA(cudaMemcpy(h->d_ek2, h->h_ek2.data(), sizeof(double) * (size_t)h->nk, cudaMemcpyHostToDevice));
+    PG_CREATE_CUDA(cudaMemcpy(h->d_kvec, h->h_kvec.data(), sizeof(double4) * (size_t)h->nk, cudaMemcpyHostToDevice));
   }
 #undef PG_CREATE_CUDA
+  {
+    const char* tm = getenv("PLUM_B200_TIMING");
+    if (tm && tm[0] == '1') {
+      if (cudaMalloc((void**)&h->d_timing, sizeof(unsigned long long) * 8 * 8192) != cudaSuccess) h->d_timing = nullptr;
+    }
+  }
   const char* mb = getenv("PLUM_B200_NO_MAILBOX");
   h->use_mailbox = !(mb && mb[0] == '1');
   h->mol_first.assign(1, 0);
@@ -595,6 +763,7 @@ int pg_upload_system(pg_engine* h, int n_beads, const double* xyz, const double*
   h->n = n_beads;
   h->n_mol = n_mol;
   h->pending = false;
+  h->pc.valid = false;
   return PG_OK;
 }
 
@@ -615,6 +784,7 @@ int pg_get_totals(const pg_engine* hc, pg_totals* out) {
   pg_engine* h = const_cast<pg_engine*>(hc);
   if (!h || !out) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   PgState st;
   PG_CUDA(h, cudaMemcpyAsync(&st, h->d_state, sizeof(PgState), cudaMemcpyDeviceToHost, h->stream));
   PG_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -627,6 +797,7 @@ int pg_download_positions(pg_engine* h, double* xyz) {
   if (!h || (!xyz && h->n > 0)) return PG_ERR_INVALID;
   if (h->n == 0) return PG_OK;
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   std::vector<double2> hxy(h->n), hzq(h->n);
   PG_CUDA(h, cudaMemcpyAsync(hxy.data(), h->xy, sizeof(double2) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
   PG_CUDA(h, cudaMemcpyAsync(hzq.data(), h->zq, sizeof(double2) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
@@ -643,29 +814,35 @@ int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* mo
   const int g0 = h->mol_first[mol], glen = h->mol_first[mol + 1] - g0;
   int rc = ensure_group(h, glen);
   if (rc) return rc;
-  StageView sv = stage_view(h->h_stage, h->gcap);
+  next_slot(h);   // the other slot still holds the previous trial (deferred commit)
+  // compact layout: only stage_size(glen) bytes cross PCIe
+  StageView sv = stage_view(h->h_stage, glen);
   memcpy(sv.trial, trial_xyz, sizeof(double) * 3 * (size_t)glen);
   for (int i = 0; i < glen; i++) {
     sv.gq[i] = h->h_q[g0 + i];
     sv.gtype[i] = h->h_type[g0 + i];
     sv.moved[i] = moved[i] ? 1 : 0;
   }
-  PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, h->stage_bytes, cudaMemcpyHostToDevice, h->stream));
-  rc = launch_delta(h, PG_MODE_MOVE, g0, glen, glen, 0, glen, h->d_stage, h->gcap, false, 0.0, 0, true);
+  PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, stage_size(glen), cudaMemcpyHostToDevice, h->stream));
+  rc = launch_move(h, g0, glen, h->d_stage, glen, false, 0.0, 0, true, false);
   if (rc) return rc;
-  rc = wait_result(h, h->seq);
+  rc = wait_mail(h, h->seq, out);
   if (rc) return rc;
-  fill_delta(h->h_result, out);
   h->pending = true;
-  h->pend_mode = PG_MODE_MOVE; h->pend_g0 = g0; h->pend_glen = glen;
+  h->pend_mode = PG_MODE_MOVE; h->pend_g0 = g0; h->pend_glen = glen; h->pend_group = h->d_stage; h->pend_cap = glen;
   return PG_OK;
 }
 
+// FinalizeEnergies: records the decision; the next k_move launch (or the next call that needs
+// the state) applies it on the device.
 int pg_commit(pg_engine* h, int accept) {
   if (!h) return PG_ERR_INVALID;
   if (!h->pending) { h->err = "no pending trial"; return PG_ERR_STATE; }
   h->pending = false;
-  return launch_commit(h, accept ? 1 : 0, h->pend_mode, h->pend_g0, h->pend_glen, h->d_stage, h->gcap);
+  h->pc.valid = true;
+  h->pc.accept = accept ? 1 : 0;
+  h->pc.g0 = h->pend_g0; h->pc.glen = h->pend_glen; h->pc.d_group = h->pend_group; h->pc.cap = h->pend_cap;
+  return PG_OK;
 }
 
 // ------------------------------------------------------------------ replay
@@ -673,6 +850,7 @@ int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_
                      const uint8_t* moved) {
   if (!h || n_moves < 0 || (n_moves > 0 && (!moves || !trial_xyz || !moved))) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   h->rp_moves.clear();
   cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
   h->d_rp = nullptr; h->d_rp_dE = nullptr; h->d_rp_acc = nullptr;
@@ -698,42 +876,49 @@ int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_
   return PG_OK;
 }
 
-static int replay_launch(pg_engine* h, int m, bool commit) {
-  const ReplayMove& r = h->rp_moves[m];
-  // The packed buffer has the StageView layout with capacity rp_beads; the group at bead offset
-  // `off` is that view with every sub-array shifted by `off` elements.
+// Device pointers of replay move m inside the packed proposal buffer (StageView layout with
+// capacity rp_beads, every sub-array shifted by the move's bead offset).
+static void replay_view(pg_engine* h, int m, StageView& v) {
   StageView base = stage_view(h->d_rp, (int)h->rp_beads);
-  PgDeltaArgs A;
+  const ReplayMove& r = h->rp_moves[m];
+  v.trial = base.trial + 3 * (size_t)r.off; v.gq = base.gq + r.off; v.gtype = base.gtype + r.off;
+  v.moved = base.moved + r.off;
+}
+
+static int replay_launch(pg_engine* h, int m, int prev, bool log) {
+  const ReplayMove& r = h->rp_moves[m];
+  PgMoveArgs A;
   memset(&A, 0, sizeof(A));
-  A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n_partners = h->n;
-  A.g0 = r.g0; A.glen = r.glen; A.mode = PG_MODE_MOVE; A.has_old = 1; A.has_new = 1;
-  A.trial = base.trial + 3 * (size_t)r.off; A.gq = base.gq + r.off; A.gtype = base.gtype + r.off;
-  A.moved = base.moved + r.off;
-  A.chain_len_first = r.glen; A.bond_first = 0; A.bond_len = r.glen;
-  A.kl = h->d_kl; A.ek2 = h->d_ek2; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->nk;
-  A.n_tiles = std::max(1, (h->n + PG_TILE - 1) / PG_TILE);
-  A.n_chunks = std::max(1, (r.glen + PG_GCHUNK - 1) / PG_GCHUNK);
-  A.chunk_size = std::max(1, (r.glen + A.n_chunks - 1) / A.n_chunks);
-  A.n_pair_ctas = A.n_tiles * A.n_chunks;
-  A.n_k_ctas = h->P.use_ewald ? (h->nk + PG_KTILE - 1) / PG_KTILE : 0;
-  int n_ctas = A.n_pair_ctas + A.n_k_ctas;
+  A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n = h->n;
+  A.g0 = r.g0; A.glen = r.glen;
+  StageView v;
+  replay_view(h, m, v);
+  A.trial = v.trial; A.gq = v.gq; A.gtype = v.gtype; A.moved = v.moved;
+  if (prev >= 0) {
+    const ReplayMove& pr = h->rp_moves[prev];
+    StageView pv;
+    replay_view(h, prev, pv);
+    A.prev_valid = 1; A.prev_accept = -1; A.pg0 = pr.g0; A.pglen = pr.glen; A.ptrial = pv.trial;
+  }
+  A.kvec = h->d_kvec; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->P.use_ewald ? h->nk : 0;
+  move_tiling(h, r.glen, A);
+  const int n_ctas = A.n_pair_ctas + A.n_k_ctas + A.n_intra_ctas;
   int rc = ensure_partials(h, n_ctas);
   if (rc) return rc;
-  A.partial = h->d_partial; A.partial_i = h->d_partial_i; A.state = h->d_state; A.result = nullptr;
+  A.partial = h->d_partial; A.state = h->d_state; A.mail = nullptr;
   A.decide_on_device = 1; A.u = r.u;
-  A.replay_dE = commit ? h->d_rp_dE : nullptr;
-  A.replay_acc = commit ? h->d_rp_acc : nullptr;
+  A.replay_dE = log ? h->d_rp_dE : nullptr;
+  A.replay_acc = log ? h->d_rp_acc : nullptr;
   A.replay_index = m;
   A.seq = ++h->seq;
-  k_delta<<<n_ctas, PG_TILE, 0, h->stream>>>(h->P, A);
+  A.Pg = h->d_P;
+  A.timing = (h->d_timing && n_ctas <= 8192) ? h->d_timing : nullptr;
+  h->timing_ctas = n_ctas;
+  if (h->fast)
+    k_move<true><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
+  else
+    k_move<false><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
   h->launches++;
-  if (commit) {
-    int nthreads = std::max(std::max(r.glen, h->nk), 1);
-    k_commit<<<(nthreads + 255) / 256, 256, 0, h->stream>>>(h->P, -1, PG_MODE_MOVE, r.g0, r.glen, A.trial, A.gq,
-                                                            A.gtype, h->xy, h->zq, h->type, h->d_S, h->d_dS,
-                                                            h->P.use_ewald ? h->nk : 0, h->d_state);
-    h->launches++;
-  }
   return PG_OK;
 }
 
@@ -741,10 +926,23 @@ int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* a
   if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
+  int rc = flush_commit(h);
+  if (rc) return rc;
   PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   for (int m = first; m < first + count; m++) {
-    int rc = replay_launch(h, m, true);
+    rc = replay_launch(h, m, m > first ? m - 1 : -1, true);
     if (rc) return rc;
+  }
+  if (count > 0) {
+    // the last move's decision (taken on the device) is applied by a stand-alone commit
+    const ReplayMove& r = h->rp_moves[first + count - 1];
+    StageView v;
+    replay_view(h, first + count - 1, v);
+    int nthreads = std::max(std::max(r.glen, h->nk), 1);
+    k_commit<<<(nthreads + 255) / 256, 256, 0, h->stream>>>(h->P, -1, PG_MODE_MOVE, r.g0, r.glen, v.trial, v.gq,
+                                                            v.gtype, h->xy, h->zq, h->type, h->d_S, h->d_dS,
+                                                            h->P.use_ewald ? h->nk : 0, h->d_state);
+    h->launches++;
   }
   PG_CUDA(h, cudaGetLastError());
   PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -761,9 +959,11 @@ int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms) 
   if (!h || !elapsed_ms || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
+  int rc = flush_commit(h);
+  if (rc) return rc;
   PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   for (int m = first; m < first + count; m++) {
-    int rc = replay_launch(h, m, false);
+    rc = replay_launch(h, m, -1, false);   // no commit rides along: the state does not advance
     if (rc) return rc;
   }
   PG_CUDA(h, cudaGetLastError());
@@ -793,6 +993,7 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
     return PG_ERR_INVALID;
   }
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   if (nt > h->tcap || n_chain > h->ccap) {
     int tcap = std::max(64, nt * 2), ccap = std::max(64, n_chain * 2);
     if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
@@ -877,6 +1078,7 @@ int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, con
   if (!h || n_new_mol <= 0 || !mol_len || !xyz || !q || !type) return PG_ERR_INVALID;
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   int n_add = 0;
   for (int m = 0; m < n_new_mol; m++) {
     if (mol_len[m] <= 0) { h->err = "molecule length must be positive"; return PG_ERR_INVALID; }
@@ -920,6 +1122,7 @@ int pg_delete_molecules(pg_engine* h, int mf, int ml, pg_totals* removed) {
   if (!h || mf < 0 || ml < mf || ml >= h->n_mol) return PG_ERR_INVALID;
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   const int b0 = h->mol_first[mf], b1 = h->mol_first[ml + 1], glen = b1 - b0;
   int rc = ensure_group(h, glen);
   if (rc) return rc;
@@ -965,6 +1168,7 @@ int pg_sk_compute_slice(pg_engine* h, int k_first, int k_count, double* sk_dev) 
   if (!h || k_first < 0 || k_count < 0 || k_first + k_count > h->nk) return PG_ERR_INVALID;
   if (k_count == 0) return PG_OK;
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   double2* out = sk_dev ? reinterpret_cast<double2*>(sk_dev) : (h->d_S + k_first);
   k_sk_slice<<<(k_count + PG_TILE - 1) / PG_TILE, PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->n, h->d_kl, k_first,
                                                                           k_count, out);
@@ -977,6 +1181,7 @@ int pg_sk_compute_slice(pg_engine* h, int k_first, int k_count, double* sk_dev) 
 int pg_sk_set(pg_engine* h, const double* sk_dev) {
   if (!h || !sk_dev) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   if (h->nk > 0)
     PG_CUDA(h, cudaMemcpyAsync(h->d_S, sk_dev, sizeof(double2) * (size_t)h->nk, cudaMemcpyDeviceToDevice, h->stream));
   PG_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -986,6 +1191,7 @@ int pg_sk_set(pg_engine* h, const double* sk_dev) {
 int pg_sk_energy(pg_engine* h, int k_first, int k_count, double* e_out) {
   if (!h || !e_out || k_first < 0 || k_count < 0 || k_first + k_count > h->nk) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   k_sk_energy<<<1, 256, 0, h->stream>>>(h->P, h->d_S, h->d_ek2, k_first, k_count, h->d_out8);
   h->launches++;
   PG_CUDA(h, cudaGetLastError());
@@ -998,10 +1204,20 @@ int pg_sk_energy(pg_engine* h, int k_first, int k_count, double* e_out) {
 int pg_sk_download(pg_engine* h, double* sk_host) {
   if (!h || (!sk_host && h->nk > 0)) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
   if (h->nk > 0)
     PG_CUDA(h, cudaMemcpyAsync(sk_host, h->d_S, sizeof(double2) * (size_t)h->nk, cudaMemcpyDeviceToHost, h->stream));
   PG_CUDA(h, cudaStreamSynchronize(h->stream));
   return PG_OK;
+}
+
+// Debug only (not part of the ABI header): per-CTA %globaltimer stamps of the last k_move launch.
+int pgx_read_timing(pg_engine* h, unsigned long long* out, int max_ctas) {
+  if (!h || !h->d_timing) return 0;
+  cudaStreamSynchronize(h->stream);
+  int n = std::min(h->timing_ctas, max_ctas);
+  cudaMemcpy(out, h->d_timing, sizeof(unsigned long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost);
+  return n;
 }
 
 // --------------------------------------------------------- instrumentation
