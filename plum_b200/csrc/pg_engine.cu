@@ -38,7 +38,7 @@ const double k213 = 1.25992104989;
 const double k216 = 1.12246204831;
 
 struct ReplayMove {
-  int mol, g0, glen, off;  // off: bead offset into the packed proposal buffers
+  int mol, g0, glen, off, nq;  // off: bead offset into the packed proposal buffers
   double u;
 };
 
@@ -101,6 +101,7 @@ struct pg_engine {
   PgMailRec* h_mail = nullptr;  // mapped pinned: k_move's self-validating result records
   PgMailRec* d_mail = nullptr;
   int move_slots = 0;           // resident k_move CTAs on the device (one wave)
+  int n_sm = 0;
   unsigned int seq = 0;
   bool use_mailbox = true;
 
@@ -143,16 +144,30 @@ struct StageView {
   double* trial;   // [cap][3]
   double* gq;      // [cap]
   int* gtype;      // [cap]
+  int* qidx;       // [cap] group-relative indices of the moved AND charged beads (first nq entries)
   uint8_t* moved;  // [cap]
 };
-size_t stage_size(int cap) { return sizeof(double) * 4 * (size_t)cap + sizeof(int) * (size_t)cap + (size_t)cap + 64; }
+size_t stage_size(int cap) { return sizeof(double) * 4 * (size_t)cap + sizeof(int) * 2 * (size_t)cap + (size_t)cap + 64; }
 StageView stage_view(char* base, int cap) {
   StageView v;
   v.trial = reinterpret_cast<double*>(base);
   v.gq = v.trial + 3 * (size_t)cap;
   v.gtype = reinterpret_cast<int*>(v.gq + cap);
-  v.moved = reinterpret_cast<uint8_t*>(v.gtype + cap);
+  v.qidx = v.gtype + cap;
+  v.moved = reinterpret_cast<uint8_t*>(v.qidx + cap);
   return v;
+}
+// Fills qidx from gq / moved; returns nq.
+int stage_fill_qidx(const StageView& v, int off, int glen) {
+  int nq = 0;
+  for (int i = 0; i < glen; i++)
+    if (v.moved[off + i] && v.gq[off + i] != 0.0) v.qidx[off + nq++] = i;
+  return nq;
+}
+int lanes_per_k(int nq) {
+  int l = 2;
+  while (l < 2 * nq && l < 32) l <<= 1;
+  return l;
 }
 
 // PotentialEwaldCoul::ReadParameters, potential_ewald_coul.cc:29-132.
@@ -279,6 +294,7 @@ int build_params(pg_engine* h, const pg_params* p) {
         P.lj_rcut[tp] = rcut;
         double rr = rcut * (1.0 + 1e-9);
         P.lj_rcut2_relaxed[tp] = rr * rr;
+        P.lj_rcut2_relaxed_max = std::max(P.lj_rcut2_relaxed_max, rr * rr);
       } else if (p->pair_kind == PG_PAIR_HARD_SPHERE) {
         P.hs_allowed[tp] = p->hs_radius[a] + p->hs_radius[b];
       }
@@ -457,37 +473,69 @@ int launch_commit(pg_engine* h, int accept_flag, int mode, int g0, int glen, con
   return PG_OK;
 }
 
-// Fills the tiling of a k_move launch: (partner tile x group chunk) CTAs + k CTAs sized so the
-// whole grid is resident at once (one wave on the 148 SMs) whenever the chunk fits shared memory.
-void move_tiling(pg_engine* h, int glen, PgMoveArgs& A) {
+// Grid of a k_move launch, at most the CTAs resident at once (one wave on the 148 SMs).  Helper CTAs
+// come first in block-index order — for a big move exactly one per SM — and share the reciprocal part
+// (lanes-per-k chosen so a helper's k slice fits its threads in one pass whenever possible) and the
+// intra-molecular pairs; the remaining CTAs split the (partner tile x moved bead) units evenly.
+int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
+  {
+    const PgDev& P = h->P;
+    PgMoveDev& D = A.D;
+    for (int i = 0; i < 3; i++) {
+      D.box[i] = P.box[i]; D.inv_box[i] = P.inv_box[i]; D.ebox[i] = P.ebox[i]; D.inv_ebox[i] = P.inv_ebox[i];
+      D.pbc[i] = P.pbc[i];
+    }
+    D.rc2_relaxed = P.rc2_relaxed; D.ljc2max = P.lj_rcut2_relaxed_max; D.recip_pref = P.recip_pref;
+    D.dipole_pref = P.dipole_pref; D.beta = P.beta;
+    D.pair_kind = P.pair_kind; D.use_ewald = P.use_ewald; D.dipole = P.dipole; D.bond_kind = P.bond_kind;
+    D.ext_kind = P.ext_kind;
+  }
   A.n_tiles = std::max(1, (h->n + MV_THREADS - 1) / MV_THREADS);
-  A.n_k_ctas = h->P.use_ewald ? (h->nk + MV_THREADS - 1) / MV_THREADS : 0;
-  int min_chunks = std::max(1, (glen + MV_GCHUNK - 1) / MV_GCHUNK);
-  const int n_intra = (glen * (glen - 1) / 2 + MV_THREADS - 1) / MV_THREADS;
-  int fit = std::max(1, (h->move_slots - A.n_k_ctas - n_intra) / A.n_tiles);
-  A.n_chunks = std::max(min_chunks, std::min(fit, std::max(glen, 1)));
-  A.chunk_size = std::max(1, (glen + A.n_chunks - 1) / A.n_chunks);
-  A.n_chunks = std::max(1, (glen + A.chunk_size - 1) / A.chunk_size);
-  A.n_pair_ctas = A.n_tiles * A.n_chunks;
-  A.n_intra_ctas = (glen * (glen - 1) / 2 + MV_THREADS - 1) / MV_THREADS;
+  const int slots = h->move_slots, n_sm = std::max(1, h->n_sm);
+  const long long units = (long long)A.n_tiles * std::max(glen, 1);
+  const long long npairs = (long long)glen * (glen - 1) / 2;
+  if (units >= (1LL << 31) || npairs >= (1LL << 31)) { h->err = "move too large for 32-bit work indexing"; return -1; }
+  const int nk = (h->P.use_ewald ? h->nk : 0);
+  const bool big = units >= (long long)(slots - n_sm);
+  int lpk = lanes_per_k(nq);
+  int helpers;
+  if (big) {
+    helpers = n_sm;
+  } else {
+    // small move: as few helpers as hold the k slice (at >= 2 lanes per k) and the intra pairs
+    helpers = (int)std::max<long long>(((long long)nk * lpk + MV_THREADS - 1) / MV_THREADS,
+                                       (npairs + MV_THREADS - 1) / MV_THREADS);
+    helpers = std::min(std::max(helpers, (nk > 0 || npairs > 0) ? 1 : 0), n_sm);
+  }
+  if (helpers > 0) {
+    // shrink lanes-per-k until a helper's k slice fits one pass of its threads
+    const int k_per_helper = (nk + helpers - 1) / helpers;
+    while (lpk > 2 && k_per_helper * lpk > MV_THREADS) lpk >>= 1;
+  }
+  A.lpk = lpk;
+  A.n_helpers = helpers;
+  const long long room = std::max(1, slots - helpers);
+  A.n_pair_ctas = (int)std::max(1LL, std::min(units, room));
+  return A.n_helpers + A.n_pair_ctas;
 }
 
 // One launch per move: energy change of the trial in `d_group` + deferred commit of h->pc.
-int launch_move(pg_engine* h, int g0, int glen, const char* d_group, int group_cap, bool decide_on_device, double u,
-                int replay_index, bool want_result, bool log_replay) {
+int launch_move(pg_engine* h, int g0, int glen, int nq, const char* d_group, int group_cap, bool decide_on_device,
+                double u, int replay_index, bool want_result, bool log_replay) {
   PgMoveArgs A;
   memset(&A, 0, sizeof(A));
   A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n = h->n;
   A.g0 = g0; A.glen = glen;
   StageView dv = stage_view(const_cast<char*>(d_group), group_cap);
   A.trial = dv.trial; A.gq = dv.gq; A.gtype = dv.gtype; A.moved = dv.moved;
+  A.qidx = dv.qidx; A.nq = h->P.use_ewald ? nq : 0;
   if (h->pc.valid) {
     StageView pv = stage_view(const_cast<char*>(h->pc.d_group), h->pc.cap);
     A.prev_valid = 1; A.prev_accept = h->pc.accept; A.pg0 = h->pc.g0; A.pglen = h->pc.glen; A.ptrial = pv.trial;
   }
   A.kvec = h->d_kvec; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->P.use_ewald ? h->nk : 0;
-  move_tiling(h, glen, A);
-  const int n_ctas = A.n_pair_ctas + A.n_k_ctas + A.n_intra_ctas;
+  const int n_ctas = move_grid(h, glen, A.nq, A);
+  if (n_ctas < 0) return PG_ERR_CAPACITY;
   int rc = ensure_partials(h, n_ctas);
   if (rc) return rc;
   A.partial = h->d_partial;
@@ -503,9 +551,9 @@ int launch_move(pg_engine* h, int g0, int glen, const char* d_group, int group_c
   A.timing = (h->d_timing && n_ctas <= 8192) ? h->d_timing : nullptr;
   h->timing_ctas = n_ctas;
   if (h->fast)
-    k_move<true><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
+    k_move<true><<<n_ctas, MV_THREADS, 0, h->stream>>>(A);
   else
-    k_move<false><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
+    k_move<false><<<n_ctas, MV_THREADS, 0, h->stream>>>(A);
   h->launches++;
   h->pc.valid = false;   // the launch applies it
   PG_CUDA(h, cudaGetLastError());
@@ -672,9 +720,13 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   PG_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_mail, (void*)h->h_mail, 0));
   {
     int per_sm = 0, n_sm = 0;
-    PG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move<true>, MV_THREADS, 0));
+    if (h->fast)
+      PG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move<true>, MV_THREADS, 0));
+    else
+      PG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move<false>, MV_THREADS, 0));
     PG_CREATE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     h->move_slots = std::max(1, per_sm * n_sm);
+    h->n_sm = n_sm;
   }
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_out8, sizeof(double) * 8));
   PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_out8, sizeof(double) * 8, cudaHostAllocDefault));
@@ -823,8 +875,9 @@ int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* mo
     sv.gtype[i] = h->h_type[g0 + i];
     sv.moved[i] = moved[i] ? 1 : 0;
   }
+  const int nq = stage_fill_qidx(sv, 0, glen);
   PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, stage_size(glen), cudaMemcpyHostToDevice, h->stream));
-  rc = launch_move(h, g0, glen, h->d_stage, glen, false, 0.0, 0, true, false);
+  rc = launch_move(h, g0, glen, nq, h->d_stage, glen, false, 0.0, 0, true, false);
   if (rc) return rc;
   rc = wait_mail(h, h->seq, out);
   if (rc) return rc;
@@ -867,6 +920,7 @@ int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_
     r.u = moves[m].u;
     if (r.off < 0 || r.off + r.glen > n_xyz_beads) { h->err = "replay: xyz_offset out of range"; return PG_ERR_INVALID; }
     for (int i = 0; i < r.glen; i++) { sv.gq[r.off + i] = h->h_q[r.g0 + i]; sv.gtype[r.off + i] = h->h_type[r.g0 + i]; }
+    r.nq = stage_fill_qidx(sv, r.off, r.glen);
     h->rp_moves.push_back(r);
   }
   PG_CUDA(h, cudaMalloc((void**)&h->d_rp, host.size()));
@@ -882,7 +936,7 @@ static void replay_view(pg_engine* h, int m, StageView& v) {
   StageView base = stage_view(h->d_rp, (int)h->rp_beads);
   const ReplayMove& r = h->rp_moves[m];
   v.trial = base.trial + 3 * (size_t)r.off; v.gq = base.gq + r.off; v.gtype = base.gtype + r.off;
-  v.moved = base.moved + r.off;
+  v.qidx = base.qidx + r.off; v.moved = base.moved + r.off;
 }
 
 static int replay_launch(pg_engine* h, int m, int prev, bool log) {
@@ -894,6 +948,7 @@ static int replay_launch(pg_engine* h, int m, int prev, bool log) {
   StageView v;
   replay_view(h, m, v);
   A.trial = v.trial; A.gq = v.gq; A.gtype = v.gtype; A.moved = v.moved;
+  A.qidx = v.qidx; A.nq = h->P.use_ewald ? r.nq : 0;
   if (prev >= 0) {
     const ReplayMove& pr = h->rp_moves[prev];
     StageView pv;
@@ -901,8 +956,8 @@ static int replay_launch(pg_engine* h, int m, int prev, bool log) {
     A.prev_valid = 1; A.prev_accept = -1; A.pg0 = pr.g0; A.pglen = pr.glen; A.ptrial = pv.trial;
   }
   A.kvec = h->d_kvec; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->P.use_ewald ? h->nk : 0;
-  move_tiling(h, r.glen, A);
-  const int n_ctas = A.n_pair_ctas + A.n_k_ctas + A.n_intra_ctas;
+  const int n_ctas = move_grid(h, r.glen, A.nq, A);
+  if (n_ctas < 0) return PG_ERR_CAPACITY;
   int rc = ensure_partials(h, n_ctas);
   if (rc) return rc;
   A.partial = h->d_partial; A.state = h->d_state; A.mail = nullptr;
@@ -915,9 +970,9 @@ static int replay_launch(pg_engine* h, int m, int prev, bool log) {
   A.timing = (h->d_timing && n_ctas <= 8192) ? h->d_timing : nullptr;
   h->timing_ctas = n_ctas;
   if (h->fast)
-    k_move<true><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
+    k_move<true><<<n_ctas, MV_THREADS, 0, h->stream>>>(A);
   else
-    k_move<false><<<n_ctas, MV_THREADS, 0, h->stream>>>(h->P, A);
+    k_move<false><<<n_ctas, MV_THREADS, 0, h->stream>>>(A);
   h->launches++;
   return PG_OK;
 }

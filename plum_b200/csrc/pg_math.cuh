@@ -45,6 +45,7 @@ struct PgDev {
   double lj_rcut[PG_MAX_TYPES * PG_MAX_TYPES];    // k216*sigma or lj_cutoff
   double lj_eref[PG_MAX_TYPES * PG_MAX_TYPES];    // energy_ref
   double lj_rcut2_relaxed[PG_MAX_TYPES * PG_MAX_TYPES];  // (rcut*(1+1e-9))^2, candidate filter
+  double lj_rcut2_relaxed_max;                            // max over the type pairs in use
   double hs_allowed[PG_MAX_TYPES * PG_MAX_TYPES]; // R1+R2
   int use_ewald;
   int dipole;

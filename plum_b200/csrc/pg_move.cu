@@ -16,8 +16,13 @@
 //    the erfc / LJ arithmetic sits behind it in a non-inlined function that only the few
 //    in-range pairs call.  Everything else (multi-image sums, hard spheres, padded slab
 //    boxes, intra-molecular pairs) goes through the exact generic routines of pg_math.cuh.
-//  * one wave — the host sizes (partner tile x group chunk) so the grid fits the resident
-//    CTA slots of the 148 SMs once (no tail wave), see move_tiling() in pg_engine.cu.
+//  * one wave, two roles — the grid is at most the number of CTAs resident at once on the
+//    148 SMs.  For a big move the first 148 CTAs (one per SM, block indices are dealt round-robin
+//    over the SMs) are "helpers": each takes an equal slice of the k vectors (several lanes per k,
+//    so no thread carries a long serial sincos chain while its neighbours saturate the FP64 pipe)
+//    and of the intra-molecular pairs (one pair per thread).  All other CTAs split the
+//    (partner tile x moved bead) units evenly, so every SM carries the same load; there is no tail
+//    wave and no straggler CTA.
 //  * result first — the last CTA writes dE to the host mailbox as self-validating 16-byte
 //    records (value + sequence number in one store, no system-wide fence) before it does
 //    the bookkeeping the host is not waiting for.
@@ -30,6 +35,7 @@
 #define MV_WARPS (MV_THREADS / 32)
 #define MV_GCHUNK 32      // max group beads per CTA chunk (shared-memory staging)
 #define MV_NSLOT 8        // mailbox records
+#define MV_QCAP 192       // per-warp queue capacity (flushed when fewer than 64 slots remain)
 
 // One self-validating mailbox record: written with a single 16-byte store, so a reader that
 // sees `seq` sees `value` and `aux` of the same launch.
@@ -41,11 +47,23 @@ struct __align__(16) PgMailRec {
 // slot: 0 dE (aux = stage | accept << 8), 1 pair (aux = n_overlap), 2 ext, 3 ewald, 4 bond,
 //       5 real, 6 recip, 7 mz_current
 
+// The scalars k_move needs on its critical path, passed by value (one or two constant-bank lines)
+// instead of the 3.7 KB PgDev block, whose scattered first-touch misses cost a microsecond per CTA.
+struct PgMoveDev {
+  double box[3], inv_box[3], ebox[3], inv_ebox[3];
+  double rc2_relaxed, ljc2max, recip_pref, dipole_pref, beta;
+  int pbc[3];
+  int pair_kind, use_ewald, dipole, bond_kind, ext_kind;
+};
+
 struct PgMoveArgs {
+  PgMoveDev D;
   double2* xy; double2* zq; int* type; int n;
   // current trial (device pointers into the staging block)
   int g0, glen;
   const double* trial; const double* gq; const int* gtype; const uint8_t* moved;
+  const int* qidx; int nq;   // group-relative indices of the moved AND charged beads (built by the host)
+  int lpk;                   // lanes per k vector in the reciprocal part: power of two, 2..32
   // previous trial whose commit is still pending
   int prev_valid;
   int prev_accept;      // 0/1: decided by the host; -1: decided on the device (state->accept)
@@ -55,7 +73,8 @@ struct PgMoveArgs {
   const double4* kvec;  // [nk] (kx, ky, kz, ek2), half space, built on the host with the reference's expressions
   double2* S; double2* dS; int nk;
   // tiling
-  int n_tiles, n_chunks, chunk_size, n_pair_ctas, n_k_ctas, n_intra_ctas;
+  int n_tiles;          // partner tiles of MV_THREADS beads
+  int n_helpers, n_pair_ctas;   // CTA roles in block-index order: helpers (k slice + intra slice), then pair (move_grid)
   double* partial;      // [n_ctas][8]
   PgState* state;
   PgMailRec* mail;      // mapped host memory (NULL in replay)
@@ -65,6 +84,14 @@ struct PgMoveArgs {
   const PgDev* Pg;      // copy of the parameter block in global memory, for the non-inlined rare paths
                         // (passing the by-value kernel parameter by reference would spill all of it to local memory)
 };
+
+// Balanced partition of n items over G workers in 32-bit arithmetic (64-bit integer division is
+// emulated with hundreds of instructions): worker w gets [lo, hi).
+__device__ __forceinline__ void mv_share(unsigned n, unsigned G, unsigned w, unsigned& lo, unsigned& hi) {
+  const unsigned q = n / G, r = n - q * G;
+  lo = q * w + min(w, r);
+  hi = lo + q + (w < r ? 1u : 0u);
+}
 
 __device__ __forceinline__ unsigned long long mv_now() {
   unsigned long long t;
@@ -79,6 +106,22 @@ __device__ __forceinline__ double mv_rint(double x) {
   return (x + M) - M;
 }
 
+// FP32 helpers of the pre-filter: box fraction of a coordinate in [-0.5, 0.5], float rint by add-magic,
+// and the relaxed squared radius (sqrt(c) + delta)^2 that absorbs the FP32 error (negative: never).
+__device__ __forceinline__ float mv_frac(double x, double invL) {
+  const double s = x * invL;
+  return (float)(s - mv_rint(s));
+}
+__device__ __forceinline__ float mv_rintf(float x) {
+  const float M = 12582912.0f;   // 1.5 * 2^23
+  return (x + M) - M;
+}
+__device__ __forceinline__ float mv_relax_f(double c2, double delta) {
+  if (c2 < 0.0) return -1.0f;
+  const double r = sqrt(c2) + delta;
+  return (float)(r * r * (1.0 + 1e-6));
+}
+
 __device__ __forceinline__ void mv_mail(PgMailRec* m, int slot, double value, unsigned int seq, int aux) {
   // one 16-byte store
   asm volatile("st.volatile.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(&m[slot]), "r"(__double2loint(value)),
@@ -88,22 +131,43 @@ __device__ __forceinline__ void mv_mail(PgMailRec* m, int slot, double value, un
 
 // The rare in-range pair: exact LJ / real-space arithmetic for one configuration whose squared
 // separation r2 passed one of the relaxed filters.  Single central image, no fold needed.
-__device__ __noinline__ void mv_pair_inrange(const PgDev* __restrict__ Pg, double r2, double qq, int tp,
-                                             double& e_lj, double& e_real) {
+// Returns (e_lj, e_real) in registers (reference parameters would go through local memory).
+__device__ __noinline__ double2 mv_pair_inrange(const PgDev* __restrict__ Pg, double r2, double qq, int tp) {
   const PgDev& P = *Pg;
-  e_lj = 0.0;
-  e_real = 0.0;
+  double e_lj = 0.0, e_real = 0.0;
   const double r = sqrt(r2);
   if (P.pair_kind == 1 && r2 <= P.lj_rcut2_relaxed[tp]) e_lj = pg_pair_energy_r(P, r, tp);
   if (qq != 0 && r2 <= P.rc2_relaxed) {
     if (r > 0 && r <= P.real_cutoff) e_real = P.lB * qq * erfc(P.sqrt_alpha * r) / r;
   }
+  return make_double2(e_lj, e_real);
 }
 
-__device__ __noinline__ void mv_pair_generic(const PgDev* __restrict__ Pg, double ax, double ay, double az, double qa,
-                                             int ta, double bx, double by, double bz, double qb, int tb, int do_lj,
-                                             double& e_lj, double& e_real) {
+__device__ __noinline__ double2 mv_pair_generic(const PgDev* __restrict__ Pg, double ax, double ay, double az,
+                                                double qa, int ta, double bx, double by, double bz, double qb, int tb,
+                                                int do_lj) {
+  double e_lj, e_real;
   pg_pair_both(*Pg, ax, ay, az, qa, ta, bx, by, bz, qb, tb, do_lj, e_lj, e_real);
+  return make_double2(e_lj, e_real);
+}
+
+// Evaluate this warp's queued in-range configurations, one per lane, and add them to the lane's
+// accumulators (entries are in loop order and lane e takes entries e, e+32, ...: deterministic).
+__device__ __forceinline__ void mv_queue_flush(const PgDev* __restrict__ Pg, const double* r2, const double* qq,
+                                               const int* tp, int n, int lane, double& acc_pair, double& acc_real,
+                                               double& acc_ov) {
+  __syncwarp();
+  for (int e = lane; e < n; e += 32) {
+    const int t = tp[e];
+    const double2 en = mv_pair_inrange(Pg, r2[e], qq[e], t & 0xffff);
+    if (t & 0x10000) {
+      acc_pair -= en.x; acc_real -= en.y;
+    } else {
+      if (en.x >= PG_VLE) acc_ov += 1.0;
+      acc_pair += en.x; acc_real += en.y;
+    }
+  }
+  __syncwarp();
 }
 
 // Sum 5 values over the CTA with one barrier; result valid in thread 0.
@@ -128,11 +192,17 @@ __device__ __forceinline__ void mv_block_sum5(double (&v)[5], double* smem /* [M
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(MV_THREADS, 3) k_move(const PgDev P, const PgMoveArgs A) {
-  // pair CTAs stage one chunk of <= MV_GCHUNK group beads; k CTAs stage up to MV_THREADS beads per round
-  __shared__ double s_n[3][MV_THREADS], s_o[3][MV_THREADS], s_q[MV_THREADS];
+__global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveArgs A) {
+  const PgMoveDev& P = A.D;
+  __shared__ double s_n[3][MV_GCHUNK], s_o[3][MV_GCHUNK], s_q[MV_GCHUNK];
   __shared__ int s_t[MV_GCHUNK], s_mv[MV_GCHUNK];
-  __shared__ double s_ljc2[PG_MAX_TYPES * PG_MAX_TYPES];
+  __shared__ double s_cut[2][MV_GCHUNK];
+  // FP32 pre-filter copies: box-fraction coordinates of the new / old position + relaxed radii^2
+  // (.w of s_fn: against a charged partner, .w of s_fo: against a neutral partner)
+  __shared__ float4 s_fn[MV_GCHUNK], s_fo[MV_GCHUNK];
+  // per-warp queues of in-range configurations (FAST path): r^2, q1*q2, type pair | old flag
+  __shared__ double q_r2[FAST ? MV_WARPS : 1][FAST ? MV_QCAP : 1], q_qq[FAST ? MV_WARPS : 1][FAST ? MV_QCAP : 1];
+  __shared__ int q_tp[FAST ? MV_WARPS : 1][FAST ? MV_QCAP : 1];
   __shared__ double s_red[MV_WARPS * 5];
   __shared__ int s_last;
 
@@ -146,203 +216,260 @@ __global__ void __launch_bounds__(MV_THREADS, 3) k_move(const PgDev P, const PgM
 
   double acc_pair = 0.0, acc_real = 0.0, acc_mz = 0.0, acc_rec = 0.0, acc_ov = 0.0;
 
-  if (b < A.n_pair_ctas) {
-    const int tile = b % A.n_tiles, chunk = b / A.n_tiles;
-    const int gbeg = chunk * A.chunk_size;
-    const int gcnt = min(A.glen, gbeg + A.chunk_size) - gbeg;
-    // partner first: its loads are the longest dependency chain of the CTA
-    const int j = tile * MV_THREADS + tid;
-    double px = 0, py = 0, pz = 0, pq = 0;
-    int pt = 0;
-    if (j < A.n) {
-      const double2 c = A.zq[j];
-      const double2 a = A.xy[j];
-      pt = A.type[j];
-      pq = c.y;
-      px = a.x; py = a.y; pz = c.x;
-      if (j >= pg0 && j < pg1) {
-        px = A.ptrial[3 * (j - pg0)]; py = A.ptrial[3 * (j - pg0) + 1]; pz = A.ptrial[3 * (j - pg0) + 2];
-      }
-      if (chunk == 0) acc_mz = pq * pz;
-    }
-    if (tid < gcnt) {
-      const int g = gbeg + tid, jg = A.g0 + g;
-      double ox, oy, oz;
-      if (jg >= pg0 && jg < pg1) {
-        ox = A.ptrial[3 * (jg - pg0)]; oy = A.ptrial[3 * (jg - pg0) + 1]; oz = A.ptrial[3 * (jg - pg0) + 2];
-      } else {
-        double2 a = A.xy[jg], c = A.zq[jg];
-        ox = a.x; oy = a.y; oz = c.x;
-      }
-      s_o[0][tid] = ox; s_o[1][tid] = oy; s_o[2][tid] = oz;
-      s_n[0][tid] = A.trial[3 * g]; s_n[1][tid] = A.trial[3 * g + 1]; s_n[2][tid] = A.trial[3 * g + 2];
-      s_q[tid] = A.gq[g];
-      s_t[tid] = A.gtype[g];
-      s_mv[tid] = A.moved[g];
-    } else if (FAST && tid >= 64 && tid < 64 + PG_MAX_TYPES * PG_MAX_TYPES) {
-      const int e = tid - 64;
-      s_ljc2[e] = (P.pair_kind == 1) ? A.Pg->lj_rcut2_relaxed[e] : -1.0;   // coalesced global read, not 64 LDCs
-    }
-    __syncthreads();
-    MV_STAMP(1);
-    if (j < A.n) {
-      const bool in_group = (j >= A.g0) && (j < A.g0 + A.glen);
-      const int do_lj = (P.pair_kind != 0);
-      if (!in_group) {
-        if (FAST) {
-          const double Lx = P.box[0], Ly = P.box[1], Lz = P.box[2];
-          const double iLx = P.inv_box[0], iLy = P.inv_box[1], iLz = P.inv_box[2];
-          const double rc2 = P.use_ewald ? P.rc2_relaxed : -1.0;
-#pragma unroll 2
-          for (int i = 0; i < gcnt; i++) {
-            if (!s_mv[i]) continue;
-            const double gq = s_q[i];
-            const int tp = s_t[i] * PG_MAX_TYPES + pt;
-            double dxn = px - s_n[0][i], dyn = py - s_n[1][i], dzn = pz - s_n[2][i];
-            double dxo = px - s_o[0][i], dyo = py - s_o[1][i], dzo = pz - s_o[2][i];
-            dxn -= Lx * mv_rint(dxn * iLx); dyn -= Ly * mv_rint(dyn * iLy); dzn -= Lz * mv_rint(dzn * iLz);
-            dxo -= Lx * mv_rint(dxo * iLx); dyo -= Ly * mv_rint(dyo * iLy); dzo -= Lz * mv_rint(dzo * iLz);
-            const double r2n = dxn * dxn + dyn * dyn + dzn * dzn;
-            const double r2o = dxo * dxo + dyo * dyo + dzo * dzo;
-            const double ljc2 = s_ljc2[tp];
-            const double qq = gq * pq;
-            const double cut = (qq != 0.0) ? fmax(rc2, ljc2) : ljc2;
-            if (fmin(r2n, r2o) <= cut) {
-              double lj_n = 0.0, re_n = 0.0, lj_o = 0.0, re_o = 0.0;
-              if (r2n <= cut) mv_pair_inrange(A.Pg, r2n, qq, tp, lj_n, re_n);
-              if (r2o <= cut) mv_pair_inrange(A.Pg, r2o, qq, tp, lj_o, re_o);
-              if (lj_n >= PG_VLE) acc_ov += 1.0;
-              acc_pair += (lj_n - lj_o);
-              acc_real += (re_n - re_o);
+  // ---------------- (a) reciprocal space: k vectors [k0, k1) of this CTA, LPK lanes per k.
+  // Lane e of a k group handles the terms e, e+LPK, ... of the 2*nq list (bead, new|old); a shuffle
+  // tree adds them up; lane 0 owns S(k): it folds the previous trial's dS in first (deferred commit).
+  if (b < A.n_helpers && A.nk > 0) {
+    unsigned k0u, k1u;
+    mv_share((unsigned)A.nk, (unsigned)A.n_helpers, (unsigned)b, k0u, k1u);
+    const int k0 = (int)k0u, k1 = (int)k1u;
+    const int LPK = A.lpk, KPP = MV_THREADS / LPK;   // k vectors per pass
+    const int kl = tid / LPK, e0 = tid % LPK;
+    for (int kb = k0; kb < k1; kb += KPP) {
+      const int k = kb + kl;
+      const bool active = k < k1;
+      double dre = 0.0, dim = 0.0;
+      double4 kv = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (active) {
+        kv = A.kvec[k];
+        for (int e = e0; e < 2 * A.nq; e += LPK) {
+          const int g = A.qidx[e >> 1];
+          const double q = A.gq[g];
+          double x, y, z;
+          if (e & 1) {   // old configuration, through the overlay
+            const int jg = A.g0 + g;
+            if (jg >= pg0 && jg < pg1) {
+              x = A.ptrial[3 * (jg - pg0)]; y = A.ptrial[3 * (jg - pg0) + 1]; z = A.ptrial[3 * (jg - pg0) + 2];
+            } else {
+              const double2 a = A.xy[jg], c = A.zq[jg];
+              x = a.x; y = a.y; z = c.x;
             }
-          }
-        } else {
-          for (int i = 0; i < gcnt; i++) {
-            if (!s_mv[i]) continue;
-            double lj_n, re_n, lj_o, re_o;
-            mv_pair_generic(A.Pg, s_n[0][i], s_n[1][i], s_n[2][i], s_q[i], s_t[i], px, py, pz, pq, pt, do_lj, lj_n, re_n);
-            mv_pair_generic(A.Pg, s_o[0][i], s_o[1][i], s_o[2][i], s_q[i], s_t[i], px, py, pz, pq, pt, do_lj, lj_o, re_o);
-            if (lj_n >= PG_VLE) acc_ov += 1.0;
-            acc_pair += (lj_n - lj_o);
-            acc_real += (re_n - re_o);
-          }
-        }
-      }
-      // partners that are beads of the moved molecule itself are handled by the intra CTAs below
-    }
-  } else if (b < A.n_pair_ctas + A.n_k_ctas) {
-    // reciprocal part: one k per thread.  The previous trial's dS is folded into S first.
-    const int k = (b - A.n_pair_ctas) * MV_THREADS + tid;
-    double4 kv = make_double4(0.0, 0.0, 0.0, 0.0);
-    double2 S = make_double2(0.0, 0.0);
-    if (k < A.nk) {
-      kv = A.kvec[k];
-      S = A.S[k];
-      if (apply_prev) {
-        const double2 d = A.dS[k];
-        S.x += d.x; S.y += d.y;
-        A.S[k] = S;
-      }
-    }
-    double dre = 0.0, dim = 0.0;
-    for (int gbeg = 0; gbeg < A.glen; gbeg += MV_THREADS) {
-      const int gcnt = min(A.glen - gbeg, MV_THREADS);
-      if (gbeg > 0) __syncthreads();
-      if (tid < gcnt) {
-        const int g = gbeg + tid, jg = A.g0 + g;
-        const double q = A.moved[g] ? A.gq[g] : 0.0;   // unmoved or neutral beads drop out of dS
-        s_q[tid] = q;
-        if (q != 0.0) {
-          double ox, oy, oz;
-          if (jg >= pg0 && jg < pg1) {
-            ox = A.ptrial[3 * (jg - pg0)]; oy = A.ptrial[3 * (jg - pg0) + 1]; oz = A.ptrial[3 * (jg - pg0) + 2];
           } else {
-            double2 a = A.xy[jg], c = A.zq[jg];
-            ox = a.x; oy = a.y; oz = c.x;
+            x = A.trial[3 * g]; y = A.trial[3 * g + 1]; z = A.trial[3 * g + 2];
           }
-          s_o[0][tid] = pg_wrap_pos(ox, P.ebox[0], P.inv_ebox[0], P.pbc[0]);
-          s_o[1][tid] = pg_wrap_pos(oy, P.ebox[1], P.inv_ebox[1], P.pbc[1]);
-          s_o[2][tid] = pg_wrap_pos(oz, P.ebox[2], P.inv_ebox[2], P.pbc[2]);
-          s_n[0][tid] = pg_wrap_pos(A.trial[3 * g], P.ebox[0], P.inv_ebox[0], P.pbc[0]);
-          s_n[1][tid] = pg_wrap_pos(A.trial[3 * g + 1], P.ebox[1], P.inv_ebox[1], P.pbc[1]);
-          s_n[2][tid] = pg_wrap_pos(A.trial[3 * g + 2], P.ebox[2], P.inv_ebox[2], P.pbc[2]);
+          x = pg_wrap_pos(x, P.ebox[0], P.inv_ebox[0], P.pbc[0]);
+          y = pg_wrap_pos(y, P.ebox[1], P.inv_ebox[1], P.pbc[1]);
+          z = pg_wrap_pos(z, P.ebox[2], P.inv_ebox[2], P.pbc[2]);
+          double sn, cs;
+          sincos(kv.x * x + kv.y * y + kv.z * z, &sn, &cs);
+          const double w = (e & 1) ? -q : q;
+          dre += w * cs; dim += w * sn;
         }
       }
-      __syncthreads();
-      if (k < A.nk) {
-        for (int i = 0; i < gcnt; i++) {
-          const double q = s_q[i];
-          if (q == 0) continue;
-          double sn, cn, so, co;
-          sincos(kv.x * s_n[0][i] + kv.y * s_n[1][i] + kv.z * s_n[2][i], &sn, &cn);
-          sincos(kv.x * s_o[0][i] + kv.y * s_o[1][i] + kv.z * s_o[2][i], &so, &co);
-          dre += q * cn; dim += q * sn;
-          dre -= q * co; dim -= q * so;
-        }
+      for (int o = LPK >> 1; o > 0; o >>= 1) {
+        dre += __shfl_xor_sync(0xffffffffu, dre, o);
+        dim += __shfl_xor_sync(0xffffffffu, dim, o);
       }
-    }
-    if (k < A.nk) {
-      // never |S_new|^2 - |S_old|^2: 2 Re(conj(S) dS) + |dS|^2; x2 for the -k half
-      acc_rec = 2.0 * kv.w * (2.0 * (S.x * dre + S.y * dim) + (dre * dre + dim * dim));
-      A.dS[k] = make_double2(dre, dim);
+      if (active && e0 == 0) {
+        double2 S = A.S[k];
+        if (apply_prev) {
+          const double2 d = A.dS[k];
+          S.x += d.x; S.y += d.y;
+          A.S[k] = S;
+        }
+        // never |S_new|^2 - |S_old|^2: 2 Re(conj(S) dS) + |dS|^2; x2 for the -k half
+        acc_rec += 2.0 * kv.w * (2.0 * (S.x * dre + S.y * dim) + (dre * dre + dim * dim));
+        A.dS[k] = make_double2(dre, dim);
+      }
     }
   }
 
-  else if (b < A.n_pair_ctas + A.n_k_ctas + A.n_intra_ctas) {
-    // intra-molecular pairs (g, jj), g < jj, of the moved molecule, one pair per thread
-    // (potential_pair.cc:157-178, potential_ewald.cc:436-477; the g == jj self-image term is
-    // identical before and after a move).  Sized by the host: glen*(glen-1)/2 threads.
-    const int p = (b - A.n_pair_ctas - A.n_k_ctas) * MV_THREADS + tid;
-    const int npairs = A.glen * (A.glen - 1) / 2;
-    if (p < npairs) {
+  // ---------------- (b) intra-molecular pairs (g, jj), g < jj, of the moved molecule: this CTA's
+  // slice [p0, p1), one pair per thread (potential_pair.cc:157-178, potential_ewald.cc:436-477;
+  // the g == jj self-image term is identical before and after a move)
+  if (b < A.n_helpers) {
+    unsigned p0, p1;
+    mv_share((unsigned)(A.glen * (A.glen - 1) / 2), (unsigned)A.n_helpers, (unsigned)b, p0, p1);
+    for (unsigned pp = p0 + tid; pp < p1; pp += MV_THREADS) {
+      const int p = (int)pp;
       int jj = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
       while (jj * (jj - 1) / 2 > p) jj--;
       while ((jj + 1) * jj / 2 <= p) jj++;
       const int g = p - jj * (jj - 1) / 2;
-      if (A.moved[g] || A.moved[jj]) {
-        const int ja = A.g0 + g, jb = A.g0 + jj;
-        double aox, aoy, aoz, box_, boy, boz;
-        if (ja >= pg0 && ja < pg1) {
-          aox = A.ptrial[3 * (ja - pg0)]; aoy = A.ptrial[3 * (ja - pg0) + 1]; aoz = A.ptrial[3 * (ja - pg0) + 2];
-        } else {
-          double2 a = A.xy[ja], c = A.zq[ja];
-          aox = a.x; aoy = a.y; aoz = c.x;
-        }
-        if (jb >= pg0 && jb < pg1) {
-          box_ = A.ptrial[3 * (jb - pg0)]; boy = A.ptrial[3 * (jb - pg0) + 1]; boz = A.ptrial[3 * (jb - pg0) + 2];
-        } else {
-          double2 a = A.xy[jb], c = A.zq[jb];
-          box_ = a.x; boy = a.y; boz = c.x;
-        }
-        const double anx = A.trial[3 * g], any_ = A.trial[3 * g + 1], anz = A.trial[3 * g + 2];
-        const double bnx = A.trial[3 * jj], bny = A.trial[3 * jj + 1], bnz = A.trial[3 * jj + 2];
-        const double qa = A.gq[g], qb = A.gq[jj];
-        const int ta = A.gtype[g], tb = A.gtype[jj];
-        double lj_n = 0.0, re_n = 0.0, lj_o = 0.0, re_o = 0.0;
-        if (FAST) {
-          const double Lx = P.box[0], Ly = P.box[1], Lz = P.box[2];
-          const double iLx = P.inv_box[0], iLy = P.inv_box[1], iLz = P.inv_box[2];
-          double dxn = bnx - anx, dyn = bny - any_, dzn = bnz - anz;
-          double dxo = box_ - aox, dyo = boy - aoy, dzo = boz - aoz;
-          dxn -= Lx * mv_rint(dxn * iLx); dyn -= Ly * mv_rint(dyn * iLy); dzn -= Lz * mv_rint(dzn * iLz);
-          dxo -= Lx * mv_rint(dxo * iLx); dyo -= Ly * mv_rint(dyo * iLy); dzo -= Lz * mv_rint(dzo * iLz);
-          const double r2n = dxn * dxn + dyn * dyn + dzn * dzn;
-          const double r2o = dxo * dxo + dyo * dyo + dzo * dzo;
-          const int tp = ta * PG_MAX_TYPES + tb;
-          const double qq = qa * qb;
-          mv_pair_inrange(A.Pg, r2n, qq, tp, lj_n, re_n);
-          mv_pair_inrange(A.Pg, r2o, qq, tp, lj_o, re_o);
-        } else {
-          int lj_here = (P.pair_kind != 0);
-          if (P.pair_kind == 2 && jj == g + 1) lj_here = 0;   // bonded hard spheres, potential_pair.cc:165-169
-          mv_pair_generic(A.Pg, anx, any_, anz, qa, ta, bnx, bny, bnz, qb, tb, lj_here, lj_n, re_n);
-          mv_pair_generic(A.Pg, aox, aoy, aoz, qa, ta, box_, boy, boz, qb, tb, lj_here, lj_o, re_o);
-        }
-        if (lj_n >= PG_VLE) acc_ov += 1.0;
-        acc_pair += (lj_n - lj_o);
-        acc_real += (re_n - re_o);
+      if (!(A.moved[g] || A.moved[jj])) continue;
+      const int ja = A.g0 + g, jb = A.g0 + jj;
+      double aox, aoy, aoz, box_, boy, boz;
+      if (ja >= pg0 && ja < pg1) {
+        aox = A.ptrial[3 * (ja - pg0)]; aoy = A.ptrial[3 * (ja - pg0) + 1]; aoz = A.ptrial[3 * (ja - pg0) + 2];
+      } else {
+        double2 a = A.xy[ja], c = A.zq[ja];
+        aox = a.x; aoy = a.y; aoz = c.x;
       }
+      if (jb >= pg0 && jb < pg1) {
+        box_ = A.ptrial[3 * (jb - pg0)]; boy = A.ptrial[3 * (jb - pg0) + 1]; boz = A.ptrial[3 * (jb - pg0) + 2];
+      } else {
+        double2 a = A.xy[jb], c = A.zq[jb];
+        box_ = a.x; boy = a.y; boz = c.x;
+      }
+      const double anx = A.trial[3 * g], any_ = A.trial[3 * g + 1], anz = A.trial[3 * g + 2];
+      const double bnx = A.trial[3 * jj], bny = A.trial[3 * jj + 1], bnz = A.trial[3 * jj + 2];
+      const double qa = A.gq[g], qb = A.gq[jj];
+      const int ta = A.gtype[g], tb = A.gtype[jj];
+      double lj_n = 0.0, re_n = 0.0, lj_o = 0.0, re_o = 0.0;
+      if (FAST) {
+        const double Lx = P.box[0], Ly = P.box[1], Lz = P.box[2];
+        const double iLx = P.inv_box[0], iLy = P.inv_box[1], iLz = P.inv_box[2];
+        double dxn = bnx - anx, dyn = bny - any_, dzn = bnz - anz;
+        double dxo = box_ - aox, dyo = boy - aoy, dzo = boz - aoz;
+        dxn -= Lx * mv_rint(dxn * iLx); dyn -= Ly * mv_rint(dyn * iLy); dzn -= Lz * mv_rint(dzn * iLz);
+        dxo -= Lx * mv_rint(dxo * iLx); dyo -= Ly * mv_rint(dyo * iLy); dzo -= Lz * mv_rint(dzo * iLz);
+        const double r2n = dxn * dxn + dyn * dyn + dzn * dzn;
+        const double r2o = dxo * dxo + dyo * dyo + dzo * dzo;
+        const int tp = ta * PG_MAX_TYPES + tb;
+        const double qq = qa * qb;
+        const double2 en = mv_pair_inrange(A.Pg, r2n, qq, tp), eo = mv_pair_inrange(A.Pg, r2o, qq, tp);
+        lj_n = en.x; re_n = en.y; lj_o = eo.x; re_o = eo.y;
+      } else {
+        int lj_here = (P.pair_kind != 0);
+        if (P.pair_kind == 2 && jj == g + 1) lj_here = 0;   // bonded hard spheres, potential_pair.cc:165-169
+        const double2 en = mv_pair_generic(A.Pg, anx, any_, anz, qa, ta, bnx, bny, bnz, qb, tb, lj_here);
+        const double2 eo = mv_pair_generic(A.Pg, aox, aoy, aoz, qa, ta, box_, boy, boz, qb, tb, lj_here);
+        lj_n = en.x; re_n = en.y; lj_o = eo.x; re_o = eo.y;
+      }
+      if (lj_n >= PG_VLE) acc_ov += 1.0;
+      acc_pair += (lj_n - lj_o);
+      acc_real += (re_n - re_o);
     }
+  }
+
+  // ---------------- (c) moved beads x partners.  The work is n_tiles x glen equal "units" (one
+  // partner tile against one moved bead); this CTA owns the contiguous unit range [u0, u1) in
+  // tile-major order: one tile segment, or the tail of one tile and the head of the next.
+  else {
+    unsigned u, u1;
+    mv_share((unsigned)(A.n_tiles * A.glen), (unsigned)A.n_pair_ctas, (unsigned)(b - A.n_helpers), u, u1);
+    const double Lx = P.box[0], Ly = P.box[1], Lz = P.box[2];
+    const double iLx = P.inv_box[0], iLy = P.inv_box[1], iLz = P.inv_box[2];
+    const double rc2 = P.use_ewald ? P.rc2_relaxed : -1.0;
+    const int do_lj = (P.pair_kind != 0);
+    const double ljc2max = (P.pair_kind == 1) ? P.ljc2max : -1.0;
+    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
+    const double fdelta = 1e-6 * fmax(Lx, fmax(Ly, Lz));   // >= 3x the worst-case FP32 error of a separation
+    const int lane = tid & 31, warp = tid >> 5;
+    int qn = 0;   // entries in this warp's queue (warp-uniform)
+    bool first = true;
+    while (u < u1) {
+      const int tile = (int)(u / (unsigned)A.glen);
+      const int gbeg = (int)(u - (unsigned)tile * (unsigned)A.glen);
+      const int gcnt = min(min(A.glen - gbeg, MV_GCHUNK), (int)(u1 - u));
+      // partner first: its loads are the longest dependency chain of the segment
+      const int j = tile * MV_THREADS + tid;
+      double px = 0, py = 0, pz = 0, pq = 0;
+      int pt = 0;
+      if (j < A.n) {
+        const double2 c = A.zq[j];
+        const double2 a = A.xy[j];
+        pt = A.type[j];
+        pq = c.y;
+        px = a.x; py = a.y; pz = c.x;
+        if (j >= pg0 && j < pg1) {
+          px = A.ptrial[3 * (j - pg0)]; py = A.ptrial[3 * (j - pg0) + 1]; pz = A.ptrial[3 * (j - pg0) + 2];
+        }
+        if (gbeg == 0) acc_mz += pq * pz;   // each tile's dipole moment is counted by the segment that starts it
+      }
+      if (!first) __syncthreads();   // previous segment's shared staging is still being read
+      first = false;
+      if (tid < gcnt) {
+        const int g = gbeg + tid, jg = A.g0 + g;
+        double ox, oy, oz;
+        if (jg >= pg0 && jg < pg1) {
+          ox = A.ptrial[3 * (jg - pg0)]; oy = A.ptrial[3 * (jg - pg0) + 1]; oz = A.ptrial[3 * (jg - pg0) + 2];
+        } else {
+          double2 a = A.xy[jg], c = A.zq[jg];
+          ox = a.x; oy = a.y; oz = c.x;
+        }
+        s_o[0][tid] = ox; s_o[1][tid] = oy; s_o[2][tid] = oz;
+        s_n[0][tid] = A.trial[3 * g]; s_n[1][tid] = A.trial[3 * g + 1]; s_n[2][tid] = A.trial[3 * g + 2];
+        const double gq = A.gq[g];
+        s_q[tid] = gq;
+        s_t[tid] = A.gtype[g];
+        s_mv[tid] = A.moved[g];
+        // conservative filter radii^2 of this moved bead: against a charged partner / a neutral one
+        // (the exact per-pair cutoffs are re-applied by mv_pair_inrange)
+        const double c0 = ljc2max, c1 = (gq != 0.0) ? fmax(rc2, ljc2max) : ljc2max;
+        s_cut[0][tid] = c0;
+        s_cut[1][tid] = c1;
+        if (FAST) {
+          const double nx = s_n[0][tid], ny = s_n[1][tid], nz = s_n[2][tid];
+          s_fn[tid] = make_float4(mv_frac(nx, iLx), mv_frac(ny, iLy), mv_frac(nz, iLz), mv_relax_f(c1, fdelta));
+          s_fo[tid] = make_float4(mv_frac(ox, iLx), mv_frac(oy, iLy), mv_frac(oz, iLz), mv_relax_f(c0, fdelta));
+        }
+      }
+      __syncthreads();
+      MV_STAMP(1);
+      // partners that are beads of the moved molecule itself were handled in (b)
+      const bool valid = (j < A.n) && !((j >= A.g0) && (j < A.g0 + A.glen));
+      if (FAST) {
+        // Every lane runs the filter (invalid lanes never hit) so the warp can vote: in-range
+        // configurations are rare, so instead of evaluating erfc / LJ in a nearly empty diverged warp
+        // they are compacted into this warp's queue and evaluated 32 at a time (mv_queue_flush).
+        const double* __restrict__ cutv = s_cut[pq != 0.0 ? 1 : 0];
+        const bool pchg = (pq != 0.0);
+        const float psx = mv_frac(px, iLx), psy = mv_frac(py, iLy), psz = mv_frac(pz, iLz);
+#pragma unroll 4
+        for (int i = 0; i < gcnt; i++) {
+          if (!s_mv[i]) continue;
+          // FP32 pre-filter in box fractions (full-rate pipe); it can only over-accept
+          const float4 fn = s_fn[i], fo = s_fo[i];
+          float axn = psx - fn.x, ayn = psy - fn.y, azn = psz - fn.z;
+          float axo = psx - fo.x, ayo = psy - fo.y, azo = psz - fo.z;
+          axn -= mv_rintf(axn); ayn -= mv_rintf(ayn); azn -= mv_rintf(azn);
+          axo -= mv_rintf(axo); ayo -= mv_rintf(ayo); azo -= mv_rintf(azo);
+          axn *= fLx; ayn *= fLy; azn *= fLz;
+          axo *= fLx; ayo *= fLy; azo *= fLz;
+          const float f2n = fmaf(axn, axn, fmaf(ayn, ayn, azn * azn));
+          const float f2o = fmaf(axo, axo, fmaf(ayo, ayo, azo * azo));
+          const float fcut = pchg ? fn.w : fo.w;
+          const bool fhit = valid && (fminf(f2n, f2o) <= fcut);
+          if (__ballot_sync(0xffffffffu, fhit) == 0u) continue;
+          // exact FP64 separations for the lanes the filter let through
+          bool hn = false, ho = false;
+          double r2n = 0.0, r2o = 0.0;
+          if (fhit) {
+            double dxn = px - s_n[0][i], dyn = py - s_n[1][i], dzn = pz - s_n[2][i];
+            double dxo = px - s_o[0][i], dyo = py - s_o[1][i], dzo = pz - s_o[2][i];
+            dxn -= Lx * mv_rint(dxn * iLx); dyn -= Ly * mv_rint(dyn * iLy); dzn -= Lz * mv_rint(dzn * iLz);
+            dxo -= Lx * mv_rint(dxo * iLx); dyo -= Ly * mv_rint(dyo * iLy); dzo -= Lz * mv_rint(dzo * iLz);
+            r2n = dxn * dxn + dyn * dyn + dzn * dzn;
+            r2o = dxo * dxo + dyo * dyo + dzo * dzo;
+            const double cut = cutv[i];
+            hn = r2n <= cut;
+            ho = r2o <= cut;
+          }
+          const unsigned mn = __ballot_sync(0xffffffffu, hn), mo = __ballot_sync(0xffffffffu, ho);
+          if (mn | mo) {
+            const int tp = s_t[i] * PG_MAX_TYPES + pt;
+            const double qq = s_q[i] * pq;
+            const unsigned lt = (1u << lane) - 1u;
+            if (hn) {
+              const int pos = qn + __popc(mn & lt);
+              q_r2[warp][pos] = r2n; q_qq[warp][pos] = qq; q_tp[warp][pos] = tp;
+            }
+            qn += __popc(mn);
+            if (ho) {
+              const int pos = qn + __popc(mo & lt);
+              q_r2[warp][pos] = r2o; q_qq[warp][pos] = qq; q_tp[warp][pos] = tp | 0x10000;   // old: subtract
+            }
+            qn += __popc(mo);
+            if (qn > MV_QCAP - 64) {
+              mv_queue_flush(A.Pg, q_r2[warp], q_qq[warp], q_tp[warp], qn, lane, acc_pair, acc_real, acc_ov);
+              qn = 0;
+            }
+          }
+        }
+      } else if (valid) {
+        for (int i = 0; i < gcnt; i++) {
+          if (!s_mv[i]) continue;
+          const double2 en = mv_pair_generic(A.Pg, s_n[0][i], s_n[1][i], s_n[2][i], s_q[i], s_t[i], px, py, pz, pq, pt, do_lj);
+          const double2 eo = mv_pair_generic(A.Pg, s_o[0][i], s_o[1][i], s_o[2][i], s_q[i], s_t[i], px, py, pz, pq, pt, do_lj);
+          if (en.x >= PG_VLE) acc_ov += 1.0;
+          acc_pair += (en.x - eo.x);
+          acc_real += (en.y - eo.y);
+        }
+      }
+      u += gcnt;
+    }
+    if (FAST && qn > 0) mv_queue_flush(A.Pg, q_r2[warp], q_qq[warp], q_tp[warp], qn, lane, acc_pair, acc_real, acc_ov);
   }
 
   // ---------------- per-CTA partials; the last CTA to finish finalises
@@ -355,7 +482,12 @@ __global__ void __launch_bounds__(MV_THREADS, 3) k_move(const PgDev P, const PgM
       pp[0] = make_double2(v[0], v[1]);
       pp[1] = make_double2(v[2], v[3]);
       pp[2] = make_double2(v[4], 0.0);
-      if (A.timing) A.timing[8 * b + 3] = mv_now();
+      if (A.timing) {
+        A.timing[8 * b + 3] = mv_now();
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        A.timing[8 * b + 6] = smid;
+      }
       // release our partials / acquire everybody else's in one atomic
       unsigned int done;
       asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(done) : "l"(&A.state->done_counter) : "memory");
@@ -394,9 +526,9 @@ __global__ void __launch_bounds__(MV_THREADS, 3) k_move(const PgDev P, const PgM
       }
       if (P.ext_kind != 0 && A.moved[g]) {
         const int t = A.gtype[g];
-        const double en = pg_wall_energy(P, A.trial[3 * g + 2], t);
+        const double en = pg_wall_energy(*A.Pg, A.trial[3 * g + 2], t);
         if (en >= PG_VLE) w_out = 1.0;
-        w_sum += en - pg_wall_energy(P, oz, t);
+        w_sum += en - pg_wall_energy(*A.Pg, oz, t);
       }
       if (P.bond_kind != 0 && g + 1 < A.glen) {
         const int jg2 = jg + 1;
@@ -407,9 +539,9 @@ __global__ void __launch_bounds__(MV_THREADS, 3) k_move(const PgDev P, const PgM
           double2 a = A.xy[jg2], c = A.zq[jg2];
           ox2 = a.x; oy2 = a.y; oz2 = c.x;
         }
-        b_sum += pg_bond_energy(P, A.trial[3 * g], A.trial[3 * g + 1], A.trial[3 * g + 2], A.trial[3 * g + 3],
+        b_sum += pg_bond_energy(*A.Pg, A.trial[3 * g], A.trial[3 * g + 1], A.trial[3 * g + 2], A.trial[3 * g + 3],
                                 A.trial[3 * g + 4], A.trial[3 * g + 5]) -
-                 pg_bond_energy(P, ox, oy, oz, ox2, oy2, oz2);
+                 pg_bond_energy(*A.Pg, ox, oy, oz, ox2, oy2, oz2);
       }
     }
     __syncthreads();   // s_red is reused

@@ -32,14 +32,35 @@ for name, pool in (("ion", ions), ("chain", chains)):
     print(f"{name}: ctas={n} last_cta_start={a[0]:.0f}ns stage={a[1]:.0f}ns median_main_done={a[2]:.0f}ns all_main_done={a[3]:.0f}ns "
           f"all_atomic_done={a[4]:.0f}ns final_start={a[5]:.0f}ns final_serial_start={a[6]:.0f}ns end={a[7]:.0f}ns | fence+atomic={a[8]:.0f}ns blocksum={a[9]:.0f}ns")
 
-# detail of the last chain launch: slowest CTAs
+# detail of the last chain launch
 t = buf[:n].astype(np.int64); t0 = t[:, 0].min()
-order = np.argsort(-(t[:, 4] - t0))[:12]
-n_tiles = (s.n + 255) // 256
-print("slowest CTAs (index, tile, chunk | start, stage_done, main_done(thread0), partial_written, atomic_done) ns:")
+d = t[:, 4] - t0
+print("atomic_done percentiles (ns):", [int(np.percentile(d, q)) for q in (5, 25, 50, 75, 90, 95, 99, 100)])
+order = np.argsort(-d)[:16]
+print("slowest CTAs: index [start, stage_done, main_done(thread0), partial_written, atomic_done]")
 for c in order:
-    print(int(c), int(c % n_tiles), int(c // n_tiles), [int(x - t0) for x in t[c, :5]])
-print("k CTAs:")
-for c in range(n - 7, n):
     print(int(c), [int(x - t0) for x in t[c, :5]])
-print("moved mol", m, "first bead", int(s.mol_first[m]), "tile", int(s.mol_first[m]) // 256)
+print("first 6 CTAs (k role):")
+for c in range(6):
+    print(int(c), [int(x - t0) for x in t[c, :5]])
+print("CTAs 56..60 (intra role):")
+for c in range(56, 61):
+    print(int(c), [int(x - t0) for x in t[c, :5]])
+# per-SM view
+sm = t[:, 6]
+role = np.where(np.arange(n) < 148, 0, 1)
+print("per SM: n_ctas, n_helpers, last finish(ns) -- first 12 SMs and the 6 slowest")
+rows = []
+for sid in np.unique(sm):
+    m_ = sm == sid
+    rows.append((int(sid), int(m_.sum()), int((m_ & (role == 0)).sum()), int(d[m_].max()), int(d[m_].min())))
+for r_ in rows[:12]: print(r_)
+print("slowest SMs:", sorted(rows, key=lambda r_: -r_[3])[:6])
+print("fastest SMs:", sorted(rows, key=lambda r_: r_[3])[:6])
+hd = d[:148]; pdur = d[148:]
+print("helpers finish: min/med/max", int(hd.min()), int(np.median(hd)), int(hd.max()))
+print("pair finish: min/med/max", int(pdur.min()), int(np.median(pdur)), int(pdur.max()))
+
+print("pair CTAs 148..170: [start, last_stage_done, main_done(thread0), partial_written, atomic_done] smid")
+for c in range(148, 171):
+    print(int(c), [int(x - t0) for x in t[c, :5]], int(t[c, 6]))
