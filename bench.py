@@ -14,7 +14,7 @@ One *step* = MOVES_PER_STEP sequential Metropolis moves (move mix 0.5 ion transl
          caller (plum_b200/host/mc_bench.cc) so no interpreter is inside the timed region.
   value  the SAME move sequence replayed device-resident (pg_replay_run): proposals already in
          HBM, acceptance taken on the device from the recorded variates, CUDA-event time.
-  roofline  dominant kernel k_delta: algorithmic FP64 flops (SURVEY.md §8(d) formula) over its
+  roofline  dominant kernel k_move: algorithmic FP64 flops (SURVEY.md §8(d) formula) over its
          CUDA-event time, against an FP64 FMA peak measured in this run (MEASURED_PEAKS.json
          carries no FP64 figure); the byte view against MEASURED_PEAKS.json's hbm_gbs is added.
   cpu_baseline  the CPU oracle port (pairwise reciprocal form = the reference's algorithm,
@@ -124,6 +124,11 @@ def cpu_sample(args):
     r, sysm, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
     o = Oracle(params, repl_mode=0)
     o.upload(sysm.xyz, sysm.q, types.ids(sysm.symbol), sysm.mol_first)
+    # The reference evaluates only the NEW pair energies of a trial (the old ones come from its N^2
+    # std::map caches), so the port is timed in that mode: same arithmetic, same pair count, none of
+    # the map overhead (measured on a 1320-bead cut of this system the real plum_ref is 2.7x slower
+    # than this) — the most favourable stand-in for the reference.
+    o.set_timing_new_only(True)
     rng = np.random.default_rng(seed)
     chains = [m for m in range(sysm.n_mol) if sysm.mol_first[m + 1] - sysm.mol_first[m] > 1]
     ions = [m for m in range(sysm.n_mol) if sysm.mol_first[m + 1] - sysm.mol_first[m] == 1]
@@ -180,7 +185,8 @@ def run_reference(a):
     value = float(np.mean([r for r, _ in step_rates]))
     ms_per_step = 1e3 * MOVES_PER_STEP * cores / value
     sample = (f"per step and core: {n_ion} ion move(s) + {n_chain} chain move(s) (100 beads flagged) of the same "
-              f"22000-bead system evaluated with the reference's pairwise algorithm (oracle port, map-free); "
+              f"22000-bead system evaluated with the reference's pairwise algorithm (oracle port, map-free, new-configuration "
+              f"energies only like the reference); "
               f"moves/s = cores / (0.5 t_ion + 0.5 t_chain); plum_ref itself cannot hold N=22000 "
               f"(70-115 GB of std::map nodes, SURVEY.md §0.8)")
     line = {
@@ -338,11 +344,25 @@ def run_ours(a):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # traffic: dram bytes per k_move launch from the committed `ncu --set full` capture of this command
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "r01_ncu_summary.json")) as f:
+            prof = json.load(f)["k_move_full"]
+        vals = []
+        for p_ in prof:
+            rd, wr = p_["dram__bytes_read.sum"].split(), p_["dram__bytes_write.sum"].split()
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals.append(float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]])
+        traffic = float(np.mean(vals))
+    except Exception:
+        traffic = None
     achieved_tflops = float(flops.sum()) / (kd_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_gflops / 1e3, "unit": "TFLOP/s",
-        "frac": achieved_tflops / (fp64_peak_gflops / 1e3), "traffic": None,
-        "kernel": "k_delta", "launches": int(K * M), "avg_launch_us": kd_ms * 1e3 / (K * M),
+        "frac": achieved_tflops / (fp64_peak_gflops / 1e3), "traffic": traffic,
+        "traffic_note": "dram__bytes_read+write per k_move launch, ncu --set full (cold cache), profiles/r01_ncu_summary.json",
+        "kernel": "k_move", "launches": int(K * M), "avg_launch_us": kd_ms * 1e3 / (K * M),
         "peak_source": "FP64 FMA microbenchmark measured in this run (pg_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flops_per_launch": float(flops.mean()),
         "bytes_view": {"bound": "hbm", "achieved": float(bytes_.sum()) / (kd_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -370,7 +390,7 @@ def run_ours(a):
         cpu = {"value": v, "unit": "moves/s", "cores": 1, "kind": "port",
                "sample": f"3 ion moves ({np.mean(t_ion):.3f} s each) + 2 chain moves of 100 flagged beads "
                          f"({np.mean(t_chain):.3f} s each) on the same 22000-bead system, reference pairwise algorithm "
-                         f"(oracle port, map-free), mixed with the realised ion fraction {p_ion:.3f}; plum_ref cannot "
+                         f"(oracle port, map-free, new-configuration energies only like the reference), mixed with the realised ion fraction {p_ion:.3f}; plum_ref cannot "
                          f"hold N=22000 (SURVEY.md §0.8)"}
 
     if rank == 0:

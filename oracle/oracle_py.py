@@ -34,6 +34,7 @@ def lib():
         L.po_create.argtypes = [C.POINTER(PgParams)]
         L.po_destroy.argtypes = [C.c_void_p]
         L.po_set_repl_mode.argtypes = [C.c_void_p, C.c_int]
+        L.po_set_timing_new_only.argtypes = [C.c_void_p, C.c_int]
         L.po_get_ewald_info.argtypes = [C.c_void_p, C.POINTER(PgEwaldInfo)]
         L.po_upload_system.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_int32_p, C.c_int, c_int32_p]
         L.po_num_beads.argtypes = [C.c_void_p]
@@ -92,6 +93,10 @@ class Oracle:
 
     def set_repl_mode(self, mode: int):
         self.L.po_set_repl_mode(self.h, mode)
+
+    def set_timing_new_only(self, flag: bool):
+        """Bench only: evaluate new-configuration energies only (the reference's per-move work)."""
+        self.L.po_set_timing_new_only(self.h, int(bool(flag)))
 
     def ewald_info(self) -> PgEwaldInfo:
         o = PgEwaldInfo()

@@ -88,6 +88,8 @@ typedef struct po_system {
   unsigned char *moved; /* [n] flags for pending trial */
   double dE_pair, dE_ewald, dE_bond, dE_ext;
   int repl_mode; /* 0 = pairwise cube scan (reference form), 1 = S(k) form */
+  int timing_new_only; /* bench only: skip the recomputation of "old" pair energies, which the reference
+                          reads from its std::map caches — the work left is exactly the reference's */
 } po_system;
 
 static double *dup_d(const double *p, int n) {
@@ -181,6 +183,10 @@ void po_destroy(po_system *s) {
 }
 
 void po_set_repl_mode(po_system *s, int mode) { s->repl_mode = mode; }
+/* TIMING ONLY (bench.py cpu_baseline / --impl reference): with flag = 1 po_delta_e evaluates the
+ * new-configuration energies only, like the reference (potential_pair.cc:186-192,
+ * potential_ewald.cc:488-500 read the old ones from maps); the returned dE is then meaningless. */
+void po_set_timing_new_only(po_system *s, int flag) { s->timing_new_only = flag; }
 
 int po_get_ewald_info(const po_system *s, pg_ewald_info *o) {
   memset(o, 0, sizeof(*o));
@@ -619,7 +625,7 @@ int po_delta_e(po_system *s, int mol, const double *trial_xyz, const uint8_t *mo
             new_e = 0; old_e = 0;
           } else {
             new_e = pair_energy(s, T + 3 * i, s->type[i], T + 3 * j, s->type[j]);
-            old_e = pair_energy(s, C + 3 * i, s->type[i], C + 3 * j, s->type[j]);
+            old_e = s->timing_new_only ? 0.0 : pair_energy(s, C + 3 * i, s->type[i], C + 3 * j, s->type[j]);
           }
           if (new_e >= kVeryLargeEnergy) o->n_overlap++;
           d += (new_e - old_e);
@@ -629,7 +635,7 @@ int po_delta_e(po_system *s, int mol, const double *trial_xyz, const uint8_t *mo
       for (int k = f; k < l; k++)
         if (s->moved[k]) {
           double new_e = pair_energy(s, T + 3 * k, s->type[k], C + 3 * j, s->type[j]);
-          double old_e = pair_energy(s, C + 3 * k, s->type[k], C + 3 * j, s->type[j]);
+          double old_e = s->timing_new_only ? 0.0 : pair_energy(s, C + 3 * k, s->type[k], C + 3 * j, s->type[j]);
           if (new_e >= kVeryLargeEnergy) o->n_overlap++;
           d += (new_e - old_e);
         }
@@ -660,11 +666,11 @@ int po_delta_e(po_system *s, int mol, const double *trial_xyz, const uint8_t *mo
       for (int j = i; j < l; j++)
         if (s->moved[i] || s->moved[j]) {
           double nr = pair_real(s, T + 3 * i, s->q[i], T + 3 * j, s->q[j]);
-          double orr = pair_real(s, C + 3 * i, s->q[i], C + 3 * j, s->q[j]);
+          double orr = s->timing_new_only ? 0.0 : pair_real(s, C + 3 * i, s->q[i], C + 3 * j, s->q[j]);
           double nk = 0, ok = 0;
           if (s->repl_mode == 0) {
             nk = pair_repl(s, T + 3 * i, s->q[i], T + 3 * j, s->q[j]);
-            ok = pair_repl(s, C + 3 * i, s->q[i], C + 3 * j, s->q[j]);
+            ok = s->timing_new_only ? 0.0 : pair_repl(s, C + 3 * i, s->q[i], C + 3 * j, s->q[j]);
           }
           if (j == i) { nr *= 0.5; nk *= 0.5; orr *= 0.5; ok *= 0.5; }
           d += (nr + nk - (orr + ok));
@@ -675,11 +681,11 @@ int po_delta_e(po_system *s, int mol, const double *trial_xyz, const uint8_t *mo
       for (int k = f; k < l; k++)
         if (s->moved[k]) {
           double nr = pair_real(s, T + 3 * k, s->q[k], C + 3 * j, s->q[j]);
-          double orr = pair_real(s, C + 3 * k, s->q[k], C + 3 * j, s->q[j]);
+          double orr = s->timing_new_only ? 0.0 : pair_real(s, C + 3 * k, s->q[k], C + 3 * j, s->q[j]);
           double nk = 0, ok = 0;
           if (s->repl_mode == 0) {
             nk = pair_repl(s, T + 3 * k, s->q[k], C + 3 * j, s->q[j]);
-            ok = pair_repl(s, C + 3 * k, s->q[k], C + 3 * j, s->q[j]);
+            ok = s->timing_new_only ? 0.0 : pair_repl(s, C + 3 * k, s->q[k], C + 3 * j, s->q[j]);
           }
           d += (nr + nk - (orr + ok));
           dr += nr - orr; dk += nk - ok;

@@ -1,0 +1,88 @@
+"""Multi-GPU use of the path, limited to where it shards naturally.
+
+1. Independent Markov-chain replicas, one process + engine per GPU, no communication:
+   `replica_seed` gives each rank its own random stream.
+2. k-vector-sharded full S(k) recompute for large systems: positions are replicated on every
+   rank; rank r computes S(k) for a contiguous slice of the (host-ordered, half-space) k list
+   and the slices are all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests), after
+   which every rank holds the full S(k) and adopts it.  The reciprocal energy is the all-reduced
+   sum of the per-slice energies.
+
+The collective is `torch.distributed` plumbing; the compute is the engine's k_sk_slice kernel
+(`pg_sk_compute_slice`).  Nothing here is on the per-move path.
+"""
+from __future__ import annotations
+
+from typing import Callable, Tuple
+
+import numpy as np
+
+
+def replica_seed(base_seed: int, rank: int) -> int:
+    """Seed of the rank-th independent replica (what PLUM_SEED is set to for rank's plum_gpu)."""
+    return int(base_seed) + 1000 * int(rank)
+
+
+def k_slice(n_k: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first, count) of rank's contiguous share of n_k vectors; shares differ by at most one."""
+    q, r = divmod(int(n_k), int(world))
+    first = q * rank + min(rank, r)
+    return first, q + (1 if rank < r else 0)
+
+
+def padded_count(n_k: int, world: int) -> int:
+    return (int(n_k) + int(world) - 1) // int(world)
+
+
+def gather_sk(compute_slice: Callable[[int, int], "object"], n_k: int, rank: int, world: int, device="cpu", group=None):
+    """All-gather of S(k) slices.  `compute_slice(first, count)` returns this rank's [count, 2] slice
+    (numpy array or torch tensor on `device`).  Returns the full [n_k, 2] torch tensor on every rank."""
+    import torch
+    import torch.distributed as dist
+    first, count = k_slice(n_k, rank, world)
+    pad = padded_count(n_k, world)
+    local = torch.zeros((pad, 2), dtype=torch.float64, device=device)
+    if count:
+        sl = compute_slice(first, count)
+        local[:count] = torch.as_tensor(sl, dtype=torch.float64, device=device).reshape(count, 2)
+    if world == 1:
+        return local[:n_k].clone()
+    full = torch.empty((world * pad, 2), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full, local, group=group)
+    parts = []
+    for r in range(world):
+        _, c = k_slice(n_k, r, world)
+        parts.append(full[r * pad:r * pad + c])
+    return torch.cat(parts, dim=0)
+
+
+def sharded_sk_recompute(engine, rank: int, world: int, group=None):
+    """GPU path: every rank fills its k slice with the engine's kernel straight into a torch CUDA
+    buffer, NCCL all-gathers, the engine adopts the full S(k).  Returns (full S(k) tensor,
+    reciprocal energy summed over ranks)."""
+    import torch
+    import torch.distributed as dist
+    n_k = engine.ewald_info().n_k_half
+    first, count = k_slice(n_k, rank, world)
+    pad = padded_count(n_k, world)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    local = torch.zeros((pad, 2), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    if count:
+        engine.sk_compute_slice(first, count, local.data_ptr())   # synchronous on the engine's stream
+    if world > 1:
+        full = torch.empty((world * pad, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full, local, group=group)
+        parts = []
+        for r in range(world):
+            _, c = k_slice(n_k, r, world)
+            parts.append(full[r * pad:r * pad + c])
+        sk = torch.cat(parts, dim=0).contiguous()
+    else:
+        sk = local[:n_k].contiguous()
+    torch.cuda.synchronize()
+    engine.sk_set(sk.data_ptr())
+    e_local = torch.tensor([engine.sk_energy(first, count) if count else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_local, op=dist.ReduceOp.SUM, group=group)
+    return sk, float(e_local.item())
