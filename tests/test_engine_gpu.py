@@ -66,28 +66,55 @@ def test_structure_factor_matches_oracle():
     eng.close()
 
 
-def _random_system(rng, n_chain, chain_len, n_ion, box, charged_every=1, slab=False):
+def _random_system(rng, n_chain, chain_len, n_ion, box, charged_every=1, slab=False, rmin=1.6):
+    """Random chains (bond 2.5) + ions with a minimum separation: without it random beads overlap so
+    strongly that single pair energies reach 1e7-1e8 kT and every dE is a difference of terms whose
+    own rounding (ulp(1e8) = 1.5e-8) exceeds the 1e-10 bar — for the oracle and the reference alike."""
+    pts = []
+
+    def ok(p):
+        if not pts:
+            return True
+        d = np.array(pts) - p
+        for a in range(3 if not slab else 2):
+            d[:, a] -= box[a] * np.round(d[:, a] / box[a])
+        return float(np.min(np.einsum("ij,ij->i", d, d))) >= rmin * rmin
+
     xyz, q, sym, first = [], [], [], [0]
     for _ in range(n_chain):
-        p = rng.uniform(0.1, 0.9, 3) * box
+        while True:
+            p = rng.uniform(0.1, 0.9, 3) * box
+            if ok(p):
+                break
         for b in range(chain_len):
+            pts.append(p.copy())
             xyz.append(p.copy())
             q.append(-1.0 if b % charged_every == 0 else 0.0)
             sym.append("P")
-            step = rng.normal(size=3)
-            p = p + 2.5 * step / np.linalg.norm(step)
-            if slab:
-                p[2] = min(max(p[2], 1.2), box[2] - 1.2)
+            for _try in range(200):
+                step = rng.normal(size=3)
+                c = p + 2.5 * step / np.linalg.norm(step)
+                if slab:
+                    c[2] = min(max(c[2], 1.2), box[2] - 1.2)
+                if ok(c):
+                    break
+            p = c
         first.append(len(q))
     for _ in range(n_ion):
-        xyz.append(rng.uniform(0.05, 0.95, 3) * box)
+        while True:
+            p = rng.uniform(0.05, 0.95, 3) * box
+            if ok(p):
+                break
+        pts.append(p.copy())
+        xyz.append(p)
         q.append(1.0)
         sym.append("C")
         first.append(len(q))
     return runin.System(np.array(xyz), np.array(q), sym, np.array(first, dtype=np.int32), list(box))
 
 
-def _params(box, npbc=3, alpha=0.01, dipole=0, ext=0, bond=0, lj_cutoff=-1.0, pair="TruncatedLJ"):
+def _params(box, npbc=3, alpha=0.01, dipole=0, ext=0, bond=0, lj_cutoff=-1.0, pair="TruncatedLJ", ext_name="TruncatedLJWall",
+            wall_cut=-1.0, graft=False):
     r = runin.RunIn()
     r.npbc = npbc
     r.beta = 1.0
@@ -109,11 +136,16 @@ def _params(box, npbc=3, alpha=0.01, dipole=0, ext=0, bond=0, lj_cutoff=-1.0, pa
         r.bond_r0 = 2.5
     if ext:
         r.use_ext = 1
-        r.ext_name = "TruncatedLJWall"
-        r.wall_cut = -1.0
-        r.wall_sigma = {"P": 1.0, "C": 0.9}
-        r.wall_epsilon = {"P": 0.1, "C": 0.2}
-    types = runin.TypeTable(r, ["P", "C"])
+        r.ext_name = ext_name
+        r.wall_cut = wall_cut
+        r.wall_sigma = {"P": 1.0, "C": 0.9, "L": 1.0, "R": 1.0}
+        r.wall_epsilon = {"P": 0.1, "C": 0.2, "L": 0.15, "R": 0.15}
+        r.well_width = 2.0
+        r.well_depth = -0.7
+    if graft:
+        r.lj_sigma.update({"L": 2.2, "R": 2.2})
+        r.lj_epsilon.update({"L": 0.1, "R": 0.1})
+    types = runin.TypeTable(r, ["P", "C"] + (["L", "R"] if graft else []))
     return r, types, runin.params_dict(r, box, types)
 
 
@@ -124,6 +156,15 @@ CASES = [
     dict(box=[40.0, 40.0, 40.0], alpha=0.03, n_chain=4, chain_len=70, n_ion=20, bond=1),               # > 2 group chunks, springs
     dict(box=[35.0, 35.0, 35.0], alpha=0.02, n_chain=5, chain_len=9, n_ion=33, lj_cutoff=6.0),         # attractive LJ
     dict(box=[35.0, 35.0, 35.0], alpha=0.02, n_chain=5, chain_len=9, n_ion=33, pair="HardSphere"),
+    dict(box=[25.0, 25.0, 40.0], alpha=0.02, n_chain=4, chain_len=10, n_ion=30, npbc=2, dipole=1, ext=1, slab=True,
+         ext_name="HardWall"),
+    dict(box=[25.0, 25.0, 40.0], alpha=0.02, n_chain=4, chain_len=10, n_ion=30, npbc=2, dipole=1, ext=1, slab=True,
+         ext_name="WellWall"),
+    dict(box=[25.0, 25.0, 40.0], alpha=0.02, n_chain=4, chain_len=10, n_ion=30, npbc=2, dipole=1, ext=1, slab=True,
+         wall_cut=3.0),                                                                                   # full 9-3 LJ wall
+    dict(box=[25.0, 25.0, 40.0], alpha=0.02, n_chain=4, chain_len=10, n_ion=30, npbc=2, dipole=1, ext=1, slab=True,
+         graft=True),                                                                                     # L / R tethered beads (FENE branch)
+    dict(box=[30.0, 30.0, 30.0], alpha=0.02, n_chain=3, chain_len=300, n_ion=40, charged_every=3),      # group > one staging chunk, many charged
 ]
 
 
@@ -135,6 +176,11 @@ def test_random_moves_match_oracle(case):
     sysm = _random_system(rng, c.pop("n_chain"), c.pop("chain_len"), c.pop("n_ion"), np.array(box),
                           c.pop("charged_every", 1), c.pop("slab", False))
     r, types, params = _params(box, **c)
+    if c.get("graft"):
+        for m in range(4):
+            f = int(sysm.mol_first[m])
+            sysm.symbol[f] = "L" if m % 2 == 0 else "R"
+            sysm.xyz[f, 2] = 1.3 if m % 2 == 0 else box[2] - 1.3
     eng, orc = _engine(params, sysm.n), _oracle(params)
     ids = types.ids(sysm.symbol)
     eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
