@@ -84,7 +84,8 @@ struct pg_engine {
   bool fast = false;            // k_move<true> hot loop is valid for this force field
 
   // deferred commit of the last trial (applied by the next k_move or by flush_commit)
-  struct { bool valid; int accept; int g0, glen; const char* d_group; int cap; } pc = {false, 0, 0, 0, nullptr, 0};
+  struct { bool valid; int accept; int g0, glen; const char* d_group; int cap; const char* h_group; bool on_device; }
+      pc = {false, 0, 0, 0, nullptr, 0, nullptr, true};
 
   // scratch
   int partial_cap = 0;
@@ -104,11 +105,14 @@ struct pg_engine {
   int n_sm = 0;
   unsigned int seq = 0;
   bool use_mailbox = true;
+  bool use_inline = true;       // small groups travel in the kernel parameters (PLUM_B200_NO_INLINE=1 disables)
 
   // pending trial
   bool pending = false;
   int pend_mode = 0, pend_g0 = 0, pend_glen = 0, pend_cap = 0;
   const char* pend_group = nullptr;
+  const char* pend_hgroup = nullptr;
+  bool pend_on_device = true;
 
   // CBMC staging
   int tcap = 0;       // trials capacity
@@ -124,6 +128,11 @@ struct pg_engine {
   double* d_rp_dE = nullptr;
   uint8_t* d_rp_acc = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // CUDA graphs of replay batches, keyed by (first, count, commit): the per-move launches of a batch are
+  // captured once so that the replay is not bound by the host's launch rate
+  struct RpGraph { int first, count, commit; cudaGraphExec_t exec; };
+  std::vector<RpGraph> rp_graphs;
+  bool use_graph = true;        // PLUM_B200_NO_GRAPH=1 disables
 };
 
 #define PG_CUDA(h, call)                                                                     \
@@ -484,6 +493,7 @@ int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
     for (int i = 0; i < 3; i++) {
       D.box[i] = P.box[i]; D.inv_box[i] = P.inv_box[i]; D.ebox[i] = P.ebox[i]; D.inv_ebox[i] = P.inv_ebox[i];
       D.pbc[i] = P.pbc[i];
+      D.fbox[i] = (float)P.box[i];
     }
     D.rc2_relaxed = P.rc2_relaxed; D.ljc2max = P.lj_rcut2_relaxed_max; D.recip_pref = P.recip_pref;
     D.dipole_pref = P.dipole_pref; D.beta = P.beta;
@@ -521,7 +531,7 @@ int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
 
 // One launch per move: energy change of the trial in `d_group` + deferred commit of h->pc.
 int launch_move(pg_engine* h, int g0, int glen, int nq, const char* d_group, int group_cap, bool decide_on_device,
-                double u, int replay_index, bool want_result, bool log_replay) {
+                double u, int replay_index, bool want_result, bool log_replay, const char* h_inline = nullptr) {
   PgMoveArgs A;
   memset(&A, 0, sizeof(A));
   A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n = h->n;
@@ -529,9 +539,23 @@ int launch_move(pg_engine* h, int g0, int glen, int nq, const char* d_group, int
   StageView dv = stage_view(const_cast<char*>(d_group), group_cap);
   A.trial = dv.trial; A.gq = dv.gq; A.gtype = dv.gtype; A.moved = dv.moved;
   A.qidx = dv.qidx; A.nq = h->P.use_ewald ? nq : 0;
+  if (h_inline) {
+    // small group: the trial data ride in the kernel parameters (no H2D copy before the launch)
+    StageView hv = stage_view(const_cast<char*>(h_inline), group_cap);
+    A.inl_n = glen;
+    for (int i = 0; i < glen; i++) {
+      A.inl_trial[3 * i] = hv.trial[3 * i]; A.inl_trial[3 * i + 1] = hv.trial[3 * i + 1]; A.inl_trial[3 * i + 2] = hv.trial[3 * i + 2];
+      A.inl_gq[i] = hv.gq[i]; A.inl_gtype[i] = hv.gtype[i]; A.inl_qidx[i] = hv.qidx[i]; A.inl_moved[i] = hv.moved[i];
+    }
+  }
   if (h->pc.valid) {
     StageView pv = stage_view(const_cast<char*>(h->pc.d_group), h->pc.cap);
     A.prev_valid = 1; A.prev_accept = h->pc.accept; A.pg0 = h->pc.g0; A.pglen = h->pc.glen; A.ptrial = pv.trial;
+    if (!h->pc.on_device) {
+      StageView hv = stage_view(const_cast<char*>(h->pc.h_group), h->pc.cap);
+      A.pinl_n = h->pc.glen;
+      for (int i = 0; i < 3 * h->pc.glen; i++) A.pinl_trial[i] = hv.trial[i];
+    }
   }
   A.kvec = h->d_kvec; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->P.use_ewald ? h->nk : 0;
   const int n_ctas = move_grid(h, glen, A.nq, A);
@@ -565,6 +589,9 @@ int launch_move(pg_engine* h, int g0, int glen, int nq, const char* d_group, int
 int flush_commit(pg_engine* h) {
   if (!h->pc.valid) return PG_OK;
   h->pc.valid = false;
+  if (!h->pc.on_device)
+    PG_CUDA(h, cudaMemcpyAsync(const_cast<char*>(h->pc.d_group), h->pc.h_group, stage_size(h->pc.cap), cudaMemcpyHostToDevice,
+                               h->stream));
   return launch_commit(h, h->pc.accept, PG_MODE_MOVE, h->pc.g0, h->pc.glen, h->pc.d_group, h->pc.cap);
 }
 
@@ -653,6 +680,8 @@ void free_all(pg_engine* h) {
   if (h->h_trial_out) cudaFreeHost(h->h_trial_out);
   cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_trial_out);
   cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
+  for (auto& g : h->rp_graphs) cudaGraphExecDestroy(g.exec);
+  h->rp_graphs.clear();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -751,6 +780,14 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
     if (tm && tm[0] == '1') {
       if (cudaMalloc((void**)&h->d_timing, sizeof(unsigned long long) * 8 * 8192) != cudaSuccess) h->d_timing = nullptr;
     }
+  }
+  {
+    const char* ng = getenv("PLUM_B200_NO_GRAPH");
+    h->use_graph = !(ng && ng[0] == '1');
+  }
+  {
+    const char* ni = getenv("PLUM_B200_NO_INLINE");
+    h->use_inline = !(ni && ni[0] == '1');
   }
   const char* mb = getenv("PLUM_B200_NO_MAILBOX");
   h->use_mailbox = !(mb && mb[0] == '1');
@@ -876,13 +913,15 @@ int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* mo
     sv.moved[i] = moved[i] ? 1 : 0;
   }
   const int nq = stage_fill_qidx(sv, 0, glen);
-  PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, stage_size(glen), cudaMemcpyHostToDevice, h->stream));
-  rc = launch_move(h, g0, glen, nq, h->d_stage, glen, false, 0.0, 0, true, false);
+  const bool inl = (glen <= MV_INL) && h->use_inline;
+  if (!inl) PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, stage_size(glen), cudaMemcpyHostToDevice, h->stream));
+  rc = launch_move(h, g0, glen, nq, h->d_stage, glen, false, 0.0, 0, true, false, inl ? h->h_stage : nullptr);
   if (rc) return rc;
   rc = wait_mail(h, h->seq, out);
   if (rc) return rc;
   h->pending = true;
   h->pend_mode = PG_MODE_MOVE; h->pend_g0 = g0; h->pend_glen = glen; h->pend_group = h->d_stage; h->pend_cap = glen;
+  h->pend_hgroup = h->h_stage; h->pend_on_device = !inl;
   return PG_OK;
 }
 
@@ -895,16 +934,19 @@ int pg_commit(pg_engine* h, int accept) {
   h->pc.valid = true;
   h->pc.accept = accept ? 1 : 0;
   h->pc.g0 = h->pend_g0; h->pc.glen = h->pend_glen; h->pc.d_group = h->pend_group; h->pc.cap = h->pend_cap;
+  h->pc.h_group = h->pend_hgroup; h->pc.on_device = h->pend_on_device;
   return PG_OK;
 }
 
 // ------------------------------------------------------------------ replay
+static void replay_drop_graphs(pg_engine* h);
 int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_xyz_beads, const double* trial_xyz,
                      const uint8_t* moved) {
   if (!h || n_moves < 0 || (n_moves > 0 && (!moves || !trial_xyz || !moved))) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
   { int frc_ = flush_commit(h); if (frc_) return frc_; }
   h->rp_moves.clear();
+  replay_drop_graphs(h);
   cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
   h->d_rp = nullptr; h->d_rp_dE = nullptr; h->d_rp_acc = nullptr;
   h->rp_beads = (size_t)std::max(n_xyz_beads, 1);
@@ -977,18 +1019,18 @@ static int replay_launch(pg_engine* h, int m, int prev, bool log) {
   return PG_OK;
 }
 
-int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, float* elapsed_ms) {
-  if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
-  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
-  PG_CUDA(h, cudaSetDevice(h->device));
-  int rc = flush_commit(h);
-  if (rc) return rc;
-  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+static void replay_drop_graphs(pg_engine* h) {
+  for (auto& g : h->rp_graphs) cudaGraphExecDestroy(g.exec);
+  h->rp_graphs.clear();
+}
+
+// Enqueue the launches of one replay batch on the engine stream (directly, or into a capture).
+static int replay_enqueue(pg_engine* h, int first, int count, bool commit) {
   for (int m = first; m < first + count; m++) {
-    rc = replay_launch(h, m, m > first ? m - 1 : -1, true);
+    int rc = replay_launch(h, m, (commit && m > first) ? m - 1 : -1, commit);
     if (rc) return rc;
   }
-  if (count > 0) {
+  if (commit && count > 0) {
     // the last move's decision (taken on the device) is applied by a stand-alone commit
     const ReplayMove& r = h->rp_moves[first + count - 1];
     StageView v;
@@ -998,6 +1040,51 @@ int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* a
                                                             v.gtype, h->xy, h->zq, h->type, h->d_S, h->d_dS,
                                                             h->P.use_ewald ? h->nk : 0, h->d_state);
     h->launches++;
+  }
+  return PG_OK;
+}
+
+// Returns the instantiated graph of a batch (captured on first use), or nullptr when graphs are off.
+static int replay_graph(pg_engine* h, int first, int count, bool commit, cudaGraphExec_t* out) {
+  *out = nullptr;
+  if (!h->use_graph || count <= 0) return PG_OK;
+  for (auto& g : h->rp_graphs)
+    if (g.first == first && g.count == count && g.commit == (int)commit) { *out = g.exec; return PG_OK; }
+  int rc = ensure_partials(h, h->move_slots + h->n_sm + 8);   // no allocation inside a capture
+  if (rc) return rc;
+  const uint64_t launches0 = h->launches;
+  PG_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  rc = replay_enqueue(h, first, count, commit);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  h->launches = launches0;   // captured, not launched
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) { h->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return PG_ERR_CUDA; }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return PG_ERR_CUDA; }
+  h->rp_graphs.push_back({first, count, (int)commit, exec});
+  *out = exec;
+  return PG_OK;
+}
+
+int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, float* elapsed_ms) {
+  if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  int rc = flush_commit(h);
+  if (rc) return rc;
+  cudaGraphExec_t exec = nullptr;
+  rc = replay_graph(h, first, count, true, &exec);   // built outside the timed events
+  if (rc) return rc;
+  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  if (exec) {
+    PG_CUDA(h, cudaGraphLaunch(exec, h->stream));
+    h->launches += (uint64_t)count + 1;
+  } else {
+    rc = replay_enqueue(h, first, count, true);
+    if (rc) return rc;
   }
   PG_CUDA(h, cudaGetLastError());
   PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -1016,9 +1103,15 @@ int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms) 
   PG_CUDA(h, cudaSetDevice(h->device));
   int rc = flush_commit(h);
   if (rc) return rc;
+  cudaGraphExec_t exec = nullptr;
+  rc = replay_graph(h, first, count, false, &exec);   // no commit rides along: the state does not advance
+  if (rc) return rc;
   PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  for (int m = first; m < first + count; m++) {
-    rc = replay_launch(h, m, -1, false);   // no commit rides along: the state does not advance
+  if (exec) {
+    PG_CUDA(h, cudaGraphLaunch(exec, h->stream));
+    h->launches += (uint64_t)count;
+  } else {
+    rc = replay_enqueue(h, first, count, false);
     if (rc) return rc;
   }
   PG_CUDA(h, cudaGetLastError());

@@ -35,6 +35,7 @@
 #define MV_WARPS (MV_THREADS / 32)
 #define MV_GCHUNK 32      // max group beads per CTA chunk (shared-memory staging)
 #define MV_NSLOT 8        // mailbox records
+#define MV_INL 8          // largest group whose trial data ride in the kernel parameters
 #define MV_QCAP 192       // per-warp queue capacity (flushed when fewer than 64 slots remain)
 
 // One self-validating mailbox record: written with a single 16-byte store, so a reader that
@@ -52,6 +53,7 @@ struct __align__(16) PgMailRec {
 struct PgMoveDev {
   double box[3], inv_box[3], ebox[3], inv_ebox[3];
   double rc2_relaxed, ljc2max, recip_pref, dipole_pref, beta;
+  float fbox[3];        // box lengths in FP32 for the pre-filter
   int pbc[3];
   int pair_kind, use_ewald, dipole, bond_kind, ext_kind;
 };
@@ -64,6 +66,12 @@ struct PgMoveArgs {
   const double* trial; const double* gq; const int* gtype; const uint8_t* moved;
   const int* qidx; int nq;   // group-relative indices of the moved AND charged beads (built by the host)
   int lpk;                   // lanes per k vector in the reciprocal part: power of two, 2..32
+  // small groups (glen <= MV_INL, e.g. every single-ion move) travel inside the kernel parameters:
+  // no H2D copy in front of the launch.  inl_n = glen or 0; pinl_n likewise for the previous trial.
+  int inl_n, pinl_n;
+  double inl_trial[3 * MV_INL], inl_gq[MV_INL], pinl_trial[3 * MV_INL];
+  int inl_gtype[MV_INL], inl_qidx[MV_INL];
+  unsigned char inl_moved[MV_INL];
   // previous trial whose commit is still pending
   int prev_valid;
   int prev_accept;      // 0/1: decided by the host; -1: decided on the device (state->accept)
@@ -153,22 +161,23 @@ __device__ __noinline__ double2 mv_pair_generic(const PgDev* __restrict__ Pg, do
 
 // Evaluate this warp's queued in-range configurations, one per lane, and add them to the lane's
 // accumulators (entries are in loop order and lane e takes entries e, e+32, ...: deterministic).
-__device__ __forceinline__ void mv_queue_flush(const PgDev* __restrict__ Pg, const double* r2, const double* qq,
-                                               const int* tp, int n, int lane, double& acc_pair, double& acc_real,
-                                               double& acc_ov) {
-  __syncwarp();
-  for (int e = lane; e < n; e += 32) {
-    const int t = tp[e];
-    const double2 en = mv_pair_inrange(Pg, r2[e], qq[e], t & 0xffff);
-    if (t & 0x10000) {
-      acc_pair -= en.x; acc_real -= en.y;
-    } else {
-      if (en.x >= PG_VLE) acc_ov += 1.0;
-      acc_pair += en.x; acc_real += en.y;
-    }
-  }
-  __syncwarp();
-}
+// A macro so that the queues are addressed as shared memory (LDS), not through generic pointers.
+#define MV_QUEUE_FLUSH()                                                              \
+  do {                                                                                \
+    __syncwarp();                                                                     \
+    for (int e_ = lane; e_ < qn; e_ += 32) {                                          \
+      const int t_ = q_tp[warp][e_];                                                  \
+      const double2 en_ = mv_pair_inrange(A.Pg, q_r2[warp][e_], q_qq[warp][e_], t_ & 0xffff); \
+      if (t_ & 0x10000) {                                                             \
+        acc_pair -= en_.x; acc_real -= en_.y;                                         \
+      } else {                                                                        \
+        if (en_.x >= PG_VLE) acc_ov += 1.0;                                           \
+        acc_pair += en_.x; acc_real += en_.y;                                         \
+      }                                                                               \
+    }                                                                                 \
+    __syncwarp();                                                                     \
+    qn = 0;                                                                           \
+  } while (0)
 
 // Sum 5 values over the CTA with one barrier; result valid in thread 0.
 __device__ __forceinline__ void mv_block_sum5(double (&v)[5], double* smem /* [MV_WARPS][5] */) {
@@ -192,7 +201,7 @@ __device__ __forceinline__ void mv_block_sum5(double (&v)[5], double* smem /* [M
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveArgs A) {
+__global__ void __launch_bounds__(MV_THREADS, FAST ? 3 : 2) k_move(const PgMoveArgs A) {
   const PgMoveDev& P = A.D;
   __shared__ double s_n[3][MV_GCHUNK], s_o[3][MV_GCHUNK], s_q[MV_GCHUNK];
   __shared__ int s_t[MV_GCHUNK], s_mv[MV_GCHUNK];
@@ -206,9 +215,29 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
   __shared__ double s_red[MV_WARPS * 5];
   __shared__ int s_last;
 
+  __shared__ double s_it[3 * MV_INL], s_iq[MV_INL], s_pit[3 * MV_INL];
+  __shared__ int s_ity[MV_INL], s_iqi[MV_INL];
+  __shared__ unsigned char s_imv[MV_INL];
+
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   MV_STAMP(0);
+  const double* __restrict__ trial = A.trial;
+  const double* __restrict__ gqv = A.gq;
+  const int* __restrict__ gtypev = A.gtype;
+  const int* __restrict__ qidxv = A.qidx;
+  const unsigned char* __restrict__ movedv = A.moved;
+  const double* __restrict__ ptrial = A.ptrial;
+  if (A.inl_n | A.pinl_n) {
+    if (tid < 3 * MV_INL) { s_it[tid] = A.inl_trial[tid]; s_pit[tid] = A.pinl_trial[tid]; }
+    if (tid < MV_INL) {
+      s_iq[tid] = A.inl_gq[tid]; s_ity[tid] = A.inl_gtype[tid]; s_iqi[tid] = A.inl_qidx[tid];
+      s_imv[tid] = A.inl_moved[tid];
+    }
+    __syncthreads();
+    if (A.inl_n) { trial = s_it; gqv = s_iq; gtypev = s_ity; qidxv = s_iqi; movedv = s_imv; }
+    if (A.pinl_n) ptrial = s_pit;
+  }
   // decision on the previous trial (uniform over the grid)
   int apply_prev = 0;
   if (A.prev_valid) apply_prev = (A.prev_accept >= 0) ? A.prev_accept : __ldcg(&A.state->accept);
@@ -233,19 +262,19 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
       if (active) {
         kv = A.kvec[k];
         for (int e = e0; e < 2 * A.nq; e += LPK) {
-          const int g = A.qidx[e >> 1];
-          const double q = A.gq[g];
+          const int g = qidxv[e >> 1];
+          const double q = gqv[g];
           double x, y, z;
           if (e & 1) {   // old configuration, through the overlay
             const int jg = A.g0 + g;
             if (jg >= pg0 && jg < pg1) {
-              x = A.ptrial[3 * (jg - pg0)]; y = A.ptrial[3 * (jg - pg0) + 1]; z = A.ptrial[3 * (jg - pg0) + 2];
+              x = ptrial[3 * (jg - pg0)]; y = ptrial[3 * (jg - pg0) + 1]; z = ptrial[3 * (jg - pg0) + 2];
             } else {
               const double2 a = A.xy[jg], c = A.zq[jg];
               x = a.x; y = a.y; z = c.x;
             }
           } else {
-            x = A.trial[3 * g]; y = A.trial[3 * g + 1]; z = A.trial[3 * g + 2];
+            x = trial[3 * g]; y = trial[3 * g + 1]; z = trial[3 * g + 2];
           }
           x = pg_wrap_pos(x, P.ebox[0], P.inv_ebox[0], P.pbc[0]);
           y = pg_wrap_pos(y, P.ebox[1], P.inv_ebox[1], P.pbc[1]);
@@ -286,25 +315,25 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
       while (jj * (jj - 1) / 2 > p) jj--;
       while ((jj + 1) * jj / 2 <= p) jj++;
       const int g = p - jj * (jj - 1) / 2;
-      if (!(A.moved[g] || A.moved[jj])) continue;
+      if (!(movedv[g] || movedv[jj])) continue;
       const int ja = A.g0 + g, jb = A.g0 + jj;
       double aox, aoy, aoz, box_, boy, boz;
       if (ja >= pg0 && ja < pg1) {
-        aox = A.ptrial[3 * (ja - pg0)]; aoy = A.ptrial[3 * (ja - pg0) + 1]; aoz = A.ptrial[3 * (ja - pg0) + 2];
+        aox = ptrial[3 * (ja - pg0)]; aoy = ptrial[3 * (ja - pg0) + 1]; aoz = ptrial[3 * (ja - pg0) + 2];
       } else {
         double2 a = A.xy[ja], c = A.zq[ja];
         aox = a.x; aoy = a.y; aoz = c.x;
       }
       if (jb >= pg0 && jb < pg1) {
-        box_ = A.ptrial[3 * (jb - pg0)]; boy = A.ptrial[3 * (jb - pg0) + 1]; boz = A.ptrial[3 * (jb - pg0) + 2];
+        box_ = ptrial[3 * (jb - pg0)]; boy = ptrial[3 * (jb - pg0) + 1]; boz = ptrial[3 * (jb - pg0) + 2];
       } else {
         double2 a = A.xy[jb], c = A.zq[jb];
         box_ = a.x; boy = a.y; boz = c.x;
       }
-      const double anx = A.trial[3 * g], any_ = A.trial[3 * g + 1], anz = A.trial[3 * g + 2];
-      const double bnx = A.trial[3 * jj], bny = A.trial[3 * jj + 1], bnz = A.trial[3 * jj + 2];
-      const double qa = A.gq[g], qb = A.gq[jj];
-      const int ta = A.gtype[g], tb = A.gtype[jj];
+      const double anx = trial[3 * g], any_ = trial[3 * g + 1], anz = trial[3 * g + 2];
+      const double bnx = trial[3 * jj], bny = trial[3 * jj + 1], bnz = trial[3 * jj + 2];
+      const double qa = gqv[g], qb = gqv[jj];
+      const int ta = gtypev[g], tb = gtypev[jj];
       double lj_n = 0.0, re_n = 0.0, lj_o = 0.0, re_o = 0.0;
       if (FAST) {
         const double Lx = P.box[0], Ly = P.box[1], Lz = P.box[2];
@@ -343,7 +372,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
     const double rc2 = P.use_ewald ? P.rc2_relaxed : -1.0;
     const int do_lj = (P.pair_kind != 0);
     const double ljc2max = (P.pair_kind == 1) ? P.ljc2max : -1.0;
-    const float fLx = (float)Lx, fLy = (float)Ly, fLz = (float)Lz;
+    const float fLx = P.fbox[0], fLy = P.fbox[1], fLz = P.fbox[2];
     const double fdelta = 1e-6 * fmax(Lx, fmax(Ly, Lz));   // >= 3x the worst-case FP32 error of a separation
     const int lane = tid & 31, warp = tid >> 5;
     int qn = 0;   // entries in this warp's queue (warp-uniform)
@@ -363,7 +392,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
         pq = c.y;
         px = a.x; py = a.y; pz = c.x;
         if (j >= pg0 && j < pg1) {
-          px = A.ptrial[3 * (j - pg0)]; py = A.ptrial[3 * (j - pg0) + 1]; pz = A.ptrial[3 * (j - pg0) + 2];
+          px = ptrial[3 * (j - pg0)]; py = ptrial[3 * (j - pg0) + 1]; pz = ptrial[3 * (j - pg0) + 2];
         }
         if (gbeg == 0) acc_mz += pq * pz;   // each tile's dipole moment is counted by the segment that starts it
       }
@@ -373,17 +402,17 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
         const int g = gbeg + tid, jg = A.g0 + g;
         double ox, oy, oz;
         if (jg >= pg0 && jg < pg1) {
-          ox = A.ptrial[3 * (jg - pg0)]; oy = A.ptrial[3 * (jg - pg0) + 1]; oz = A.ptrial[3 * (jg - pg0) + 2];
+          ox = ptrial[3 * (jg - pg0)]; oy = ptrial[3 * (jg - pg0) + 1]; oz = ptrial[3 * (jg - pg0) + 2];
         } else {
           double2 a = A.xy[jg], c = A.zq[jg];
           ox = a.x; oy = a.y; oz = c.x;
         }
         s_o[0][tid] = ox; s_o[1][tid] = oy; s_o[2][tid] = oz;
-        s_n[0][tid] = A.trial[3 * g]; s_n[1][tid] = A.trial[3 * g + 1]; s_n[2][tid] = A.trial[3 * g + 2];
-        const double gq = A.gq[g];
+        s_n[0][tid] = trial[3 * g]; s_n[1][tid] = trial[3 * g + 1]; s_n[2][tid] = trial[3 * g + 2];
+        const double gq = gqv[g];
         s_q[tid] = gq;
-        s_t[tid] = A.gtype[g];
-        s_mv[tid] = A.moved[g];
+        s_t[tid] = gtypev[g];
+        s_mv[tid] = movedv[g];
         // conservative filter radii^2 of this moved bead: against a charged partner / a neutral one
         // (the exact per-pair cutoffs are re-applied by mv_pair_inrange)
         const double c0 = ljc2max, c1 = (gq != 0.0) ? fmax(rc2, ljc2max) : ljc2max;
@@ -403,8 +432,8 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
         // Every lane runs the filter (invalid lanes never hit) so the warp can vote: in-range
         // configurations are rare, so instead of evaluating erfc / LJ in a nearly empty diverged warp
         // they are compacted into this warp's queue and evaluated 32 at a time (mv_queue_flush).
-        const double* __restrict__ cutv = s_cut[pq != 0.0 ? 1 : 0];
         const bool pchg = (pq != 0.0);
+        const int csel = pchg ? 1 : 0;
         const float psx = mv_frac(px, iLx), psy = mv_frac(py, iLy), psz = mv_frac(pz, iLz);
 #pragma unroll 4
         for (int i = 0; i < gcnt; i++) {
@@ -432,7 +461,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
             dxo -= Lx * mv_rint(dxo * iLx); dyo -= Ly * mv_rint(dyo * iLy); dzo -= Lz * mv_rint(dzo * iLz);
             r2n = dxn * dxn + dyn * dyn + dzn * dzn;
             r2o = dxo * dxo + dyo * dyo + dzo * dzo;
-            const double cut = cutv[i];
+            const double cut = s_cut[csel][i];
             hn = r2n <= cut;
             ho = r2o <= cut;
           }
@@ -451,10 +480,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
               q_r2[warp][pos] = r2o; q_qq[warp][pos] = qq; q_tp[warp][pos] = tp | 0x10000;   // old: subtract
             }
             qn += __popc(mo);
-            if (qn > MV_QCAP - 64) {
-              mv_queue_flush(A.Pg, q_r2[warp], q_qq[warp], q_tp[warp], qn, lane, acc_pair, acc_real, acc_ov);
-              qn = 0;
-            }
+            if (qn > MV_QCAP - 64) MV_QUEUE_FLUSH();
           }
         }
       } else if (valid) {
@@ -469,7 +495,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
       }
       u += gcnt;
     }
-    if (FAST && qn > 0) mv_queue_flush(A.Pg, q_r2[warp], q_qq[warp], q_tp[warp], qn, lane, acc_pair, acc_real, acc_ov);
+    if (FAST && qn > 0) MV_QUEUE_FLUSH();
   }
 
   // ---------------- per-CTA partials; the last CTA to finish finalises
@@ -519,14 +545,14 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
       const int jg = A.g0 + g;
       double ox, oy, oz;
       if (jg >= pg0 && jg < pg1) {
-        ox = A.ptrial[3 * (jg - pg0)]; oy = A.ptrial[3 * (jg - pg0) + 1]; oz = A.ptrial[3 * (jg - pg0) + 2];
+        ox = ptrial[3 * (jg - pg0)]; oy = ptrial[3 * (jg - pg0) + 1]; oz = ptrial[3 * (jg - pg0) + 2];
       } else {
         double2 a = A.xy[jg], c = A.zq[jg];
         ox = a.x; oy = a.y; oz = c.x;
       }
-      if (P.ext_kind != 0 && A.moved[g]) {
-        const int t = A.gtype[g];
-        const double en = pg_wall_energy(*A.Pg, A.trial[3 * g + 2], t);
+      if (P.ext_kind != 0 && movedv[g]) {
+        const int t = gtypev[g];
+        const double en = pg_wall_energy(*A.Pg, trial[3 * g + 2], t);
         if (en >= PG_VLE) w_out = 1.0;
         w_sum += en - pg_wall_energy(*A.Pg, oz, t);
       }
@@ -534,13 +560,13 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
         const int jg2 = jg + 1;
         double ox2, oy2, oz2;
         if (jg2 >= pg0 && jg2 < pg1) {
-          ox2 = A.ptrial[3 * (jg2 - pg0)]; oy2 = A.ptrial[3 * (jg2 - pg0) + 1]; oz2 = A.ptrial[3 * (jg2 - pg0) + 2];
+          ox2 = ptrial[3 * (jg2 - pg0)]; oy2 = ptrial[3 * (jg2 - pg0) + 1]; oz2 = ptrial[3 * (jg2 - pg0) + 2];
         } else {
           double2 a = A.xy[jg2], c = A.zq[jg2];
           ox2 = a.x; oy2 = a.y; oz2 = c.x;
         }
-        b_sum += pg_bond_energy(*A.Pg, A.trial[3 * g], A.trial[3 * g + 1], A.trial[3 * g + 2], A.trial[3 * g + 3],
-                                A.trial[3 * g + 4], A.trial[3 * g + 5]) -
+        b_sum += pg_bond_energy(*A.Pg, trial[3 * g], trial[3 * g + 1], trial[3 * g + 2], trial[3 * g + 3],
+                                trial[3 * g + 4], trial[3 * g + 5]) -
                  pg_bond_energy(*A.Pg, ox, oy, oz, ox2, oy2, oz2);
       }
     }
@@ -614,9 +640,9 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
   // write the previous trial's coordinates back: every other CTA has finished reading them
   if (apply_prev) {
     for (int i = tid; i < A.pglen; i += MV_THREADS) {
-      A.xy[A.pg0 + i] = make_double2(A.ptrial[3 * i], A.ptrial[3 * i + 1]);
+      A.xy[A.pg0 + i] = make_double2(ptrial[3 * i], ptrial[3 * i + 1]);
       double2 c = A.zq[A.pg0 + i];
-      c.x = A.ptrial[3 * i + 2];
+      c.x = ptrial[3 * i + 2];
       A.zq[A.pg0 + i] = c;
     }
   }
