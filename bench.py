@@ -238,157 +238,226 @@ def run_ours(a):
         return float(t.item())
 
     M, K, W = a.moves_per_step, a.steps, a.warmup
+    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else min(8, max(1, ((os.cpu_count() or 2) // world) // 2))
     r, sysm, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
     ids = types.ids(sysm.symbol)
-    eng = Engine(params, device=local_rank, capacity_beads=sysm.n)
-    eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
-    eng.init_energy()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def flush_l2():
         flush_buf.fill_(1)
+        torch.cuda.synchronize()
 
-    # ---------------- e2e leg: host-driven Metropolis loop through the C ABI (native caller)
     L = mcbench_lib()
     dp, ip, bp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
     xyz0 = np.ascontiguousarray(sysm.xyz)
     box = np.array(sysm.box, dtype=np.float64)
     prob = np.array(MOVE_PROB, dtype=np.float64)
     mf = np.ascontiguousarray(sysm.mol_first, dtype=np.int32)
-    ctx = L.pb_create(eng.h, sysm.n_mol, mf.ctypes.data_as(ip), xyz0.ctypes.data_as(dp), box.ctypes.data_as(dp),
-                      C.c_double(r.beta), C.c_double(r.move_size), C.c_double(r.rigid_bond), prob.ctypes.data_as(dp),
-                      0, C.c_uint(12345 + 1000 * rank))
     n_total = (W + K) * M
-    cap_beads = n_total * 100
-    rec_mol = np.zeros(n_total, dtype=np.int32)
-    rec_off = np.zeros(n_total, dtype=np.int32)
-    rec_u = np.zeros(n_total)
-    rec_dE = np.zeros(n_total)
-    rec_acc = np.zeros(n_total, dtype=np.uint8)
-    rec_trial = np.zeros((cap_beads, 3))
-    rec_moved = np.zeros(cap_beads, dtype=np.uint8)
-    used_total = 0
-    e2e_wall, e2e_inner = [], []
 
-    def run_step(s):
-        nonlocal used_total
-        used = C.c_int32()
-        wall = C.c_double()
-        ev = C.c_double()
-        fl = C.c_double()
-        nacc = C.c_int32()
-        sl = slice(s * M, (s + 1) * M)
-        rc = L.pb_run(ctx, M, rec_mol[sl].ctypes.data_as(ip), rec_off[sl].ctypes.data_as(ip),
-                      rec_u[sl].ctypes.data_as(dp), rec_dE[sl].ctypes.data_as(dp), rec_acc[sl].ctypes.data_as(bp),
-                      rec_trial[used_total:].ctypes.data_as(dp), rec_moved[used_total:].ctypes.data_as(bp),
-                      cap_beads - used_total, C.byref(used), C.byref(wall), C.byref(ev), C.byref(fl), C.byref(nacc),
-                      K_FULL)
-        if rc != 0:
-            raise RuntimeError(f"pb_run failed ({rc}): {eng.L.pg_last_error(eng.h).decode()}")
-        rec_off[sl] += used_total
-        used_total += used.value
-        return wall.value
+    def measure(R):
+        class Replica:
+            """One independent Markov chain: its own engine (stream, resident state) and random stream."""
 
-    for s in range(W):
-        run_step(s)
-        flush_l2()
-    launches0 = eng.launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(W, W + K):
-        e2e_inner.append(run_step(s))
-        flush_l2()
-    barrier()
-    t_e2e = time.perf_counter() - t0
-    e2e_launches = eng.launch_count() - launches0
-    L.pb_destroy(ctx)
-    t_e2e = max_over_ranks(t_e2e)
-    final_e2e = eng.totals()
+            def __init__(self, idx):
+                self.eng = Engine(params, device=local_rank, capacity_beads=sysm.n)
+                self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
+                self.eng.init_energy()
+                self.ctx = L.pb_create(self.eng.h, sysm.n_mol, mf.ctypes.data_as(ip), xyz0.ctypes.data_as(dp),
+                                       box.ctypes.data_as(dp), C.c_double(r.beta), C.c_double(r.move_size),
+                                       C.c_double(r.rigid_bond), prob.ctypes.data_as(dp), 0,
+                                       C.c_uint(12345 + 1000 * rank + 17 * idx))
+                self.cap_beads = n_total * 100
+                self.rec_mol = np.zeros(n_total, dtype=np.int32)
+                self.rec_off = np.zeros(n_total, dtype=np.int32)
+                self.rec_u = np.zeros(n_total)
+                self.rec_dE = np.zeros(n_total)
+                self.rec_acc = np.zeros(n_total, dtype=np.uint8)
+                self.rec_trial = np.zeros((self.cap_beads, 3))
+                self.rec_moved = np.zeros(self.cap_beads, dtype=np.uint8)
+                self.used_total = 0
+                self.replay_dE = []
+                self.replay_ms = []
+                self.kd_ms = 0.0
 
-    # ---------------- value leg: the same sequence, device-resident replay
-    eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
-    eng.init_energy()
-    eng.replay_upload(rec_mol, rec_off, rec_u, rec_trial[:used_total], rec_moved[:used_total])
-    for s in range(W):
-        eng.replay_run(s * M, M)
-        flush_l2()
-    launches0 = eng.launch_count()
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    dE_replay = []
-    for s in range(W, W + K):
-        dE, acc, ms = eng.replay_run(s * M, M)
-        dev_ms += ms
-        dE_replay.append(dE)
-        flush_l2()
-    barrier()
-    t_wall_replay = time.perf_counter() - t0
-    gpu_launches = eng.launch_count() - launches0
-    clock_info = clocks.stop()
-    dev_s = max_over_ranks(dev_ms * 1e-3)
-    replay_matches = bool(np.array_equal(np.concatenate(dE_replay), rec_dE[W * M:]) and eng.totals() == final_e2e)
+            def e2e_step(self, s):
+                used, wall, ev, fl, nacc = C.c_int32(), C.c_double(), C.c_double(), C.c_double(), C.c_int32()
+                sl = slice(s * M, (s + 1) * M)
+                rc = L.pb_run(self.ctx, M, self.rec_mol[sl].ctypes.data_as(ip), self.rec_off[sl].ctypes.data_as(ip),
+                              self.rec_u[sl].ctypes.data_as(dp), self.rec_dE[sl].ctypes.data_as(dp),
+                              self.rec_acc[sl].ctypes.data_as(bp), self.rec_trial[self.used_total:].ctypes.data_as(dp),
+                              self.rec_moved[self.used_total:].ctypes.data_as(bp), self.cap_beads - self.used_total,
+                              C.byref(used), C.byref(wall), C.byref(ev), C.byref(fl), C.byref(nacc), K_FULL)
+                if rc != 0:
+                    raise RuntimeError(f"pb_run failed ({rc}): {self.eng.L.pg_last_error(self.eng.h).decode()}")
+                self.rec_off[sl] += self.used_total
+                self.used_total += used.value
 
-    # ---------------- roofline of the dominant kernel (k_delta), timed alone, same proposals
-    timed = np.arange(W * M, (W + K) * M)
-    evals, flops, bytes_ = alg_flops_per_move(sysm, rec_mol[timed])
-    eng.replay_time_delta(W * M, min(M, 256))   # warm
-    kd_ms = eng.replay_time_delta(W * M, K * M)
-    fp64_peak_gflops = eng.measure_fp64_peak()
-    peaks = {}
-    try:
-        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # traffic: dram bytes per k_move launch from the committed `ncu --set full` capture of this command
-    traffic = None
-    try:
-        with open(os.path.join(REPO, "profiles", "r01_ncu_summary.json")) as f:
-            prof = json.load(f)["k_move_full"]
-        vals = []
-        for p_ in prof:
-            rd, wr = p_["dram__bytes_read.sum"].split(), p_["dram__bytes_write.sum"].split()
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            vals.append(float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]])
-        traffic = float(np.mean(vals))
-    except Exception:
+            def reset_for_replay(self):
+                L.pb_destroy(self.ctx)
+                self.final_e2e = self.eng.totals()
+                self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
+                self.eng.init_energy()
+                self.eng.replay_upload(self.rec_mol, self.rec_off, self.rec_u, self.rec_trial[:self.used_total],
+                                       self.rec_moved[:self.used_total])
+
+            def replay_step(self, s, keep):
+                dE, acc, ms = self.eng.replay_run(s * M, M)
+                if keep:
+                    self.replay_dE.append(dE)
+                    self.replay_ms.append(ms)
+
+            def time_delta(self):
+                self.kd_ms = self.eng.replay_time_delta(W * M, K * M)
+
+        reps = [Replica(i) for i in range(R)]
+
+        def run_all(fn):
+            """Run fn(replica) for every replica concurrently (ctypes releases the GIL inside the C ABI)."""
+            if R == 1:
+                fn(reps[0])
+                return
+            errs = []
+
+            def wrap(rp):
+                try:
+                    fn(rp)
+                except Exception as e:   # noqa: BLE001
+                    errs.append(e)
+            ths = [threading.Thread(target=wrap, args=(rp,)) for rp in reps]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            if errs:
+                raise errs[0]
+
+        # ---------------- e2e leg: host-driven Metropolis loops through the C ABI (native callers)
+        for s in range(W):
+            run_all(lambda rp: rp.e2e_step(s))
+            flush_l2()
+        launches0 = sum(rp.eng.launch_count() for rp in reps)
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(W, W + K):
+            run_all(lambda rp: rp.e2e_step(s))
+            flush_l2()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        e2e_launches = sum(rp.eng.launch_count() for rp in reps) - launches0
+        t_e2e = max_over_ranks(t_e2e)
+
+        # ---------------- value leg: the same sequences, device-resident replay (one CUDA graph per step)
+        run_all(lambda rp: rp.reset_for_replay())
+        for s in range(W):
+            run_all(lambda rp: rp.replay_step(s, False))
+            flush_l2()
+        for s in range(W, W + K):   # instantiate the timed steps' graphs outside the timed region
+            for rp in reps:
+                rp.eng.replay_prepare(s * M, M, True)
+        launches0 = sum(rp.eng.launch_count() for rp in reps)
+        barrier()
+        t0 = time.perf_counter()
+        t_flush = 0.0
+        for s in range(W, W + K):
+            run_all(lambda rp: rp.replay_step(s, True))
+            tf = time.perf_counter()
+            flush_l2()
+            t_flush += time.perf_counter() - tf
+        barrier()
+        t_wall_replay = time.perf_counter() - t0
+        gpu_launches = sum(rp.eng.launch_count() for rp in reps) - launches0
+        clock_info = clocks.stop()
+        # device time of a step = the slowest replica's CUDA-event time (replicas run concurrently)
+        dev_ms = float(sum(max(rp.replay_ms[i] for rp in reps) for i in range(K)))
+        dev_s = max_over_ranks(dev_ms * 1e-3)
+        replay_matches = all(bool(np.array_equal(np.concatenate(rp.replay_dE), rp.rec_dE[W * M:]) and
+                                  rp.eng.totals() == rp.final_e2e) for rp in reps)
+
+        # ---------------- roofline of the dominant kernel (k_move), timed alone, same proposals
+        timed = np.arange(W * M, (W + K) * M)
+        evals = flops = bytes_ = 0.0
+        for rp in reps:
+            e_, f_, b_ = alg_flops_per_move(sysm, rp.rec_mol[timed])
+            evals += float(e_.sum()); flops += float(f_.sum()); bytes_ += float(b_.sum())
+            rp.eng.replay_time_delta(W * M, min(M, 256))   # warm + instantiate
+            rp.eng.replay_prepare(W * M, K * M, False)
+        torch.cuda.synchronize()
+        run_all(lambda rp: rp.time_delta())
+        kd_ms = max(rp.kd_ms for rp in reps)
+        fp64_peak_gflops = reps[0].eng.measure_fp64_peak()
+        peaks = {}
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # traffic: dram bytes per k_move launch from the committed `ncu --set full` capture of this command
         traffic = None
-    achieved_tflops = float(flops.sum()) / (kd_ms * 1e-3) / 1e12
-    roofline = {
-        "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_gflops / 1e3, "unit": "TFLOP/s",
-        "frac": achieved_tflops / (fp64_peak_gflops / 1e3), "traffic": traffic,
-        "traffic_note": "dram__bytes_read+write per k_move launch, ncu --set full (cold cache), profiles/r01_ncu_summary.json",
-        "kernel": "k_move", "launches": int(K * M), "avg_launch_us": kd_ms * 1e3 / (K * M),
-        "peak_source": "FP64 FMA microbenchmark measured in this run (pg_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-        "algorithmic_flops_per_launch": float(flops.mean()),
-        "bytes_view": {"bound": "hbm", "achieved": float(bytes_.sum()) / (kd_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                       "unit": "GB/s", "frac": float(bytes_.sum()) / (kd_ms * 1e-3) / 1e9 / hbm_peak,
-                       "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                       "note": "the 0.9 MB working set is L2-resident by design; HBM is the conservative denominator"},
-    }
+        try:
+            with open(os.path.join(REPO, "profiles", "r01_ncu_summary.json")) as f:
+                prof = json.load(f)["k_move_full"]
+            vals = []
+            for p_ in prof:
+                rd, wr = p_["dram__bytes_read.sum"].split(), p_["dram__bytes_write.sum"].split()
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                vals.append(float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]])
+            traffic = float(np.mean(vals))
+        except Exception:
+            traffic = None
+        n_launch = R * K * M
+        achieved_tflops = flops / (kd_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_gflops / 1e3, "unit": "TFLOP/s",
+            "frac": achieved_tflops / (fp64_peak_gflops / 1e3), "traffic": traffic,
+            "traffic_note": "dram__bytes_read+write per k_move launch, ncu --set full (cold cache), profiles/r01_ncu_summary.json",
+            "kernel": "k_move", "launches": int(n_launch), "avg_launch_us": kd_ms * 1e3 / (K * M),
+            "avg_launch_note": f"CUDA-event time of {K * M} back-to-back k_move launches per replica, {R} replica stream(s) "
+                               f"running concurrently; achieved = algorithmic flops of all replicas / that time",
+            "peak_source": "FP64 FMA microbenchmark measured in this run (pg_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+            "algorithmic_flops_per_launch": flops / n_launch,
+            "bytes_view": {"bound": "hbm", "achieved": bytes_ / (kd_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": bytes_ / (kd_ms * 1e-3) / 1e9 / hbm_peak,
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                           "note": "the 0.9 MB working set per replica is L2-resident by design; HBM is the conservative denominator"},
+        }
 
-    # ---------------- totals over ranks
-    moves_total = sum_over_ranks(float(K * M))
-    evals_total = sum_over_ranks(float(evals.sum()))
-    value = moves_total / dev_s
-    e2e_value = moves_total / t_e2e
-    # bytes crossing PCIe per step: staged group block H2D (trial xyz + q + type + moved) and the result mailbox D2H
-    lens = (sysm.mol_first[rec_mol[timed] + 1] - sysm.mol_first[rec_mol[timed]]).astype(np.float64)
-    h2d = float((lens * (24 + 8 + 4 + 1)).sum() / K)
-    d2h = float(M * 112)
+        # ---------------- totals over ranks
+        moves_total = sum_over_ranks(float(R * K * M))
+        evals_total = sum_over_ranks(evals)
+        value = moves_total / dev_s
+        e2e_value = moves_total / t_e2e
+        # bytes crossing PCIe per step: staged group block H2D (trial xyz + q + type + index + moved) and the mailbox D2H
+        lens = np.concatenate([(sysm.mol_first[rp.rec_mol[timed] + 1] - sysm.mol_first[rp.rec_mol[timed]]) for rp in reps]).astype(np.float64)
+        h2d = float((lens * (24 + 8 + 4 + 4 + 1)).sum() / K)
+        d2h = float(R * M * 128)
+        rec_acc_all = np.concatenate([rp.rec_acc[W * M:] for rp in reps])
+
+        for rp in reps:
+            rp.eng.close()
+        return dict(R=R, value=value, e2e_value=e2e_value, dev_s=dev_s, t_e2e=t_e2e, evals_total=evals_total,
+                    e2e_launches=e2e_launches, gpu_launches=gpu_launches, roofline=roofline, clock_info=clock_info,
+                    replay_matches=replay_matches, wall_replay=(t_wall_replay - t_flush), h2d=h2d, d2h=d2h,
+                    accept=float(rec_acc_all.mean()), p_ion=float(np.mean(lens == 1)))
+
+    single = measure(1) if (R_auto > 1 and not a.no_single) else None
+    res = measure(R_auto)
+    R = res["R"]
+    value, e2e_value, dev_s, t_e2e, evals_total = res["value"], res["e2e_value"], res["dev_s"], res["t_e2e"], res["evals_total"]
+    e2e_launches, gpu_launches, roofline, clock_info = res["e2e_launches"], res["gpu_launches"], res["roofline"], res["clock_info"]
+    replay_matches, t_wall_replay, t_flush, h2d, d2h = res["replay_matches"], res["wall_replay"], 0.0, res["h2d"], res["d2h"]
 
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        t_ion, t_chain = cpu_sample((7, 3, 2))
-        p_ion = float(np.mean(lens == 1))
+        t_ion, t_chain = cpu_sample((7, 6, 2))
+        p_ion = res["p_ion"]
         v = mix_rate(t_ion, t_chain, p_ion)
         cpu = {"value": v, "unit": "moves/s", "cores": 1, "kind": "port",
-               "sample": f"3 ion moves ({np.mean(t_ion):.3f} s each) + 2 chain moves of 100 flagged beads "
+               "sample": f"6 ion moves ({np.mean(t_ion):.3f} s each) + 2 chain moves of 100 flagged beads "
                          f"({np.mean(t_chain):.3f} s each) on the same 22000-bead system, reference pairwise algorithm "
                          f"(oracle port, map-free, new-configuration energies only like the reference), mixed with the realised ion fraction {p_ion:.3f}; plum_ref cannot "
                          f"hold N=22000 (SURVEY.md §0.8)"}
@@ -398,7 +467,7 @@ def run_ours(a):
             "metric": "MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_s * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "moves_per_step": M, "replicas_per_gpu": 1,
+            "config": {"workload": WORKLOAD, "moves_per_step": M, "replicas_per_gpu": R,
                        "l2": "flushed between steps (256 MiB fill, inside the timed region); within a step the "
                              "0.9 MB working set stays L2-resident by design (north_star)"},
             "pair_dE_evals_per_s": evals_total / dev_s,
@@ -407,11 +476,14 @@ def run_ours(a):
                     "caller": "native C++ Metropolis loop over pg_delta_e/pg_commit (plum_b200/host/mc_bench.cc)",
                     "launches": int(e2e_launches)},
             "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
-            "replay_matches_e2e": replay_matches, "wall_ms_per_step_replay": t_wall_replay * 1e3 / K,
-            "accept_ratio": float(rec_acc[W * M:].mean()),
+            "replay_matches_e2e": replay_matches, "wall_ms_per_step_replay": (t_wall_replay - t_flush) * 1e3 / K,
+            "accept_ratio": res["accept"],
+            "single_replica": None if single is None else {
+                "value": single["value"], "e2e": single["e2e_value"], "unit": "moves/s", "roofline_frac": single["roofline"]["frac"],
+                "avg_launch_us": single["roofline"]["avg_launch_us"], "replay_matches_e2e": single["replay_matches"],
+                "note": "one Markov chain on the GPU (latency-bound): the rate a single Plum run sees"},
         }
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -425,6 +497,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--moves-per-step", type=int, default=MOVES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="skip the extra single-replica measurement")
+    ap.add_argument("--replicas-per-gpu", type=int, default=0,
+                    help="independent Markov chains per GPU, each with its own engine/stream; 0 = auto (half the host cores per GPU, at most 8)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

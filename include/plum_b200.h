@@ -187,6 +187,9 @@ int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* a
  * CUDA-event time of `count` back-to-back launches of the dominant kernel, for the
  * roofline figure. */
 int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms);
+/* Builds (captures + instantiates) the CUDA graph of a replay batch ahead of time so that the
+ * first pg_replay_run / pg_replay_time_delta (with_commit 1 / 0) of that batch does not pay for it. */
+int pg_replay_prepare(pg_engine* h, int first, int count, int with_commit);
 
 /* ---- configurational-bias trial energies (ForceField::BeadsEnergy) ------- */
 /* One launch evaluates n_trials candidate (monomer, counter-ion) pairs against

@@ -1097,6 +1097,13 @@ int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* a
   return PG_OK;
 }
 
+int pg_replay_prepare(pg_engine* h, int first, int count, int with_commit) {
+  if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  cudaGraphExec_t exec = nullptr;
+  return replay_graph(h, first, count, with_commit != 0, &exec);
+}
+
 int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms) {
   if (!h || !elapsed_ms || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }

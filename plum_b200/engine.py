@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "libplum_b200.so")
 ABI_SYMBOLS = [
     "pg_create", "pg_destroy", "pg_last_error", "pg_abi_version", "pg_get_ewald_info", "pg_upload_system",
     "pg_init_energy", "pg_recompute_totals", "pg_get_totals", "pg_download_positions", "pg_num_beads", "pg_delta_e",
-    "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_trial_energies", "pg_insert_molecules",
+    "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_trial_energies", "pg_insert_molecules",
     "pg_delete_molecules", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
     "pg_stream", "pg_measure_fp64_peak",
 ]
@@ -58,6 +58,7 @@ def lib():
         L.pg_replay_upload.argtypes = [vp, C.c_int, C.POINTER(PgProposal), C.c_int, c_double_p, c_uint8_p]
         L.pg_replay_run.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_uint8_p, C.POINTER(C.c_float)]
         L.pg_replay_time_delta.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.pg_replay_prepare.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.pg_trial_energies.argtypes = [vp, C.POINTER(PgTrialSet), c_double_p, c_double_p, c_double_p, c_double_p,
                                         c_int32_p, c_double_p, c_double_p, c_double_p]
         L.pg_insert_molecules.argtypes = [vp, C.c_int, c_int32_p, c_double_p, c_double_p, c_int32_p,
@@ -180,6 +181,9 @@ class Engine:
         ms = C.c_float()
         self._check(self.L.pg_replay_run(self.h, first, count, dptr(dE), bptr(acc), C.byref(ms)), "pg_replay_run")
         return dE[:count], acc[:count], ms.value
+
+    def replay_prepare(self, first: int, count: int, with_commit: bool = True):
+        self._check(self.L.pg_replay_prepare(self.h, first, count, int(with_commit)), "pg_replay_prepare")
 
     def replay_time_delta(self, first: int, count: int) -> float:
         ms = C.c_float()
