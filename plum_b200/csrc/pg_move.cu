@@ -435,9 +435,53 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 3 : 2) k_move(const PgMoveA
         const bool pchg = (pq != 0.0);
         const int csel = pchg ? 1 : 0;
         const float psx = mv_frac(px, iLx), psy = mv_frac(py, iLy), psz = mv_frac(pz, iLz);
-#pragma unroll 4
-        for (int i = 0; i < gcnt; i++) {
-          if (!s_mv[i]) continue;
+        // Warp-level culling.  The 32 partners of a warp are consecutive beads — a chain segment, i.e. a
+        // compact cloud.  Its extent around one reference partner (per-axis half widths, minimum image)
+        // gives a lower bound on the separation of ANY of them from a moved bead:
+        //   |wrap(g - p)| >= |wrap(g - c)| - hw   (triangle inequality on the circle, per axis).
+        // Lane i applies the bound to moved bead i (a chunk has <= 32 beads); the warp then runs the
+        // per-partner filter only for the beads that survive.  It can only over-accept.
+        unsigned keep = 0u;
+        {
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          if (vmask) {
+            const int ref = __ffs(vmask) - 1;
+            const float cx = __shfl_sync(0xffffffffu, psx, ref), cy = __shfl_sync(0xffffffffu, psy, ref),
+                        cz = __shfl_sync(0xffffffffu, psz, ref);
+            float ex = psx - cx, ey = psy - cy, ez = psz - cz;
+            ex = valid ? fabsf(ex - mv_rintf(ex)) : 0.0f;
+            ey = valid ? fabsf(ey - mv_rintf(ey)) : 0.0f;
+            ez = valid ? fabsf(ez - mv_rintf(ez)) : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+              ey = fmaxf(ey, __shfl_xor_sync(0xffffffffu, ey, o));
+              ez = fmaxf(ez, __shfl_xor_sync(0xffffffffu, ez, o));
+            }
+            const float hwx = ex + 1e-6f, hwy = ey + 1e-6f, hwz = ez + 1e-6f;   // + FP32 slack in box fractions
+            const bool anyq = __ballot_sync(0xffffffffu, valid && pchg) != 0u;
+            bool k = false;
+            if (lane < gcnt && s_mv[lane]) {
+              const float4 fn = s_fn[lane], fo = s_fo[lane];
+              const float cutf = anyq ? fn.w : fo.w;
+              float bxn = fn.x - cx, byn = fn.y - cy, bzn = fn.z - cz;
+              float bxo = fo.x - cx, byo = fo.y - cy, bzo = fo.z - cz;
+              bxn = fmaxf(fabsf(bxn - mv_rintf(bxn)) - hwx, 0.0f) * fLx;
+              byn = fmaxf(fabsf(byn - mv_rintf(byn)) - hwy, 0.0f) * fLy;
+              bzn = fmaxf(fabsf(bzn - mv_rintf(bzn)) - hwz, 0.0f) * fLz;
+              bxo = fmaxf(fabsf(bxo - mv_rintf(bxo)) - hwx, 0.0f) * fLx;
+              byo = fmaxf(fabsf(byo - mv_rintf(byo)) - hwy, 0.0f) * fLy;
+              bzo = fmaxf(fabsf(bzo - mv_rintf(bzo)) - hwz, 0.0f) * fLz;
+              const float lbn = fmaf(bxn, bxn, fmaf(byn, byn, bzn * bzn));
+              const float lbo = fmaf(bxo, bxo, fmaf(byo, byo, bzo * bzo));
+              k = fminf(lbn, lbo) <= cutf;
+            }
+            keep = __ballot_sync(0xffffffffu, k);
+          }
+        }
+        while (keep) {
+          const int i = __ffs(keep) - 1;
+          keep &= keep - 1u;
           // FP32 pre-filter in box fractions (full-rate pipe); it can only over-accept
           const float4 fn = s_fn[i], fo = s_fo[i];
           float axn = psx - fn.x, ayn = psy - fn.y, azn = psz - fn.z;
