@@ -754,7 +754,11 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
     else
       PG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move<false>, MV_THREADS, 0));
     PG_CREATE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-    h->move_slots = std::max(1, per_sm * n_sm);
+    // CTAs per SM one k_move grid may take (<= what fits): leaving a slot free lets the kernels of other
+    // replicas (other engines / streams on the same GPU) co-run and hide each other's latencies
+    int use_per_sm = std::max(1, per_sm - 1);   // measured best: 3 of 4 (tools/sweep_ctas.sh)
+    if (const char* e = getenv("PLUM_B200_CTAS_PER_SM")) use_per_sm = std::max(1, std::min(per_sm, atoi(e)));
+    h->move_slots = std::max(1, use_per_sm * n_sm);
     h->n_sm = n_sm;
   }
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_out8, sizeof(double) * 8));

@@ -201,7 +201,7 @@ __device__ __forceinline__ void mv_block_sum5(double (&v)[5], double* smem /* [M
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(MV_THREADS, FAST ? 3 : 2) k_move(const PgMoveArgs A) {
+__global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveArgs A) {
   const PgMoveDev& P = A.D;
   __shared__ double s_n[3][MV_GCHUNK], s_o[3][MV_GCHUNK], s_q[MV_GCHUNK];
   __shared__ int s_t[MV_GCHUNK], s_mv[MV_GCHUNK];
