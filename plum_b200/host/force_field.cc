@@ -654,12 +654,70 @@ int ForceField::CBMCFChainDeletion(vector<Molecule>& mols, mt19937& rand_gen) {
   return -1;
 }
 
+// Widom-style chemical potential by ghost CBMC insertions (cbmc.cc:444-531): the same growth as
+// CBMCFChainInsertion without the acceptance step, mu_tot_ins times.  It draws random numbers, so it
+// is on the trajectory whenever s1_calc_chem_pot is 1.
 double ForceField::CalcChemicalPotentialF(vector<Molecule>& mols, mt19937& rand_gen) {
-  (void)mols; (void)rand_gen;
-  cout << "  plum_b200: the Widom chemical-potential sampler (cbmc.cc:444-531) is not part of the" << endl;
-  cout << "  per-move energy path yet (SURVEY.md 8(f) #3); set s1_calc_chem_pot 0. Exiting! Program complete." << endl;
-  exit(1);
-  return 0;
+  double total = 0;
+  const bool charged = (gc_bead_charge != 0);
+  const int k = cbmc_no_of_trials;
+
+  int spc1;
+  if (gc_chain_len > 1) spc1 = n_chain;
+  else if (gc_bead_charge >= 0) spc1 = n_cion - coion;
+  else spc1 = n_aion - coion;
+  int spc2;
+  if (gc_bead_charge == 0) spc2 = 0;
+  else if (gc_bead_charge > 0) spc2 = n_aion;
+  else spc2 = n_cion;
+  int spc1_add = 1;
+  int spc2_add = charged ? gc_chain_len : 0;
+  double factorial = 1;
+  double m1 = gc_chain_len, m2 = 1;
+  double vol_over_lam = 1;
+  for (int i = spc1 + 1; i <= spc1 + spc1_add; i++) factorial *= i;
+  for (int i = spc2 + 1; i <= spc2 + spc2_add; i++) factorial *= i;
+  vol_over_lam *= pow(vol / 15.625 / (gc_deBroglie_prefactor / pow(m1, 1.5)), spc1_add);
+  vol_over_lam *= pow(vol / 15.625 / (gc_deBroglie_prefactor / pow(m2, 1.5)), spc2_add);
+  double C = vol_over_lam * (1.0 / (double)factorial);
+
+  for (int c = 0; c < mu_tot_ins; c++) {
+    double weight = 1.0;
+    double xyz[3];
+    const int initial_beads = charged ? 2 : 1;
+    for (int i = 0; i < initial_beads; i++) {
+      for (int j = 0; j < 3; j++) xyz[j] = Uniform(rand_gen) * box_l[j];
+      cbmc_chain[i * gc_chain_len].SetAllCrd(xyz);
+    }
+    double b1[3], b2[3] = {0, 0, 0}, dE;
+    for (int j = 0; j < 3; j++) b1[j] = cbmc_chain[0].GetCrd(1, j);
+    if (charged)
+      for (int j = 0; j < 3; j++) b2[j] = cbmc_chain[gc_chain_len].GetCrd(1, j);
+    TrialEnergies(1, b1, b2, 0, -1, &dE);
+    if (dE == kVeryLargeEnergy) weight *= 0;
+    else weight *= exp(-beta * dE);
+
+    for (int i = 1; i < gc_chain_len; i++) {
+      double Wi = CBMCFGenTrialBeads(cbmc_chain[i - 1], mols, i, rand_gen, -1);
+      weight *= Wi / k;
+      if (weight <= 0) break;
+      double rand_num = Uniform(rand_gen) * Wi;
+      int current_bead = 0;
+      double cumulate_weight = cbmc_trial_weights[0];
+      while (cumulate_weight < rand_num && current_bead < k - 1) {
+        current_bead++;
+        cumulate_weight += cbmc_trial_weights[current_bead];
+      }
+      for (int j = 0; j < 3; j++) xyz[j] = cbmc_trial_beads[current_bead].GetCrd(0, j);
+      cbmc_chain[i].SetAllCrd(xyz);
+      if (charged) {
+        for (int j = 0; j < 3; j++) xyz[j] = cbmc_trial_beads[current_bead + k].GetCrd(0, j);
+        cbmc_chain[i + gc_chain_len].SetAllCrd(xyz);
+      }
+    }
+    total += weight * C;
+  }
+  return total / (double)mu_tot_ins;
 }
 
 // ------------------------------------------------------------------ samplers

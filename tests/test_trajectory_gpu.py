@@ -75,3 +75,53 @@ def test_accept_reject_sequence_identical_over_1e5_moves(name):
     has = ~np.isnan(tot[tidx, 0])
     err = np.abs(tot[tidx][has] - gold["tot"][has]) / np.maximum(1.0, np.abs(gold["tot"][has]))
     assert err.max() <= 1e-9, err.max()   # 10^5 accumulated += of 1e-16-level differences
+
+
+def test_chemical_potential_sampler_on_trajectory():
+    """s1_calc_chem_pot 1: CalcChemicalPotentialF (cbmc.cc:444-531) draws random numbers, so the
+    accept/reject sequence AFTER the first sample only matches if the ghost insertions consume the
+    stream exactly like the reference; the sampled mu must agree too (SURVEY.md §8(f) #3)."""
+    import gzip
+    import os
+    import subprocess
+    import tempfile
+    assert replay.have_plum_gpu()
+    with gzip.open(os.path.join(replay.GOLDEN, "short", "bulk_nvt_mu_seed1.trace.gz"), "rt") as f:
+        ref_lines = [ln for ln in f.read().split("\n") if ln.startswith("T")]
+    with open(os.path.join(replay.GOLDEN, "short", "bulk_nvt_mu_seed1.stat.dat")) as f:
+        ref_stat = [ln.split() for ln in f.read().split("\n") if ln and not ln.startswith("#")]
+    ex = replay.golden_example_dir("bulk_nvt")
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(ex, "run.in")) as f:
+            text = f.read()
+        out = []
+        for ln in text.split("\n"):
+            key = ln.split()[0] if ln.split() else ""
+            if key == "s1_total_simulation_steps":
+                ln = "s1_total_simulation_steps 230"
+            if key == "s1_calc_chem_pot":
+                ln = "s1_calc_chem_pot 1"
+            out.append(ln)
+        with open(os.path.join(tmp, "run.in"), "w") as f:
+            f.write("\n".join(out))
+        for fn in ("input_crd.dat", "input_top.dat"):
+            with open(os.path.join(ex, fn)) as fi, open(os.path.join(tmp, fn), "w") as fo:
+                fo.write(fi.read())
+        env = dict(os.environ, PLUM_SEED="1", PLUM_TRACE=os.path.join(tmp, "trace.txt"))
+        with open(os.path.join(tmp, "run.in")) as fin, open(os.path.join(tmp, "run.log"), "w") as fout:
+            subprocess.check_call([replay.PLUM_GPU], stdin=fin, stdout=fout, cwd=tmp, env=env)
+        with open(os.path.join(tmp, "trace.txt")) as f:
+            got_lines = [ln for ln in f.read().split("\n") if ln.startswith("T")]
+        with open(os.path.join(tmp, "output_stat.dat")) as f:
+            got_stat = [ln.split() for ln in f.read().split("\n") if ln and not ln.startswith("#")]
+    assert len(got_lines) == len(ref_lines) == 230
+    for g, r_ in zip(got_lines, ref_lines):
+        g, r_ = g.split(), r_.split()
+        assert g[1:4] == r_[1:4] and g[5] == r_[5], (g[:6], r_[:6])     # step, move type, molecule, accept
+        a, b = replay.hx(g[4]), replay.hx(r_[4])
+        assert (a >= 1e8) == (b >= 1e8)
+        if b < 1e8:
+            assert abs(a - b) <= TOL * max(1.0, abs(b))
+    # mu column (6th) of the step-200 line
+    mu_got, mu_ref = float(got_stat[1][5]), float(ref_stat[1][5])
+    assert abs(mu_got - mu_ref) <= 1e-6 * abs(mu_ref), (mu_got, mu_ref)
