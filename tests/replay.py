@@ -35,7 +35,7 @@ def have_plum_gpu() -> bool:
 
 
 def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, binary: str = None,
-                 overrides: dict = None) -> List[str]:
+                 overrides: dict = None, want_files=()) -> List[str]:
     """Run a driver binary (default: the reference, oracle/_ref/plum_ref; or bin/plum_gpu) on an example
     (inputs copied to a temp dir) and return its trace lines.  `overrides` replaces run.in values by key."""
     binary = binary or PLUM_REF
@@ -61,7 +61,14 @@ def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, bina
         with open(os.path.join(tmp, "run.in")) as fin, open(os.path.join(tmp, "run.log"), "w") as fout:
             subprocess.check_call([binary], stdin=fin, stdout=fout, cwd=tmp, env=env)
         with open(os.path.join(tmp, "trace.txt")) as f:
-            return f.read().split("\n")
+            lines = f.read().split("\n")
+        if want_files:
+            extra = {}
+            for fn in want_files:
+                with open(os.path.join(tmp, fn)) as f:
+                    extra[fn] = f.read()
+            return lines, extra
+        return lines
 
 
 @dataclasses.dataclass
