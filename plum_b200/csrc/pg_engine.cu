@@ -497,16 +497,21 @@ int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
     }
     D.rc2_relaxed = P.rc2_relaxed; D.ljc2max = P.lj_rcut2_relaxed_max; D.recip_pref = P.recip_pref;
     D.dipole_pref = P.dipole_pref; D.beta = P.beta;
+    for (int i = 0; i < 3; i++) { D.half_box[i] = P.half_box[i]; D.real_cell[i] = P.real_cell[i]; D.same_box[i] = P.same_box[i]; }
+    D.real_cutoff = P.real_cutoff; D.rc_relaxed = P.rc_relaxed; D.lB = P.lB; D.sqrt_alpha = P.sqrt_alpha;
+    D.img_ny = (P.use_ewald && !h->fast) ? 2 * P.real_cell[1] + 1 : 1;
+    D.img_split = (P.use_ewald && !h->fast) ? (2 * P.real_cell[0] + 1) * D.img_ny : 1;
     D.pair_kind = P.pair_kind; D.use_ewald = P.use_ewald; D.dipole = P.dipole; D.bond_kind = P.bond_kind;
     D.ext_kind = P.ext_kind;
   }
-  A.n_tiles = std::max(1, (h->n + MV_THREADS - 1) / MV_THREADS);
+  A.n_tiles = (int)std::max<long long>(1, ((long long)h->n * A.D.img_split + MV_THREADS - 1) / MV_THREADS);
   const int slots = h->move_slots, n_sm = std::max(1, h->n_sm);
   const long long units = (long long)A.n_tiles * std::max(glen, 1);
   const long long npairs = (long long)glen * (glen - 1) / 2;
-  if (units >= (1LL << 31) || npairs >= (1LL << 31)) { h->err = "move too large for 32-bit work indexing"; return -1; }
+  if (units >= (1LL << 31) || npairs * A.D.img_split >= (1LL << 31)) { h->err = "move too large for 32-bit work indexing"; return -1; }
   const int nk = (h->P.use_ewald ? h->nk : 0);
-  const bool big = units >= (long long)(slots - n_sm);
+  // generic path: 2 CTAs/SM of multi-image work per unit, so helpers never get an SM each
+  const bool big = h->fast && units >= (long long)(slots - n_sm);
   int lpk = lanes_per_k(nq);
   int helpers;
   if (big) {
@@ -514,7 +519,7 @@ int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
   } else {
     // small move: as few helpers as hold the k slice (at >= 2 lanes per k) and the intra pairs
     helpers = (int)std::max<long long>(((long long)nk * lpk + MV_THREADS - 1) / MV_THREADS,
-                                       (npairs + MV_THREADS - 1) / MV_THREADS);
+                                       (npairs * A.D.img_split + MV_THREADS - 1) / MV_THREADS);
     helpers = std::min(std::max(helpers, (nk > 0 || npairs > 0) ? 1 : 0), n_sm);
   }
   if (helpers > 0) {
@@ -756,7 +761,8 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
     PG_CREATE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     // CTAs per SM one k_move grid may take (<= what fits): leaving a slot free lets the kernels of other
     // replicas (other engines / streams on the same GPU) co-run and hide each other's latencies
-    int use_per_sm = std::max(1, per_sm - 1);   // measured best: 3 of 4 (tools/sweep_ctas.sh)
+    // (fast path, measured best: 3 of 4, tools/sweep_ctas.sh).  The generic path runs small systems: take them all.
+    int use_per_sm = h->fast ? std::max(1, per_sm - 1) : std::max(1, per_sm);
     if (const char* e = getenv("PLUM_B200_CTAS_PER_SM")) use_per_sm = std::max(1, std::min(per_sm, atoi(e)));
     h->move_slots = std::max(1, use_per_sm * n_sm);
     h->n_sm = n_sm;

@@ -54,6 +54,10 @@ struct PgMoveDev {
   double box[3], inv_box[3], ebox[3], inv_ebox[3];
   double rc2_relaxed, ljc2max, recip_pref, dipole_pref, beta;
   float fbox[3];        // box lengths in FP32 for the pre-filter
+  // generic path (multi-image real space, padded slab box, hard spheres)
+  double half_box[3], real_cutoff, rc_relaxed, lB, sqrt_alpha;
+  int real_cell[3], same_box[3];
+  int img_split, img_ny;   // threads per partner = x-images * y-images, each runs the z column of its (ix, iy)
   int pbc[3];
   int pair_kind, use_ewald, dipole, bond_kind, ext_kind;
 };
@@ -151,12 +155,56 @@ __device__ __noinline__ double2 mv_pair_inrange(const PgDev* __restrict__ Pg, do
   return make_double2(e_lj, e_real);
 }
 
-__device__ __noinline__ double2 mv_pair_generic(const PgDev* __restrict__ Pg, double ax, double ay, double az,
-                                                double qa, int ta, double bx, double by, double bz, double qb, int tb,
-                                                int do_lj) {
-  double e_lj, e_real;
-  pg_pair_both(*Pg, ax, ay, az, qa, ta, bx, by, bz, qb, tb, do_lj, e_lj, e_real);
-  return make_double2(e_lj, e_real);
+// LJ / hard-sphere energy from the (folded) squared separation, tables from the global parameter copy.
+__device__ __noinline__ double mv_lj_r2(const PgDev* __restrict__ Pg, double l2, int tp) {
+  return pg_pair_energy_r(*Pg, sqrt(l2), tp);
+}
+
+// Generic exact path: one configuration of a pair (a = group bead, p = partner), restricted to ONE
+// column of periodic images (ix, iy fixed by `sub`, all iz) for the Ewald real-space term
+// (potential_ewald_coul.cc real-space image loops, pruned to the images that can reach the cutoff; the
+// reference's own `r <= real_cutoff` test decides).  Thread sub == 0 also owns the LJ / hard-sphere term
+// (BBDist with the |d| > L/2 fold).  Returns (pair energy, real-space energy).
+__device__ __forceinline__ double2 mv_generic_column(const PgMoveDev& P, const PgDev* __restrict__ Pg, double ax, double ay,
+                                                     double az, double px, double py, double pz, double qq, int tp,
+                                                     int sub, bool do_lj) {
+  const bool wx = P.pbc[0] != 0, wy = P.pbc[1] != 0, wz = P.pbc[2] != 0;
+  double e_lj = 0.0, e_re = 0.0;
+  // GetDistVector: partner - group bead, wrapped in the (padded) Ewald box
+  double dx = px - ax, dy = py - ay, dz = pz - az;
+  if (wx) dx -= P.ebox[0] * rint(dx * P.inv_ebox[0]);
+  if (wy) dy -= P.ebox[1] * rint(dy * P.inv_ebox[1]);
+  if (wz) dz -= P.ebox[2] * rint(dz * P.inv_ebox[2]);
+  if (sub == 0 && do_lj) {
+    double lx = dx, ly = dy, lz = dz;
+    if (!P.same_box[0]) lx = wx ? pg_wrap(ax - px, P.box[0], P.inv_box[0]) : ax - px;
+    if (!P.same_box[1]) ly = wy ? pg_wrap(ay - py, P.box[1], P.inv_box[1]) : ay - py;
+    if (!P.same_box[2]) lz = wz ? pg_wrap(az - pz, P.box[2], P.inv_box[2]) : az - pz;
+    if (wx && fabs(lx) > P.half_box[0]) lx = P.box[0] - fabs(lx);
+    if (wy && fabs(ly) > P.half_box[1]) ly = P.box[1] - fabs(ly);
+    if (wz && fabs(lz) > P.half_box[2]) lz = P.box[2] - fabs(lz);
+    const double l2 = lx * lx + ly * ly + lz * lz;
+    if (P.pair_kind == 2 || l2 <= P.ljc2max) e_lj = mv_lj_r2(Pg, l2, tp);
+  }
+  if (P.use_ewald && qq != 0.0) {
+    const int ix = sub / P.img_ny - P.real_cell[0], iy = sub % P.img_ny - P.real_cell[1];
+    const double rx = dx + ix * P.ebox[0], ry = dy + iy * P.ebox[1];
+    const double rxy2 = rx * rx + ry * ry;
+    const double rc2r = P.rc2_relaxed;
+    if (rxy2 <= rc2r) {
+      const double rcr = P.rc_relaxed, rc = P.real_cutoff, pref = P.lB * qq, sa = P.sqrt_alpha;
+      int k0 = (int)ceil((-rcr - dz) * P.inv_ebox[2]), k1 = (int)floor((rcr - dz) * P.inv_ebox[2]);
+      k0 = max(k0, -P.real_cell[2]); k1 = min(k1, P.real_cell[2]);
+      for (int k = k0; k <= k1; k++) {
+        const double rz = dz + k * P.ebox[2];
+        const double r2 = rxy2 + rz * rz;
+        if (r2 > rc2r) continue;
+        const double r = sqrt(r2);
+        if (r > 0 && r <= rc) e_re += pref * erfc(sa * r) / r;
+      }
+    }
+  }
+  return make_double2(e_lj, e_re);
 }
 
 // Evaluate this warp's queued in-range configurations, one per lane, and add them to the lane's
@@ -308,9 +356,12 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
   // the g == jj self-image term is identical before and after a move)
   if (b < A.n_helpers) {
     unsigned p0, p1;
-    mv_share((unsigned)(A.glen * (A.glen - 1) / 2), (unsigned)A.n_helpers, (unsigned)b, p0, p1);
+    // generic path: img_split threads per pair, one image column each
+    const int isplit = FAST ? 1 : P.img_split;
+    mv_share((unsigned)(A.glen * (A.glen - 1) / 2 * isplit), (unsigned)A.n_helpers, (unsigned)b, p0, p1);
     for (unsigned pp = p0 + tid; pp < p1; pp += MV_THREADS) {
-      const int p = (int)pp;
+      const int p = FAST ? (int)pp : (int)pp / isplit;
+      const int sub = FAST ? 0 : (int)pp - p * isplit;
       int jj = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
       while (jj * (jj - 1) / 2 > p) jj--;
       while ((jj + 1) * jj / 2 <= p) jj++;
@@ -351,8 +402,9 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
       } else {
         int lj_here = (P.pair_kind != 0);
         if (P.pair_kind == 2 && jj == g + 1) lj_here = 0;   // bonded hard spheres, potential_pair.cc:165-169
-        const double2 en = mv_pair_generic(A.Pg, anx, any_, anz, qa, ta, bnx, bny, bnz, qb, tb, lj_here);
-        const double2 eo = mv_pair_generic(A.Pg, aox, aoy, aoz, qa, ta, box_, boy, boz, qb, tb, lj_here);
+        const int tp = ta * PG_MAX_TYPES + tb;
+        const double2 en = mv_generic_column(P, A.Pg, anx, any_, anz, bnx, bny, bnz, qa * qb, tp, sub, lj_here != 0);
+        const double2 eo = mv_generic_column(P, A.Pg, aox, aoy, aoz, box_, boy, boz, qa * qb, tp, sub, lj_here != 0);
         lj_n = en.x; re_n = en.y; lj_o = eo.x; re_o = eo.y;
       }
       if (lj_n >= PG_VLE) acc_ov += 1.0;
@@ -382,7 +434,10 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
       const int gbeg = (int)(u - (unsigned)tile * (unsigned)A.glen);
       const int gcnt = min(min(A.glen - gbeg, MV_GCHUNK), (int)(u1 - u));
       // partner first: its loads are the longest dependency chain of the segment
-      const int j = tile * MV_THREADS + tid;
+      // FAST: one partner per thread.  Generic: img_split threads per partner, one (ix, iy) image column each.
+      const int slot = tile * MV_THREADS + tid;
+      const int j = FAST ? slot : slot / P.img_split;
+      const int sub = FAST ? 0 : slot - j * P.img_split;
       double px = 0, py = 0, pz = 0, pq = 0;
       int pt = 0;
       if (j < A.n) {
@@ -394,7 +449,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
         if (j >= pg0 && j < pg1) {
           px = ptrial[3 * (j - pg0)]; py = ptrial[3 * (j - pg0) + 1]; pz = ptrial[3 * (j - pg0) + 2];
         }
-        if (gbeg == 0) acc_mz += pq * pz;   // each tile's dipole moment is counted by the segment that starts it
+        if (gbeg == 0 && sub == 0) acc_mz += pq * pz;   // each partner's dipole moment is counted once: by the segment that starts its tile
       }
       if (!first) __syncthreads();   // previous segment's shared staging is still being read
       first = false;
@@ -528,10 +583,14 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveA
           }
         }
       } else if (valid) {
+        // Generic exact path (all four reference examples): this thread owns one column of periodic
+        // images of its partner, thread sub == 0 also the LJ / hard-sphere term.
         for (int i = 0; i < gcnt; i++) {
           if (!s_mv[i]) continue;
-          const double2 en = mv_pair_generic(A.Pg, s_n[0][i], s_n[1][i], s_n[2][i], s_q[i], s_t[i], px, py, pz, pq, pt, do_lj);
-          const double2 eo = mv_pair_generic(A.Pg, s_o[0][i], s_o[1][i], s_o[2][i], s_q[i], s_t[i], px, py, pz, pq, pt, do_lj);
+          const double qq = s_q[i] * pq;
+          const int tp = s_t[i] * PG_MAX_TYPES + pt;
+          const double2 en = mv_generic_column(P, A.Pg, s_n[0][i], s_n[1][i], s_n[2][i], px, py, pz, qq, tp, sub, do_lj != 0);
+          const double2 eo = mv_generic_column(P, A.Pg, s_o[0][i], s_o[1][i], s_o[2][i], px, py, pz, qq, tp, sub, do_lj != 0);
           if (en.x >= PG_VLE) acc_ov += 1.0;
           acc_pair += (en.x - eo.x);
           acc_real += (en.y - eo.y);

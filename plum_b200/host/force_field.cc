@@ -23,6 +23,8 @@
 #include "../utilities/misc.h"
 #include "plum_b200.h"
 
+#include <cstdlib>
+#include <ctime>
 using namespace std;
 
 // Set by the driver's trace hook build (plum_b200/host/driver_hooks.py); harmless otherwise.
@@ -30,11 +32,36 @@ double plum_trace_weight __attribute__((weak)) = -1;
 
 namespace {
 double Uniform(mt19937& g) { return (double)g() / g.max(); }
+
+// PLUM_B200_PROFILE=1: wall time spent inside each ABI entry point, printed to stderr at exit.
+enum { kTDelta, kTCommit, kTTrials, kTInsert, kTDelete, kTTotals, kTSites };
+const char* const kSiteName[kTSites] = {"pg_delta_e", "pg_commit", "pg_trial_energies", "pg_insert_molecules",
+                                        "pg_delete_molecules", "pg_get_totals"};
+bool prof_on = getenv("PLUM_B200_PROFILE") != NULL;
+double prof_s[kTSites];
+long prof_n[kTSites];
+struct SiteTimer {
+  int site;
+  timespec t0;
+  explicit SiteTimer(int s) : site(s) { if (prof_on) clock_gettime(CLOCK_MONOTONIC, &t0); }
+  ~SiteTimer() {
+    if (!prof_on) return;
+    timespec t1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    prof_s[site] += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    prof_n[site]++;
+  }
+};
 }  // namespace
 
 ForceField::ForceField() : engine(NULL), pending_mol(-1) {}
 
 ForceField::~ForceField() {
+  if (prof_on)
+    for (int i = 0; i < kTSites; i++)
+      if (prof_n[i])
+        cerr << "plum_b200 profile: " << kSiteName[i] << " calls " << prof_n[i] << " total " << prof_s[i] << " s, "
+             << 1e6 * prof_s[i] / prof_n[i] << " us/call" << endl;
   if (engine) pg_destroy(engine);
 }
 
@@ -378,7 +405,8 @@ double ForceField::EnergyDifference(vector<Molecule>& mols, int moved_mol) {
     moved[i] = m.bds[i].GetMoved() ? 1 : 0;
   }
   pg_delta d;
-  int rc = pg_delta_e(engine, moved_mol, trial.data(), moved.data(), &d);
+  int rc;
+  { SiteTimer st_(kTDelta); rc = pg_delta_e(engine, moved_mol, trial.data(), moved.data(), &d); }
   if (rc) Fail("pg_delta_e", rc);
   pending_mol = moved_mol;
   return d.dE;
@@ -387,7 +415,8 @@ double ForceField::EnergyDifference(vector<Molecule>& mols, int moved_mol) {
 void ForceField::FinalizeEnergies(vector<Molecule>& mols, bool accept, int moved_mol) {
   (void)mols;
   if (pending_mol != moved_mol) return;   // EnergyDifference was skipped by the driver
-  int rc = pg_commit(engine, accept ? 1 : 0);
+  int rc;
+  { SiteTimer st_(kTCommit); rc = pg_commit(engine, accept ? 1 : 0); }
   if (rc) Fail("pg_commit", rc);
   pending_mol = -1;
 }
@@ -422,7 +451,8 @@ void ForceField::TrialEnergies(int n_trials, const double* b1, const double* b2,
     cx[3 * i + 2] = b.GetCrd(1, 2);
     cq[i] = b.Charge();
   }
-  int rc = pg_trial_energies(engine, &set, b1, b2, cx.data(), cq.data(), ct.data(), energy_out, NULL, NULL);
+  int rc;
+  { SiteTimer st_(kTTrials); rc = pg_trial_energies(engine, &set, b1, b2, cx.data(), cq.data(), ct.data(), energy_out, NULL, NULL); }
   if (rc) Fail("pg_trial_energies", rc);
 }
 
@@ -573,7 +603,8 @@ void ForceField::EnergyInitForAddedMolecule(vector<Molecule>& mols) {
       type.push_back(TypeId(b.Symbol()));
     }
   }
-  int rc = pg_insert_molecules(engine, added, lens.data(), xyz.data(), q.data(), type.data(), NULL);
+  int rc;
+  { SiteTimer st_(kTInsert); rc = pg_insert_molecules(engine, added, lens.data(), xyz.data(), q.data(), type.data(), NULL); }
   if (rc) Fail("pg_insert_molecules", rc);
 }
 
@@ -647,7 +678,8 @@ int ForceField::CBMCFChainDeletion(vector<Molecule>& mols, mt19937& rand_gen) {
     // Monovalent counter-ions, as the reference assumes (potential_pair.cc:251-255).
     int counterion = 0;
     for (int i = 0; i < mols[delete_id].Size(); i++) counterion += (int)abs(round(mols[delete_id].bds[i].Charge()));
-    int rc = pg_delete_molecules(engine, delete_id, delete_id + counterion, NULL);
+    int rc;
+    { SiteTimer st_(kTDelete); rc = pg_delete_molecules(engine, delete_id, delete_id + counterion, NULL); }
     if (rc) Fail("pg_delete_molecules", rc);
     return delete_id;
   }
@@ -743,25 +775,29 @@ bool ForceField::UseExtPot() { return use_ext_pot; }
 
 double ForceField::TotPairEnergy() {
   pg_totals t;
-  int rc = pg_get_totals(engine, &t);
+  int rc;
+  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
   if (rc) Fail("pg_get_totals", rc);
   return t.pair;
 }
 double ForceField::TotEwaldEnergy() {
   pg_totals t;
-  int rc = pg_get_totals(engine, &t);
+  int rc;
+  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
   if (rc) Fail("pg_get_totals", rc);
   return t.ewald;
 }
 double ForceField::TotBondEnergy() {
   pg_totals t;
-  int rc = pg_get_totals(engine, &t);
+  int rc;
+  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
   if (rc) Fail("pg_get_totals", rc);
   return t.bond;
 }
 double ForceField::TotExtEnergy() {
   pg_totals t;
-  int rc = pg_get_totals(engine, &t);
+  int rc;
+  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
   if (rc) Fail("pg_get_totals", rc);
   return t.ext;
 }
