@@ -27,6 +27,7 @@
 #include "../../include/plum_b200.h"
 #include "pg_kernels.cu"
 #include "pg_move.cu"
+#include "pg_trials.cu"
 
 namespace {
 
@@ -70,7 +71,7 @@ struct pg_engine {
   double4* d_kvec = nullptr;
   int* d_kl = nullptr;
   double* d_ek2 = nullptr;
-  double2 *d_S = nullptr, *d_dS = nullptr, *d_Sp = nullptr, *d_Stmp = nullptr;
+  double2 *d_S = nullptr, *d_dS = nullptr, *d_Stmp = nullptr;
 
   // group staging: two pinned + two device blocks (ping-pong: the previous trial's block must
   // stay intact until its deferred commit has been applied by the next k_move launch)
@@ -115,11 +116,15 @@ struct pg_engine {
   bool pend_on_device = true;
 
   // CBMC staging
-  int tcap = 0;       // trials capacity
-  int ccap = 0;       // chain capacity
-  double *h_trial_in = nullptr, *d_trial_in = nullptr;    // b1 | b2 | chain_xyz | chain_q
+  // k_trials: staging for growth steps too large for the kernel parameters, partial sums, mailbox
+  int ccap = 0;       // chain capacity of the staging block
+  double *h_trial_in = nullptr, *d_trial_in = nullptr;    // b1[3 TR_MAXT] | b2[3 TR_MAXT] | chain_xyz[3 ccap] | chain_q[ccap]
   int *h_trial_ct = nullptr, *d_trial_ct = nullptr;
-  double *h_trial_out = nullptr, *d_trial_out = nullptr;  // energy | pair | ewald
+  double2* d_tr_partial = nullptr; size_t tr_partial_cap = 0;
+  double* d_tr_mz = nullptr; size_t tr_mz_cap = 0;
+  unsigned int* d_tr_counter = nullptr;
+  PgMailRec *h_tmail = nullptr, *d_tmail = nullptr;       // mapped, [3 TR_MAXT]
+  int trial_slots = 0;                                    // resident k_trials CTAs
 
   // replay
   std::vector<ReplayMove> rp_moves;
@@ -256,6 +261,8 @@ void ewald_setup(pg_engine* h, const pg_params* p) {
   for (int i = 0; i < 3; i++)
     if (!(P.rc_relaxed < 0.5 * box_l[i] * (1.0 - 1e-9))) single = false;
   P.single_image = single ? 1 : 0;
+  // a bead's own periodic images: position independent, so summed once here (potential_ewald.cc self-image term)
+  P.real_self_unit = 0.5 * pg_pair_real_d(P, 0.0, 0.0, 0.0, 1.0);
 }
 
 int build_params(pg_engine* h, const pg_params* p) {
@@ -486,24 +493,28 @@ int launch_commit(pg_engine* h, int accept_flag, int mode, int g0, int glen, con
 // come first in block-index order — for a big move exactly one per SM — and share the reciprocal part
 // (lanes-per-k chosen so a helper's k slice fits its threads in one pass whenever possible) and the
 // intra-molecular pairs; the remaining CTAs split the (partner tile x moved bead) units evenly.
-int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
-  {
-    const PgDev& P = h->P;
-    PgMoveDev& D = A.D;
-    for (int i = 0; i < 3; i++) {
-      D.box[i] = P.box[i]; D.inv_box[i] = P.inv_box[i]; D.ebox[i] = P.ebox[i]; D.inv_ebox[i] = P.inv_ebox[i];
-      D.pbc[i] = P.pbc[i];
-      D.fbox[i] = (float)P.box[i];
-    }
-    D.rc2_relaxed = P.rc2_relaxed; D.ljc2max = P.lj_rcut2_relaxed_max; D.recip_pref = P.recip_pref;
-    D.dipole_pref = P.dipole_pref; D.beta = P.beta;
-    for (int i = 0; i < 3; i++) { D.half_box[i] = P.half_box[i]; D.real_cell[i] = P.real_cell[i]; D.same_box[i] = P.same_box[i]; }
-    D.real_cutoff = P.real_cutoff; D.rc_relaxed = P.rc_relaxed; D.lB = P.lB; D.sqrt_alpha = P.sqrt_alpha;
-    D.img_ny = (P.use_ewald && !h->fast) ? 2 * P.real_cell[1] + 1 : 1;
-    D.img_split = (P.use_ewald && !h->fast) ? (2 * P.real_cell[0] + 1) * D.img_ny : 1;
-    D.pair_kind = P.pair_kind; D.use_ewald = P.use_ewald; D.dipole = P.dipole; D.bond_kind = P.bond_kind;
-    D.ext_kind = P.ext_kind;
+// The by-value scalar block of k_move / k_trials.
+void fill_move_dev(const pg_engine* h, PgMoveDev& D) {
+  const PgDev& P = h->P;
+  for (int i = 0; i < 3; i++) {
+    D.box[i] = P.box[i]; D.inv_box[i] = P.inv_box[i]; D.ebox[i] = P.ebox[i]; D.inv_ebox[i] = P.inv_ebox[i];
+    D.pbc[i] = P.pbc[i];
+    D.fbox[i] = (float)P.box[i];
+    D.half_box[i] = P.half_box[i]; D.same_box[i] = P.same_box[i];
   }
+  D.rc2_relaxed = P.rc2_relaxed; D.ljc2max = P.lj_rcut2_relaxed_max; D.recip_pref = P.recip_pref;
+  D.dipole_pref = P.dipole_pref; D.beta = P.beta;
+  D.real_cutoff = P.real_cutoff; D.rc_relaxed = P.rc_relaxed; D.lB = P.lB; D.sqrt_alpha = P.sqrt_alpha;
+  const bool multi = P.use_ewald && !P.single_image;
+  D.img_cx = multi ? P.real_cell[0] : 0; D.img_cy = multi ? P.real_cell[1] : 0; D.img_cz = multi ? P.real_cell[2] : 0;
+  D.img_ny = 2 * D.img_cy + 1;
+  D.img_split = (2 * D.img_cx + 1) * D.img_ny;
+  D.pair_kind = P.pair_kind; D.use_ewald = P.use_ewald; D.dipole = P.dipole; D.bond_kind = P.bond_kind;
+  D.ext_kind = P.ext_kind;
+}
+
+int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
+  fill_move_dev(h, A.D);
   A.n_tiles = (int)std::max<long long>(1, ((long long)h->n * A.D.img_split + MV_THREADS - 1) / MV_THREADS);
   const int slots = h->move_slots, n_sm = std::max(1, h->n_sm);
   const long long units = (long long)A.n_tiles * std::max(glen, 1);
@@ -669,7 +680,7 @@ int compute_totals(pg_engine* h, bool set_state, pg_totals* out) {
 void free_all(pg_engine* h) {
   cudaFree(h->xy); cudaFree(h->zq); cudaFree(h->type); cudaFree(h->mol);
   cudaFree(h->t_xy); cudaFree(h->t_zq); cudaFree(h->t_type); cudaFree(h->t_mol);
-  cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_kvec); cudaFree(h->d_S); cudaFree(h->d_dS); cudaFree(h->d_Sp); cudaFree(h->d_Stmp);
+  cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_kvec); cudaFree(h->d_S); cudaFree(h->d_dS); cudaFree(h->d_Stmp);
   for (int s = 0; s < 2; s++) {
     if (h->h_stage2[s]) cudaFreeHost(h->h_stage2[s]);
     cudaFree(h->d_stage2[s]);
@@ -682,8 +693,8 @@ void free_all(pg_engine* h) {
   if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
   if (h->h_trial_ct) cudaFreeHost(h->h_trial_ct);
-  if (h->h_trial_out) cudaFreeHost(h->h_trial_out);
-  cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_trial_out);
+  if (h->h_tmail) cudaFreeHost(h->h_tmail);
+  cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_tr_partial); cudaFree(h->d_tr_mz); cudaFree(h->d_tr_counter);
   cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
   for (auto& g : h->rp_graphs) cudaGraphExecDestroy(g.exec);
   h->rp_graphs.clear();
@@ -767,6 +778,16 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
     h->move_slots = std::max(1, use_per_sm * n_sm);
     h->n_sm = n_sm;
   }
+  {
+    int per_sm = 0;
+    PG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trials, TR_THREADS, 0));
+    h->trial_slots = std::max(1, per_sm) * std::max(1, h->n_sm);
+    PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_tmail, sizeof(PgMailRec) * 3 * TR_MAXT, cudaHostAllocMapped));
+    memset((void*)h->h_tmail, 0, sizeof(PgMailRec) * 3 * TR_MAXT);
+    PG_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_tmail, (void*)h->h_tmail, 0));
+    PG_CREATE_CUDA(cudaMalloc((void**)&h->d_tr_counter, sizeof(unsigned int)));
+    PG_CREATE_CUDA(cudaMemset(h->d_tr_counter, 0, sizeof(unsigned int)));
+  }
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_out8, sizeof(double) * 8));
   PG_CREATE_CUDA(cudaHostAlloc((void**)&h->h_out8, sizeof(double) * 8, cudaHostAllocDefault));
   int nk_alloc = std::max(h->nk, 1);
@@ -775,7 +796,6 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_kvec, sizeof(double4) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_S, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_dS, sizeof(double2) * (size_t)nk_alloc));
-  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_Sp, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_Stmp, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMemset(h->d_S, 0, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMemset(h->d_dS, 0, sizeof(double2) * (size_t)nk_alloc));
@@ -1157,43 +1177,8 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
     h->err = "trial bead type id out of range";
     return PG_ERR_INVALID;
   }
-  PG_CUDA(h, cudaSetDevice(h->device));
-  { int frc_ = flush_commit(h); if (frc_) return frc_; }
-  if (nt > h->tcap || n_chain > h->ccap) {
-    int tcap = std::max(64, nt * 2), ccap = std::max(64, n_chain * 2);
-    if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
-    if (h->h_trial_ct) cudaFreeHost(h->h_trial_ct);
-    if (h->h_trial_out) cudaFreeHost(h->h_trial_out);
-    cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_trial_out);
-    h->h_trial_in = nullptr; h->h_trial_ct = nullptr; h->h_trial_out = nullptr;
-    h->d_trial_in = nullptr; h->d_trial_ct = nullptr; h->d_trial_out = nullptr;
-    size_t in_d = (size_t)tcap * 6 + (size_t)ccap * 4;
-    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_in, sizeof(double) * in_d, cudaHostAllocDefault));
-    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_in, sizeof(double) * in_d));
-    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_ct, sizeof(int) * (size_t)ccap, cudaHostAllocDefault));
-    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_ct, sizeof(int) * (size_t)ccap));
-    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_out, sizeof(double) * 3 * (size_t)tcap, cudaHostAllocDefault));
-    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_out, sizeof(double) * 3 * (size_t)tcap));
-    h->tcap = tcap; h->ccap = ccap;
-  }
-  const int tcap = h->tcap, ccap = h->ccap;
-  double* hb1 = h->h_trial_in;
-  double* hb2 = hb1 + 3 * (size_t)tcap;
-  double* hcx = hb2 + 3 * (size_t)tcap;
-  double* hcq = hcx + 3 * (size_t)ccap;
-  memcpy(hb1, bead1_xyz, sizeof(double) * 3 * (size_t)nt);
-  if (use2) memcpy(hb2, bead2_xyz, sizeof(double) * 3 * (size_t)nt);
-  for (int i = 0; i < n_chain; i++) {
-    hcx[3 * i] = chain_xyz[3 * i]; hcx[3 * i + 1] = chain_xyz[3 * i + 1]; hcx[3 * i + 2] = chain_xyz[3 * i + 2];
-    hcq[i] = chain_q[i];
+  for (int i = 0; i < n_chain; i++)
     if (chain_type[i] < 0 || chain_type[i] >= h->P.n_types) { h->err = "chain type id out of range"; return PG_ERR_INVALID; }
-    h->h_trial_ct[i] = chain_type[i];
-  }
-  size_t in_d = (size_t)tcap * 6 + (size_t)ccap * 4;
-  PG_CUDA(h, cudaMemcpyAsync(h->d_trial_in, h->h_trial_in, sizeof(double) * in_d, cudaMemcpyHostToDevice, h->stream));
-  if (n_chain > 0)
-    PG_CUDA(h, cudaMemcpyAsync(h->d_trial_ct, h->h_trial_ct, sizeof(int) * (size_t)n_chain, cudaMemcpyHostToDevice,
-                               h->stream));
   int skip_b0 = 0, skip_b1 = 0;
   if (set->skip_mol_first >= 0) {
     if (set->skip_mol_last < set->skip_mol_first || set->skip_mol_last >= h->n_mol) {
@@ -1203,32 +1188,120 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
     skip_b0 = h->mol_first[set->skip_mol_first];
     skip_b1 = h->mol_first[set->skip_mol_last + 1];
   }
-  double* db1 = h->d_trial_in;
-  double* db2 = db1 + 3 * (size_t)tcap;
-  double* dcx = db2 + 3 * (size_t)tcap;
-  double* dcq = dcx + 3 * (size_t)ccap;
-  if (h->P.use_ewald && h->nk > 0) {
-    k_sprime<<<(h->nk + PG_TILE - 1) / PG_TILE, PG_TILE, 0, h->stream>>>(h->P, h->d_S, h->d_kl, h->nk, h->xy, h->zq,
-                                                                        skip_b0, skip_b1, dcx, dcq, n_chain, h->d_Sp);
-    h->launches++;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
+  // small growth steps ride in the kernel parameters; larger ones are staged (chain once, trials per chunk)
+  const bool inl = (nt <= TR_INL_T && n_chain <= TR_INL_C);
+  if (!inl && (!h->h_trial_in || n_chain > h->ccap)) {
+    const int ccap = std::max(64, n_chain * 2);
+    if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
+    if (h->h_trial_ct) cudaFreeHost(h->h_trial_ct);
+    cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct);
+    h->h_trial_in = nullptr; h->h_trial_ct = nullptr; h->d_trial_in = nullptr; h->d_trial_ct = nullptr;
+    h->ccap = 0;
+    const size_t in_d = (size_t)6 * TR_MAXT + (size_t)ccap * 4;
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_in, sizeof(double) * in_d, cudaHostAllocDefault));
+    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_in, sizeof(double) * in_d));
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_trial_ct, sizeof(int) * (size_t)ccap, cudaHostAllocDefault));
+    PG_CUDA(h, cudaMalloc((void**)&h->d_trial_ct, sizeof(int) * (size_t)ccap));
+    h->ccap = ccap;
   }
   PgTrialArgs A;
   memset(&A, 0, sizeof(A));
+  fill_move_dev(h, A.D);
   A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n = h->n;
   A.skip_b0 = skip_b0; A.skip_b1 = skip_b1;
-  A.b1 = db1; A.b2 = db2; A.use_b2 = use2; A.t1 = set->type1; A.t2 = set->type2; A.q1 = set->q1; A.q2 = use2 ? set->q2 : 0.0;
-  A.chain_xyz = dcx; A.chain_q = dcq; A.chain_type = h->d_trial_ct; A.current_len = cl;
-  A.kl = h->d_kl; A.ek2 = h->d_ek2; A.Sp = h->d_Sp; A.nk = h->P.use_ewald ? h->nk : 0;
-  A.out_energy = h->d_trial_out; A.out_pair = h->d_trial_out + tcap; A.out_ewald = h->d_trial_out + 2 * (size_t)tcap;
-  k_trials<<<nt, PG_TILE, 0, h->stream>>>(h->P, A);
-  h->launches++;
-  PG_CUDA(h, cudaGetLastError());
-  PG_CUDA(h, cudaMemcpyAsync(h->h_trial_out, h->d_trial_out, sizeof(double) * 3 * (size_t)tcap, cudaMemcpyDeviceToHost,
-                             h->stream));
-  PG_CUDA(h, cudaStreamSynchronize(h->stream));
-  memcpy(out_energy, h->h_trial_out, sizeof(double) * (size_t)nt);
-  if (out_pair) memcpy(out_pair, h->h_trial_out + tcap, sizeof(double) * (size_t)nt);
-  if (out_ewald) memcpy(out_ewald, h->h_trial_out + 2 * (size_t)tcap, sizeof(double) * (size_t)nt);
+  A.nc = n_chain; A.current_len = cl; A.use_b2 = use2; A.t1 = set->type1; A.t2 = set->type2;
+  A.q1 = set->q1; A.q2 = use2 ? set->q2 : 0.0;
+  A.inl = inl ? 1 : 0;
+  A.kvec = h->d_kvec; A.S = h->d_S; A.nk = (h->P.use_ewald ? h->nk : 0);
+  A.counter = h->d_tr_counter; A.mail = h->d_tmail; A.Pg = h->d_P;
+  const size_t ccap = (size_t)h->ccap;
+  if (inl) {
+    for (int i = 0; i < n_chain; i++) {
+      A.inl_cxyz[3 * i] = chain_xyz[3 * i]; A.inl_cxyz[3 * i + 1] = chain_xyz[3 * i + 1]; A.inl_cxyz[3 * i + 2] = chain_xyz[3 * i + 2];
+      A.inl_cq[i] = chain_q[i]; A.inl_ct[i] = chain_type[i];
+    }
+  } else {
+    double* hcx = h->h_trial_in + 6 * TR_MAXT;
+    double* hcq = hcx + 3 * ccap;
+    if (n_chain > 0) {
+      memcpy(hcx, chain_xyz, sizeof(double) * 3 * (size_t)n_chain);
+      memcpy(hcq, chain_q, sizeof(double) * (size_t)n_chain);
+      memcpy(h->h_trial_ct, chain_type, sizeof(int) * (size_t)n_chain);
+      PG_CUDA(h, cudaMemcpyAsync(h->d_trial_in + 6 * TR_MAXT, hcx, sizeof(double) * 4 * ccap, cudaMemcpyHostToDevice, h->stream));
+      PG_CUDA(h, cudaMemcpyAsync(h->d_trial_ct, h->h_trial_ct, sizeof(int) * (size_t)n_chain, cudaMemcpyHostToDevice, h->stream));
+    }
+    A.b1 = h->d_trial_in; A.b2 = h->d_trial_in + 3 * TR_MAXT;
+    A.cxyz = h->d_trial_in + 6 * TR_MAXT; A.cq = A.cxyz + 3 * ccap; A.ctype = h->d_trial_ct;
+  }
+  const int n_sm = std::max(1, h->n_sm);
+  const long long slots_all = (long long)(h->n + n_chain) * A.D.img_split;
+  if (slots_all >= (1LL << 31) / TR_MAXT) { h->err = "growth step too large for 32-bit work indexing"; return PG_ERR_CAPACITY; }
+  A.n_tiles = (int)std::max<long long>(1, (slots_all + TR_THREADS - 1) / TR_THREADS);
+  for (int t0 = 0; t0 < nt; t0 += TR_MAXT) {
+    const int ntc = std::min(TR_MAXT, nt - t0);
+    A.nt = ntc;
+    if (inl) {
+      memcpy(A.inl_b1, bead1_xyz + 3 * (size_t)t0, sizeof(double) * 3 * (size_t)ntc);
+      if (use2) memcpy(A.inl_b2, bead2_xyz + 3 * (size_t)t0, sizeof(double) * 3 * (size_t)ntc);
+    } else {
+      memcpy(h->h_trial_in, bead1_xyz + 3 * (size_t)t0, sizeof(double) * 3 * (size_t)ntc);
+      if (use2) memcpy(h->h_trial_in + 3 * TR_MAXT, bead2_xyz + 3 * (size_t)t0, sizeof(double) * 3 * (size_t)ntc);
+      PG_CUDA(h, cudaMemcpyAsync(h->d_trial_in, h->h_trial_in, sizeof(double) * 6 * TR_MAXT, cudaMemcpyHostToDevice, h->stream));
+    }
+    // lanes per k vector: enough for the longer of the two term lists (S' terms, trials)
+    int lpk = TR_MIN_LPK;
+    while (lpk < 32 && lpk < std::max(skip_b1 - skip_b0 + n_chain, ntc)) lpk <<= 1;
+    int helpers = A.nk > 0 ? (int)std::min<long long>(n_sm, ((long long)A.nk * lpk + TR_THREADS - 1) / TR_THREADS) : 0;
+    A.lpk = lpk; A.n_helpers = helpers;
+    const long long units = (long long)A.n_tiles * ntc;
+    A.n_pair_ctas = (int)std::max(1LL, std::min(units, (long long)std::max(1, h->trial_slots - helpers)));
+    const size_t need = (size_t)(helpers + A.n_tiles) * (size_t)ntc;
+    if (need > h->tr_partial_cap) {
+      cudaFree(h->d_tr_partial); h->d_tr_partial = nullptr; h->tr_partial_cap = 0;
+      PG_CUDA(h, cudaMalloc((void**)&h->d_tr_partial, sizeof(double2) * need * 2));
+      h->tr_partial_cap = need * 2;
+    }
+    if ((size_t)A.n_tiles > h->tr_mz_cap) {
+      cudaFree(h->d_tr_mz); h->d_tr_mz = nullptr; h->tr_mz_cap = 0;
+      PG_CUDA(h, cudaMalloc((void**)&h->d_tr_mz, sizeof(double) * (size_t)A.n_tiles * 2));
+      h->tr_mz_cap = (size_t)A.n_tiles * 2;
+    }
+    A.partial = h->d_tr_partial; A.mz_partial = h->d_tr_mz;
+    A.seq = ++h->seq;
+    k_trials<<<helpers + A.n_pair_ctas, TR_THREADS, 0, h->stream>>>(A);
+    h->launches++;
+    PG_CUDA(h, cudaGetLastError());
+    // wait for the 3 ntc self-validating records
+    volatile PgMailRec* m = h->h_tmail;
+    auto w0 = std::chrono::steady_clock::now();
+    unsigned long spins = 0;
+    for (int r = 0; r < 3 * ntc; r++) {
+      double v;
+      for (;;) {
+        if (m[r].seq == A.seq) {
+          v = m[r].value;
+          if (m[r].seq == A.seq) break;
+        }
+        if ((++spins & 0xfffff) == 0) {
+          cudaError_t q = cudaStreamQuery(h->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) {
+            h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
+            return PG_ERR_CUDA;
+          }
+          if (std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count() > 30.0) {
+            h->err = "device did not answer within 30 s";
+            return PG_ERR_TIMEOUT;
+          }
+        }
+      }
+      const int t = t0 + r / 3;
+      if (r % 3 == 0) out_energy[t] = v;
+      else if (r % 3 == 1) { if (out_pair) out_pair[t] = v; }
+      else if (out_ewald) out_ewald[t] = v;
+    }
+  }
   return PG_OK;
 }
 

@@ -572,148 +572,6 @@ __global__ void __launch_bounds__(256) k_tot_final(const PgDev P, const double2*
   }
 }
 
-// ------------------------------------------------------------------ k_sprime
-// S'(k) = S(k) - sum_{skipped beads} q e^{ik.r} + sum_{partial chain} q e^{ik.r}: the
-// structure factor of the partners one CBMC growth step sees (cbmc.cc:22-90).
-__global__ void __launch_bounds__(PG_TILE) k_sprime(const PgDev P, const double2* __restrict__ S,
-                                                    const int* __restrict__ kl, int nk,
-                                                    const double2* __restrict__ xy, const double2* __restrict__ zq,
-                                                    int skip_b0, int skip_b1, const double* __restrict__ chain_xyz,
-                                                    const double* __restrict__ chain_q, int n_chain, double2* Sp) {
-  const int k = blockIdx.x * PG_TILE + threadIdx.x;
-  if (k >= nk) return;
-  const int4 l = reinterpret_cast<const int4*>(kl)[k];
-  const double kPi = 3.14159265359;
-  const double kx = l.x * 2 * kPi / P.ebox[0], ky = l.y * 2 * kPi / P.ebox[1], kz = l.z * 2 * kPi / P.ebox[2];
-  double2 s = S[k];
-  for (int i = skip_b0; i < skip_b1; i++) {
-    double2 a = xy[i], c = zq[i];
-    if (c.y == 0) continue;
-    double sn, cs;
-    sincos(kx * pg_wrap_pos(a.x, P.ebox[0], P.inv_ebox[0], P.pbc[0]) +
-           ky * pg_wrap_pos(a.y, P.ebox[1], P.inv_ebox[1], P.pbc[1]) +
-           kz * pg_wrap_pos(c.x, P.ebox[2], P.inv_ebox[2], P.pbc[2]), &sn, &cs);
-    s.x -= c.y * cs; s.y -= c.y * sn;
-  }
-  for (int i = 0; i < n_chain; i++) {
-    const double q = chain_q[i];
-    if (q == 0) continue;
-    double sn, cs;
-    sincos(kx * pg_wrap_pos(chain_xyz[3 * i], P.ebox[0], P.inv_ebox[0], P.pbc[0]) +
-           ky * pg_wrap_pos(chain_xyz[3 * i + 1], P.ebox[1], P.inv_ebox[1], P.pbc[1]) +
-           kz * pg_wrap_pos(chain_xyz[3 * i + 2], P.ebox[2], P.inv_ebox[2], P.pbc[2]), &sn, &cs);
-    s.x += q * cs; s.y += q * sn;
-  }
-  Sp[k] = s;
-}
-
-// ------------------------------------------------------------------ k_trials
-// ForceField::BeadsEnergy (cbmc.cc:5-151) for a batch: one CTA per trial
-// (monomer bead1 + optional counter-ion bead2) against all resident beads except
-// [skip_b0, skip_b1), the partial chain, each other, the walls, and reciprocal space
-// through S'(k).  out: energy, pair_e, ewald_e per trial.
-struct PgTrialArgs {
-  const double2* xy; const double2* zq; const int* type; int n;
-  int skip_b0, skip_b1;
-  const double* b1; const double* b2;   // [n_trials][3]
-  int use_b2, t1, t2; double q1, q2;
-  const double* chain_xyz; const double* chain_q; const int* chain_type; int current_len;  // monomers then ions
-  const int* kl; const double* ek2; const double2* Sp; int nk;
-  double* out_energy; double* out_pair; double* out_ewald;
-};
-
-__global__ void __launch_bounds__(PG_TILE) k_trials(const PgDev P, const PgTrialArgs A) {
-  __shared__ double s_red[8 * 32];
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const double x1 = A.b1[3 * t], y1 = A.b1[3 * t + 1], z1 = A.b1[3 * t + 2];
-  double x2 = 0, y2 = 0, z2 = 0;
-  if (A.use_b2) { x2 = A.b2[3 * t]; y2 = A.b2[3 * t + 1]; z2 = A.b2[3 * t + 2]; }
-  const int do_lj = (P.pair_kind != 0);
-  double e_lj = 0.0, e_re = 0.0, mz_o = 0.0, e_rec = 0.0;
-  // resident partners
-  for (int j = tid; j < A.n; j += PG_TILE) {
-    if (j >= A.skip_b0 && j < A.skip_b1) continue;
-    const double2 a = A.xy[j], c = A.zq[j];
-    const int pt = A.type[j];
-    double lj, re;
-    pg_pair_both(P, x1, y1, z1, A.q1, A.t1, a.x, a.y, c.x, c.y, pt, do_lj, lj, re);
-    e_lj += lj; e_re += re;
-    if (A.use_b2) {
-      pg_pair_both(P, x2, y2, z2, A.q2, A.t2, a.x, a.y, c.x, c.y, pt, do_lj, lj, re);
-      e_lj += lj; e_re += re;
-    }
-    mz_o += c.y * c.x;
-  }
-  // partial chain: current_len monomers then (if use_b2) current_len ions
-  const int n_chain = A.current_len * (A.use_b2 ? 2 : 1);
-  for (int i = tid; i < n_chain; i += PG_TILE) {
-    const double cx = A.chain_xyz[3 * i], cy = A.chain_xyz[3 * i + 1], cz = A.chain_xyz[3 * i + 2];
-    const double cq = A.chain_q[i];
-    const int ct = A.chain_type[i];
-    const bool is_monomer = i < A.current_len;
-    // LJ with the bonded neighbour (last grown monomer) is skipped for bead1 only (cbmc.cc:57-58)
-    const int lj1 = do_lj && !(is_monomer && i == A.current_len - 1);
-    double lj, re;
-    pg_pair_both(P, x1, y1, z1, A.q1, A.t1, cx, cy, cz, cq, ct, lj1, lj, re);
-    e_lj += lj; e_re += re;
-    if (A.use_b2) {
-      pg_pair_both(P, x2, y2, z2, A.q2, A.t2, cx, cy, cz, cq, ct, do_lj, lj, re);
-      e_lj += lj; e_re += re;
-    }
-    mz_o += cq * cz;
-  }
-  // reciprocal space through S'
-  if (P.use_ewald) {
-    const double w1x = pg_wrap_pos(x1, P.ebox[0], P.inv_ebox[0], P.pbc[0]);
-    const double w1y = pg_wrap_pos(y1, P.ebox[1], P.inv_ebox[1], P.pbc[1]);
-    const double w1z = pg_wrap_pos(z1, P.ebox[2], P.inv_ebox[2], P.pbc[2]);
-    const double w2x = pg_wrap_pos(x2, P.ebox[0], P.inv_ebox[0], P.pbc[0]);
-    const double w2y = pg_wrap_pos(y2, P.ebox[1], P.inv_ebox[1], P.pbc[1]);
-    const double w2z = pg_wrap_pos(z2, P.ebox[2], P.inv_ebox[2], P.pbc[2]);
-    const double kPi = 3.14159265359;
-    for (int k = tid; k < A.nk; k += PG_TILE) {
-      const int4 l = reinterpret_cast<const int4*>(A.kl)[k];
-      const double kx = l.x * 2 * kPi / P.ebox[0], ky = l.y * 2 * kPi / P.ebox[1], kz = l.z * 2 * kPi / P.ebox[2];
-      double s1, c1, s2 = 0, c2 = 0;
-      sincos(kx * w1x + ky * w1y + kz * w1z, &s1, &c1);
-      double dre = A.q1 * c1, dim = A.q1 * s1;
-      if (A.use_b2) {
-        sincos(kx * w2x + ky * w2y + kz * w2z, &s2, &c2);
-        dre += A.q2 * c2; dim += A.q2 * s2;
-      }
-      const double2 S = A.Sp[k];
-      e_rec += 2.0 * A.ek2[k] * (2.0 * (S.x * dre + S.y * dim) + (dre * dre + dim * dim));
-    }
-  }
-  double v[4] = {e_lj, e_re, mz_o, e_rec};
-  block_sum<4>(v, s_red);
-  if (tid != 0) return;
-  double pair_e = v[0], ewald_e = 0.0;
-  if (do_lj && A.use_b2) pair_e += pg_pair_energy(P, x1, y1, z1, A.t1, x2, y2, z2, A.t2);
-  if (P.use_ewald && pair_e < PG_VLE) {
-    ewald_e = v[1] + P.recip_pref * v[3];
-    ewald_e += P.self_pref * A.q1 * A.q1;
-    if (A.q1 != 0) ewald_e += 0.5 * pg_pair_real_d(P, 0.0, 0.0, 0.0, A.q1 * A.q1);
-    if (A.use_b2) {
-      ewald_e += P.self_pref * A.q2 * A.q2;
-      ewald_e += pg_pair_real(P, x1, y1, z1, A.q1, x2, y2, z2, A.q2);
-      if (A.q2 != 0) ewald_e += 0.5 * pg_pair_real_d(P, 0.0, 0.0, 0.0, A.q2 * A.q2);
-    }
-    if (P.dipole) {
-      double mz_n = v[2] + A.q1 * z1;
-      if (A.use_b2) mz_n += A.q2 * z2;
-      ewald_e += P.dipole_pref * (mz_n * mz_n - v[2] * v[2]);
-    }
-  }
-  if (P.ext_kind != 0) {
-    pair_e += pg_wall_energy(P, z1, A.t1);
-    if (A.use_b2) pair_e += pg_wall_energy(P, z2, A.t2);
-  }
-  A.out_pair[t] = pair_e;
-  A.out_ewald[t] = ewald_e;
-  A.out_energy[t] = (pair_e >= PG_VLE) ? PG_VLE : (pair_e + ewald_e);
-}
-
 // --------------------------------------------------------------- FP64 peak
 // Dependent-chain-free DFMA loop: 8 independent accumulators per thread.
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {

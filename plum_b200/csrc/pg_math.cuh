@@ -55,6 +55,7 @@ struct PgDev {
   int single_image;                           // 1: only the central image can ever pass r<=real_cutoff
   double recip_pref;                          // 2*kPi*lB/V
   double self_pref;                           // -lB*sqrt(alpha/kPi)
+  double real_self_unit;                      // half the real-space energy of a unit charge with its own periodic images
   double dipole_pref;                         // lB*2*kPi/V
   int bond_kind;
   int ext_kind;

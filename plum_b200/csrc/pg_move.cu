@@ -56,8 +56,9 @@ struct PgMoveDev {
   float fbox[3];        // box lengths in FP32 for the pre-filter
   // generic path (multi-image real space, padded slab box, hard spheres)
   double half_box[3], real_cutoff, rc_relaxed, lB, sqrt_alpha;
-  int real_cell[3], same_box[3];
-  int img_split, img_ny;   // threads per partner = x-images * y-images, each runs the z column of its (ix, iy)
+  int same_box[3];
+  int img_cx, img_cy, img_cz;   // periodic images per axis on each side (0, 0, 0: minimum image only)
+  int img_split, img_ny;        // threads per partner = x-images * y-images, each runs the z column of its (ix, iy)
   int pbc[3];
   int pair_kind, use_ewald, dipole, bond_kind, ext_kind;
 };
@@ -187,14 +188,14 @@ __device__ __forceinline__ double2 mv_generic_column(const PgMoveDev& P, const P
     if (P.pair_kind == 2 || l2 <= P.ljc2max) e_lj = mv_lj_r2(Pg, l2, tp);
   }
   if (P.use_ewald && qq != 0.0) {
-    const int ix = sub / P.img_ny - P.real_cell[0], iy = sub % P.img_ny - P.real_cell[1];
+    const int ix = sub / P.img_ny - P.img_cx, iy = sub % P.img_ny - P.img_cy;
     const double rx = dx + ix * P.ebox[0], ry = dy + iy * P.ebox[1];
     const double rxy2 = rx * rx + ry * ry;
     const double rc2r = P.rc2_relaxed;
     if (rxy2 <= rc2r) {
       const double rcr = P.rc_relaxed, rc = P.real_cutoff, pref = P.lB * qq, sa = P.sqrt_alpha;
       int k0 = (int)ceil((-rcr - dz) * P.inv_ebox[2]), k1 = (int)floor((rcr - dz) * P.inv_ebox[2]);
-      k0 = max(k0, -P.real_cell[2]); k1 = min(k1, P.real_cell[2]);
+      k0 = max(k0, -P.img_cz); k1 = min(k1, P.img_cz);
       for (int k = k0; k <= k1; k++) {
         const double rz = dz + k * P.ebox[2];
         const double r2 = rxy2 + rz * rz;

@@ -20,7 +20,8 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("PLUM_REFERENCE", "/root/reference")
-OUT = os.path.join(REPO, "bin", "plum_gpu")
+PROFILE = bool(os.environ.get("PLUM_HOST_GPROF"))   # -pg build for gprof (bin/plum_gpu_prof)
+OUT = os.path.join(REPO, "bin", "plum_gpu_prof" if PROFILE else "plum_gpu")
 sys.path.insert(0, REPO)
 from plum_b200.host import driver_hooks  # noqa: E402
 
@@ -58,7 +59,7 @@ def main():
             files += sorted(os.path.join(src, d, f) for f in os.listdir(os.path.join(src, d)) if f.endswith(".cc"))
         eigen = os.environ.get("EIGEN_INCLUDE", os.path.join(HERE, "eigen_standin"))
         libdir = os.path.join(REPO, "plum_b200")
-        cmd = ["g++", "-std=c++11", "-O3", "-w", "-I", eigen, "-I", os.path.join(REPO, "include"), "-o", OUT] + files + \
+        cmd = ["g++", "-std=c++11", "-O3", "-w"] + (["-pg", "-fno-inline-functions"] if PROFILE else []) + ["-I", eigen, "-I", os.path.join(REPO, "include"), "-o", OUT] + files + \
               ["-L", libdir, "-lplum_b200", "-Wl,-rpath,$ORIGIN/../plum_b200", "-lm"]
         subprocess.check_call(cmd)
         print("build_host: built", OUT)

@@ -239,6 +239,61 @@ def test_random_moves_match_oracle(case):
     eng.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [0, 1, 2, 4, 5, 6, 9])
+def test_batched_growth_steps_match_oracle(case):
+    """pg_trial_energies (one k_trials launch per growth step) against the oracle's BeadsEnergy
+    (cbmc.cc:5-151) trial by trial: inline and staged inputs, more trials than one launch holds,
+    skipped molecules (deletion), partial chains with and without the counter-ion, trial beads on top
+    of resident beads (1e8 sentinel) and outside a slab."""
+    c = dict(CASES[case])
+    rng = np.random.default_rng(500 + case)
+    box = c.pop("box")
+    sysm = _random_system(rng, c.pop("n_chain"), c.pop("chain_len"), c.pop("n_ion"), np.array(box),
+                          c.pop("charged_every", 1), c.pop("slab", False))
+    r, types, params = _params(box, **c)
+    eng, orc = _engine(params, sysm.n), _oracle(params)
+    ids = types.ids(sysm.symbol)
+    eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
+    orc.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
+    eng.init_energy(); orc.init_energy()
+    tP, tC = types.ids(["P"])[0], types.ids(["C"])[0]
+    b = np.array(box)
+    #        n_trials, current_len, use_bead2, skip range
+    plans = [(1, 0, 1, None), (7, 3, 1, None), (30, 8, 1, None), (30, 5, 0, None), (70, 2, 1, None),
+             (12, 12, 1, None), (9, 20, 0, (1, 2)), (30, 4, 1, (0, 0)), (33, 0, 0, (2, 3))]
+    for nt, cl, use2, skip in plans:
+        n_chain = cl * (2 if use2 else 1)
+        # a partial chain: a random walk of monomers (bond 2.5) and, with use2, one ion near each
+        cx = np.zeros((max(n_chain, 1), 3)); cq = np.zeros(max(n_chain, 1)); ct = np.zeros(max(n_chain, 1), dtype=np.int32)
+        p = rng.uniform(0.3, 0.7, 3) * b
+        for i in range(cl):
+            cx[i] = p; cq[i] = -1.0; ct[i] = tP
+            step = rng.normal(size=3); p = p + 2.5 * step / np.linalg.norm(step)
+            if use2:
+                cx[cl + i] = cx[i] + rng.normal(scale=2.0, size=3); cq[cl + i] = 1.0; ct[cl + i] = tC
+        anchor = cx[cl - 1] if cl else rng.uniform(0.3, 0.7, 3) * b
+        d = rng.normal(size=(nt, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+        b1 = anchor + 2.5 * d
+        b2 = b1 + rng.normal(scale=2.0, size=(nt, 3))
+        if nt >= 7:
+            b1[3] = sysm.xyz[5] + 1e-3          # overlap with a resident bead: LJ huge / hard-sphere sentinel
+            b2[4] = sysm.xyz[-1]                 # exactly on top of an ion: r = 0
+            b1[5, 2] = -0.5                      # below the lower wall of a slab
+        sf, sl = skip if skip else (-1, -1)
+        eg, pg_, wg = eng.trial_energies(b1, b2, tP, -1.0, tC, 1.0, use2, cx[:max(n_chain, 1)], cq, ct, cl, sf, sl)
+        for t in range(nt):
+            eo, po, wo = orc.beads_energy(b1[t], tP, -1.0, b2[t], tC, 1.0, use2, cx, cq, ct, cl, sf, sl)
+            tag = (case, nt, cl, use2, skip, t)
+            if eo >= 1e8:
+                assert eg[t] >= 1e8, tag
+                continue
+            assert abs(eg[t] - eo) <= TOL * max(1.0, abs(eo)), tag + (eg[t], eo)
+            assert abs(pg_[t] - po) <= TOL * max(1.0, abs(po)), tag + (pg_[t], po)
+            assert abs(wg[t] - wo) <= TOL * max(1.0, abs(wo)), tag + (wg[t], wo)
+    eng.close()
+
+
 def test_edge_cases():
     """r == 0 overlap, bead exactly on a cutoff, q == 0 partners, single bead system, empty system."""
     box = [30.0, 30.0, 30.0]
