@@ -120,6 +120,7 @@ struct pg_engine {
   int ccap = 0;       // chain capacity of the staging block
   double *h_trial_in = nullptr, *d_trial_in = nullptr;    // b1[3 TR_MAXT] | b2[3 TR_MAXT] | chain_xyz[3 ccap] | chain_q[ccap]
   int *h_trial_ct = nullptr, *d_trial_ct = nullptr;
+  double2* d_sk_partial = nullptr; size_t sk_partial_cap = 0;   // k_sk_slice [chunk][k]
   double2* d_tr_partial = nullptr; size_t tr_partial_cap = 0;
   double* d_tr_mz = nullptr; size_t tr_mz_cap = 0;
   unsigned int* d_tr_counter = nullptr;
@@ -646,15 +647,34 @@ int wait_mail(pg_engine* h, unsigned int seq, pg_delta* o) {
 }
 
 
+// S(k) of the k slice [k_first, k_first + k_count) into `out` (device): bead chunks x k tiles, then the
+// ordered reduction over the chunks.  At most 128 chunks, whole 256-bead tiles each.
+int launch_sk_slice(pg_engine* h, int k_first, int k_count, double2* out) {
+  if (k_count <= 0) return PG_OK;
+  int chunk = PG_TILE * std::max(1, ((h->n + 127) / 128 + PG_TILE - 1) / PG_TILE);
+  const int n_chunks = std::max(1, (h->n + chunk - 1) / chunk);
+  const size_t need = (size_t)n_chunks * (size_t)k_count;
+  if (need > h->sk_partial_cap) {
+    cudaFree(h->d_sk_partial); h->d_sk_partial = nullptr; h->sk_partial_cap = 0;
+    PG_CUDA(h, cudaMalloc((void**)&h->d_sk_partial, sizeof(double2) * need));
+    h->sk_partial_cap = need;
+  }
+  const int kt = (k_count + PG_TILE - 1) / PG_TILE;
+  k_sk_slice<<<dim3(kt, n_chunks), PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->n, h->d_kvec, k_first, k_count, chunk,
+                                                          h->d_sk_partial);
+  k_sk_reduce<<<kt, PG_TILE, 0, h->stream>>>(h->d_sk_partial, n_chunks, k_count, out);
+  h->launches += 2;
+  PG_CUDA(h, cudaGetLastError());
+  return PG_OK;
+}
+
 int compute_totals(pg_engine* h, bool set_state, pg_totals* out) {
   int frc = flush_commit(h);
   if (frc) return frc;
   double2* S = set_state ? h->d_S : h->d_Stmp;
   if (h->P.use_ewald && h->nk > 0) {
-    int nb = (h->nk + PG_TILE - 1) / PG_TILE;
-    k_sk_slice<<<nb, PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->n, h->d_kl, 0, h->nk, S);
-    h->launches++;
-    PG_CUDA(h, cudaGetLastError());
+    int src = launch_sk_slice(h, 0, h->nk, S);
+    if (src) return src;
   }
   int n_tiles = (h->n + PG_TILE - 1) / PG_TILE;
   int rc = ensure_partials(h, n_tiles);
@@ -694,7 +714,7 @@ void free_all(pg_engine* h) {
   if (h->h_trial_in) cudaFreeHost(h->h_trial_in);
   if (h->h_trial_ct) cudaFreeHost(h->h_trial_ct);
   if (h->h_tmail) cudaFreeHost(h->h_tmail);
-  cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_tr_partial); cudaFree(h->d_tr_mz); cudaFree(h->d_tr_counter);
+  cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_tr_partial); cudaFree(h->d_sk_partial); cudaFree(h->d_tr_mz); cudaFree(h->d_tr_counter);
   cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
   for (auto& g : h->rp_graphs) cudaGraphExecDestroy(g.exec);
   h->rp_graphs.clear();
@@ -1408,10 +1428,7 @@ int pg_sk_compute_slice(pg_engine* h, int k_first, int k_count, double* sk_dev) 
   PG_CUDA(h, cudaSetDevice(h->device));
   { int frc_ = flush_commit(h); if (frc_) return frc_; }
   double2* out = sk_dev ? reinterpret_cast<double2*>(sk_dev) : (h->d_S + k_first);
-  k_sk_slice<<<(k_count + PG_TILE - 1) / PG_TILE, PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->n, h->d_kl, k_first,
-                                                                          k_count, out);
-  h->launches++;
-  PG_CUDA(h, cudaGetLastError());
+  { int src_ = launch_sk_slice(h, k_first, k_count, out); if (src_) return src_; }
   PG_CUDA(h, cudaStreamSynchronize(h->stream));
   return PG_OK;
 }

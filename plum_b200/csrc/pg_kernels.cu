@@ -468,28 +468,25 @@ __global__ void __launch_bounds__(PG_TILE) k_tot_pairs(const PgDev P, const doub
 
 // ---------------------------------------------------------------- k_sk_slice
 // S(k) = sum_i q_i exp(i k.r_i) for k in [k_first, k_first + k_count) of the half list.
-// One k per thread; charged beads staged tile by tile in shared memory (wrapped once).
+// Grid (k tiles, bead chunks): one k per thread, the CTA's bead chunk staged tile by tile in shared
+// memory (wrapped once).  Each (chunk, k) partial sum has one writer; k_sk_reduce adds the chunks in
+// index order, so the result does not depend on how the k list is sliced over ranks.
 __global__ void __launch_bounds__(PG_TILE) k_sk_slice(const PgDev P, const double2* __restrict__ xy,
                                                       const double2* __restrict__ zq, int n,
-                                                      const int* __restrict__ kl, int k_first, int k_count,
-                                                      double2* out) {
+                                                      const double4* __restrict__ kvec, int k_first, int k_count,
+                                                      int chunk_beads, double2* partial) {
   __shared__ double s_x[PG_TILE], s_y[PG_TILE], s_z[PG_TILE], s_q[PG_TILE];
   const int tid = threadIdx.x;
   const int kk = blockIdx.x * PG_TILE + tid;
   const bool active = kk < k_count;
-  double kx = 0, ky = 0, kz = 0;
-  if (active) {
-    const int4 l = reinterpret_cast<const int4*>(kl)[k_first + kk];
-    const double kPi = 3.14159265359;
-    kx = l.x * 2 * kPi / P.ebox[0];
-    ky = l.y * 2 * kPi / P.ebox[1];
-    kz = l.z * 2 * kPi / P.ebox[2];
-  }
+  double4 kv = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (active) kv = kvec[k_first + kk];
+  const int j0 = blockIdx.y * chunk_beads, j1 = min(n, j0 + chunk_beads);
   double re = 0.0, im = 0.0;
-  for (int t0 = 0; t0 < n; t0 += PG_TILE) {
+  for (int t0 = j0; t0 < j1; t0 += PG_TILE) {
     __syncthreads();
     const int j = t0 + tid;
-    if (j < n) {
+    if (j < j1) {
       double2 a = xy[j], c = zq[j];
       s_x[tid] = pg_wrap_pos(a.x, P.ebox[0], P.inv_ebox[0], P.pbc[0]);
       s_y[tid] = pg_wrap_pos(a.y, P.ebox[1], P.inv_ebox[1], P.pbc[1]);
@@ -500,17 +497,29 @@ __global__ void __launch_bounds__(PG_TILE) k_sk_slice(const PgDev P, const doubl
     }
     __syncthreads();
     if (active) {
-      const int cnt = min(PG_TILE, n - t0);
+      const int cnt = min(PG_TILE, j1 - t0);
       for (int jj = 0; jj < cnt; jj++) {
         const double q = s_q[jj];
         if (q == 0) continue;
         double s, c;
-        sincos(kx * s_x[jj] + ky * s_y[jj] + kz * s_z[jj], &s, &c);
+        sincos(kv.x * s_x[jj] + kv.y * s_y[jj] + kv.z * s_z[jj], &s, &c);
         re += q * c; im += q * s;
       }
     }
   }
-  if (active) out[kk] = make_double2(re, im);
+  if (active) partial[(size_t)blockIdx.y * k_count + kk] = make_double2(re, im);
+}
+
+__global__ void __launch_bounds__(PG_TILE) k_sk_reduce(const double2* __restrict__ partial, int n_chunks, int k_count,
+                                                       double2* out) {
+  const int kk = blockIdx.x * PG_TILE + threadIdx.x;
+  if (kk >= k_count) return;
+  double re = 0.0, im = 0.0;
+  for (int c = 0; c < n_chunks; c++) {
+    const double2 v = partial[(size_t)c * k_count + kk];
+    re += v.x; im += v.y;
+  }
+  out[kk] = make_double2(re, im);
 }
 
 // Reciprocal energy of a k slice: recip_pref * sum 2 ek2 |S|^2 (single CTA).

@@ -1,0 +1,14 @@
+#!/bin/bash
+# One gpurun call that regenerates the round's measured evidence (tests, bench lines, ncu captures).
+# usage: tools/round_evidence.sh r01   -> gpurun_out/{pytest_gpu,bench_n1,bench_ref,launches,prof_*}_<tag>.*
+tag=${1:-r01}
+mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1; tail -2 gpurun_out/smoke_$tag.log
+python bench.py > gpurun_out/bench_n1_$tag.json 2> gpurun_out/bench_n1_$tag.err; tail -c 600 gpurun_out/bench_n1_$tag.json
+python bench.py --impl reference > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err; tail -c 400 gpurun_out/bench_ref_$tag.json
+ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 600 --csv --log-file gpurun_out/launches_$tag.csv \
+    python bench.py --steps 1 --warmup 3 --moves-per-step 64 --no-cpu-baseline --replicas-per-gpu 1 > gpurun_out/ncu_bench1_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_move -s 400 -c 8 -f -o gpurun_out/prof_${tag}_kmove \
+    python bench.py --steps 1 --warmup 3 --moves-per-step 64 --no-cpu-baseline --replicas-per-gpu 1 > gpurun_out/ncu_bench2_$tag.log 2>&1
+ls -la gpurun_out | tail -12
