@@ -30,6 +30,10 @@ import sys
 import threading
 import time
 
+# more replica streams than the default 8 hardware work queues would alias onto shared queues and
+# serialise falsely; must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -99,6 +103,11 @@ def mcbench_lib():
     L.pb_create.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, C.c_double, C.c_double, C.c_double, dp, C.c_int, C.c_uint]
     L.pb_destroy.argtypes = [C.c_void_p]
     L.pb_run.argtypes = [C.c_void_p, C.c_int, ip, ip, dp, dp, bp, dp, bp, C.c_int, ip, dp, dp, dp, ip, C.c_int]
+    L.pb_set_records.argtypes = [C.c_void_p, ip, ip, dp, dp, bp, dp, bp, C.c_int]
+    L.pb_set_records.restype = None
+    L.pb_stats.argtypes = [C.c_void_p, ip, dp, dp, ip]
+    L.pb_stats.restype = None
+    L.pb_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp]
     return L
 
 
@@ -238,7 +247,8 @@ def run_ours(a):
         return float(t.item())
 
     M, K, W = a.moves_per_step, a.steps, a.warmup
-    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else min(8, max(1, ((os.cpu_count() or 2) // world) // 2))
+    # fixed per GPU whatever N is (weak scaling); each replica has one host thread in the e2e leg
+    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else 16
     r, sysm, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
     ids = types.ids(sysm.symbol)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -263,6 +273,7 @@ def run_ours(a):
                 self.eng = Engine(params, device=local_rank, capacity_beads=sysm.n)
                 self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
                 self.eng.init_energy()
+                self.stream = torch.cuda.ExternalStream(self.eng.stream(), device=torch.device("cuda", local_rank))
                 self.ctx = L.pb_create(self.eng.h, sysm.n_mol, mf.ctypes.data_as(ip), xyz0.ctypes.data_as(dp),
                                        box.ctypes.data_as(dp), C.c_double(r.beta), C.c_double(r.move_size),
                                        C.c_double(r.rigid_bond), prob.ctypes.data_as(dp), 0,
@@ -280,17 +291,17 @@ def run_ours(a):
                 self.replay_ms = []
                 self.kd_ms = 0.0
 
-            def e2e_step(self, s):
-                used, wall, ev, fl, nacc = C.c_int32(), C.c_double(), C.c_double(), C.c_double(), C.c_int32()
+            def set_records(self, s):
                 sl = slice(s * M, (s + 1) * M)
-                rc = L.pb_run(self.ctx, M, self.rec_mol[sl].ctypes.data_as(ip), self.rec_off[sl].ctypes.data_as(ip),
-                              self.rec_u[sl].ctypes.data_as(dp), self.rec_dE[sl].ctypes.data_as(dp),
-                              self.rec_acc[sl].ctypes.data_as(bp), self.rec_trial[self.used_total:].ctypes.data_as(dp),
-                              self.rec_moved[self.used_total:].ctypes.data_as(bp), self.cap_beads - self.used_total,
-                              C.byref(used), C.byref(wall), C.byref(ev), C.byref(fl), C.byref(nacc), K_FULL)
-                if rc != 0:
-                    raise RuntimeError(f"pb_run failed ({rc}): {self.eng.L.pg_last_error(self.eng.h).decode()}")
-                self.rec_off[sl] += self.used_total
+                L.pb_set_records(self.ctx, self.rec_mol[sl].ctypes.data_as(ip), self.rec_off[sl].ctypes.data_as(ip),
+                                 self.rec_u[sl].ctypes.data_as(dp), self.rec_dE[sl].ctypes.data_as(dp),
+                                 self.rec_acc[sl].ctypes.data_as(bp), self.rec_trial[self.used_total:].ctypes.data_as(dp),
+                                 self.rec_moved[self.used_total:].ctypes.data_as(bp), self.cap_beads - self.used_total)
+
+            def collect(self, s):
+                used = C.c_int32()
+                L.pb_stats(self.ctx, C.byref(used), None, None, None)
+                self.rec_off[s * M:(s + 1) * M] += self.used_total
                 self.used_total += used.value
 
             def reset_for_replay(self):
@@ -332,9 +343,60 @@ def run_ours(a):
             if errs:
                 raise errs[0]
 
-        # ---------------- e2e leg: host-driven Metropolis loops through the C ABI (native callers)
+        def device_ms(fn):
+            """Device time of `fn` run on every replica concurrently: every replica stream first waits on a start
+            event, the end event is recorded after all of them have joined — robust against replicas that do
+            not overlap (queueing, launch skew), unlike a max over per-replica event times."""
+            cur = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            for rp in reps:
+                rp.stream.wait_event(e0)
+            run_all(fn)
+            for rp in reps:
+                ej = torch.cuda.Event()
+                ej.record(rp.stream)
+                cur.wait_event(ej)
+            e1.record(cur)
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+
+        # ---------------- e2e leg: host-driven Metropolis loops through the C ABI (native callers).
+        # T host threads, each driving its share of the replicas through pg_delta_e_begin / _poll so that
+        # their round trips overlap; every chain stays strictly sequential.
+        T = max(1, min(R, a.host_threads if a.host_threads > 0 else max(1, (os.cpu_count() or 2) // world - 2)))
+        groups = [reps[i::T] for i in range(T)]
+
+        def e2e_step(s):
+            errs = []
+
+            def drive(group):
+                try:
+                    for rp in group:
+                        rp.set_records(s)
+                    arr = (C.c_void_p * len(group))(*[rp.ctx for rp in group])
+                    wall = C.c_double()
+                    rc = L.pb_run_multi(arr, len(group), M, C.byref(wall))
+                    if rc != 0:
+                        msgs = [rp.eng.L.pg_last_error(rp.eng.h).decode() for rp in group]
+                        raise RuntimeError(f"pb_run_multi failed ({rc}): {msgs}")
+                    for rp in group:
+                        rp.collect(s)
+                except Exception as e:   # noqa: BLE001
+                    errs.append(e)
+            if T == 1:
+                drive(groups[0])
+            else:
+                ths = [threading.Thread(target=drive, args=(g_,)) for g_ in groups]
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+            if errs:
+                raise errs[0]
+
         for s in range(W):
-            run_all(lambda rp: rp.e2e_step(s))
+            e2e_step(s)
             flush_l2()
         launches0 = sum(rp.eng.launch_count() for rp in reps)
         clocks = ClockSampler(local_rank)
@@ -342,7 +404,7 @@ def run_ours(a):
         barrier()
         t0 = time.perf_counter()
         for s in range(W, W + K):
-            run_all(lambda rp: rp.e2e_step(s))
+            e2e_step(s)
             flush_l2()
         barrier()
         t_e2e = time.perf_counter() - t0
@@ -361,8 +423,9 @@ def run_ours(a):
         barrier()
         t0 = time.perf_counter()
         t_flush = 0.0
+        step_ms = []
         for s in range(W, W + K):
-            run_all(lambda rp: rp.replay_step(s, True))
+            step_ms.append(device_ms(lambda rp: rp.replay_step(s, True)))
             tf = time.perf_counter()
             flush_l2()
             t_flush += time.perf_counter() - tf
@@ -370,8 +433,7 @@ def run_ours(a):
         t_wall_replay = time.perf_counter() - t0
         gpu_launches = sum(rp.eng.launch_count() for rp in reps) - launches0
         clock_info = clocks.stop()
-        # device time of a step = the slowest replica's CUDA-event time (replicas run concurrently)
-        dev_ms = float(sum(max(rp.replay_ms[i] for rp in reps) for i in range(K)))
+        dev_ms = float(sum(step_ms))   # fork/join CUDA events around all replicas of a step
         dev_s = max_over_ranks(dev_ms * 1e-3)
         replay_matches = all(bool(np.array_equal(np.concatenate(rp.replay_dE), rp.rec_dE[W * M:]) and
                                   rp.eng.totals() == rp.final_e2e) for rp in reps)
@@ -385,8 +447,7 @@ def run_ours(a):
             rp.eng.replay_time_delta(W * M, min(M, 256))   # warm + instantiate
             rp.eng.replay_prepare(W * M, K * M, False)
         torch.cuda.synchronize()
-        run_all(lambda rp: rp.time_delta())
-        kd_ms = max(rp.kd_ms for rp in reps)
+        kd_ms = device_ms(lambda rp: rp.time_delta())
         fp64_peak_gflops = reps[0].eng.measure_fp64_peak()
         peaks = {}
         try:
@@ -398,7 +459,9 @@ def run_ours(a):
         # traffic: dram bytes per k_move launch from the committed `ncu --set full` capture of this command
         traffic = None
         try:
-            with open(os.path.join(REPO, "profiles", "r01_ncu_summary.json")) as f:
+            import glob
+            prof_file = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_summary.json")))[-1]
+            with open(prof_file) as f:
                 prof = json.load(f)["k_move_full"]
             vals = []
             for p_ in prof:
@@ -413,10 +476,10 @@ def run_ours(a):
         roofline = {
             "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_gflops / 1e3, "unit": "TFLOP/s",
             "frac": achieved_tflops / (fp64_peak_gflops / 1e3), "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write per k_move launch, ncu --set full (cold cache), profiles/r01_ncu_summary.json",
+            "traffic_note": "dram__bytes_read+write per k_move launch, ncu --set full (cold cache), profiles/" + (os.path.basename(prof_file) if traffic is not None else "-"),
             "kernel": "k_move", "launches": int(n_launch), "avg_launch_us": kd_ms * 1e3 / (K * M),
-            "avg_launch_note": f"CUDA-event time of {K * M} back-to-back k_move launches per replica, {R} replica stream(s) "
-                               f"running concurrently; achieved = algorithmic flops of all replicas / that time",
+            "avg_launch_note": f"CUDA-event time (fork/join over the {R} replica stream(s)) of {K * M} back-to-back k_move launches "
+                               f"per replica / {K * M}; achieved = algorithmic flops of all replicas / that time",
             "peak_source": "FP64 FMA microbenchmark measured in this run (pg_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
             "algorithmic_flops_per_launch": flops / n_launch,
             "bytes_view": {"bound": "hbm", "achieved": bytes_ / (kd_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -438,7 +501,7 @@ def run_ours(a):
 
         for rp in reps:
             rp.eng.close()
-        return dict(R=R, value=value, e2e_value=e2e_value, dev_s=dev_s, t_e2e=t_e2e, evals_total=evals_total,
+        return dict(R=R, T=T, value=value, e2e_value=e2e_value, dev_s=dev_s, t_e2e=t_e2e, evals_total=evals_total,
                     e2e_launches=e2e_launches, gpu_launches=gpu_launches, roofline=roofline, clock_info=clock_info,
                     replay_matches=replay_matches, wall_replay=(t_wall_replay - t_flush), h2d=h2d, d2h=d2h,
                     accept=float(rec_acc_all.mean()), p_ion=float(np.mean(lens == 1)))
@@ -473,7 +536,7 @@ def run_ours(a):
             "pair_dE_evals_per_s": evals_total / dev_s,
             "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e * 1e3 / K, "pair_dE_evals_per_s": evals_total / t_e2e,
-                    "caller": "native C++ Metropolis loop over pg_delta_e/pg_commit (plum_b200/host/mc_bench.cc)",
+                    "caller": f"native C++ Metropolis loops over pg_delta_e_begin/_poll/pg_commit (plum_b200/host/mc_bench.cc): {res['T']} host thread(s) per GPU driving {R} replicas",
                     "launches": int(e2e_launches)},
             "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
             "replay_matches_e2e": replay_matches, "wall_ms_per_step_replay": (t_wall_replay - t_flush) * 1e3 / K,
@@ -499,7 +562,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-replica measurement")
     ap.add_argument("--replicas-per-gpu", type=int, default=0,
-                    help="independent Markov chains per GPU, each with its own engine/stream; 0 = auto (half the host cores per GPU, at most 8)")
+                    help="independent Markov chains per GPU, each with its own engine/stream; 0 = 16 (fixed per GPU: weak scaling)")
+    ap.add_argument("--host-threads", type=int, default=0,
+                    help="host threads per GPU driving the replicas in the e2e leg (0 = host cores per GPU - 2, at most one per replica)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -162,6 +162,13 @@ int pg_num_beads(const pg_engine* h);
  * (potential_ewald.cc:527-531) fed from out->mz_current. */
 int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* moved,
                pg_delta* out);
+/* The same call in two halves, for a host thread that drives several replicas
+ * (one handle each) and overlaps their round trips: _begin stages the trial and
+ * launches, _poll returns 1 while the device has not answered, 0 once `out` is
+ * filled (the trial then awaits pg_commit), < 0 on error.  The trial_xyz / moved
+ * buffers may be reused as soon as _begin returns. */
+int pg_delta_e_begin(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* moved);
+int pg_delta_e_poll(pg_engine* h, pg_delta* out);
 /* ForceField::FinalizeEnergies (force_field.cc:436-451): accept applies the
  * position deltas and S(k) += dS(k) on the device and adds the components to
  * the running totals; reject drops the trial.  Asynchronous on the device. */

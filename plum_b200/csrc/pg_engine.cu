@@ -14,6 +14,7 @@
 //   *::AdjustEnergyUponMolDeletion              src/force_field/cbmc.cc:422-436
 //   PotentialEwaldCoul::ReadParameters          src/force_field/potential_ewald_coul.cc:29-132
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <chrono>
@@ -82,6 +83,7 @@ struct pg_engine {
   char* d_stage = nullptr;
   int slot = 0;
   size_t stage_bytes = 0;
+  bool inflight = false;        // pg_delta_e_begin issued, pg_delta_e_poll has not returned 0 yet
   bool fast = false;            // k_move<true> hot loop is valid for this force field
 
   // deferred commit of the last trial (applied by the next k_move or by flush_commit)
@@ -420,7 +422,8 @@ int wait_result(pg_engine* h, unsigned int seq) {
     auto t0 = std::chrono::steady_clock::now();
     unsigned long spins = 0;
     while (h->h_result->seq != seq) {
-      if ((++spins & 0xfffff) == 0) {
+      if ((++spins & 0x1fff) == 0) sched_yield();   // long wait or oversubscribed host: let a sibling replica's thread run
+      if ((spins & 0xfffff) == 0) {
         cudaError_t q = cudaStreamQuery(h->stream);
         if (q != cudaSuccess && q != cudaErrorNotReady) {
           h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
@@ -627,7 +630,8 @@ int wait_mail(pg_engine* h, unsigned int seq, pg_delta* o) {
         aux[s] = m[s].aux;
         if (m[s].seq == seq) break;
       }
-      if ((++spins & 0xfffff) == 0) {
+      if ((++spins & 0x1fff) == 0) sched_yield();   // long wait or oversubscribed host: let a sibling replica's thread run
+      if ((spins & 0xfffff) == 0) {
         cudaError_t q = cudaStreamQuery(h->stream);
         if (q != cudaSuccess && q != cudaErrorNotReady) {
           h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
@@ -771,8 +775,13 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   } while (0)
   PG_CREATE_CUDA(cudaSetDevice(device));
   PG_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  PG_CREATE_CUDA(cudaEventCreate(&h->ev0));
-  PG_CREATE_CUDA(cudaEventCreate(&h->ev1));
+  // blocking sync: a host thread waiting for a replay batch sleeps instead of spinning (many replicas per GPU)
+  {
+    const char* es = getenv("PLUM_B200_EVENT_SPIN");
+    const unsigned ef = (es && es[0] == '1') ? cudaEventDefault : cudaEventBlockingSync;
+    PG_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev0, ef));
+    PG_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev1, ef));
+  }
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_state, sizeof(PgState)));
   PG_CREATE_CUDA(cudaMemset(h->d_state, 0, sizeof(PgState)));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_P, sizeof(PgDev)));
@@ -946,10 +955,12 @@ int pg_download_positions(pg_engine* h, double* xyz) {
 }
 
 // ------------------------------------------------------------ per-move path
-int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* moved, pg_delta* out) {
-  if (!h || !trial_xyz || !moved || !out) return PG_ERR_INVALID;
+// Asynchronous half of pg_delta_e: stages the trial and launches k_move, returns without waiting.
+int pg_delta_e_begin(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* moved) {
+  if (!h || !trial_xyz || !moved) return PG_ERR_INVALID;
   if (mol < 0 || mol >= h->n_mol) { h->err = "molecule index out of range"; return PG_ERR_INVALID; }
-  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  if (h->pending || h->inflight) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
   const int g0 = h->mol_first[mol], glen = h->mol_first[mol + 1] - g0;
   int rc = ensure_group(h, glen);
   if (rc) return rc;
@@ -967,11 +978,35 @@ int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* mo
   if (!inl) PG_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, stage_size(glen), cudaMemcpyHostToDevice, h->stream));
   rc = launch_move(h, g0, glen, nq, h->d_stage, glen, false, 0.0, 0, true, false, inl ? h->h_stage : nullptr);
   if (rc) return rc;
-  rc = wait_mail(h, h->seq, out);
-  if (rc) return rc;
-  h->pending = true;
+  h->inflight = true;
   h->pend_mode = PG_MODE_MOVE; h->pend_g0 = g0; h->pend_glen = glen; h->pend_group = h->d_stage; h->pend_cap = glen;
   h->pend_hgroup = h->h_stage; h->pend_on_device = !inl;
+  return PG_OK;
+}
+
+// Second half: 1 while the device has not answered (returns at once), 0 when `out` is filled and the
+// trial is pending its pg_commit, < 0 on error.
+int pg_delta_e_poll(pg_engine* h, pg_delta* out) {
+  if (!h || !out) return PG_ERR_INVALID;
+  if (!h->inflight) { h->err = "no trial in flight"; return PG_ERR_STATE; }
+  volatile PgMailRec* m = h->h_mail;
+  for (int s = MV_NSLOT - 1; s >= 0; s--)
+    if (m[s].seq != h->seq) return 1;
+  int rc = wait_mail(h, h->seq, out);
+  if (rc) return rc;
+  h->inflight = false;
+  h->pending = true;
+  return PG_OK;
+}
+
+int pg_delta_e(pg_engine* h, int mol, const double* trial_xyz, const uint8_t* moved, pg_delta* out) {
+  if (!out) return PG_ERR_INVALID;
+  int rc = pg_delta_e_begin(h, mol, trial_xyz, moved);
+  if (rc) return rc;
+  rc = wait_mail(h, h->seq, out);
+  if (rc) { h->inflight = false; return rc; }
+  h->inflight = false;
+  h->pending = true;
   return PG_OK;
 }
 
@@ -1304,7 +1339,8 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
           v = m[r].value;
           if (m[r].seq == A.seq) break;
         }
-        if ((++spins & 0xfffff) == 0) {
+        if ((++spins & 0x1fff) == 0) sched_yield();   // long wait or oversubscribed host: let a sibling replica's thread run
+        if ((spins & 0xfffff) == 0) {
           cudaError_t q = cudaStreamQuery(h->stream);
           if (q != cudaSuccess && q != cudaErrorNotReady) {
             h->err = std::string("kernel failed: ") + cudaGetErrorString(q);

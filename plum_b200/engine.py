@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "libplum_b200.so")
 ABI_SYMBOLS = [
     "pg_create", "pg_destroy", "pg_last_error", "pg_abi_version", "pg_get_ewald_info", "pg_upload_system",
     "pg_init_energy", "pg_recompute_totals", "pg_get_totals", "pg_download_positions", "pg_num_beads", "pg_delta_e",
-    "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_trial_energies", "pg_insert_molecules",
+    "pg_delta_e_begin", "pg_delta_e_poll", "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_trial_energies", "pg_insert_molecules",
     "pg_delete_molecules", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
     "pg_stream", "pg_measure_fp64_peak",
 ]
@@ -54,6 +54,8 @@ def lib():
         L.pg_download_positions.argtypes = [vp, c_double_p]
         L.pg_num_beads.argtypes = [vp]
         L.pg_delta_e.argtypes = [vp, C.c_int, c_double_p, c_uint8_p, C.POINTER(PgDelta)]
+        L.pg_delta_e_begin.argtypes = [vp, C.c_int, c_double_p, c_uint8_p]
+        L.pg_delta_e_poll.argtypes = [vp, C.POINTER(PgDelta)]
         L.pg_commit.argtypes = [vp, C.c_int]
         L.pg_replay_upload.argtypes = [vp, C.c_int, C.POINTER(PgProposal), C.c_int, c_double_p, c_uint8_p]
         L.pg_replay_run.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_uint8_p, C.POINTER(C.c_float)]
@@ -159,6 +161,21 @@ class Engine:
     def delta_e_raw(self, mol: int, xyz: np.ndarray, mv: np.ndarray, out: PgDelta):
         """No-allocation variant for timing loops (arrays must be contiguous f64 / u8)."""
         return self.L.pg_delta_e(self.h, mol, dptr(xyz), bptr(mv), C.byref(out))
+
+    def delta_e_begin(self, mol: int, trial_xyz, moved) -> None:
+        """Asynchronous half of delta_e (several engines driven by one thread)."""
+        xyz = _f64(trial_xyz).reshape(-1, 3)
+        mv = np.ascontiguousarray(moved, dtype=np.uint8)
+        self._check(self.L.pg_delta_e_begin(self.h, int(mol), dptr(xyz), bptr(mv)), "pg_delta_e_begin")
+
+    def delta_e_poll(self):
+        """None while the device has not answered, else the same dict delta_e returns."""
+        d = PgDelta()
+        rc = self.L.pg_delta_e_poll(self.h, C.byref(d))
+        if rc == 1:
+            return None
+        self._check(rc, "pg_delta_e_poll")
+        return d.as_dict()
 
     def commit(self, accept: bool):
         self._check(self.L.pg_commit(self.h, int(bool(accept))), "pg_commit")

@@ -422,6 +422,51 @@ def test_replay_on_device_matches_host_driven_path():
     eng.close()
 
 
+def test_async_halves_interleave_two_replicas():
+    """pg_delta_e_begin / pg_delta_e_poll: two engines driven by one thread with their round trips
+    overlapped give exactly the numbers of the synchronous pg_delta_e, and state errors are reported."""
+    from plum_b200.engine import EngineError
+    rng = np.random.default_rng(11)
+    box = [40.0, 40.0, 40.0]
+    r, types, params = _params(box, alpha=0.03)
+    sysm = _random_system(rng, 5, 14, 50, np.array(box))
+    ids = types.ids(sysm.symbol)
+    engs = [_engine(params, sysm.n) for _ in range(3)]
+    for e in engs:
+        e.upload(sysm.xyz, sysm.q, ids, sysm.mol_first); e.init_energy()
+    a, b, ref = engs
+    pos = [sysm.xyz.copy(), sysm.xyz.copy()]
+    for it in range(40):
+        props = []
+        for k, e in enumerate((a, b)):
+            mol = int(rng.integers(0, sysm.n_mol))
+            f, l = int(sysm.mol_first[mol]), int(sysm.mol_first[mol + 1])
+            trial = pos[k][f:l] + rng.normal(scale=0.4, size=(l - f, 3))
+            e.delta_e_begin(mol, trial, np.ones(l - f, dtype=np.uint8))
+            props.append((mol, f, l, trial))
+        with pytest.raises(EngineError):
+            a.delta_e_begin(0, pos[0][:int(sysm.mol_first[1])], np.ones(int(sysm.mol_first[1]), dtype=np.uint8))   # one in flight already
+        out = [None, None]
+        while out[0] is None or out[1] is None:
+            for k, e in enumerate((a, b)):
+                if out[k] is None:
+                    out[k] = e.delta_e_poll()
+        for k, e in enumerate((a, b)):
+            mol, f, l, trial = props[k]
+            # the third engine replays replica k's history synchronously
+            ref.upload(pos[k], sysm.q, ids, sysm.mol_first); ref.init_energy()
+            d = ref.delta_e(mol, trial, np.ones(l - f, dtype=np.uint8)); ref.commit(False)
+            assert abs(out[k]["dE"] - d["dE"]) <= 1e-9 * max(1.0, abs(d["dE"])), (it, k, out[k]["dE"], d["dE"])
+            acc = bool(out[k]["dE"] < 0.5)
+            e.commit(acc)
+            if acc:
+                pos[k][f:l] = trial
+    for k, e in enumerate((a, b)):
+        assert np.max(np.abs(e.positions() - pos[k])) == 0.0
+    for e in engs:
+        e.close()
+
+
 def test_k_sharded_recompute_single_rank_matches_init():
     """pg_sk_compute_slice / pg_sk_set / pg_sk_energy (the k-sharded recompute, world = 1 here):
     slices written into a torch CUDA buffer reproduce the engine's own S(k) and reciprocal energy."""
