@@ -33,6 +33,8 @@ import time
 # more replica streams than the default 8 hardware work queues would alias onto shared queues and
 # serialise falsely; must be set before the CUDA context exists
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# keep stdout to the one JSON line: NCCL's version / debug lines go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np
 
