@@ -237,6 +237,17 @@ int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, con
 int pg_delete_molecules(pg_engine* h, int mol_first, int mol_last, pg_totals* removed);
 
 /* ---- reciprocal space, shardable ------------------------------------------ */
+/* One sample of the slab wall-force pressure, the force sums of
+ * ForceField::CalcPressureForceLJELSlit (src/force_field/pressure.cc:404-469) on the
+ * resident configuration: out6 = {LJ ion, LJ polymer, LJ wall-wall, EL ion, EL polymer,
+ * EL wall-wall}.  The first n_phantom molecules are the wall sites (one bead each, the
+ * first half on the z = 0 plate).  The caller keeps the running averages
+ * (p_tensor[6..11], wall-wall terms from the first sample only).  The LJ site-site
+ * term follows the evident intent of PotentialTruncatedLJ::PairForce
+ * (potential_truncated_lj.cc:87-122), whose test of an uninitialised r6 is undefined
+ * behaviour in the reference. */
+int pg_wall_force(pg_engine* h, int n_phantom, double* out6);
+
 /* Full S(k) over all charged beads for the k slice [k_first, k_first+k_count)
  * of the half-space list; writes interleaved (re,im) to sk_dev (device pointer,
  * may alias a torch tensor) or, if NULL, into the engine's own S(k).  Used by

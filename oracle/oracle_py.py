@@ -46,6 +46,8 @@ def lib():
         L.po_commit.argtypes = [C.c_void_p, C.c_int]
         L.po_mz_current.restype = C.c_double
         L.po_mz_current.argtypes = [C.c_void_p]
+        L.po_wall_force.restype = C.c_int
+        L.po_wall_force.argtypes = [C.c_void_p, C.c_int, c_double_p]
         L.po_beads_energy.restype = C.c_double
         L.po_beads_energy.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_double, c_double_p, C.c_int, C.c_double,
                                       C.c_int, C.c_int, c_double_p, c_double_p, c_int32_p, C.c_int, C.c_int,
@@ -146,6 +148,15 @@ class Oracle:
     def commit(self, accept: bool):
         rc = self.L.po_commit(self.h, int(bool(accept)))
         assert rc == 0, rc
+
+    def wall_force(self, phantom: int) -> np.ndarray:
+        """One sample of CalcPressureForceLJELSlit (pressure.cc:404-469): the six force sums
+        {LJ ion, LJ polymer, LJ wall-wall, EL ion, EL polymer, EL wall-wall}."""
+        out = np.zeros(6)
+        rc = self.L.po_wall_force(self.h, int(phantom), dptr(out))
+        if rc:
+            raise RuntimeError("po_wall_force failed")
+        return out
 
     def beads_energy(self, b1, t1, q1, b2, t2, q2, use_bead2, chain_xyz, chain_q, chain_type, current_len,
                      skip_first=-1, skip_last=-1):

@@ -1001,6 +1001,179 @@ int po_delete_molecules(po_system *s, int mf, int ml, pg_totals *removed) {
   return 0;
 }
 
+/* ------------------------------------------- wall-force pressure sampler -- */
+
+/* src/force_field/potential_truncated_lj.cc:87-122 as written for r > 0; the reference tests an
+ * uninitialised r6 there (undefined behaviour - gcc -O3 folds it to "always 1e8"), so the LJ columns of
+ * its output cannot be pinned: this is the evident intent (r <= 0 -> 1e8, else the LJ force).
+ * potential_hard_sphere.cc:51-57 returns 0. */
+static double pair_force(const po_system *s, const double *a, int ta, const double *b, int tb) {
+  if (s->pair_kind == PG_PAIR_HARD_SPHERE) return 0.0;
+  double r = bbdist(s, a, b, s->npbc);
+  double sigma = (s->lj_sigma[ta] + s->lj_sigma[tb]) / 2;
+  double epsilon = sqrt(s->lj_epsilon[ta] * s->lj_epsilon[tb]);
+  double force = 0, r6;
+  if (r <= 0) {
+    force = kVeryLargeEnergy;
+  } else if (s->lj_cutoff < 0) {
+    if (r < k216 * sigma) {
+      r6 = pow((sigma / r), 6);
+      force = 4 * epsilon * (r6 * r6 * 12 / r - r6 * 6 / r);
+    }
+  } else if (r < s->lj_cutoff) {
+    r6 = pow((sigma / r), 6);
+    force = 4 * epsilon * (r6 * r6 * 12 / r - r6 * 6 / r);
+  } else {
+    r6 = pow((sigma / s->lj_cutoff), 6);
+    force = 4 * epsilon * (r6 * r6 * 12 / r - r6 * 6 / r);
+  }
+  return force;
+}
+
+/* src/force_field/potential_ewald_coul.cc:261-293: z force on bead 1 (the wall site) */
+static double pair_force_z_real(const po_system *s, const double *b1, double q1, const double *b2, double q2) {
+  double force_z = 0;
+  if (q1 * q2 == 0) return force_z;
+  double r[3];
+  dist_vector(s, b2, b1, r);
+  double prefactor = s->lB * q1 * q2;
+  double prefactor2 = 2 * sqrt(s->alpha / kPi);
+  for (int i = -s->real_cell[0]; i <= s->real_cell[0]; i++)
+    for (int j = -s->real_cell[1]; j <= s->real_cell[1]; j++)
+      for (int k = -s->real_cell[2]; k <= s->real_cell[2]; k++) {
+        double rx = r[0] + i * s->ebox[0], ry = r[1] + j * s->ebox[1], rz = r[2] + k * s->ebox[2];
+        double d = sqrt(rx * rx + ry * ry + rz * rz);
+        if (d > 0 && d <= s->real_cutoff)
+          force_z += prefactor * ((prefactor2 * exp(-s->alpha * d * d)) + (erfc(sqrt(s->alpha) * d) / d)) * rz / (d * d);
+      }
+  return force_z;
+}
+
+/* src/force_field/potential_ewald_coul.cc:297-324 */
+static double pair_force_z_repl(const po_system *s, const double *b1, double q1, const double *b2, double q2) {
+  double force_z = 0;
+  if (q1 * q2 == 0) return force_z;
+  double r[3];
+  dist_vector(s, b2, b1, r);
+  double prefactor = s->lB * 4 * kPi * q1 * q2 / s->box_vol;
+  for (int lx = 0; lx < s->repl_ceto[0]; lx++)
+    for (int ly = 0; ly < s->repl_ceto[1]; ly++)
+      for (int lz = 0; lz < s->repl_ceto[2]; lz++) {
+        size_t idx = (size_t)s->repl_ceto[1] * s->repl_ceto[2] * lx + (size_t)s->repl_ceto[2] * ly + lz;
+        if (s->k2[idx] > 0 && s->k2[idx] <= s->repl_cutoff)
+          force_z += prefactor * s->kz[lz] * s->ek2[idx] * sin(s->kx[lx] * r[0] + s->ky[ly] * r[1] + s->kz[lz] * r[2]);
+      }
+  return force_z;
+}
+
+/* src/force_field/potential_truncated_lj_wall.cc:136-217 (hard and well walls: 0,
+ * potential_hard_wall.cc:49-53, potential_well_wall.cc:57-62) */
+static double bead_force_on_wall(const po_system *s, const double *p, int t) {
+  if (s->ext_kind != PG_EXT_TRUNCATED_LJ_WALL) return 0.0;
+  double force = 0;
+  double z = p[2], Lz = s->box[2];
+  double sigma = s->wall_sigma[t], epsilon = s->wall_epsilon[t];
+  double R0 = 3 * k213 * sigma, K = 1;
+  int graft = s->graft_kind[t];
+  if (epsilon == 0) return 0.0;
+  if (z <= 0 || z >= Lz) return kVeryLargeEnergy;
+  if (s->wall_cut < 0 && graft == 0) {
+    if (z < k213 * sigma) {
+      double r3 = pow((sigma / z), 3);
+      force += 2.59807621135 * epsilon * (r3 * r3 * 6 / z - r3 * 3 / z);
+    }
+    if (Lz - z < k213 * sigma) {
+      double r3 = pow((sigma / (Lz - z)), 3);
+      force += 2.59807621135 * epsilon * (r3 * r3 * 6 / (Lz - z) - r3 * 3 / (Lz - z));
+    }
+  } else if (graft == 1) { /* "L" */
+    double r3 = pow((sigma / z), 3);
+    force += 2.59807621135 * epsilon * (r3 * r3 * 6 / z - r3 * 3 / z);
+    force += -K * R0 * z / (1 - pow(z / R0, 2));
+    if (Lz - z < k213 * sigma) {
+      double r3b = pow((sigma / (Lz - z)), 3);
+      force += 2.59807621135 * epsilon * (r3b * r3b * 6 / (Lz - z) - r3b * 3 / (Lz - z));
+    }
+  } else if (graft == 2) { /* "R" */
+    double r3 = pow((sigma / (Lz - z)), 3);
+    force += 2.59807621135 * epsilon * (r3 * r3 * 6 / (Lz - z) - r3 * 3 / (Lz - z));
+    force += -K * R0 * (Lz - z) / (1 - pow((Lz - z) / R0, 2));
+    if (z < k213 * sigma) {
+      double r3b = pow((sigma / z), 3);
+      force += 2.59807621135 * epsilon * (r3b * r3b * 6 / z - r3b * 3 / z);
+    }
+  } else {
+    double m_cut = s->wall_cut;
+    if (z < m_cut) {
+      double r3 = pow((sigma / z), 3);
+      force += 2.59807621135 * epsilon * (r3 * r3 * 6 / z - r3 * 3 / z);
+    } else {
+      double r3 = pow((sigma / m_cut), 3);
+      force += 2.59807621135 * epsilon * (r3 * r3 * 6 / z - r3 * 3 / z);
+    }
+    if (Lz - z < m_cut) {
+      double r3 = pow((sigma / (Lz - z)), 3);
+      force += 2.59807621135 * epsilon * (r3 * r3 * 6 / (Lz - z) - r3 * 3 / (Lz - z));
+    } else {
+      double r3 = pow((sigma / m_cut), 3);
+      force += 2.59807621135 * epsilon * (r3 * r3 * 6 / z - r3 * 3 / z);
+    }
+  }
+  return force;
+}
+
+/* One sample of ForceField::CalcPressureForceLJELSlit, src/force_field/pressure.cc:404-469: the six
+ * force sums of this configuration, out = {LJ ion, LJ polymer, LJ wall-wall, EL ion, EL polymer, EL wall-wall}
+ * (the caller accumulates them into p_tensor[6..11]; wall-wall only on its first sample).
+ * `phantom` wall sites are the first molecules (one bead each), half on each plate. */
+int po_wall_force(const po_system *s, int phantom, double out[6]) {
+  for (int i = 0; i < 6; i++) out[i] = 0;
+  if (phantom < 0 || phantom > s->n_mol) return -1;
+  for (int i = 0; i < phantom; i++) {
+    const double *pi = s->cur + 3 * (size_t)s->mol_first[i];
+    int ti = s->type[s->mol_first[i]];
+    double qi = s->q[s->mol_first[i]];
+    for (int j = phantom / 2; j < s->n_mol; j++) {
+      int len = s->mol_first[j + 1] - s->mol_first[j];
+      for (int k = 0; k < len; k++) {
+        int b = s->mol_first[j] + k;
+        const double *pj = s->cur + 3 * (size_t)b;
+        double C;
+        if (i < phantom / 2 && j >= phantom) C = -0.5;
+        else if (i < phantom && j >= phantom) C = 0.5;
+        else C = -1;
+        int k_id = 2;
+        if (j >= phantom) k_id = (len > 1) ? 1 : 0;
+        if (s->pair_kind != PG_PAIR_NONE && (i < phantom / 2 || j >= phantom)) {
+          double r[3];
+          for (int a = 0; a < 3; a++) { /* GetDistVector(mols[j], mols[i], ForceField::box_l) */
+            double di = pi[a] - pj[a];
+            if (a < s->npbc) di -= s->box[a] * round(di / s->box[a]);
+            r[a] = di;
+          }
+          double zc = r[2] / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+          out[k_id] += C * zc * pair_force(s, pj, s->type[b], pi, ti);
+        }
+        if (s->use_ewald && (i < phantom / 2 || j >= phantom)) {
+          double f = C * pair_force_z_real(s, pi, qi, pj, s->q[b]);
+          f += C * pair_force_z_repl(s, pi, qi, pj, s->q[b]);
+          out[3 + k_id] += f;
+        }
+      }
+    }
+  }
+  if (s->ext_kind != PG_EXT_NONE) {
+    for (int i = phantom; i < s->n_mol; i++) {
+      int len = s->mol_first[i + 1] - s->mol_first[i];
+      for (int j = 0; j < len; j++) {
+        int b = s->mol_first[i] + j;
+        out[len > 1 ? 1 : 0] += 0.5 * bead_force_on_wall(s, s->cur + 3 * (size_t)b, s->type[b]);
+      }
+    }
+  }
+  return 0;
+}
+
 /* --------------------------------------------------- standalone helpers -- */
 /* Single-pair entry points for unit tests of the primitives. */
 double po_pair_energy(const po_system *s, const double *a, int ta, const double *b, int tb) {

@@ -29,6 +29,7 @@
 #include "pg_kernels.cu"
 #include "pg_move.cu"
 #include "pg_trials.cu"
+#include "pg_pressure.cu"
 
 namespace {
 
@@ -1454,6 +1455,51 @@ int pg_delete_molecules(pg_engine* h, int mf, int ml, pg_totals* removed) {
   h->mol_first.swap(mfirst);
   h->n -= glen;
   h->n_mol -= nm;
+  return PG_OK;
+}
+
+// --------------------------------------------------- wall-force pressure
+int pg_wall_force(pg_engine* h, int n_phantom, double* out6) {
+  if (!h || !out6 || n_phantom < 0 || n_phantom > h->n_mol) return PG_ERR_INVALID;
+  for (int m = 0; m < n_phantom; m++)
+    if (h->mol_first[m + 1] - h->mol_first[m] != 1) { h->err = "wall sites must be single-bead molecules"; return PG_ERR_INVALID; }
+  for (int k = 0; k < 6; k++) out6[k] = 0.0;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
+  const int n = h->n;
+  if (n == 0) return PG_OK;
+  std::vector<unsigned char> klass((size_t)n);
+  for (int m = 0; m < h->n_mol; m++) {
+    const int len = h->mol_first[m + 1] - h->mol_first[m];
+    const unsigned char c = (m < n_phantom) ? 2 : (len > 1 ? 1 : 0);
+    for (int b = h->mol_first[m]; b < h->mol_first[m + 1]; b++) klass[b] = c;
+  }
+  PgWallForceArgs A;
+  A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.n = n; A.phantom = n_phantom;
+  A.b_first = h->mol_first[n_phantom / 2];
+  A.kvec = h->d_kvec; A.nk = h->P.use_ewald ? h->nk : 0;
+  const long long work = (long long)n_phantom * (n - A.b_first) + (n - n_phantom);
+  if (work <= 0) return PG_OK;
+  const long long blocks = (work + WF_THREADS - 1) / WF_THREADS;
+  if (blocks > (1LL << 30)) { h->err = "wall-force sample too large"; return PG_ERR_CAPACITY; }
+  unsigned char* d_klass = nullptr;
+  double* d_part = nullptr;
+  std::vector<double> part((size_t)blocks * 6);
+  cudaError_t e = cudaMalloc((void**)&d_klass, (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_part, sizeof(double) * part.size());
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_klass, klass.data(), (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    A.klass = d_klass; A.partial = d_part;
+    k_wall_force<<<(unsigned)blocks, WF_THREADS, 0, h->stream>>>(h->P, A);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_klass); cudaFree(d_part);
+  if (e != cudaSuccess) { h->err = std::string("pg_wall_force: ") + cudaGetErrorString(e); return PG_ERR_CUDA; }
+  for (long long b = 0; b < blocks; b++)
+    for (int k = 0; k < 6; k++) out6[k] += part[(size_t)b * 6 + k];
   return PG_OK;
 }
 

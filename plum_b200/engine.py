@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "pg_create", "pg_destroy", "pg_last_error", "pg_abi_version", "pg_get_ewald_info", "pg_upload_system",
     "pg_init_energy", "pg_recompute_totals", "pg_get_totals", "pg_download_positions", "pg_num_beads", "pg_delta_e",
     "pg_delta_e_begin", "pg_delta_e_poll", "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_trial_energies", "pg_insert_molecules",
-    "pg_delete_molecules", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
+    "pg_delete_molecules", "pg_wall_force", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
     "pg_stream", "pg_measure_fp64_peak",
 ]
 
@@ -54,6 +54,7 @@ def lib():
         L.pg_download_positions.argtypes = [vp, c_double_p]
         L.pg_num_beads.argtypes = [vp]
         L.pg_delta_e.argtypes = [vp, C.c_int, c_double_p, c_uint8_p, C.POINTER(PgDelta)]
+        L.pg_wall_force.argtypes = [vp, C.c_int, c_double_p]
         L.pg_delta_e_begin.argtypes = [vp, C.c_int, c_double_p, c_uint8_p]
         L.pg_delta_e_poll.argtypes = [vp, C.POINTER(PgDelta)]
         L.pg_commit.argtypes = [vp, C.c_int]
@@ -232,6 +233,12 @@ class Engine:
         e, pe, ee = self.trial_energies(np.asarray(b1).reshape(1, 3), np.asarray(b2).reshape(1, 3), t1, q1, t2, q2,
                                         use_bead2, chain_xyz, chain_q, chain_type, current_len, skip_first, skip_last)
         return float(e[0]), float(pe[0]), float(ee[0])
+
+    def wall_force(self, phantom: int) -> np.ndarray:
+        """One sample of the slab wall-force pressure sums (pg_wall_force)."""
+        out = np.zeros(6)
+        self._check(self.L.pg_wall_force(self.h, int(phantom), dptr(out)), "pg_wall_force")
+        return out
 
     # -- GC ----------------------------------------------------------------
     def insert_molecules(self, mol_len, xyz, q, type_ids) -> dict:

@@ -34,9 +34,9 @@ namespace {
 double Uniform(mt19937& g) { return (double)g() / g.max(); }
 
 // PLUM_B200_PROFILE=1: wall time spent inside each ABI entry point, printed to stderr at exit.
-enum { kTDelta, kTCommit, kTTrials, kTInsert, kTDelete, kTTotals, kTSites };
+enum { kTDelta, kTCommit, kTTrials, kTInsert, kTDelete, kTTotals, kTWallForce, kTSites };
 const char* const kSiteName[kTSites] = {"pg_delta_e", "pg_commit", "pg_trial_energies", "pg_insert_molecules",
-                                        "pg_delete_molecules", "pg_get_totals"};
+                                        "pg_delete_molecules", "pg_get_totals", "pg_wall_force"};
 bool prof_on = getenv("PLUM_B200_PROFILE") != NULL;
 double prof_s[kTSites];
 long prof_n[kTSites];
@@ -54,7 +54,9 @@ struct SiteTimer {
 };
 }  // namespace
 
-ForceField::ForceField() : engine(NULL), pending_mol(-1) {}
+ForceField::ForceField() : engine(NULL), pending_mol(-1), vp_z(0) {
+  for (int i = 0; i < 12; i++) p_tensor[i] = 0;
+}
 
 ForceField::~ForceField() {
   if (prof_on)
@@ -753,13 +755,46 @@ double ForceField::CalcChemicalPotentialF(vector<Molecule>& mols, mt19937& rand_
 }
 
 // ------------------------------------------------------------------ samplers
+// Bulk volume-perturbation sampler (pressure.cc:187-387): its results are never printed for systems
+// without walls (GetPressure returns "nan", pressure.cc:490-500) and it draws no random numbers.
 void ForceField::CalcPressureVolScalingHSELSlit(vector<Molecule>& mols) { (void)mols; }
-void ForceField::CalcPressureForceLJELSlit(vector<Molecule>& mols) { (void)mols; }
+// Slab wall-force pressure, src/force_field/pressure.cc:404-484.  The six force sums of the current
+// configuration come from one pg_wall_force launch (site-site LJ + Ewald real/reciprocal z-forces between
+// the wall sites and everything else, plus the plate LJ force); the running averages below are the
+// reference's.  The reference never initialises vp_z on this branch (force_field.cc:293-322 sets it only
+// for bulk systems); it starts at zero here.
+void ForceField::CalcPressureForceLJELSlit(vector<Molecule>& mols) {
+  (void)mols;
+  vp_z++;
+  double f[6];
+  int rc;
+  { SiteTimer st_(kTWallForce); rc = pg_wall_force(engine, phantom, f); }
+  if (rc) Fail("pg_wall_force", rc);
+  p_tensor[6] += f[0];
+  p_tensor[7] += f[1];
+  p_tensor[9] += f[3];
+  p_tensor[10] += f[4];
+  if (vp_z == 1) {   // the walls are fixed: wall-wall terms once
+    p_tensor[8] += f[2];
+    p_tensor[11] += f[5];
+    p_tensor[2] = p_tensor[8] / (box_l[0] * box_l[1]);
+    p_tensor[5] = p_tensor[11] / (box_l[0] * box_l[1]);
+  }
+  p_tensor[0] = p_tensor[6] / (vp_z * box_l[0] * box_l[1]);
+  p_tensor[1] = p_tensor[7] / (vp_z * box_l[0] * box_l[1]);
+  p_tensor[3] = p_tensor[9] / (vp_z * box_l[0] * box_l[1]);
+  p_tensor[4] = p_tensor[10] / (vp_z * box_l[0] * box_l[1]);
+}
 
+// pressure.cc:490-500
 string ForceField::GetPressure() {
-  // Pressure sampling is "next" (SURVEY.md 8(f) #1): columns are kept so output_stat.dat parses.
-  if (use_ext_pot) return "0 0 0 0 0 0";
-  return "nan";
+  std::ostringstream foo;
+  if (use_ext_pot)
+    foo << p_tensor[0] << " " << p_tensor[1] << " " << p_tensor[2] << " " << p_tensor[3] << " " << p_tensor[4] << " "
+        << p_tensor[5];
+  else
+    foo << "nan";
+  return foo.str();
 }
 
 // ----------------------------------------------------------------- utilities

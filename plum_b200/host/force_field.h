@@ -43,6 +43,8 @@ class ForceField {
   double beta;
   int npbc;
   double box_l[3];
+  double p_tensor[12];   // wall-force pressure: [0..5] running averages, [6..11] cumulative sums (pressure.cc:389-403)
+  int vp_z;              // pressure samples taken
   int n_mol, phantom, coion, grafted, grafted_counterion;
   int chain_len, n_chain, n_cion, n_aion;
   bool use_gc, use_pair_pot, use_ewald_pot, use_bond_pot, use_bond_rigid;

@@ -85,13 +85,37 @@ def compact_long(lines, path, n_steps):
         tot=np.array(tot_val))
 
 
+def extras():
+    """Fixtures of the two samplers that sit next to the per-move path:
+       short/bulk_nvt_mu_seed1.{trace.gz,stat.dat}            230 steps with s1_calc_chem_pot 1 (Widom sampler
+                                                              on the trajectory, mu column of output_stat.dat);
+       short/confined_nvt_pressure_seed1.{trace.gz,stat.dat}  3000 steps with coordinates: the wall-force
+                                                              pressure columns of output_stat.dat at steps
+                                                              1000/2000/3000 (CalcPressureForceLJELSlit)."""
+    jobs = [("bulk_nvt", "bulk_nvt_mu_seed1", 230, False, {"s1_calc_chem_pot": 1}),
+            ("confined_nvt", "confined_nvt_pressure_seed1", 3000, True, {})]
+    for ex, name, steps, xyz, over in jobs:
+        lines, files = replay.run_plum_ref(os.path.join(REF_EXAMPLES, ex), steps, 1, xyz=xyz, overrides=over,
+                                           want_files=("output_stat.dat",))
+        with gzip.open(os.path.join(HERE, "short", name + ".trace.gz"), "wt") as f:
+            f.write("\n".join(lines))
+        with open(os.path.join(HERE, "short", name + ".stat.dat"), "w") as f:
+            f.write(files["output_stat.dat"])
+        print("extra", name, len(lines), "lines")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--long-from", default=None)
     ap.add_argument("--skip-long", action="store_true")
+    ap.add_argument("--extras-only", action="store_true", help="only the sampler fixtures (extras())")
     a = ap.parse_args()
     if not replay.have_plum_ref():
         raise SystemExit("oracle/_ref/plum_ref missing: run python oracle/build_ref.py")
+    if a.extras_only:
+        os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
+        extras()
+        return
     os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
     os.makedirs(os.path.join(HERE, "long"), exist_ok=True)
     for ex in EXAMPLES:
@@ -114,6 +138,7 @@ def main():
             lines = replay.run_plum_ref(src, LONG_STEPS, 1, xyz=False)
         compact_long(lines, os.path.join(HERE, "long", f"{ex}_seed1.npz"), LONG_STEPS)
         print("long", ex, len(lines), "lines")
+    extras()
 
 
 if __name__ == "__main__":

@@ -90,7 +90,8 @@ def rel(a: float, b: float, floor: float = 1.0) -> float:
 
 
 def replay(engine, r: runin.RunIn, sysm: runin.System, types: runin.TypeTable, lines: List[str],
-           max_steps: Optional[int] = None, check_totals_every: int = 1, beads_energy=True) -> ReplayReport:
+           max_steps: Optional[int] = None, check_totals_every: int = 1, beads_energy=True,
+           on_step=None) -> ReplayReport:
     """`engine` needs: upload, init_energy, delta_e, commit, totals, insert_molecules,
     delete_molecules, and (optionally) beads_energy."""
     rep = ReplayReport()
@@ -140,6 +141,8 @@ def replay(engine, r: runin.RunIn, sysm: runin.System, types: runin.TypeTable, l
                     rep.worst = f"step {step} mol {mol}: dE {d['dE']!r} vs {dE_ref!r}"
             engine.commit(bool(acc))
             step_count += 1
+            if on_step is not None:
+                on_step(step)   # the configuration Simulation::Sample sees after this step
             if check_totals_every and step_count % check_totals_every == 0:
                 tot = engine.totals()
                 ref = dict(pair=hx(t[6]), ewald=hx(t[7]), bond=hx(t[8]), ext=hx(t[9]))
@@ -232,6 +235,46 @@ def golden_short_trace(name: str, seed: int) -> List[str]:
     import gzip
     with gzip.open(os.path.join(GOLDEN, "short", f"{name}_seed{seed}.trace.gz"), "rt") as f:
         return f.read().split("\n")
+
+
+def golden_pressure_fixture():
+    """confined_nvt, seed 1, 3000 steps: (trace lines, {step: [six pressure columns]}) from the reference's
+    own output_stat.dat (tests/golden/make_golden.py extras())."""
+    import gzip
+    with gzip.open(os.path.join(GOLDEN, "short", "confined_nvt_pressure_seed1.trace.gz"), "rt") as f:
+        lines = f.read().split("\n")
+    cols = {}
+    with open(os.path.join(GOLDEN, "short", "confined_nvt_pressure_seed1.stat.dat")) as f:
+        rows = [ln.split() for ln in f.read().split("\n") if ln]
+    hdr = rows[0]
+    i0 = hdr.index("<Pzz_LJ_ion>")
+    for row in rows[1:]:
+        cols[int(row[0])] = [float(x) for x in row[i0:i0 + 6]]
+    return lines, cols
+
+
+class WallForceAverager:
+    """Host-side bookkeeping of ForceField::CalcPressureForceLJELSlit (pressure.cc:404-484) around an
+    engine that returns the six force sums of one configuration: wall-wall terms only from the first
+    sample, running averages per unit area."""
+
+    def __init__(self, box):
+        self.area = box[0] * box[1]
+        self.vp_z = 0
+        self.cum = [0.0] * 6
+
+    def add(self, f6):
+        self.vp_z += 1
+        for k in (0, 1, 3, 4):
+            self.cum[k] += f6[k]
+        if self.vp_z == 1:
+            self.cum[2] += f6[2]
+            self.cum[5] += f6[5]
+
+    def p_tensor(self):
+        a = self.area
+        return [self.cum[0] / (self.vp_z * a), self.cum[1] / (self.vp_z * a), self.cum[2] / a,
+                self.cum[3] / (self.vp_z * a), self.cum[4] / (self.vp_z * a), self.cum[5] / a]
 
 
 def golden_long(name: str):

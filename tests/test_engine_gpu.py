@@ -422,6 +422,81 @@ def test_replay_on_device_matches_host_driven_path():
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["confined_nvt", "confined_muvt"])
+def test_wall_force_matches_oracle_on_examples(name):
+    """pg_wall_force (CalcPressureForceLJELSlit, pressure.cc:404-469) on the slab examples: the six force
+    sums against the oracle (itself pinned to the reference's printed columns, test_oracle_vs_reference)
+    at the start and after replayed reference moves."""
+    r, s, types, params = replay.load_golden(name)
+    eng, orc = _engine(params, s.n + 64), _oracle(params)
+    lines = replay.golden_short_trace(name, 1)
+    seen = []
+
+    def check(step):
+        if step % 40 == 0:
+            g, o = eng.wall_force(r.phantom), orc.wall_force(r.phantom)
+            scale = max(1.0, float(np.max(np.abs(o))))
+            assert np.max(np.abs(g - o)) <= TOL * scale, (step, g, o)
+            seen.append(step)
+
+    class Both:
+        """Drives engine and oracle through the same trace."""
+        def upload(self, *a): eng.upload(*a); orc.upload(*a)
+        def init_energy(self): orc.init_energy(); return eng.init_energy()
+        def delta_e(self, *a): orc.delta_e(*a); return eng.delta_e(*a)
+        def commit(self, acc): orc.commit(acc); eng.commit(acc)
+        def totals(self): return eng.totals()
+        def insert_molecules(self, *a): orc.insert_molecules(*a); return eng.insert_molecules(*a)
+        def delete_molecules(self, *a): orc.delete_molecules(*a); return eng.delete_molecules(*a)
+
+    replay.replay(Both(), r, s, types, lines, max_steps=200, check_totals_every=0, beads_energy=False, on_step=check)
+    assert len(seen) >= 3
+    eng.close()
+
+
+@pytest.mark.parametrize("case", [2, 6, 7, 8, 9])
+def test_wall_force_plate_term_matches_oracle(case):
+    """No wall sites (phantom = 0): only 0.5 * BeadForceOnWall is left — repulsive, full 9-3 (wall_cut),
+    grafted L/R (FENE) branches, and the force-free hard / well walls."""
+    c = dict(CASES[case])
+    rng = np.random.default_rng(900 + case)
+    box = c.pop("box")
+    sysm = _random_system(rng, c.pop("n_chain"), c.pop("chain_len"), c.pop("n_ion"), np.array(box),
+                          c.pop("charged_every", 1), c.pop("slab", False))
+    r, types, params = _params(box, **c)
+    if c.get("graft"):
+        for m in range(4):
+            f = int(sysm.mol_first[m])
+            sysm.symbol[f] = "L" if m % 2 == 0 else "R"
+            sysm.xyz[f, 2] = 1.3 if m % 2 == 0 else box[2] - 1.3
+    sysm.xyz[-3:, 2] = [0.6, box[2] - 0.7, 1.0]     # ions inside the repulsive range of both plates
+    eng, orc = _engine(params, sysm.n), _oracle(params)
+    ids = types.ids(sysm.symbol)
+    eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first); orc.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
+    eng.init_energy(); orc.init_energy()
+    g, o = eng.wall_force(0), orc.wall_force(0)
+    assert np.max(np.abs(g - o)) <= TOL * max(1.0, float(np.max(np.abs(o)))), (g, o)
+    if params["ext_kind"] == 1:
+        assert abs(o[0]) > 0
+    else:
+        assert not o.any()
+    # four ions promoted to wall sites (they are single-bead molecules): the site-site terms, wall-wall included
+    perm_first = list(range(sysm.n_mol - 4, sysm.n_mol)) + list(range(sysm.n_mol - 4))
+    xyz = np.concatenate([sysm.xyz[sysm.mol_first[m]:sysm.mol_first[m + 1]] for m in perm_first])
+    q = np.concatenate([sysm.q[sysm.mol_first[m]:sysm.mol_first[m + 1]] for m in perm_first])
+    sym = [sysm.symbol[b] for m in perm_first for b in range(sysm.mol_first[m], sysm.mol_first[m + 1])]
+    lens = [int(sysm.mol_first[m + 1] - sysm.mol_first[m]) for m in perm_first]
+    mf = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    xyz[:2, 2] = 0.0; xyz[2:4, 2] = box[2]
+    ids2 = types.ids(sym)
+    eng.upload(xyz, q, ids2, mf); orc.upload(xyz, q, ids2, mf)
+    eng.init_energy(); orc.init_energy()
+    g, o = eng.wall_force(4), orc.wall_force(4)
+    assert np.max(np.abs(g - o)) <= TOL * max(1.0, float(np.max(np.abs(o)))), (g, o)
+    assert abs(o[3]) > 0 and abs(o[5]) > 0
+    eng.close()
+
+
 def test_async_halves_interleave_two_replicas():
     """pg_delta_e_begin / pg_delta_e_poll: two engines driven by one thread with their round trips
     overlapped give exactly the numbers of the synchronous pg_delta_e, and state errors are reported."""
