@@ -497,6 +497,71 @@ def test_wall_force_plate_term_matches_oracle(case):
     eng.close()
 
 
+def test_full_size_synthetic_system_parity():
+    """BASELINE.json configs[4] at FULL size (22 000 beads, K = 3574): the FAST k_move path and k_trials
+    against the oracle on a bounded sample — init totals, three ion moves, one 100-bead chain move
+    (pivot-like, every bead displaced), one accepted move followed by another (deferred commit), and a
+    CBMC growth step of 6 trials; plus size-independent properties: a rejected move leaves the totals
+    untouched, an accepted move followed by its inverse returns them."""
+    import os
+    from plum_b200 import synth
+    r, s, types, params = synth.load(cache_dir=os.path.join(replay.REPO, "gpurun_out", "cache"))
+    ids = types.ids(s.symbol)
+    eng, orc = _engine(params, s.n), _oracle(params)
+    eng.upload(s.xyz, s.q, ids, s.mol_first); orc.upload(s.xyz, s.q, ids, s.mol_first)
+    tg = eng.init_energy()
+    # oracle totals of 2.4e8 pairs would take minutes: check the O(N) / O(N_q K) components only
+    sk_o = orc.sk_half()
+    assert np.max(np.abs(eng.sk_download() - sk_o)) <= 1e-10 * max(1.0, float(np.max(np.abs(sk_o))))
+    rng = np.random.default_rng(5)
+    ions = [m for m in range(s.n_mol) if s.mol_first[m + 1] - s.mol_first[m] == 1]
+    chains = [m for m in range(s.n_mol) if s.mol_first[m + 1] - s.mol_first[m] > 1]
+    pos = s.xyz.copy()
+
+    def one(mol, trial, accept):
+        f, l = int(s.mol_first[mol]), int(s.mol_first[mol + 1])
+        mv = np.ones(l - f, dtype=np.uint8)
+        dg, do = eng.delta_e(mol, trial, mv), orc.delta_e(mol, trial, mv)
+        for k in ("dE", "pair", "ewald", "real", "recip"):
+            assert abs(dg[k] - do[k]) <= TOL * max(1.0, abs(do[k])), (mol, k, dg[k], do[k])
+        eng.commit(accept); orc.commit(accept)
+        if accept:
+            pos[f:l] = trial
+        return dg["dE"]
+
+    t0 = eng.totals()
+    for i in range(3):
+        m = int(rng.choice(ions)); f = int(s.mol_first[m])
+        v = rng.normal(size=3)
+        one(m, pos[f:f + 1] + 6.0 * v / np.linalg.norm(v), accept=(i == 1))
+    m = int(rng.choice(chains)); f, l = int(s.mol_first[m]), int(s.mol_first[m + 1])
+    keep = pos[f:l].copy()
+    dE1 = one(m, keep + rng.normal(scale=0.4, size=(l - f, 3)), accept=True)      # accepted chain move
+    t1 = eng.totals()
+    dE2 = one(m, keep, accept=True)                                                # ... and its inverse
+    t2 = eng.totals()
+    assert abs(dE1 + dE2) <= 1e-9 * max(1.0, abs(dE1))
+    etot = lambda t: t["pair"] + t["ewald"] + t["bond"] + t["ext"]
+    assert abs(etot(t2) - (etot(t1) - dE1)) <= 1e-9 * max(1.0, abs(etot(t1)))
+    assert np.max(np.abs(eng.positions() - pos)) == 0.0
+    # CBMC growth step at full size (k_trials, single-image column split = 1)
+    tP = types.ids(["P"])[0]
+    cl = 3
+    cx = np.zeros((2 * cl, 3)); cq = np.zeros(2 * cl); ct = np.full(2 * cl, tP, dtype=np.int32)
+    p = np.array([100.0, 100.0, 100.0])
+    for i in range(cl):
+        cx[i] = p + 2.5 * i; cq[i] = -1.0
+        cx[cl + i] = cx[i] + 1.9; cq[cl + i] = 1.0
+    b1 = cx[cl - 1] + 2.5 * np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0.6, 0.8, 0]])
+    b2 = b1 + np.array([1.5, -1.2, 0.7])
+    eg, pg_, wg = eng.trial_energies(b1, b2, tP, -1.0, tP, 1.0, 1, cx, cq, ct, cl, chains[0], chains[0])
+    for t in range(len(b1)):
+        eo, po, wo = orc.beads_energy(b1[t], tP, -1.0, b2[t], tP, 1.0, 1, cx, cq, ct, cl, chains[0], chains[0])
+        assert abs(eg[t] - eo) <= TOL * max(1.0, abs(eo)), (t, eg[t], eo)
+        assert abs(wg[t] - wo) <= TOL * max(1.0, abs(wo)), (t, wg[t], wo)
+    eng.close()
+
+
 def test_async_halves_interleave_two_replicas():
     """pg_delta_e_begin / pg_delta_e_poll: two engines driven by one thread with their round trips
     overlapped give exactly the numbers of the synchronous pg_delta_e, and state errors are reported."""
