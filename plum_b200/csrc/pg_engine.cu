@@ -462,7 +462,14 @@ int launch_delta(pg_engine* h, int mode, int g0, int glen, int chain_len_first, 
   A.kl = h->d_kl; A.ek2 = h->d_ek2; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->nk;
   A.n_tiles = std::max(1, (h->n + PG_TILE - 1) / PG_TILE);
   A.n_chunks = std::max(1, (glen + PG_GCHUNK - 1) / PG_GCHUNK);
+  if (h->P.use_ewald && !h->P.single_image) {
+    // multi-image real space (100+ images per pair): a thread should carry few group beads — split the
+    // group until the grid covers the device (small systems have one or two partner tiles)
+    const int want = (2 * std::max(1, h->n_sm) + A.n_tiles - 1) / A.n_tiles;
+    A.n_chunks = std::min(std::max(glen, 1), std::max(A.n_chunks, want));
+  }
   A.chunk_size = std::max(1, (glen + A.n_chunks - 1) / A.n_chunks);
+  A.n_chunks = std::max(1, (glen + A.chunk_size - 1) / A.chunk_size);
   A.n_pair_ctas = A.n_tiles * A.n_chunks;
   A.n_k_ctas = h->P.use_ewald ? (h->nk + PG_KTILE - 1) / PG_KTILE : 0;
   int n_ctas = A.n_pair_ctas + A.n_k_ctas;

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(PG_TILE) k_delta(const PgDev P, const PgDeltaA
             // g == jj: the bead with its own periodic images, x0.5 (potential_ewald.cc:445-448)
             double qq = pq * pq;
             if (qq != 0) {
-              double e = 0.5 * pg_pair_real_d(P, 0.0, 0.0, 0.0, qq);
+              double e = P.real_self_unit * qq;   // position independent: summed once on the host
               acc_real += (A.has_new ? e : 0.0) - (A.has_old ? e : 0.0);
             }
           }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(PG_TILE) k_delta(const PgDev P, const PgDeltaA
           acc_real += re_n;
         } else if (P.use_ewald) {
           double qq = A.gq[g] * A.gq[g];
-          if (qq != 0) acc_real += 0.5 * pg_pair_real_d(P, 0.0, 0.0, 0.0, qq);
+          if (qq != 0) acc_real += P.real_self_unit * qq;
         }
       }
     }
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(PG_TILE) k_tot_pairs(const PgDev P, const doub
           e_lj += lj; e_re += re;
         } else if (P.use_ewald) {
           double qq = aq * aq;
-          if (qq != 0) e_re += 0.5 * pg_pair_real_d(P, 0.0, 0.0, 0.0, qq);
+          if (qq != 0) e_re += P.real_self_unit * qq;
         }
       }
     }

@@ -50,3 +50,53 @@ print(json.dumps(out["launch_list"], indent=1))
 print(json.dumps(out["k_move_by_grid"], indent=1))
 for p in prof:
     print(p)
+
+# ---- every kernel of the path (tools/profile_kernels.py under ncu --set full): last (warm) instance per (kernel, grid)
+import os
+allrep = f"gpurun_out/prof_{tag}_all_raw.csv"   # written on the GPU box by tools/round_evidence.sh (ncu --page raw --csv)
+if os.path.exists(allrep):
+    raw = open(allrep).read()
+    rr = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rr[0], rr[1], rr[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+
+    def num(r, k):
+        try:
+            return float(r[ix[k]].replace(",", ""))
+        except Exception:
+            return 0.0
+
+    def dur_us(r):
+        v, u = num(r, "gpu__time_duration.sum"), units[ix["gpu__time_duration.sum"]]
+        return v / 1000 if u in ("ns", "nsecond") else v * 1000 if u in ("ms", "msecond") else v
+
+    def bytes_of(r, k):
+        u = units[ix[k]] if k in ix else "byte"
+        return num(r, k) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+
+    last = {}
+    for r in data:
+        key = (r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), r[ix["Grid Size"]])
+        last[key] = r
+    rows = []
+    for (kname, grid), r in last.items():
+        us = dur_us(r)
+        # --set full carries the DFMA count (x2 = flops); DADD / DMUL are not in the set: a lower bound
+        # (the derived metric is flops per elapsed cycle)
+        fl = num(r, "derived__smsp__sass_thread_inst_executed_op_dfma_pred_on_x2") * num(r, "sm__cycles_elapsed.max")
+        rows.append(dict(kernel=kname, grid=grid, duration_us=round(us, 2), regs=int(num(r, "launch__registers_per_thread")),
+                         issue_active_pct=round(num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), 1),
+                         fp64_pipe_pct=round(num(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"), 1),
+                         warps_active_pct=round(num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"), 1),
+                         warp_inst=int(num(r, "smsp__inst_executed.sum")),
+                         executed_fp64_gflops=round(fl / (us * 1e-6) / 1e9, 1) if us > 0 else 0.0,
+                         l2_gbs=round(32.0 * num(r, "lts__t_sectors.sum") / (us * 1e-6) / 1e9, 1) if us > 0 else 0.0,
+                         l2_pct=round(num(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"), 1),
+                         dram_read_bytes=int(bytes_of(r, "dram__bytes_read.sum")), dram_write_bytes=int(bytes_of(r, "dram__bytes_write.sum"))))
+    rows.sort(key=lambda x: (x["kernel"], x["grid"]))
+    json.dump(rows, open(f"profiles/{tag}_kernels.json", "w"), indent=1)
+    print("| kernel | grid | µs | regs | issue % | FP64 pipe % | executed DFMA GFLOP/s | L2 GB/s (% of peak) | DRAM rd/wr bytes |")
+    print("|---|---|---|---|---|---|---|---|---|")
+    for x in rows:
+        print(f"| `{x['kernel']}` | {x['grid']} | {x['duration_us']} | {x['regs']} | {x['issue_active_pct']} | {x['fp64_pipe_pct']} | "
+              f"{x['executed_fp64_gflops']} | {x['l2_gbs']} ({x['l2_pct']}) | {x['dram_read_bytes']} / {x['dram_write_bytes']} |")

@@ -3,7 +3,7 @@
 # usage: tools/round_evidence.sh r01   -> gpurun_out/{pytest_gpu,bench_n1,bench_ref,launches,prof_*}_<tag>.*
 tag=${1:-r01}
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log
+if [ -z "$SKIP_TESTS" ]; then python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log; fi
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1; tail -2 gpurun_out/smoke_$tag.log
 python bench.py > gpurun_out/bench_n1_$tag.json 2> gpurun_out/bench_n1_$tag.err; tail -c 600 gpurun_out/bench_n1_$tag.json
 python bench.py --impl reference > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err; tail -c 400 gpurun_out/bench_ref_$tag.json
@@ -11,4 +11,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 600 --csv --
     python bench.py --steps 1 --warmup 3 --moves-per-step 64 --no-cpu-baseline --replicas-per-gpu 1 > gpurun_out/ncu_bench1_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_move -s 400 -c 8 -f -o gpurun_out/prof_${tag}_kmove \
     python bench.py --steps 1 --warmup 3 --moves-per-step 64 --no-cpu-baseline --replicas-per-gpu 1 > gpurun_out/ncu_bench2_$tag.log 2>&1
+# every kernel of the path; only the raw-metric CSV travels back (gpurun_out is capped at 64 MiB)
+ncu --set full --clock-control none -k regex:k_ -f -o /tmp/prof_${tag}_all \
+    python tools/profile_kernels.py > gpurun_out/ncu_all_$tag.log 2>&1; tail -2 gpurun_out/ncu_all_$tag.log
+ncu -i /tmp/prof_${tag}_all.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_all_raw.csv 2>/dev/null
 ls -la gpurun_out | tail -12
