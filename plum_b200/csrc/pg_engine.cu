@@ -17,6 +17,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -106,6 +107,8 @@ struct pg_engine {
   PgMailRec* h_mail = nullptr;  // mapped pinned: k_move's self-validating result records
   PgMailRec* d_mail = nullptr;
   int move_slots = 0;           // resident k_move CTAs on the device (one wave)
+  int move_per_sm = 0;          // ... per SM
+  int move_per_sm_fixed = 0;    // PLUM_B200_CTAS_PER_SM override (0: adaptive)
   int n_sm = 0;
   unsigned int seq = 0;
   bool use_mailbox = true;
@@ -156,6 +159,9 @@ struct pg_engine {
 namespace {
 
 static std::string g_create_err;
+// engines alive in this process, per CUDA device: how many replicas share a GPU decides how wide one
+// k_move grid should be (move_slots_now)
+static std::atomic<int> g_live_engines[64];
 
 // Stage layout for a group of `cap` beads.
 struct StageView {
@@ -417,25 +423,35 @@ int ensure_capacity(pg_engine* h, int n_need) {
   return PG_OK;
 }
 
+// One step of a host spin on mapped memory: yields now and then (long wait or oversubscribed host: let a
+// sibling replica's thread run), and every ~1M spins checks the stream for a failed kernel and the 30 s
+// deadline.  Returns PG_OK to keep spinning.
+struct SpinWait {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  unsigned long spins = 0;
+  int step(pg_engine* h) {
+    if ((++spins & 0x1fff) == 0) sched_yield();
+    if ((spins & 0xfffff) != 0) return PG_OK;
+    cudaError_t q = cudaStreamQuery(h->stream);
+    if (q != cudaSuccess && q != cudaErrorNotReady) {
+      h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
+      return PG_ERR_CUDA;
+    }
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) {
+      h->err = "device did not answer within 30 s";
+      return PG_ERR_TIMEOUT;
+    }
+    return PG_OK;
+  }
+};
+
 // Wait for the result mailbox (or the stream) — the driver's call is synchronous.
 int wait_result(pg_engine* h, unsigned int seq) {
   if (h->use_mailbox) {
-    auto t0 = std::chrono::steady_clock::now();
-    unsigned long spins = 0;
+    SpinWait w;
     while (h->h_result->seq != seq) {
-      if ((++spins & 0x1fff) == 0) sched_yield();   // long wait or oversubscribed host: let a sibling replica's thread run
-      if ((spins & 0xfffff) == 0) {
-        cudaError_t q = cudaStreamQuery(h->stream);
-        if (q != cudaSuccess && q != cudaErrorNotReady) {
-          h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
-          return PG_ERR_CUDA;
-        }
-        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (dt > 30.0) {
-          h->err = "device did not answer within 30 s";
-          return PG_ERR_TIMEOUT;
-        }
-      }
+      int rc = w.step(h);
+      if (rc) return rc;
     }
     return PG_OK;
   }
@@ -505,6 +521,24 @@ int launch_commit(pg_engine* h, int accept_flag, int mode, int g0, int glen, con
 // come first in block-index order — for a big move exactly one per SM — and share the reciprocal part
 // (lanes-per-k chosen so a helper's k slice fits its threads in one pass whenever possible) and the
 // intra-molecular pairs; the remaining CTAs split the (partner tile x moved bead) units evenly.
+// CTA slots one k_move grid may take.  A single Markov chain on the GPU is latency-bound and wants the
+// widest grid that still fits one wave (all but one slot per SM).  When several replicas share the GPU
+// (engines of this process on the same device; separate processes set PLUM_B200_CTAS_PER_SM) throughput
+// is what matters and narrow grids win: kernels of different replicas overlap, tails and imbalance of one
+// hide behind the main phase of another.  Measured on S with 16 replicas and 128-thread CTAs
+// (tools/sweep_replicas.py): 7 slots/SM 283 k moves/s, 5: 341 k, 3: 379 k, 2: 376 k; one replica: 7 slots
+// 73 k, 4 slots 66 k.  The generic path runs small systems: always every slot.
+int move_slots_now(const pg_engine* h) {
+  const int n_sm = std::max(1, h->n_sm);
+  if (h->move_per_sm_fixed) return h->move_per_sm_fixed * n_sm;
+  if (!h->fast) return h->move_per_sm * n_sm;
+  const int hi = std::max(1, h->move_per_sm - 1), lo = std::min(3, hi);
+  const int live = (h->device >= 0 && h->device < 64) ? g_live_engines[h->device].load(std::memory_order_relaxed) : 1;
+  if (live <= 1) return hi * n_sm;
+  if (live >= 8) return lo * n_sm;
+  return std::max(lo, hi - ((live - 1) * (hi - lo) + 3) / 7) * n_sm;
+}
+
 // The by-value scalar block of k_move / k_trials.
 void fill_move_dev(const pg_engine* h, PgMoveDev& D) {
   const PgDev& P = h->P;
@@ -528,7 +562,7 @@ void fill_move_dev(const pg_engine* h, PgMoveDev& D) {
 int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
   fill_move_dev(h, A.D);
   A.n_tiles = (int)std::max<long long>(1, ((long long)h->n * A.D.img_split + MV_THREADS - 1) / MV_THREADS);
-  const int slots = h->move_slots, n_sm = std::max(1, h->n_sm);
+  const int slots = move_slots_now(h), n_sm = std::max(1, h->n_sm);
   const long long units = (long long)A.n_tiles * std::max(glen, 1);
   const long long npairs = (long long)glen * (glen - 1) / 2;
   if (units >= (1LL << 31) || npairs * A.D.img_split >= (1LL << 31)) { h->err = "move too large for 32-bit work indexing"; return -1; }
@@ -627,8 +661,7 @@ int flush_commit(pg_engine* h) {
 // record whose seq matches is complete (no device-side system fence on the critical path).
 int wait_mail(pg_engine* h, unsigned int seq, pg_delta* o) {
   volatile PgMailRec* m = h->h_mail;
-  auto t0 = std::chrono::steady_clock::now();
-  unsigned long spins = 0;
+  SpinWait w;
   double val[MV_NSLOT];
   int aux[MV_NSLOT];
   for (int s = 0; s < MV_NSLOT; s++) {
@@ -638,18 +671,8 @@ int wait_mail(pg_engine* h, unsigned int seq, pg_delta* o) {
         aux[s] = m[s].aux;
         if (m[s].seq == seq) break;
       }
-      if ((++spins & 0x1fff) == 0) sched_yield();   // long wait or oversubscribed host: let a sibling replica's thread run
-      if ((spins & 0xfffff) == 0) {
-        cudaError_t q = cudaStreamQuery(h->stream);
-        if (q != cudaSuccess && q != cudaErrorNotReady) {
-          h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
-          return PG_ERR_CUDA;
-        }
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) {
-          h->err = "device did not answer within 30 s";
-          return PG_ERR_TIMEOUT;
-        }
-      }
+      int rc = w.step(h);
+      if (rc) return rc;
     }
   }
   o->dE = val[0]; o->pair = val[1]; o->ext = val[2]; o->ewald = val[3]; o->bond = val[4];
@@ -807,12 +830,10 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
     else
       PG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move<false>, MV_THREADS, 0));
     PG_CREATE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-    // CTAs per SM one k_move grid may take (<= what fits): leaving a slot free lets the kernels of other
-    // replicas (other engines / streams on the same GPU) co-run and hide each other's latencies
-    // (fast path, measured best: 3 of 4, tools/sweep_ctas.sh).  The generic path runs small systems: take them all.
-    int use_per_sm = h->fast ? std::max(1, per_sm - 1) : std::max(1, per_sm);
-    if (const char* e = getenv("PLUM_B200_CTAS_PER_SM")) use_per_sm = std::max(1, std::min(per_sm, atoi(e)));
-    h->move_slots = std::max(1, use_per_sm * n_sm);
+    // how many of them one k_move grid takes is decided per launch (move_slots_now)
+    h->move_per_sm = std::max(1, per_sm);
+    if (const char* e = getenv("PLUM_B200_CTAS_PER_SM")) h->move_per_sm_fixed = std::max(1, std::min(per_sm, atoi(e)));
+    h->move_slots = std::max(1, per_sm * n_sm);
     h->n_sm = n_sm;
   }
   {
@@ -863,12 +884,14 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   if (!rc) rc = ensure_group(h, 256);
   if (!rc) rc = ensure_partials(h, 4096);
   if (rc) { g_create_err = h->err; free_all(h); delete h; return rc; }
+  if (device >= 0 && device < 64) g_live_engines[device].fetch_add(1);
   *out = h;
   return PG_OK;
 }
 
 int pg_destroy(pg_engine* h) {
   if (!h) return PG_OK;
+  if (h->device >= 0 && h->device < 64) g_live_engines[h->device].fetch_sub(1);
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   free_all(h);
@@ -1338,8 +1361,7 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
     PG_CUDA(h, cudaGetLastError());
     // wait for the 3 ntc self-validating records
     volatile PgMailRec* m = h->h_tmail;
-    auto w0 = std::chrono::steady_clock::now();
-    unsigned long spins = 0;
+    SpinWait w;
     for (int r = 0; r < 3 * ntc; r++) {
       double v;
       for (;;) {
@@ -1347,18 +1369,8 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
           v = m[r].value;
           if (m[r].seq == A.seq) break;
         }
-        if ((++spins & 0x1fff) == 0) sched_yield();   // long wait or oversubscribed host: let a sibling replica's thread run
-        if ((spins & 0xfffff) == 0) {
-          cudaError_t q = cudaStreamQuery(h->stream);
-          if (q != cudaSuccess && q != cudaErrorNotReady) {
-            h->err = std::string("kernel failed: ") + cudaGetErrorString(q);
-            return PG_ERR_CUDA;
-          }
-          if (std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count() > 30.0) {
-            h->err = "device did not answer within 30 s";
-            return PG_ERR_TIMEOUT;
-          }
-        }
+        int wrc = w.step(h);
+        if (wrc) return wrc;
       }
       const int t = t0 + r / 3;
       if (r % 3 == 0) out_energy[t] = v;

@@ -31,11 +31,17 @@
 // working set (40 B/bead) is L2-resident and each thread streams exactly one partner.
 #include "pg_kernels.cuh"
 
-#define MV_THREADS 256
+#ifndef MV_THREADS
+#define MV_THREADS 128   // measured: 128-thread CTAs beat 256 (less waiting for the slowest warp at the CTA's barriers) and 64
+#endif
 #define MV_WARPS (MV_THREADS / 32)
 #define MV_GCHUNK 32      // max group beads per CTA chunk (shared-memory staging)
 #define MV_NSLOT 8        // mailbox records
 #define MV_INL 8          // largest group whose trial data ride in the kernel parameters
+#ifndef MV_FAST_OCC
+#define MV_FAST_OCC (1024 / MV_THREADS)   // 64 registers per thread
+#endif
+#define MV_GEN_OCC (512 / MV_THREADS)
 #define MV_QCAP 192       // per-warp queue capacity (flushed when fewer than 64 slots remain)
 
 // One self-validating mailbox record: written with a single 16-byte store, so a reader that
@@ -250,7 +256,7 @@ __device__ __forceinline__ void mv_block_sum5(double (&v)[5], double* smem /* [M
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(MV_THREADS, FAST ? 4 : 2) k_move(const PgMoveArgs A) {
+__global__ void __launch_bounds__(MV_THREADS, FAST ? MV_FAST_OCC : MV_GEN_OCC) k_move(const PgMoveArgs A) {
   const PgMoveDev& P = A.D;
   __shared__ double s_n[3][MV_GCHUNK], s_o[3][MV_GCHUNK], s_q[MV_GCHUNK];
   __shared__ int s_t[MV_GCHUNK], s_mv[MV_GCHUNK];
