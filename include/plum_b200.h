@@ -198,6 +198,49 @@ int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms);
  * first pg_replay_run / pg_replay_time_delta (with_commit 1 / 0) of that batch does not pay for it. */
 int pg_replay_prepare(pg_engine* h, int first, int count, int with_commit);
 
+/* ---- device-side proposals + Metropolis test (batched Markov-chain steps) -- */
+/* Replaces the per-move round trip of Simulation::TranslationalMove
+ * (src/simulation/simulation.cc:241-355) for a run of consecutive translational
+ * steps.  The caller walks its own std::mt19937 ahead (the draw ORDER of
+ * simulation.cc:247-331, molecule.cc:103-312 and misc.cc:95-109 is the caller's
+ * business: plum_b200/host/mc_propose.h does it) and hands over, per step, only
+ * what does not depend on the coordinates: the chosen molecule, the move kind and
+ * the random vectors.  The device builds the trial coordinates from the RESIDENT
+ * coordinates with the reference's exact operation order (round-to-nearest mul /
+ * add / div / sqrt, never fused: Molecule::BeadTranslate molecule.cc:103-134,
+ * COMTranslate :136-153, Pivot :155-237, RandomReptation :268-312), evaluates dE
+ * (k_move), takes the Metropolis decision u < exp(-beta dE) and commits — all
+ * without the host.  The reference does NOT draw the acceptance variate when
+ * dE >= 1e8 (simulation.cc:327-332), which shifts every later draw: a batch
+ * therefore stops after such a step (`n_done`), and the caller rewinds its
+ * generator to that point and continues with a new batch.
+ * Crankshaft (molecule.cc:239-265) needs Eigen's rotation and is not offered:
+ * the caller runs such a step through pg_delta_e.                              */
+enum { PG_MOVE_BEAD = 0, PG_MOVE_COM = 1, PG_MOVE_PIVOT = 2, PG_MOVE_CRANKSHAFT = 3, PG_MOVE_REPTATION = 4 };
+typedef struct pg_move_desc {
+  int32_t mol;        /* moved molecule                                                        */
+  int32_t kind;       /* PG_MOVE_* (not CRANKSHAFT)                                            */
+  int32_t i0;         /* PIVOT: the pivot bead; REPTATION: direction (+1 forward, -1 backward) */
+  int32_t rv_offset;  /* PIVOT: first of its len-1 rows in `rvec`, in draw order               */
+  double s;           /* BEAD: 3*move_size/|v| (0-length v: |v|); PIVOT: move_size_rand; REPTATION: bond_len */
+  double v[3];        /* BEAD: randSphere vector; COM: displacement; REPTATION: randSphere vector */
+  double vlen;        /* REPTATION: |v|                                                        */
+  double u;           /* uniform variate of the acceptance test                                */
+} pg_move_desc;
+/* rvec: [n_rvec][4] = (randSphere x, y, z, bond_len of that step), PIVOT only. */
+int pg_mc_upload(pg_engine* h, int n_moves, const pg_move_desc* moves, int n_rvec, const double* rvec);
+/* Runs steps [first, first+count) of the uploaded batch.  *n_done = steps whose outcome is final
+ * (== count unless a step hit dE >= 1e8; that step IS done — it is a rejection — later ones are
+ * not).  dE_out / accept_out (may be NULL) are filled for the done steps.  elapsed_ms (may be
+ * NULL) is CUDA-event time on the engine stream.  pg_mc_run = pg_mc_begin + pg_mc_end; the halves
+ * let one host thread keep several replicas busy. */
+int pg_mc_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, int* n_done,
+              float* elapsed_ms);
+int pg_mc_begin(pg_engine* h, int first, int count);
+int pg_mc_end(pg_engine* h, double* dE_out, uint8_t* accept_out, int* n_done, float* elapsed_ms);
+/* Trial coordinates the device built for step m of the batch ([len][3]; for tests). */
+int pg_mc_trial_xyz(pg_engine* h, int m, double* xyz);
+
 /* ---- configurational-bias trial energies (ForceField::BeadsEnergy) ------- */
 /* One launch evaluates n_trials candidate (monomer, counter-ion) pairs against
  * every resident bead except molecules [skip_mol_first, skip_mol_last] (the

@@ -55,6 +55,11 @@ class PgProposal(C.Structure):
     _fields_ = [("mol", C.c_int32), ("xyz_offset", C.c_int32), ("u", C.c_double)]
 
 
+class PgMoveDesc(C.Structure):
+    _fields_ = [("mol", C.c_int32), ("kind", C.c_int32), ("i0", C.c_int32), ("rv_offset", C.c_int32),
+                ("s", C.c_double), ("v", C.c_double * 3), ("vlen", C.c_double), ("u", C.c_double)]
+
+
 class PgTrialSet(C.Structure):
     _fields_ = [
         ("n_trials", C.c_int32), ("use_bead2", C.c_int32), ("type1", C.c_int32), ("type2", C.c_int32),

@@ -31,6 +31,7 @@
 #include "pg_move.cu"
 #include "pg_trials.cu"
 #include "pg_pressure.cu"
+#include "pg_propose.cu"
 
 namespace {
 
@@ -145,6 +146,19 @@ struct pg_engine {
   struct RpGraph { int first, count, commit; cudaGraphExec_t exec; };
   std::vector<RpGraph> rp_graphs;
   bool use_graph = true;        // PLUM_B200_NO_GRAPH=1 disables
+
+  // batched Markov-chain steps with device-side proposals (pg_mc_*): same packed layout as the replay,
+  // but the trial coordinates are written by k_propose and the buffers only ever grow
+  bool rp_mc = false;           // rp_moves / d_rp currently hold an MC batch
+  size_t rp_bytes_cap = 0, rp_log_cap = 0;
+  PgPropDev* d_mc_moves = nullptr; size_t mc_moves_cap = 0;
+  double4* d_mc_rv = nullptr; size_t mc_rv_cap = 0;
+  char* h_mc_pin = nullptr; size_t mc_pin_cap = 0;   // pinned upload staging
+  int* d_stop = nullptr;
+  int* h_stop = nullptr;        // pinned
+  std::vector<int> mc_mol;      // molecule of every step of the batch (wave construction)
+  int mc_first = 0, mc_count = 0;
+  bool mc_inflight = false;
 };
 
 #define PG_CUDA(h, call)                                                                     \
@@ -751,6 +765,9 @@ void free_all(pg_engine* h) {
   if (h->h_tmail) cudaFreeHost(h->h_tmail);
   cudaFree(h->d_trial_in); cudaFree(h->d_trial_ct); cudaFree(h->d_tr_partial); cudaFree(h->d_sk_partial); cudaFree(h->d_tr_mz); cudaFree(h->d_tr_counter);
   cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
+  cudaFree(h->d_mc_moves); cudaFree(h->d_mc_rv); cudaFree(h->d_stop);
+  if (h->h_mc_pin) cudaFreeHost(h->h_mc_pin);
+  if (h->h_stop) cudaFreeHost(h->h_stop);
   for (auto& g : h->rp_graphs) cudaGraphExecDestroy(g.exec);
   h->rp_graphs.clear();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1061,10 +1078,13 @@ int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_
   if (!h || n_moves < 0 || (n_moves > 0 && (!moves || !trial_xyz || !moved))) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
   { int frc_ = flush_commit(h); if (frc_) return frc_; }
+  if (h->mc_inflight) { h->err = "an MC batch is in flight"; return PG_ERR_STATE; }
   h->rp_moves.clear();
+  h->rp_mc = false;
   replay_drop_graphs(h);
   cudaFree(h->d_rp); cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc);
   h->d_rp = nullptr; h->d_rp_dE = nullptr; h->d_rp_acc = nullptr;
+  h->rp_bytes_cap = 0; h->rp_log_cap = 0;
   h->rp_beads = (size_t)std::max(n_xyz_beads, 1);
   std::vector<char> host(stage_size((int)h->rp_beads));
   StageView sv = stage_view(host.data(), (int)h->rp_beads);
@@ -1085,6 +1105,7 @@ int pg_replay_upload(pg_engine* h, int n_moves, const pg_proposal* moves, int n_
   PG_CUDA(h, cudaMemcpy(h->d_rp, host.data(), host.size(), cudaMemcpyHostToDevice));
   PG_CUDA(h, cudaMalloc((void**)&h->d_rp_dE, sizeof(double) * (size_t)std::max(n_moves, 1)));
   PG_CUDA(h, cudaMalloc((void**)&h->d_rp_acc, (size_t)std::max(n_moves, 1)));
+  h->rp_bytes_cap = host.size(); h->rp_log_cap = (size_t)std::max(n_moves, 1);
   return PG_OK;
 }
 
@@ -1123,6 +1144,7 @@ static int replay_launch(pg_engine* h, int m, int prev, bool log) {
   A.replay_dE = log ? h->d_rp_dE : nullptr;
   A.replay_acc = log ? h->d_rp_acc : nullptr;
   A.replay_index = m;
+  A.stop = h->rp_mc ? h->d_stop : nullptr;
   A.seq = ++h->seq;
   A.Pg = h->d_P;
   A.timing = (h->d_timing && n_ctas <= 8192) ? h->d_timing : nullptr;
@@ -1246,6 +1268,196 @@ int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms) 
                                     h->d_S, h->d_dS, 0, h->d_state);
   h->launches++;
   PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return PG_OK;
+}
+
+
+// --------------------------------------------- batched MC, device-side proposals
+#define PG_MC_WAVE 64   // most steps one k_propose launch builds
+
+#define PG_MC_RESERVE(h, ptr, cap, need, T)                                \
+  do {                                                                      \
+    if ((need) > (cap) || !(ptr)) {                                         \
+      size_t c_ = std::max<size_t>((need), (cap) * 2);                      \
+      cudaFree(ptr); (ptr) = nullptr; (cap) = 0;                            \
+      PG_CUDA(h, cudaMalloc((void**)&(ptr), sizeof(T) * c_));               \
+      (cap) = c_;                                                           \
+    }                                                                       \
+  } while (0)
+
+int pg_mc_upload(pg_engine* h, int n_moves, const pg_move_desc* moves, int n_rvec, const double* rvec) {
+  if (!h || n_moves < 0 || n_rvec < 0 || (n_moves > 0 && !moves) || (n_rvec > 0 && !rvec)) return PG_ERR_INVALID;
+  if (h->mc_inflight) { h->err = "an MC batch is in flight"; return PG_ERR_STATE; }
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
+  // the engine stream may still be reading the previous batch's buffers
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  replay_drop_graphs(h);
+  h->rp_moves.clear();
+  h->mc_mol.clear();
+  h->rp_mc = true;
+  size_t beads = 0;
+  for (int m = 0; m < n_moves; m++) {
+    const pg_move_desc& d = moves[m];
+    if (d.mol < 0 || d.mol >= h->n_mol) { h->err = "mc: molecule index out of range"; return PG_ERR_INVALID; }
+    const int len = h->mol_first[d.mol + 1] - h->mol_first[d.mol];
+    if (len > PP_MAXLEN) { h->err = "mc: molecule longer than PP_MAXLEN"; return PG_ERR_CAPACITY; }
+    if (d.kind == PG_MOVE_PIVOT) {
+      if (d.i0 < 0 || d.i0 >= len || d.rv_offset < 0 || d.rv_offset + (len - 1) > n_rvec) { h->err = "mc: bad pivot descriptor"; return PG_ERR_INVALID; }
+    } else if (d.kind == PG_MOVE_REPTATION) {
+      if (d.i0 != 1 && d.i0 != -1) { h->err = "mc: reptation direction must be +1 or -1"; return PG_ERR_INVALID; }
+    } else if (d.kind != PG_MOVE_BEAD && d.kind != PG_MOVE_COM) {
+      h->err = "mc: move kind not offered on the device"; return PG_ERR_INVALID;
+    }
+    beads += (size_t)len;
+  }
+  h->rp_beads = std::max<size_t>(beads, 1);
+  const int cap = (int)h->rp_beads;
+  const size_t bytes = stage_size(cap), trial_bytes = sizeof(double) * 3 * (size_t)cap, tail_bytes = bytes - trial_bytes;
+  const size_t mv_bytes = sizeof(PgPropDev) * (size_t)std::max(n_moves, 1);
+  if (bytes > h->rp_bytes_cap || !h->d_rp) {
+    size_t c = std::max(bytes, h->rp_bytes_cap * 2);
+    cudaFree(h->d_rp); h->d_rp = nullptr; h->rp_bytes_cap = 0;
+    PG_CUDA(h, cudaMalloc((void**)&h->d_rp, c));
+    h->rp_bytes_cap = c;
+  }
+  if ((size_t)std::max(n_moves, 1) > h->rp_log_cap || !h->d_rp_dE) {
+    size_t c = std::max<size_t>((size_t)std::max(n_moves, 1), h->rp_log_cap * 2);
+    cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc); h->d_rp_dE = nullptr; h->d_rp_acc = nullptr; h->rp_log_cap = 0;
+    PG_CUDA(h, cudaMalloc((void**)&h->d_rp_dE, sizeof(double) * c));
+    PG_CUDA(h, cudaMalloc((void**)&h->d_rp_acc, c));
+    h->rp_log_cap = c;
+  }
+  PG_MC_RESERVE(h, h->d_mc_moves, h->mc_moves_cap, (size_t)std::max(n_moves, 1), PgPropDev);
+  PG_MC_RESERVE(h, h->d_mc_rv, h->mc_rv_cap, (size_t)std::max(n_rvec, 1), double4);
+  if (!h->d_stop) {
+    PG_CUDA(h, cudaMalloc((void**)&h->d_stop, sizeof(int)));
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_stop, sizeof(int), cudaHostAllocDefault));
+  }
+  const size_t pin_need = tail_bytes + mv_bytes + 64;
+  if (pin_need > h->mc_pin_cap) {
+    if (h->h_mc_pin) cudaFreeHost(h->h_mc_pin);
+    h->h_mc_pin = nullptr; h->mc_pin_cap = 0;
+    size_t c = pin_need * 2;
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_mc_pin, c, cudaHostAllocDefault));
+    h->mc_pin_cap = c;
+  }
+  // host image of the block behind the trial coordinates (charges, types, charged-moved lists, moved flags):
+  // a view whose `trial` sits 3*cap doubles in front of the pinned buffer, so the sub-array offsets are the device's
+  StageView sv = stage_view(h->h_mc_pin - trial_bytes, cap);
+  PgPropDev* pm = reinterpret_cast<PgPropDev*>(h->h_mc_pin + ((tail_bytes + 15) / 16) * 16);
+  int off = 0;
+  for (int m = 0; m < n_moves; m++) {
+    const pg_move_desc& d = moves[m];
+    ReplayMove r;
+    r.mol = d.mol; r.g0 = h->mol_first[d.mol]; r.glen = h->mol_first[d.mol + 1] - r.g0; r.off = off; r.u = d.u;
+    for (int i = 0; i < r.glen; i++) {
+      sv.gq[off + i] = h->h_q[r.g0 + i]; sv.gtype[off + i] = h->h_type[r.g0 + i];
+      sv.moved[off + i] = (d.kind == PG_MOVE_BEAD) ? (i == 0) : 1;
+    }
+    r.nq = stage_fill_qidx(sv, off, r.glen);
+    h->rp_moves.push_back(r);
+    h->mc_mol.push_back(d.mol);
+    PgPropDev& q = pm[m];
+    q.g0 = r.g0; q.glen = r.glen; q.kind = d.kind; q.i0 = d.i0; q.off = off; q.rv_off = d.rv_offset; q.pad0 = q.pad1 = 0;
+    q.s = d.s; q.vx = d.v[0]; q.vy = d.v[1]; q.vz = d.v[2]; q.vlen = d.vlen; q.pad2 = 0.0;
+    off += r.glen;
+  }
+  if (n_moves > 0) {
+    PG_CUDA(h, cudaMemcpyAsync(h->d_rp + trial_bytes, h->h_mc_pin, tail_bytes, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(h->d_mc_moves, pm, sizeof(PgPropDev) * (size_t)n_moves, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (n_rvec > 0)   // pageable source: the copy is staged by the driver before the call returns
+    PG_CUDA(h, cudaMemcpyAsync(h->d_mc_rv, rvec, sizeof(double) * 4 * (size_t)n_rvec, cudaMemcpyHostToDevice, h->stream));
+  return PG_OK;
+}
+
+int pg_mc_begin(pg_engine* h, int first, int count) {
+  if (!h || !h->rp_mc || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->mc_inflight) { h->err = "an MC batch is in flight"; return PG_ERR_STATE; }
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  int rc = flush_commit(h);
+  if (rc) return rc;
+  rc = ensure_partials(h, h->move_slots + h->n_sm + 8);
+  if (rc) return rc;
+  PG_CUDA(h, cudaMemsetAsync(h->d_stop, 0, sizeof(int), h->stream));
+  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  StageView base = stage_view(h->d_rp, (int)h->rp_beads);
+  int wave_hi = first;
+  int wave_mols[PG_MC_WAVE];
+  for (int m = first; m < first + count; m++) {
+    if (m >= wave_hi) {
+      // a wave: consecutive steps that move pairwise different molecules
+      int w = 0;
+      while (m + w < first + count && w < PG_MC_WAVE) {
+        const int mol = h->mc_mol[m + w];
+        bool seen = false;
+        for (int i = 0; i < w; i++) if (wave_mols[i] == mol) { seen = true; break; }
+        if (seen) break;
+        wave_mols[w++] = mol;
+      }
+      PgProposeArgs P;
+      P.xy = h->xy; P.zq = h->zq; P.moves = h->d_mc_moves; P.rv = h->d_mc_rv; P.trial = base.trial;
+      P.first = m; P.prev = (m > first) ? m - 1 : -1; P.state = h->d_state; P.stop = h->d_stop;
+      k_propose<<<w, PP_THREADS, 0, h->stream>>>(P);
+      h->launches++;
+      wave_hi = m + w;
+    }
+    rc = replay_launch(h, m, (m > first) ? m - 1 : -1, true);
+    if (rc) return rc;
+  }
+  if (count > 0) {
+    // the last step's decision (taken on the device) is applied by a stand-alone commit
+    const ReplayMove& r = h->rp_moves[first + count - 1];
+    StageView v;
+    replay_view(h, first + count - 1, v);
+    int nthreads = std::max(std::max(r.glen, h->nk), 1);
+    k_commit<<<(nthreads + 255) / 256, 256, 0, h->stream>>>(h->P, -1, PG_MODE_MOVE, r.g0, r.glen, v.trial, v.gq,
+                                                            v.gtype, h->xy, h->zq, h->type, h->d_S, h->d_dS,
+                                                            h->P.use_ewald ? h->nk : 0, h->d_state);
+    h->launches++;
+  }
+  PG_CUDA(h, cudaGetLastError());
+  PG_CUDA(h, cudaMemcpyAsync(h->h_stop, h->d_stop, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  h->mc_first = first; h->mc_count = count; h->mc_inflight = true;
+  return PG_OK;
+}
+
+int pg_mc_end(pg_engine* h, double* dE_out, uint8_t* accept_out, int* n_done, float* elapsed_ms) {
+  if (!h) return PG_ERR_INVALID;
+  if (!h->mc_inflight) { h->err = "no MC batch in flight"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->mc_inflight = false;
+  PG_CUDA(h, cudaEventSynchronize(h->ev1));
+  if (elapsed_ms) PG_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  const int stop = *h->h_stop;
+  const int done = stop ? stop - h->mc_first : h->mc_count;
+  if (done < 0 || done > h->mc_count) { h->err = "mc: inconsistent stop index"; return PG_ERR_STATE; }
+  if (n_done) *n_done = done;
+  if (dE_out && done > 0)
+    PG_CUDA(h, cudaMemcpy(dE_out, h->d_rp_dE + h->mc_first, sizeof(double) * (size_t)done, cudaMemcpyDeviceToHost));
+  if (accept_out && done > 0)
+    PG_CUDA(h, cudaMemcpy(accept_out, h->d_rp_acc + h->mc_first, (size_t)done, cudaMemcpyDeviceToHost));
+  return PG_OK;
+}
+
+int pg_mc_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, int* n_done, float* elapsed_ms) {
+  int rc = pg_mc_begin(h, first, count);
+  if (rc) return rc;
+  return pg_mc_end(h, dE_out, accept_out, n_done, elapsed_ms);
+}
+
+int pg_mc_trial_xyz(pg_engine* h, int m, double* xyz) {
+  if (!h || !h->rp_mc || !xyz || m < 0 || m >= (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->mc_inflight) { h->err = "an MC batch is in flight"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  StageView v;
+  replay_view(h, m, v);
+  PG_CUDA(h, cudaMemcpy(xyz, v.trial, sizeof(double) * 3 * (size_t)h->rp_moves[m].glen, cudaMemcpyDeviceToHost));
   return PG_OK;
 }
 

@@ -99,6 +99,9 @@ struct PgMoveArgs {
   PgMailRec* mail;      // mapped host memory (NULL in replay)
   int decide_on_device; double u; double* replay_dE; uint8_t* replay_acc; int replay_index;
   unsigned int seq;
+  int* stop;            // batched MC (pg_mc_run): non-zero once a step of the batch returned dE >= 1e8 — the reference draws
+                        // no acceptance variate then (simulation.cc:327-332), so the host's pre-drawn stream no longer lines
+                        // up and every later kernel of the batch is a no-op; NULL otherwise
   unsigned long long* timing;   // debug only (PLUM_B200_TIMING=1): per-CTA %globaltimer stamps [n_ctas][8]
   const PgDev* Pg;      // copy of the parameter block in global memory, for the non-inlined rare paths
                         // (passing the by-value kernel parameter by reference would spill all of it to local memory)
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? MV_FAST_OCC : MV_GEN_OCC) k
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
+  if (A.stop && __ldcg(A.stop)) return;
   MV_STAMP(0);
   const double* __restrict__ trial = A.trial;
   const double* __restrict__ gqv = A.gq;
@@ -741,6 +745,7 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? MV_FAST_OCC : MV_GEN_OCC) k
     if (P.dipole) { st->cur_dipl = st_cur_dipl; st->trial_dipl = st_trial_dipl; }
     if (A.replay_dE) A.replay_dE[A.replay_index] = dE;
     if (A.replay_acc) A.replay_acc[A.replay_index] = (uint8_t)accept;
+    if (A.stop && dE >= PG_VLE) *A.stop = A.replay_index + 1;
     st->dE = dE; st->d_pair = d_pair; st->d_ext = d_ext; st->d_ewald = d_ewald; st->d_bond = d_bond;
     st->d_real = d_real; st->d_recip = d_recip; st->d_self = 0.0; st->d_dipole = d_dip;
     st->mz_current = mz_cur;

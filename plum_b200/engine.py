@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from ._abi import (ParamBlock, PgDelta, PgEwaldInfo, PgParams, PgProposal, PgTotals, PgTrialSet, bptr, c_double_p,
+from ._abi import (ParamBlock, PgDelta, PgEwaldInfo, PgMoveDesc, PgParams, PgProposal, PgTotals, PgTrialSet, bptr, c_double_p,
                    c_int32_p, c_uint8_p, dptr, iptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "libplum_b200.so")
 ABI_SYMBOLS = [
     "pg_create", "pg_destroy", "pg_last_error", "pg_abi_version", "pg_get_ewald_info", "pg_upload_system",
     "pg_init_energy", "pg_recompute_totals", "pg_get_totals", "pg_download_positions", "pg_num_beads", "pg_delta_e",
-    "pg_delta_e_begin", "pg_delta_e_poll", "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_trial_energies", "pg_insert_molecules",
+    "pg_delta_e_begin", "pg_delta_e_poll", "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_mc_upload", "pg_mc_run", "pg_mc_begin", "pg_mc_end", "pg_mc_trial_xyz", "pg_trial_energies", "pg_insert_molecules",
     "pg_delete_molecules", "pg_wall_force", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
     "pg_stream", "pg_measure_fp64_peak",
 ]
@@ -62,6 +62,11 @@ def lib():
         L.pg_replay_run.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_uint8_p, C.POINTER(C.c_float)]
         L.pg_replay_time_delta.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.pg_replay_prepare.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.pg_mc_upload.argtypes = [vp, C.c_int, C.POINTER(PgMoveDesc), C.c_int, c_double_p]
+        L.pg_mc_run.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_uint8_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.pg_mc_begin.argtypes = [vp, C.c_int, C.c_int]
+        L.pg_mc_end.argtypes = [vp, c_double_p, c_uint8_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.pg_mc_trial_xyz.argtypes = [vp, C.c_int, c_double_p]
         L.pg_trial_energies.argtypes = [vp, C.POINTER(PgTrialSet), c_double_p, c_double_p, c_double_p, c_double_p,
                                         c_int32_p, c_double_p, c_double_p, c_double_p]
         L.pg_insert_molecules.argtypes = [vp, C.c_int, c_int32_p, c_double_p, c_double_p, c_int32_p,
@@ -209,6 +214,30 @@ class Engine:
         return ms.value
 
     # -- CBMC --------------------------------------------------------------
+    # -- batched Markov-chain steps with device-side proposals --------------
+    def mc_upload(self, descs, rvec=None):
+        """descs: list/array of PgMoveDesc; rvec: [n][4] pivot rows."""
+        n = len(descs)
+        arr = (PgMoveDesc * max(n, 1))(*descs)
+        rv = _f64(rvec if rvec is not None else np.zeros((0, 4))).reshape(-1, 4)
+        self._mc_n = n
+        self._check(self.L.pg_mc_upload(self.h, n, arr, int(rv.shape[0]), dptr(rv) if rv.size else None), "pg_mc_upload")
+
+    def mc_run(self, first: int, count: int):
+        """Returns (dE[n_done], accept[n_done], n_done, elapsed_ms)."""
+        dE = np.zeros(max(count, 1))
+        acc = np.zeros(max(count, 1), dtype=np.uint8)
+        nd = C.c_int(0)
+        ms = C.c_float(0.0)
+        self._check(self.L.pg_mc_run(self.h, int(first), int(count), dptr(dE), bptr(acc), C.byref(nd), C.byref(ms)),
+                    "pg_mc_run")
+        return dE[:nd.value], acc[:nd.value], nd.value, float(ms.value)
+
+    def mc_trial_xyz(self, m: int, length: int) -> np.ndarray:
+        out = np.zeros((length, 3))
+        self._check(self.L.pg_mc_trial_xyz(self.h, int(m), dptr(out)), "pg_mc_trial_xyz")
+        return out
+
     def trial_energies(self, b1, b2, t1, q1, t2, q2, use_bead2, chain_xyz, chain_q, chain_type, current_len,
                        skip_first=-1, skip_last=-1):
         b1 = _f64(b1).reshape(-1, 3)

@@ -12,6 +12,7 @@
 // (:324-332, no variate drawn when dE >= 1e8).  It is benchmark harness code: the
 // product's real driver is Plum's own (bin/plum_gpu).  Every proposal is recorded so
 // bench.py can replay the identical sequence device-resident (pg_replay_run).
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -20,6 +21,7 @@
 #include <vector>
 
 #include "plum_b200.h"
+#include "mc_propose.h"
 
 namespace {
 
@@ -28,7 +30,9 @@ struct Ctx {
   int n_mol, phantom;
   std::vector<int> mol_first;
   std::vector<double> pos;   // host copy of accepted coordinates [n][3] (the driver's Bead::current_pos)
-  std::vector<int> chains, ions;
+  plum_mc::Proposer prop;
+  plum_mc::Batch one;        // the step in flight on the per-move path
+  plum_mc::Batch batch[2];   // batched path: the batch on the device and the one generated ahead
   double box[3];
   double beta, move_size, bond_len;
   double prob[5];
@@ -45,86 +49,20 @@ struct Ctx {
   int rec_cap_beads = 0;
 };
 
-double uni(std::mt19937& g) { return (double)g() / g.max(); }
-
-// src/utilities/misc.cc:95-109
-void rand_sphere(double v[3], std::mt19937& g) {
-  double rs = 2, r1 = 0, r2 = 0;
-  while (rs > 1) {
-    r1 = 1 - 2 * uni(g);
-    r2 = 1 - 2 * uni(g);
-    rs = r1 * r1 + r2 * r2;
-  }
-  double ranh = 2 * std::sqrt(1 - rs);
-  v[0] = r1 * ranh;
-  v[1] = r2 * ranh;
-  v[2] = 1 - 2 * rs;
-}
-
-// One proposal with the reference's move definitions; false when the system has nothing to move.
+// One proposal, drawn in the reference's order (mc_propose.h) and built on the host; false when the
+// system has nothing to move or the step is one the harness does not drive (GC, crankshaft).
 bool propose(Ctx* c) {
-  std::mt19937& g = c->rng;
-  {
-    // molecule + move type, simulation.cc:247-276
-    int wc = (int)std::floor(uni(g) * (double)c->chains.size());
-    int wi = (int)std::floor(uni(g) * (double)c->ions.size());
-    if (wc == (int)c->chains.size()) wc--;
-    if (wi == (int)c->ions.size()) wi--;
-    int move_type = 0;
-    double r = uni(g), cum = c->prob[0];
-    while (cum < r && move_type < 4) { move_type++; cum += c->prob[move_type]; }
-    int mol;
-    if (move_type == 0 && !c->ions.empty()) mol = c->ions[wi];
-    else if (!c->chains.empty()) { mol = c->chains[wc]; if (move_type == 0) move_type = 1; }
-    else return false;
-    const int f = c->mol_first[mol], len = c->mol_first[mol + 1] - f;
-    c->trial.assign(c->pos.begin() + 3 * f, c->pos.begin() + 3 * (f + len));
-    c->moved.assign(len, 1);
-    c->cur_mol = mol; c->cur_f = f; c->cur_len = len;
-    double* T = c->trial.data();
-    if (move_type == 0) {
-      double v[3];
-      rand_sphere(v, g);
-      double vl = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-      if (vl > 0) vl = 3 * c->move_size / vl;
-      for (int a = 0; a < 3; a++) T[a] += vl * v[a];
-    } else if (move_type == 1) {
-      double v[3] = {0.5 * c->move_size * uni(g), 0.5 * c->move_size * uni(g), 0.5 * c->move_size * uni(g)};
-      for (int a = 0; a < 3; a++) if (g() % 2 == 0) v[a] = -v[a];
-      for (int i = 0; i < len; i++) for (int a = 0; a < 3; a++) T[3 * i + a] += v[a];
-    } else if (move_type == 2 || move_type == 3) {
-      // pivot (crankshaft has probability 0 in every shipped run.in; it falls back to a pivot here)
-      int pivot = (int)std::floor(len * uni(g));
-      if (pivot == len) pivot--;
-      double ms = c->move_size * uni(g);
-      for (int dir = 0; dir < 2; dir++) {
-        int i = dir == 0 ? pivot + 1 : pivot - 1;
-        while (dir == 0 ? i < len : i >= 0) {
-          int prev = dir == 0 ? i - 1 : i + 1;
-          double v[3];
-          rand_sphere(v, g);
-          double dx[3], n2 = 0;
-          for (int a = 0; a < 3; a++) { dx[a] = T[3 * i + a] + ms * v[a] - T[3 * prev + a]; n2 += dx[a] * dx[a]; }
-          double norm = c->bond_len / std::sqrt(n2);
-          double m[3];
-          for (int a = 0; a < 3; a++) m[a] = norm * dx[a] + T[3 * prev + a] - T[3 * i + a];
-          if (dir == 0) { for (int j = i; j < len; j++) for (int a = 0; a < 3; a++) T[3 * j + a] += m[a]; }
-          else { for (int j = i; j >= 0; j--) for (int a = 0; a < 3; a++) T[3 * j + a] += m[a]; }
-          i += dir == 0 ? 1 : -1;
-        }
-      }
-    } else {
-      // reptation: every bead takes its neighbour's place, a new end bead is grown
-      int direction = 1, begin = 0, end = len - 1;
-      if (g() % 2 == 0) { direction = -1; begin = len - 1; end = 0; }
-      const double* C = c->pos.data() + 3 * f;
-      for (int i = begin; i != end; i += direction) for (int a = 0; a < 3; a++) T[3 * i + a] = C[3 * (i + direction) + a];
-      double v[3];
-      rand_sphere(v, g);
-      double vl = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-      for (int a = 0; a < 3; a++) T[3 * end + a] = C[3 * end + a] + c->bond_len * v[a] / vl;
-    }
+  for (;;) {
+    if (c->prop.generate(c->rng, 1, c->one) != 1) return false;
+    if (c->one.kind[0] >= 0) break;   // a step that attempts nothing: next step
   }
+  const pg_move_desc& d = c->one.moves[0];
+  const int mol = d.mol, f = c->mol_first[mol], len = c->mol_first[mol + 1] - f;
+  c->trial.resize(3 * (size_t)len);
+  c->moved.assign(len, 1);
+  if (d.kind == PG_MOVE_BEAD) for (int i = 1; i < len; i++) c->moved[i] = 0;
+  plum_mc::Proposer::apply(d, c->one.rvec.data(), len, c->pos.data() + 3 * (size_t)f, c->trial.data());
+  c->cur_mol = mol; c->cur_f = f; c->cur_len = len;
   return true;
 }
 
@@ -137,8 +75,10 @@ int finish(Ctx* c, const pg_delta& d) {
   bool accept = false;
   double u = -1.0;
   if (d.dE < PG_VERY_LARGE_ENERGY) {
-    u = uni(g);
+    u = c->one.moves[0].u;   // drawn by the generator right behind the proposal, as the reference does
     accept = u < std::exp(-c->beta * d.dE);
+  } else {
+    c->one.rewind_after_overlap(g, 1);   // simulation.cc:327-332: no variate is drawn
   }
   int rc = pg_commit(c->eng, accept ? 1 : 0);
   if (rc) return rc;
@@ -177,10 +117,15 @@ void* pb_create(pg_engine* eng, int n_mol, const int32_t* mol_first, const doubl
   c->move_size = move_size;
   c->bond_len = bond_len;
   for (int i = 0; i < 5; i++) c->prob[i] = prob5[i];
-  for (int m = phantom; m < n_mol; m++) {
-    if (mol_first[m + 1] - mol_first[m] > 1) c->chains.push_back(m);
-    else c->ions.push_back(m);
-  }
+  plum_mc::Config cfg;
+  cfg.phantom = phantom;
+  for (int m = 0; m < n_mol; m++) cfg.mol_len.push_back(mol_first[m + 1] - mol_first[m]);
+  cfg.move_size = move_size;
+  for (int i = 0; i < 5; i++) cfg.move_prob[i] = prob5[i];
+  cfg.bond_len = bond_len;
+  cfg.vary_bond = false;
+  cfg.gc_freq = 0;
+  c->prop.configure(cfg);
   c->rng.seed(seed);
   return c;
 }
@@ -264,6 +209,183 @@ int pb_run(void* p, int n_moves, int32_t* rec_mol, int32_t* rec_off, double* rec
   int rc = pb_run_multi(&p, 1, n_moves, wall_seconds);
   pb_stats(p, rec_beads, pair_evals, alg_flops, n_accept);
   return rc;
+}
+
+
+// Spring-bond variant: the generators vary the bond length by +-10 % (simulation.cc:293-296).
+void pb_set_vary_bond(void* p, int vary) {
+  Ctx* c = static_cast<Ctx*>(p);
+  plum_mc::Config cfg = c->prop.config();
+  cfg.vary_bond = vary != 0;
+  c->prop.configure(cfg);
+}
+
+// Host copy of the accepted coordinates [n][3] (after pb_run_mc: downloaded from the device).
+void pb_positions(void* p, double* xyz) {
+  Ctx* c = static_cast<Ctx*>(p);
+  std::memcpy(xyz, c->pos.data(), sizeof(double) * c->pos.size());
+}
+
+// The same Markov chains through the BATCHED path (pg_mc_upload / pg_mc_begin / pg_mc_end): this thread draws
+// each replica's random stream a batch ahead and the device does the rest — trial coordinates, dE, Metropolis
+// test, commit.  While a batch runs, the next one is generated; a batch that stopped at a dE >= 1e8 step
+// (no acceptance draw in the reference) makes the generator rewind to that step.  The records (mol, u, dE,
+// accept) are filled like pb_run_multi's; trial coordinates are not recorded (they never leave the device).
+int pb_run_mc(void** ps, int n_ctx, int n_moves, int batch_moves, double* wall_seconds) {
+  std::vector<Ctx*> cs(n_ctx);
+  for (int i = 0; i < n_ctx; i++) {
+    cs[i] = static_cast<Ctx*>(ps[i]);
+    cs[i]->done = 0; cs[i]->used = 0; cs[i]->acc_count = 0; cs[i]->evals = 0; cs[i]->flops = 0;
+  }
+  if (batch_moves <= 0) batch_moves = 1024;
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<int> cur(n_ctx, 0), ahead(n_ctx, 0), flying(n_ctx, 0);
+  std::vector<std::mt19937> rng_after(n_ctx);   // generator state behind the batch that is on the device
+  std::vector<double> dE(batch_moves);
+  std::vector<uint8_t> acc(batch_moves);
+  auto launch = [&](int i) -> int {
+    Ctx* c = cs[i];
+    plum_mc::Batch& b = c->batch[cur[i]];
+    const int want = std::min(batch_moves, n_moves - c->done);
+    if ((int)b.moves.size() > want) return PG_ERR_STATE;
+    if (b.moves.empty()) return 1;   // nothing (left) to do
+    int rc = pg_mc_upload(c->eng, (int)b.moves.size(), b.moves.data(), (int)(b.rvec.size() / 4), b.rvec.data());
+    if (rc) return rc;
+    rc = pg_mc_begin(c->eng, 0, (int)b.moves.size());
+    if (rc) return rc;
+    flying[i] = 1;
+    return 0;
+  };
+  auto generate = [&](int i, int slot, int budget) {
+    // a batch of `budget` MOVES at most (steps that attempt nothing do not count)
+    Ctx* c = cs[i];
+    c->prop.generate(c->rng, budget, c->batch[slot]);
+  };
+  int live = 0;
+  for (int i = 0; i < n_ctx; i++) {
+    generate(i, 0, std::min(batch_moves, n_moves));
+    int rc = launch(i);
+    if (rc < 0) return rc;
+    if (rc == 0) live++;
+  }
+  // generate ahead while the first batches run
+  for (int i = 0; i < n_ctx; i++)
+    if (flying[i]) {
+      Ctx* c = cs[i];
+      rng_after[i] = c->rng;
+      const int left = n_moves - c->done - (int)c->batch[cur[i]].moves.size();
+      generate(i, cur[i] ^ 1, std::max(0, std::min(batch_moves, left)));
+      ahead[i] = 1;
+    }
+  while (live > 0) {
+    for (int i = 0; i < n_ctx; i++) {
+      if (!flying[i]) continue;
+      Ctx* c = cs[i];
+      plum_mc::Batch& b = c->batch[cur[i]];
+      int n_done = 0;
+      int rc = pg_mc_end(c->eng, dE.data(), acc.data(), &n_done, nullptr);
+      if (rc) return rc;
+      flying[i] = 0;
+      const int N = c->mol_first[c->n_mol];
+      for (int m = 0; m < n_done; m++) {
+        const pg_move_desc& d = b.moves[m];
+        const int len = c->mol_first[d.mol + 1] - c->mol_first[d.mol];
+        const double n_intra = (len > 1) ? 0.5 * len * (len - 1) : 0.0;
+        const double ev = (double)len * (double)(N - len) + n_intra;
+        c->evals += ev;
+        c->flops += 2.0 * ev * 36.0;
+        if (acc[m]) c->acc_count++;
+        if (c->rec_mol) {
+          const int it = c->done + m;
+          c->rec_mol[it] = d.mol; c->rec_off[it] = 0;
+          c->rec_u[it] = (dE[m] >= PG_VERY_LARGE_ENERGY) ? 2.0 : d.u;
+          c->rec_dE[it] = dE[m]; c->rec_acc[it] = acc[m];
+        }
+      }
+      c->done += n_done;
+      if (n_done < (int)b.moves.size()) {
+        // the last done step drew no acceptance variate: everything generated behind it is void
+        b.rewind_after_overlap(c->rng, n_done);
+        ahead[i] = 0;
+      }
+      if (c->done >= n_moves) { live--; continue; }
+      if (ahead[i]) {
+        cur[i] ^= 1;
+      } else {
+        generate(i, cur[i], std::min(batch_moves, n_moves - c->done));
+      }
+      rc = launch(i);
+      if (rc < 0) return rc;
+      if (rc == 1) { live--; continue; }
+      rng_after[i] = c->rng;
+      const int left = n_moves - c->done - (int)c->batch[cur[i]].moves.size();
+      generate(i, cur[i] ^ 1, std::max(0, std::min(batch_moves, left)));
+      ahead[i] = 1;
+    }
+  }
+  for (int i = 0; i < n_ctx; i++) {
+    Ctx* c = cs[i];
+    int rc = pg_download_positions(c->eng, c->pos.data());
+    if (rc) return rc;
+    // the generator ran one batch ahead: put it back behind the last step that was executed
+    if (ahead[i]) c->rng = rng_after[i];
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  if (wall_seconds) *wall_seconds = std::chrono::duration<double>(t1 - t0).count();
+  return 0;
+}
+
+// ---- the generator alone (CPU tests pin it to the reference's own trial coordinates) ----
+struct Gen {
+  plum_mc::Proposer prop;
+  plum_mc::Batch one;
+  std::mt19937 rng;
+};
+
+void* pmc_create(int n_mol, const int32_t* mol_len, int phantom, double move_size, const double* prob5, double bond_len,
+                 int vary_bond, int gc_freq, unsigned seed) {
+  Gen* g = new Gen();
+  plum_mc::Config cfg;
+  cfg.phantom = phantom;
+  cfg.mol_len.assign(mol_len, mol_len + n_mol);
+  cfg.move_size = move_size;
+  for (int i = 0; i < 5; i++) cfg.move_prob[i] = prob5[i];
+  cfg.bond_len = bond_len;
+  cfg.vary_bond = vary_bond != 0;
+  cfg.gc_freq = gc_freq;
+  g->prop.configure(cfg);
+  g->rng.seed(seed);
+  return g;
+}
+void pmc_destroy(void* p) { delete static_cast<Gen*>(p); }
+// One step.  Returns the move kind (descriptor in *d, pivot rows in rvec, at most rvec_cap_rows), -1 for a step
+// that attempts nothing, -2 when the next step is a GC step, -3 for a move the device does not offer (the
+// generator then stands in front of that step).  The acceptance variate is already drawn (d->u): call
+// pmc_no_accept_draw when the step's dE turned out >= 1e8.
+int pmc_next(void* p, pg_move_desc* d, double* rvec, int rvec_cap_rows, int* n_rows) {
+  Gen* g = static_cast<Gen*>(p);
+  if (g->prop.generate(g->rng, 1, g->one) != 1) return g->one.stop == plum_mc::STOP_GC ? -2 : -3;
+  if (n_rows) *n_rows = 0;
+  if (g->one.kind[0] < 0) return -1;
+  *d = g->one.moves[0];
+  const int rows = (int)(g->one.rvec.size() / 4);
+  if (rows > rvec_cap_rows) return -4;
+  if (rows) std::memcpy(rvec, g->one.rvec.data(), sizeof(double) * 4 * (size_t)rows);
+  if (n_rows) *n_rows = rows;
+  return d->kind;
+}
+void pmc_no_accept_draw(void* p) {
+  Gen* g = static_cast<Gen*>(p);
+  g->one.rewind_after_overlap(g->rng, 1);
+}
+// Draws the generator consumed so far cannot be observed from outside; tests compare the NEXT raw output instead.
+unsigned pmc_peek_raw(void* p) {
+  Gen* g = static_cast<Gen*>(p);
+  std::mt19937 copy = g->rng;
+  return (unsigned)copy();
+}
+void pmc_apply(const pg_move_desc* d, const double* rvec, int len, const double* cur, double* out) {
+  plum_mc::Proposer::apply(*d, rvec, len, cur, out);
 }
 
 }  // extern "C"

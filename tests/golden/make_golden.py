@@ -104,17 +104,37 @@ def extras():
         print("extra", name, len(lines), "lines")
 
 
+def synth_spring():
+    """examples/synth_spring + short/synth_spring_seed{1,2}.trace.gz: a small cut of the synthetic polyelectrolyte
+    (plum_b200/synth.py: 4 chains x 24 beads + counter-ions, same box / alpha / move mix as the benchmark system S)
+    with the Spring bond potential on, so that Pivot and RandomReptation vary the bond length (the extra draw of
+    src/molecules/molecule.cc:184-187, :278-281) — the reference ships no spring example."""
+    from plum_b200 import synth
+    sysm = synth.make_system(n_chains=4, chain_len=24, charged_every=6)
+    dst = os.path.join(HERE, "examples", "synth_spring")
+    synth.write_inputs(dst, sysm, n_steps=400, alpha=0.004, spring=True)
+    for seed in SHORT_SEEDS:
+        lines = replay.run_plum_ref(dst, 400, seed, xyz=True)
+        with gzip.open(os.path.join(HERE, "short", f"synth_spring_seed{seed}.trace.gz"), "wt") as f:
+            f.write("\n".join(lines))
+        print("short synth_spring", seed, len(lines), "lines")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--long-from", default=None)
     ap.add_argument("--skip-long", action="store_true")
     ap.add_argument("--extras-only", action="store_true", help="only the sampler fixtures (extras())")
+    ap.add_argument("--synth-only", action="store_true", help="only the spring-bond fixture (synth_spring())")
     a = ap.parse_args()
     if not replay.have_plum_ref():
         raise SystemExit("oracle/_ref/plum_ref missing: run python oracle/build_ref.py")
     if a.extras_only:
         os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
         extras()
+        return
+    if a.synth_only:
+        synth_spring()
         return
     os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
     os.makedirs(os.path.join(HERE, "long"), exist_ok=True)
@@ -139,6 +159,7 @@ def main():
         compact_long(lines, os.path.join(HERE, "long", f"{ex}_seed1.npz"), LONG_STEPS)
         print("long", ex, len(lines), "lines")
     extras()
+    synth_spring()
 
 
 if __name__ == "__main__":
