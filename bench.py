@@ -110,6 +110,7 @@ def mcbench_lib():
     L.pb_stats.argtypes = [C.c_void_p, ip, dp, dp, ip]
     L.pb_stats.restype = None
     L.pb_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp]
+    L.pb_run_mc.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, dp]
     return L
 
 
@@ -276,10 +277,8 @@ def run_ours(a):
                 self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
                 self.eng.init_energy()
                 self.stream = torch.cuda.ExternalStream(self.eng.stream(), device=torch.device("cuda", local_rank))
-                self.ctx = L.pb_create(self.eng.h, sysm.n_mol, mf.ctypes.data_as(ip), xyz0.ctypes.data_as(dp),
-                                       box.ctypes.data_as(dp), C.c_double(r.beta), C.c_double(r.move_size),
-                                       C.c_double(r.rigid_bond), prob.ctypes.data_as(dp), 0,
-                                       C.c_uint(12345 + 1000 * rank + 17 * idx))
+                self.seed = 12345 + 1000 * rank + 17 * idx
+                self.ctx = self.new_ctx()
                 self.cap_beads = n_total * 100
                 self.rec_mol = np.zeros(n_total, dtype=np.int32)
                 self.rec_off = np.zeros(n_total, dtype=np.int32)
@@ -292,6 +291,29 @@ def run_ours(a):
                 self.replay_dE = []
                 self.replay_ms = []
                 self.kd_ms = 0.0
+
+            def new_ctx(self):
+                return L.pb_create(self.eng.h, sysm.n_mol, mf.ctypes.data_as(ip), xyz0.ctypes.data_as(dp),
+                                   box.ctypes.data_as(dp), C.c_double(r.beta), C.c_double(r.move_size),
+                                   C.c_double(r.rigid_bond), prob.ctypes.data_as(dp), 0, C.c_uint(self.seed))
+
+            def reset_for_mc(self):
+                """Back to the initial configuration and the initial random stream: the batched leg must walk the
+                very same Markov chain as the per-move leg."""
+                self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
+                self.eng.init_energy()
+                self.ctx = self.new_ctx()
+                self.mc_mol = np.zeros(n_total, dtype=np.int32)
+                self.mc_off = np.zeros(n_total, dtype=np.int32)
+                self.mc_u = np.zeros(n_total)
+                self.mc_dE = np.zeros(n_total)
+                self.mc_acc = np.zeros(n_total, dtype=np.uint8)
+
+            def set_mc_records(self, s):
+                sl = slice(s * M, (s + 1) * M)
+                L.pb_set_records(self.ctx, self.mc_mol[sl].ctypes.data_as(ip), self.mc_off[sl].ctypes.data_as(ip),
+                                 self.mc_u[sl].ctypes.data_as(dp), self.mc_dE[sl].ctypes.data_as(dp),
+                                 self.mc_acc[sl].ctypes.data_as(bp), None, None, 0)
 
             def set_records(self, s):
                 sl = slice(s * M, (s + 1) * M)
@@ -440,6 +462,7 @@ def run_ours(a):
         replay_matches = all(bool(np.array_equal(np.concatenate(rp.replay_dE), rp.rec_dE[W * M:]) and
                                   rp.eng.totals() == rp.final_e2e) for rp in reps)
 
+
         # ---------------- roofline of the dominant kernel (k_move), timed alone, same proposals
         timed = np.arange(W * M, (W + K) * M)
         evals = flops = bytes_ = 0.0
@@ -490,6 +513,71 @@ def run_ours(a):
                            "note": "the 0.9 MB working set per replica is L2-resident by design; HBM is the conservative denominator"},
         }
 
+        # ---------------- batched leg: the same chains once more, now with device-side proposals (pg_mc_*): the host
+        # only draws the random stream ahead (native caller, plum_b200/host/mc_propose.h) and uploads one descriptor
+        # block per batch; trial coordinates, dE, the Metropolis test and the commit never leave the device.
+        mc_error = None
+        try:
+            run_all(lambda rp: rp.reset_for_mc())
+
+            def mc_step(s):
+                errs = []
+
+                def drive(group):
+                    try:
+                        for rp in group:
+                            rp.set_mc_records(s)
+                        arr = (C.c_void_p * len(group))(*[rp.ctx for rp in group])
+                        wall = C.c_double()
+                        rc = L.pb_run_mc(arr, len(group), M, a.mc_batch, C.byref(wall))
+                        if rc != 0:
+                            msgs = [rp.eng.L.pg_last_error(rp.eng.h).decode() for rp in group]
+                            raise RuntimeError(f"pb_run_mc failed ({rc}): {msgs}")
+                    except Exception as e:   # noqa: BLE001
+                        errs.append(e)
+                if T == 1:
+                    drive(groups[0])
+                else:
+                    ths = [threading.Thread(target=drive, args=(g_,)) for g_ in groups]
+                    for t in ths:
+                        t.start()
+                    for t in ths:
+                        t.join()
+                if errs:
+                    raise errs[0]
+
+            for s in range(W):
+                mc_step(s)
+                flush_l2()
+        except Exception as e:   # noqa: BLE001 — keep the other legs' numbers
+            mc_error = repr(e)
+        launches0 = sum(rp.eng.launch_count() for rp in reps)
+        barrier()   # collectives stay outside the try blocks: a rank that failed still takes part
+        t0 = time.perf_counter()
+        try:
+            if mc_error is None:
+                for s in range(W, W + K):
+                    mc_step(s)
+                    flush_l2()
+        except Exception as e:   # noqa: BLE001
+            mc_error = repr(e)
+        t_mc = (time.perf_counter() - t0) if mc_error is None else float("inf")
+        barrier()
+        t_mc = max_over_ranks(t_mc)
+        mc_launches, mc_matches, mc_close = 0, False, False
+        try:
+            if mc_error is not None:
+                raise RuntimeError(mc_error)
+            mc_launches = sum(rp.eng.launch_count() for rp in reps) - launches0
+            mc_matches = all(bool(np.array_equal(rp.mc_mol, rp.rec_mol) and np.array_equal(rp.mc_acc, rp.rec_acc) and
+                                  np.array_equal(rp.mc_dE, rp.rec_dE) and rp.eng.totals() == rp.final_e2e) for rp in reps)
+            mc_close = all(bool(np.array_equal(rp.mc_mol, rp.rec_mol) and np.array_equal(rp.mc_acc, rp.rec_acc) and
+                                np.all(np.abs(rp.mc_dE - rp.rec_dE) <= 1e-10 * np.maximum(1.0, np.abs(rp.rec_dE)))) for rp in reps)
+            for rp in reps:
+                L.pb_destroy(rp.ctx)
+        except Exception as e:   # noqa: BLE001
+            mc_error = mc_error or repr(e)
+
         # ---------------- totals over ranks
         moves_total = sum_over_ranks(float(R * K * M))
         evals_total = sum_over_ranks(evals)
@@ -500,13 +588,21 @@ def run_ours(a):
         h2d = float((lens * (24 + 8 + 4 + 4 + 1)).sum() / K)
         d2h = float(R * M * 128)
         rec_acc_all = np.concatenate([rp.rec_acc[W * M:] for rp in reps])
+        # batched path: 72 B descriptor per move + 21 B per bead of the moved molecule (charge, type, index, flag)
+        # + 32 B per pivot step H2D; 9 B per move (dE, accept bit) + the stop word per batch D2H
+        chain_moves = lens > 1
+        p_piv = MOVE_PROB[2] / max(MOVE_PROB[1] + MOVE_PROB[2] + MOVE_PROB[4], 1e-12)   # pivots among the chain moves (rows are not recorded)
+        mc_h2d = float((72.0 * lens.size + 21.0 * lens.sum() + p_piv * 32.0 * (lens[chain_moves] - 1).sum()) / K)
+        mc_d2h = float(R * M * 9 + R * (M // max(a.mc_batch, 1) + 1) * 4)
 
         for rp in reps:
             rp.eng.close()
         return dict(R=R, T=T, value=value, e2e_value=e2e_value, dev_s=dev_s, t_e2e=t_e2e, evals_total=evals_total,
                     e2e_launches=e2e_launches, gpu_launches=gpu_launches, roofline=roofline, clock_info=clock_info,
                     replay_matches=replay_matches, wall_replay=(t_wall_replay - t_flush), h2d=h2d, d2h=d2h,
-                    accept=float(rec_acc_all.mean()), p_ion=float(np.mean(lens == 1)))
+                    accept=float(rec_acc_all.mean()), p_ion=float(np.mean(lens == 1)),
+                    mc_value=moves_total / t_mc, t_mc=t_mc, mc_launches=mc_launches, mc_matches=mc_matches, mc_close=mc_close,
+                    mc_h2d=mc_h2d, mc_d2h=mc_d2h, mc_error=mc_error)
 
     single = measure(1) if (R_auto > 1 and not a.no_single) else None
     res = measure(R_auto)
@@ -527,6 +623,18 @@ def run_ours(a):
                          f"(oracle port, map-free, new-configuration energies only like the reference), mixed with the realised ion fraction {p_ion:.3f}; plum_ref cannot "
                          f"hold N=22000 (SURVEY.md §0.8)"}
 
+    e2e_per_move = {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_e2e * 1e3 / K, "pair_dE_evals_per_s": evals_total / t_e2e,
+                    "caller": f"native C++ Metropolis loops over pg_delta_e_begin/_poll/pg_commit (plum_b200/host/mc_bench.cc): {res['T']} host thread(s) per GPU driving {R} replicas; trial coordinates built on the host",
+                    "launches": int(e2e_launches)}
+    e2e_batched = {"value": res["mc_value"], "unit": "moves/s", "h2d_bytes_per_step": res["mc_h2d"], "d2h_bytes_per_step": res["mc_d2h"],
+                   "ms_per_step": res["t_mc"] * 1e3 / K, "pair_dE_evals_per_s": evals_total / res["t_mc"],
+                   "caller": f"native C++ caller over pg_mc_upload/_begin/_end (plum_b200/host/mc_bench.cc), batches of {a.mc_batch} steps: the host draws the "
+                             f"std::mt19937 stream ahead in the reference's order and uploads descriptors; proposals (k_propose), dE (k_move), Metropolis test and "
+                             f"commit stay on the device; {res['T']} host thread(s) per GPU driving {R} replicas; wall clock incl. generation, uploads and result downloads",
+                   "launches": int(res["mc_launches"]),
+                   "same_chain_as_per_move": {"bit_identical": res["mc_matches"], "within_1e-10": res["mc_close"]}, "error": res["mc_error"]}
+    e2e_best = e2e_batched if (res["mc_close"] and res["mc_value"] > e2e_value) else e2e_per_move
     if rank == 0:
         line = {
             "metric": "MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -536,15 +644,14 @@ def run_ours(a):
                        "l2": "flushed between steps (256 MiB fill, inside the timed region); within a step the "
                              "0.9 MB working set stays L2-resident by design (north_star)"},
             "pair_dE_evals_per_s": evals_total / dev_s,
-            "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": t_e2e * 1e3 / K, "pair_dE_evals_per_s": evals_total / t_e2e,
-                    "caller": f"native C++ Metropolis loops over pg_delta_e_begin/_poll/pg_commit (plum_b200/host/mc_bench.cc): {res['T']} host thread(s) per GPU driving {R} replicas",
-                    "launches": int(e2e_launches)},
+            "e2e": e2e_best,
+            "e2e_per_move": e2e_per_move, "e2e_batched": e2e_batched,
             "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
             "replay_matches_e2e": replay_matches, "wall_ms_per_step_replay": (t_wall_replay - t_flush) * 1e3 / K,
             "accept_ratio": res["accept"],
             "single_replica": None if single is None else {
-                "value": single["value"], "e2e": single["e2e_value"], "unit": "moves/s", "roofline_frac": single["roofline"]["frac"],
+                "value": single["value"], "e2e": max(single["e2e_value"], single["mc_value"] if single["mc_close"] else 0.0),
+                "e2e_per_move": single["e2e_value"], "e2e_batched": single["mc_value"], "batched_same_chain": single["mc_close"], "unit": "moves/s", "roofline_frac": single["roofline"]["frac"],
                 "avg_launch_us": single["roofline"]["avg_launch_us"], "replay_matches_e2e": single["replay_matches"],
                 "note": "one Markov chain on the GPU (latency-bound): the rate a single Plum run sees"},
         }
@@ -565,6 +672,7 @@ def main():
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-replica measurement")
     ap.add_argument("--replicas-per-gpu", type=int, default=0,
                     help="independent Markov chains per GPU, each with its own engine/stream; 0 = 24 (fixed per GPU: weak scaling)")
+    ap.add_argument("--mc-batch", type=int, default=256, help="steps per uploaded batch in the batched (device-side proposal) leg")
     ap.add_argument("--host-threads", type=int, default=0,
                     help="host threads per GPU driving the replicas in the e2e leg (0 = host cores per GPU - 2, at most one per replica)")
     a = ap.parse_args()

@@ -231,7 +231,8 @@ typedef struct pg_move_desc {
 int pg_mc_upload(pg_engine* h, int n_moves, const pg_move_desc* moves, int n_rvec, const double* rvec);
 /* Runs steps [first, first+count) of the uploaded batch.  *n_done = steps whose outcome is final
  * (== count unless a step hit dE >= 1e8; that step IS done — it is a rejection — later ones are
- * not).  dE_out / accept_out (may be NULL) are filled for the done steps.  elapsed_ms (may be
+ * not).  The batch has stopped iff dE_out[n_done-1] >= 1e8 — also when that was its last step:
+ * the caller's generator must then be put back in front of that step's acceptance draw.  dE_out / accept_out (may be NULL) are filled for the done steps.  elapsed_ms (may be
  * NULL) is CUDA-event time on the engine stream.  pg_mc_run = pg_mc_begin + pg_mc_end; the halves
  * let one host thread keep several replicas busy. */
 int pg_mc_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, int* n_done,

@@ -1209,6 +1209,7 @@ static int replay_graph(pg_engine* h, int first, int count, bool commit, cudaGra
 
 int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* accept_out, float* elapsed_ms) {
   if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->rp_mc) { h->err = "the proposal buffers hold an MC batch (pg_mc_upload), not a replay"; return PG_ERR_STATE; }
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
   int rc = flush_commit(h);
@@ -1237,6 +1238,7 @@ int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* a
 
 int pg_replay_prepare(pg_engine* h, int first, int count, int with_commit) {
   if (!h || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->rp_mc) { h->err = "the proposal buffers hold an MC batch (pg_mc_upload), not a replay"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
   cudaGraphExec_t exec = nullptr;
   return replay_graph(h, first, count, with_commit != 0, &exec);
@@ -1244,6 +1246,7 @@ int pg_replay_prepare(pg_engine* h, int first, int count, int with_commit) {
 
 int pg_replay_time_delta(pg_engine* h, int first, int count, float* elapsed_ms) {
   if (!h || !elapsed_ms || first < 0 || count < 0 || first + count > (int)h->rp_moves.size()) return PG_ERR_INVALID;
+  if (h->rp_mc) { h->err = "the proposal buffers hold an MC batch (pg_mc_upload), not a replay"; return PG_ERR_STATE; }
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
   int rc = flush_commit(h);

@@ -30,7 +30,8 @@ def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, f) for f in ("force_field.h", "force_field.cc", "driver_hooks.py", "build_host.py")]
+    deps = [os.path.join(HERE, f) for f in ("force_field.h", "force_field.cc", "driver_hooks.py", "build_host.py", "mc_propose.h")]
+    deps.append(os.path.join(REPO, "plum_b200", "csrc", "pg_propose_math.h"))
     deps.append(os.path.join(REPO, "include", "plum_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -54,12 +55,13 @@ def main():
         for f in ("force_field.h", "force_field.cc"):
             shutil.copy(os.path.join(HERE, f), os.path.join(src, "force_field", f))
         driver_hooks.apply_sim_hooks(src)
+        driver_hooks.apply_batch_hook(src)
         files = [os.path.join(src, "main.cc"), os.path.join(src, "force_field", "force_field.cc")]
         for d in ("simulation", "molecules", "utilities"):
             files += sorted(os.path.join(src, d, f) for f in os.listdir(os.path.join(src, d)) if f.endswith(".cc"))
         eigen = os.environ.get("EIGEN_INCLUDE", os.path.join(HERE, "eigen_standin"))
         libdir = os.path.join(REPO, "plum_b200")
-        cmd = ["g++", "-std=c++11", "-O3", "-w"] + (["-pg", "-fno-inline-functions"] if PROFILE else []) + ["-I", eigen, "-I", os.path.join(REPO, "include"), "-o", OUT] + files + \
+        cmd = ["g++", "-std=c++11", "-O3", "-w"] + (["-pg", "-fno-inline-functions"] if PROFILE else []) + ["-ffp-contract=off", "-I", eigen, "-I", os.path.join(REPO, "include"), "-I", HERE, "-I", os.path.join(REPO, "plum_b200", "csrc"), "-o", OUT] + files + \
               ["-L", libdir, "-lplum_b200", "-Wl,-rpath,$ORIGIN/../plum_b200", "-lm"]
         subprocess.check_call(cmd)
         print("build_host: built", OUT)

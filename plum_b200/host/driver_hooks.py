@@ -104,6 +104,34 @@ def apply_sim_hooks(src):
           "      force_field.EnergyInitForAddedMolecule(mols);\n")
 
 
+def apply_batch_hook(src):
+    """bin/plum_gpu only: lets the façade run stretches of translational steps on the device
+    (ForceField::TranslationalBatch, SURVEY.md §8f #2).  This is the ONE change to the driver's control flow, and
+    the patch a maintainer would carry (INTEGRATION.md): at the top of Simulation::Run's loop
+    (src/simulation/simulation.cc:220) the façade is offered every step up to the next one at which Sample /
+    Print* act; it returns how many it executed (0: a GC step or a crankshaft is next and the untouched code below
+    runs it).  PLUM_B200_BATCH=0 disables it."""
+    sim = os.path.join(src, "simulation", "simulation.cc")
+    patch(sim, "  for (step = 1; step <= steps; step++) {\n    int rand_num = rand_gen();\n",
+          "  for (step = 1; step <= steps; step++) {\n"
+          "    if (force_field.BatchedMoves()) {\n"
+          "      int plum_until = steps;\n"
+          "      const int plum_freq[3] = {sample_freq, stat_out_freq, traj_out_freq};\n"
+          "      for (int k = 0; k < 3; k++) if (plum_freq[k] > 0) {\n"
+          "        long long nx = ((long long)(step + plum_freq[k] - 1) / plum_freq[k]) * plum_freq[k];\n"
+          "        if (nx < plum_until) plum_until = (int)nx;\n"
+          "      }\n"
+          "      const int plum_n = force_field.TranslationalBatch(mols, rand_gen, plum_until - step + 1, step, move_size,\n"
+          "                                                        move_prob, attempted, accepted);\n"
+          "      if (plum_n > 0) {\n"
+          "        step += plum_n - 1;\n"
+          "        Sample(); PrintStat(); PrintTraj(); PrintLastCrd(); PrintLastTop(); PrintLastRhoZ();\n"
+          "        continue;\n"
+          "      }\n"
+          "    }\n"
+          "    int rand_num = rand_gen();\n")
+
+
 def apply_cbmc_hooks(src):
     """Hooks in the reference's own cbmc.cc (reference binary only)."""
     cbmc = os.path.join(src, "force_field", "cbmc.cc")

@@ -22,10 +22,16 @@
 #include "../utilities/constants.h"
 #include "../utilities/misc.h"
 #include "plum_b200.h"
+#include "mc_propose.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <ctime>
 using namespace std;
+
+// Trace hooks of the driver build (plum_b200/host/driver_hooks.py); absent otherwise.
+FILE* plum_trace_file() __attribute__((weak));
+FILE* plum_trace_xyz_file() __attribute__((weak));
 
 // Set by the driver's trace hook build (plum_b200/host/driver_hooks.py); harmless otherwise.
 double plum_trace_weight __attribute__((weak)) = -1;
@@ -54,7 +60,19 @@ struct SiteTimer {
 };
 }  // namespace
 
-ForceField::ForceField() : engine(NULL), pending_mol(-1), vp_z(0) {
+namespace {
+struct McState {
+  plum_mc::Proposer prop;
+  plum_mc::Batch batch;
+  plum_mc::BatchSizer sizer;
+  int n_mol_configured = -1;   // -1: (re)build the molecule tables (set by UpdateMolCounts after every GC move)
+  bool sizer_ready = false;
+  vector<double> dE, xyz;
+  vector<uint8_t> acc;
+};
+}  // namespace
+
+ForceField::ForceField() : engine(NULL), pending_mol(-1), mc_state(NULL), vp_z(0) {
   for (int i = 0; i < 12; i++) p_tensor[i] = 0;
 }
 
@@ -421,6 +439,104 @@ void ForceField::FinalizeEnergies(vector<Molecule>& mols, bool accept, int moved
   { SiteTimer st_(kTCommit); rc = pg_commit(engine, accept ? 1 : 0); }
   if (rc) Fail("pg_commit", rc);
   pending_mol = -1;
+}
+
+
+// ------------------------------------------------- batched translational steps
+bool ForceField::BatchedMoves() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("PLUM_B200_BATCH"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, int max_steps, int first_step,
+                                   double move_size, const double move_prob[5], int attempted[], int accepted[]) {
+  if (max_steps <= 0) return 0;
+  if (!mc_state) mc_state = new McState();
+  McState& S = *static_cast<McState*>(mc_state);
+  // the molecule list only changes through GC moves, which also change its length or leave it as it was
+  if (S.n_mol_configured != (int)mols.size()) {
+    plum_mc::Config cfg;
+    cfg.phantom = phantom;
+    for (int i = 0; i < (int)mols.size(); i++) cfg.mol_len.push_back(mols[i].Size());
+    cfg.move_size = move_size;
+    for (int i = 0; i < 5; i++) cfg.move_prob[i] = move_prob[i];
+    if (use_bond_rigid) cfg.bond_len = rigid_bond;                       // simulation.cc:288-296
+    if (use_bond_pot) { cfg.bond_len = bond_r0; cfg.vary_bond = true; }
+    cfg.gc_freq = use_gc ? gc_freq : 0;
+    S.prop.configure(cfg);
+    if (!S.sizer_ready) { S.sizer.reset(4096); S.sizer_ready = true; }
+    S.n_mol_configured = (int)mols.size();
+  }
+  FILE* tf = plum_trace_file ? plum_trace_file() : NULL;
+  FILE* tx = plum_trace_xyz_file ? plum_trace_xyz_file() : NULL;
+  int executed = 0;
+  while (executed < max_steps) {
+    const int budget = min(S.sizer.next(), max_steps - executed);
+    const int n_steps = S.prop.generate(rand_gen, budget, S.batch);
+    if (n_steps == 0) break;   // a GC step or a crankshaft is next
+    plum_mc::Batch& b = S.batch;
+    const int n_moves = (int)b.moves.size();
+    int steps_done = n_steps;
+    bool stopped = false;
+    if (n_moves > 0) {
+      S.dE.resize(n_moves);
+      S.acc.resize(n_moves);
+      int n_done = 0, rc;
+      { SiteTimer st_(kTDelta);
+        rc = pg_mc_upload(engine, n_moves, b.moves.data(), (int)(b.rvec.size() / 4), b.rvec.data());
+        if (rc) Fail("pg_mc_upload", rc);
+        rc = pg_mc_run(engine, 0, n_moves, S.dE.data(), S.acc.data(), &n_done, NULL); }
+      if (rc) Fail("pg_mc_run", rc);
+      stopped = n_done > 0 && S.dE[n_done - 1] >= kVeryLargeEnergy;
+      if (!stopped && n_done != n_moves) Fail("pg_mc_run (batch ended without a stop)", PG_ERR_STATE);
+      for (int m = 0; m < n_done; m++) {
+        const pg_move_desc& d = b.moves[m];
+        attempted[d.kind]++;
+        if (S.acc[m]) accepted[d.kind]++;
+        if (tf) {
+          // running totals are not materialised per step inside a batch: "nan" except behind the last step
+          fprintf(tf, "T %d %d %d %a %d", first_step + executed + b.step_of_move[m], d.kind, d.mol, S.dE[m], (int)S.acc[m]);
+          if (m == n_done - 1) {
+            fprintf(tf, " %a %a %a %a\n", use_pair_pot ? TotPairEnergy() : 0.0, use_ewald_pot ? TotEwaldEnergy() : 0.0,
+                    use_bond_pot ? TotBondEnergy() : 0.0, use_ext_pot ? TotExtEnergy() : 0.0);
+          } else {
+            fprintf(tf, " nan nan nan nan\n");
+          }
+          if (tx) {
+            const int len = mols[d.mol].Size();
+            vector<double> t(3 * len);
+            rc = pg_mc_trial_xyz(engine, m, t.data());
+            if (rc) Fail("pg_mc_trial_xyz", rc);
+            fprintf(tx, "X %d", len);
+            for (int i = 0; i < len; i++)
+              fprintf(tx, " %d %a %a %a", (d.kind == PG_MOVE_BEAD) ? (i == 0) : 1, t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+            fprintf(tx, "\n");
+          }
+        }
+      }
+      if (stopped) steps_done = b.rewind_after_overlap(rand_gen, n_done);
+      S.sizer.update(n_done, stopped);
+    }
+    executed += steps_done;
+    if (!stopped && b.stop != plum_mc::STOP_FULL) break;   // the generator stands in front of a step the driver runs
+  }
+  if (executed > 0) {
+    // the device's coordinates are the accepted ones: bring the driver's beads (current and trial) up to date
+    int n = 0;
+    for (int i = 0; i < (int)mols.size(); i++) n += mols[i].Size();
+    S.xyz.resize(3 * (size_t)n);
+    int rc = pg_download_positions(engine, S.xyz.data());
+    if (rc) Fail("pg_download_positions", rc);
+    size_t k = 0;
+    for (int i = 0; i < (int)mols.size(); i++)
+      for (int j = 0; j < mols[i].Size(); j++, k += 3)
+        for (int a = 0; a < 3; a++) {
+          mols[i].bds[j].SetCrd(0, a, S.xyz[k + a]);
+          mols[i].bds[j].SetCrd(1, a, S.xyz[k + a]);
+        }
+  }
+  return executed;
 }
 
 // ---------------------------------------------------------------------- CBMC
@@ -846,6 +962,7 @@ void ForceField::SetBoxLen(double box_l_in[3]) {
 }
 
 void ForceField::UpdateMolCounts(vector<Molecule>& mols) {
+  if (mc_state) static_cast<McState*>(mc_state)->n_mol_configured = -1;   // the molecule list may have changed
   n_mol = (int)mols.size();
   n_chain = 0;
   n_cion = 0;

@@ -78,6 +78,7 @@ class ForceField {
   map<string, int> type_of;        // bead symbol -> dense type id
   vector<string> type_symbols;
   int pending_mol;                  // molecule of the trial awaiting FinalizeEnergies (-1: none)
+  void* mc_state;                   // batched translational steps: generator, batch buffers (force_field.cc)
 
   int TypeId(const string& symbol);
   void Fail(const char* what, int rc);
@@ -97,6 +98,18 @@ class ForceField {
 
   double EnergyDifference(vector<Molecule>&, int);
   void FinalizeEnergies(vector<Molecule>&, bool, int);
+
+  /** NEW (no reference counterpart): runs up to `max_steps` consecutive steps of
+   *  Simulation::Run (simulation.cc:216-237) whose move is translational — proposal, energy change,
+   *  Metropolis test and commit on the device (pg_mc_*), the random stream drawn ahead on the host in the
+   *  reference's order — and returns how many steps were executed.  0 means the next step is a GC step or
+   *  uses a move the device does not offer (crankshaft): the driver's own code runs that one.  On return
+   *  `mols` holds the accepted coordinates, `rand_gen` stands where the reference's generator would, and
+   *  attempted[] / accepted[] (simulation.h:110-111) are updated.  `first_step` only labels trace lines. */
+  int TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, int max_steps, int first_step, double move_size,
+                         const double move_prob[5], int attempted[], int accepted[]);
+  /** PLUM_B200_BATCH=0 turns the batched steps off (the driver then runs every step itself). */
+  bool BatchedMoves();
 
   // Pressure samplers: SURVEY.md §8(f) "next" #1 — not on the per-move path.  They
   // consume no random numbers, so leaving them out does not change the trajectory.

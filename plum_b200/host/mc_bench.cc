@@ -33,6 +33,7 @@ struct Ctx {
   plum_mc::Proposer prop;
   plum_mc::Batch one;        // the step in flight on the per-move path
   plum_mc::Batch batch[2];   // batched path: the batch on the device and the one generated ahead
+  plum_mc::BatchSizer sizer;
   double box[3];
   double beta, move_size, bond_len;
   double prob[5];
@@ -89,12 +90,14 @@ int finish(Ctx* c, const pg_delta& d) {
   c->evals += ev;
   c->flops += 2.0 * ev * 36.0;   // + reciprocal-space terms added by the caller (needs charges)
   if (c->rec_mol) {
-    if (c->used + len > c->rec_cap_beads) return PG_ERR_CAPACITY;
     c->rec_mol[it] = c->cur_mol; c->rec_off[it] = c->used; c->rec_u[it] = (u < 0) ? 2.0 : u; c->rec_dE[it] = d.dE;
     c->rec_acc[it] = accept ? 1 : 0;
-    std::memcpy(c->rec_trial + 3 * (size_t)c->used, T, sizeof(double) * 3 * len);
-    std::memcpy(c->rec_moved + c->used, c->moved.data(), len);
-    c->used += len;
+    if (c->rec_cap_beads > 0) {   // trial coordinates are recorded only when the caller gave room for them
+      if (c->used + len > c->rec_cap_beads) return PG_ERR_CAPACITY;
+      std::memcpy(c->rec_trial + 3 * (size_t)c->used, T, sizeof(double) * 3 * len);
+      std::memcpy(c->rec_moved + c->used, c->moved.data(), len);
+      c->used += len;
+    }
   }
   c->done++;
   return 0;
@@ -241,13 +244,12 @@ int pb_run_mc(void** ps, int n_ctx, int n_moves, int batch_moves, double* wall_s
   auto t0 = std::chrono::steady_clock::now();
   std::vector<int> cur(n_ctx, 0), ahead(n_ctx, 0), flying(n_ctx, 0);
   std::vector<std::mt19937> rng_after(n_ctx);   // generator state behind the batch that is on the device
-  std::vector<double> dE(batch_moves);
-  std::vector<uint8_t> acc(batch_moves);
+  std::vector<double> dE(batch_moves + 8);
+  std::vector<uint8_t> acc(batch_moves + 8);
   auto launch = [&](int i) -> int {
     Ctx* c = cs[i];
     plum_mc::Batch& b = c->batch[cur[i]];
-    const int want = std::min(batch_moves, n_moves - c->done);
-    if ((int)b.moves.size() > want) return PG_ERR_STATE;
+    if ((int)b.moves.size() > n_moves - c->done) return PG_ERR_STATE;
     if (b.moves.empty()) return 1;   // nothing (left) to do
     int rc = pg_mc_upload(c->eng, (int)b.moves.size(), b.moves.data(), (int)(b.rvec.size() / 4), b.rvec.data());
     if (rc) return rc;
@@ -263,7 +265,8 @@ int pb_run_mc(void** ps, int n_ctx, int n_moves, int batch_moves, double* wall_s
   };
   int live = 0;
   for (int i = 0; i < n_ctx; i++) {
-    generate(i, 0, std::min(batch_moves, n_moves));
+    cs[i]->sizer.reset(batch_moves);
+    generate(i, 0, std::min(cs[i]->sizer.next(), n_moves));
     int rc = launch(i);
     if (rc < 0) return rc;
     if (rc == 0) live++;
@@ -274,7 +277,7 @@ int pb_run_mc(void** ps, int n_ctx, int n_moves, int batch_moves, double* wall_s
       Ctx* c = cs[i];
       rng_after[i] = c->rng;
       const int left = n_moves - c->done - (int)c->batch[cur[i]].moves.size();
-      generate(i, cur[i] ^ 1, std::max(0, std::min(batch_moves, left)));
+      generate(i, cur[i] ^ 1, std::max(0, std::min(c->sizer.next(), left)));
       ahead[i] = 1;
     }
   while (live > 0) {
@@ -303,23 +306,27 @@ int pb_run_mc(void** ps, int n_ctx, int n_moves, int batch_moves, double* wall_s
         }
       }
       c->done += n_done;
-      if (n_done < (int)b.moves.size()) {
-        // the last done step drew no acceptance variate: everything generated behind it is void
+      const bool stopped = n_done > 0 && dE[n_done - 1] >= PG_VERY_LARGE_ENERGY;
+      if (!stopped && n_done < (int)b.moves.size()) return PG_ERR_STATE;
+      if (stopped) {
+        // the last done step drew no acceptance variate (also when it was the last step of the batch):
+        // everything generated behind it is void
         b.rewind_after_overlap(c->rng, n_done);
         ahead[i] = 0;
       }
+      c->sizer.update(n_done, stopped);
       if (c->done >= n_moves) { live--; continue; }
       if (ahead[i]) {
         cur[i] ^= 1;
       } else {
-        generate(i, cur[i], std::min(batch_moves, n_moves - c->done));
+        generate(i, cur[i], std::min(c->sizer.next(), n_moves - c->done));
       }
       rc = launch(i);
       if (rc < 0) return rc;
       if (rc == 1) { live--; continue; }
       rng_after[i] = c->rng;
       const int left = n_moves - c->done - (int)c->batch[cur[i]].moves.size();
-      generate(i, cur[i] ^ 1, std::max(0, std::min(batch_moves, left)));
+      generate(i, cur[i] ^ 1, std::max(0, std::min(c->sizer.next(), left)));
       ahead[i] = 1;
     }
   }

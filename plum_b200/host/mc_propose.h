@@ -61,6 +61,24 @@ struct Batch {
   }
 };
 
+// How many steps to hand to the device at once.  A batch that stops early (a dE >= 1e8 step) leaves the
+// kernels queued behind the stop as no-ops, so the batch length follows the observed distance between stops:
+// long batches where overlaps never happen (bulk WCA fluids at low density), short ones in dense / walled systems.
+struct BatchSizer {
+  int cap = 1024;
+  double run = 1024.0;   // smoothed number of steps between stops
+  void reset(int max_batch) { cap = max_batch < 1 ? 1 : max_batch; run = cap; }
+  void update(int n_done, bool stopped) {
+    if (stopped) run = 0.75 * run + 0.25 * n_done;
+    else run = 0.75 * run + 0.25 * (2.0 * n_done + 8.0);
+    if (run > cap) run = cap;
+  }
+  int next() const {
+    int b = (int)(1.5 * run) + 4;
+    return b < 8 ? 8 : (b > cap ? cap : b);
+  }
+};
+
 class Proposer {
  public:
   void configure(const Config& c) {

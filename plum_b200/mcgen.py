@@ -97,3 +97,91 @@ def apply(desc: PgMoveDesc, rvec: np.ndarray, cur: np.ndarray) -> np.ndarray:
     d.rv_offset = 0
     lib().pmc_apply(C.byref(d), dptr(rv) if rv.size else None, int(cur.shape[0]), dptr(cur), dptr(out))
     return out
+
+
+def _bench_lib():
+    L = lib()
+    if not getattr(L, "_pb_ready", False):
+        dp, ip, bp = c_double_p, c_int32_p, C.POINTER(C.c_uint8)
+        L.pb_create.restype = C.c_void_p
+        L.pb_create.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, C.c_double, C.c_double, C.c_double, dp, C.c_int, C.c_uint]
+        L.pb_destroy.argtypes = [C.c_void_p]
+        L.pb_set_records.argtypes = [C.c_void_p, ip, ip, dp, dp, bp, dp, bp, C.c_int]
+        L.pb_set_records.restype = None
+        L.pb_set_vary_bond.argtypes = [C.c_void_p, C.c_int]
+        L.pb_set_vary_bond.restype = None
+        L.pb_positions.argtypes = [C.c_void_p, dp]
+        L.pb_positions.restype = None
+        L.pb_stats.argtypes = [C.c_void_p, ip, dp, dp, ip]
+        L.pb_stats.restype = None
+        L.pb_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp]
+        L.pb_run_mc.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, dp]
+        L._pb_ready = True
+    return L
+
+
+class NativeChain:
+    """One Markov chain driven by the native caller (plum_b200/host/mc_bench.cc) over the C ABI: either move by
+    move (pg_delta_e / pg_commit, trial coordinates built on the host) or in batches with device-side proposals
+    (pg_mc_*).  Both walk the same std::mt19937 in the reference's draw order, so for one seed they must produce
+    the same chain."""
+
+    def __init__(self, eng, r, sysm, seed, record_moves=0, record_trials=False):
+        self.L = _bench_lib()
+        self.eng = eng
+        self.n = sysm.n
+        mf = np.ascontiguousarray(sysm.mol_first, dtype=np.int32)
+        xyz = np.ascontiguousarray(sysm.xyz, dtype=np.float64)
+        box = np.ascontiguousarray(sysm.box, dtype=np.float64)
+        prob = np.ascontiguousarray(r.move_prob, dtype=np.float64)
+        bl, vary = bond_settings(r)
+        self.ctx = self.L.pb_create(eng.h, sysm.n_mol, iptr(mf), dptr(xyz), dptr(box), float(r.beta), float(r.move_size),
+                                    float(bl), dptr(prob), int(r.phantom), int(seed))
+        self.L.pb_set_vary_bond(self.ctx, int(vary))
+        self.max_len = int(np.diff(mf).max())
+        self.cap = record_moves
+        if record_moves:
+            self.rec_mol = np.zeros(record_moves, dtype=np.int32)
+            self.rec_off = np.zeros(record_moves, dtype=np.int32)
+            self.rec_u = np.zeros(record_moves)
+            self.rec_dE = np.zeros(record_moves)
+            self.rec_acc = np.zeros(record_moves, dtype=np.uint8)
+            nb = record_moves * self.max_len if record_trials else 0
+            self.rec_trial = np.zeros((max(nb, 1), 3))
+            self.rec_moved = np.zeros(max(nb, 1), dtype=np.uint8)
+            bp = C.POINTER(C.c_uint8)
+            self.L.pb_set_records(self.ctx, iptr(self.rec_mol), iptr(self.rec_off), dptr(self.rec_u), dptr(self.rec_dE),
+                                  self.rec_acc.ctypes.data_as(bp), dptr(self.rec_trial),
+                                  self.rec_moved.ctypes.data_as(bp), nb)
+
+    def close(self):
+        if self.ctx:
+            self.L.pb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _run(self, fn, *args):
+        arr = (C.c_void_p * 1)(self.ctx)
+        wall = C.c_double(0.0)
+        rc = fn(arr, 1, *args, C.byref(wall))
+        if rc != 0:
+            raise RuntimeError(f"native chain failed ({rc}): {self.eng.L.pg_last_error(self.eng.h).decode()}")
+        return wall.value
+
+    def run_per_move(self, n_moves):
+        """n_moves Metropolis steps, one pg_delta_e + pg_commit round trip each.  Records restart at 0."""
+        return self._run(self.L.pb_run_multi, int(n_moves))
+
+    def run_batched(self, n_moves, batch_moves=1024):
+        """The same steps with device-side proposals, `batch_moves` per upload."""
+        return self._run(self.L.pb_run_mc, int(n_moves), int(batch_moves))
+
+    def positions(self):
+        out = np.zeros((self.n, 3))
+        self.L.pb_positions(self.ctx, dptr(out))
+        return out

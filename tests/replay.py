@@ -35,7 +35,7 @@ def have_plum_gpu() -> bool:
 
 
 def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, binary: str = None,
-                 overrides: dict = None, want_files=()) -> List[str]:
+                 overrides: dict = None, want_files=(), extra_env: dict = None) -> List[str]:
     """Run a driver binary (default: the reference, oracle/_ref/plum_ref; or bin/plum_gpu) on an example
     (inputs copied to a temp dir) and return its trace lines.  `overrides` replaces run.in values by key."""
     binary = binary or PLUM_REF
@@ -58,6 +58,7 @@ def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, bina
         env = dict(os.environ, PLUM_SEED=str(seed), PLUM_TRACE=os.path.join(tmp, "trace.txt"))
         if xyz:
             env["PLUM_TRACE_XYZ"] = "1"
+        env.update(extra_env or {})
         with open(os.path.join(tmp, "run.in")) as fin, open(os.path.join(tmp, "run.log"), "w") as fout:
             subprocess.check_call([binary], stdin=fin, stdout=fout, cwd=tmp, env=env)
         with open(os.path.join(tmp, "trace.txt")) as f:
