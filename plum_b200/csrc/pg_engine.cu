@@ -154,8 +154,11 @@ struct pg_engine {
   PgPropDev* d_mc_moves = nullptr; size_t mc_moves_cap = 0;
   double4* d_mc_rv = nullptr; size_t mc_rv_cap = 0;
   char* h_mc_pin = nullptr; size_t mc_pin_cap = 0;   // pinned upload staging
-  int* d_stop = nullptr;
-  int* h_stop = nullptr;        // pinned
+  int* d_stop = nullptr;         // device memory: every CTA of every k_move / k_propose of a batch reads it first
+  int* h_stop = nullptr;         // pinned copy, filled by a 4-byte async copy behind the batch
+  double *h_mc_dE = nullptr, *d_mc_dE = nullptr;     // per-step logs in mapped pinned memory (device alias d_*):
+  uint8_t *h_mc_acc = nullptr, *d_mc_acc = nullptr;  // the finalising CTA of k_move posts them straight to the host
+  size_t mc_log_cap = 0;
   std::vector<int> mc_mol;      // molecule of every step of the batch (wave construction)
   int mc_first = 0, mc_count = 0;
   bool mc_inflight = false;
@@ -768,6 +771,8 @@ void free_all(pg_engine* h) {
   cudaFree(h->d_mc_moves); cudaFree(h->d_mc_rv); cudaFree(h->d_stop);
   if (h->h_mc_pin) cudaFreeHost(h->h_mc_pin);
   if (h->h_stop) cudaFreeHost(h->h_stop);
+  if (h->h_mc_dE) cudaFreeHost(h->h_mc_dE);
+  if (h->h_mc_acc) cudaFreeHost(h->h_mc_acc);
   for (auto& g : h->rp_graphs) cudaGraphExecDestroy(g.exec);
   h->rp_graphs.clear();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1141,8 +1146,8 @@ static int replay_launch(pg_engine* h, int m, int prev, bool log) {
   if (rc) return rc;
   A.partial = h->d_partial; A.state = h->d_state; A.mail = nullptr;
   A.decide_on_device = 1; A.u = r.u;
-  A.replay_dE = log ? h->d_rp_dE : nullptr;
-  A.replay_acc = log ? h->d_rp_acc : nullptr;
+  A.replay_dE = log ? (h->rp_mc ? h->d_mc_dE : h->d_rp_dE) : nullptr;
+  A.replay_acc = log ? (h->rp_mc ? h->d_mc_acc : h->d_rp_acc) : nullptr;
   A.replay_index = m;
   A.stop = h->rp_mc ? h->d_stop : nullptr;
   A.seq = ++h->seq;
@@ -1325,12 +1330,16 @@ int pg_mc_upload(pg_engine* h, int n_moves, const pg_move_desc* moves, int n_rve
     PG_CUDA(h, cudaMalloc((void**)&h->d_rp, c));
     h->rp_bytes_cap = c;
   }
-  if ((size_t)std::max(n_moves, 1) > h->rp_log_cap || !h->d_rp_dE) {
-    size_t c = std::max<size_t>((size_t)std::max(n_moves, 1), h->rp_log_cap * 2);
-    cudaFree(h->d_rp_dE); cudaFree(h->d_rp_acc); h->d_rp_dE = nullptr; h->d_rp_acc = nullptr; h->rp_log_cap = 0;
-    PG_CUDA(h, cudaMalloc((void**)&h->d_rp_dE, sizeof(double) * c));
-    PG_CUDA(h, cudaMalloc((void**)&h->d_rp_acc, c));
-    h->rp_log_cap = c;
+  if ((size_t)std::max(n_moves, 1) > h->mc_log_cap || !h->h_mc_dE) {
+    size_t c = std::max<size_t>((size_t)std::max(n_moves, 1), h->mc_log_cap * 2);
+    if (h->h_mc_dE) cudaFreeHost(h->h_mc_dE);
+    if (h->h_mc_acc) cudaFreeHost(h->h_mc_acc);
+    h->h_mc_dE = nullptr; h->h_mc_acc = nullptr; h->mc_log_cap = 0;
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_mc_dE, sizeof(double) * c, cudaHostAllocMapped));
+    PG_CUDA(h, cudaHostAlloc((void**)&h->h_mc_acc, c, cudaHostAllocMapped));
+    PG_CUDA(h, cudaHostGetDevicePointer((void**)&h->d_mc_dE, h->h_mc_dE, 0));
+    PG_CUDA(h, cudaHostGetDevicePointer((void**)&h->d_mc_acc, h->h_mc_acc, 0));
+    h->mc_log_cap = c;
   }
   PG_MC_RESERVE(h, h->d_mc_moves, h->mc_moves_cap, (size_t)std::max(n_moves, 1), PgPropDev);
   PG_MC_RESERVE(h, h->d_mc_rv, h->mc_rv_cap, (size_t)std::max(n_rvec, 1), double4);
@@ -1434,16 +1443,28 @@ int pg_mc_end(pg_engine* h, double* dE_out, uint8_t* accept_out, int* n_done, fl
   if (!h->mc_inflight) { h->err = "no MC batch in flight"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
   h->mc_inflight = false;
-  PG_CUDA(h, cudaEventSynchronize(h->ev1));
+  {
+    // a lone Markov chain waits by polling (a blocking-sync wake-up costs tens of microseconds per batch);
+    // with many replicas per GPU the waiting threads sleep instead
+    const int live = (h->device >= 0 && h->device < 64) ? g_live_engines[h->device].load(std::memory_order_relaxed) : 1;
+    if (live <= 2) {
+      for (unsigned long spins = 1;; spins++) {
+        cudaError_t q = cudaEventQuery(h->ev1);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { h->err = std::string("mc batch failed: ") + cudaGetErrorString(q); return PG_ERR_CUDA; }
+        if ((spins & 0x3ff) == 0) sched_yield();
+      }
+    } else {
+      PG_CUDA(h, cudaEventSynchronize(h->ev1));
+    }
+  }
   if (elapsed_ms) PG_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
   const int stop = *h->h_stop;
   const int done = stop ? stop - h->mc_first : h->mc_count;
   if (done < 0 || done > h->mc_count) { h->err = "mc: inconsistent stop index"; return PG_ERR_STATE; }
   if (n_done) *n_done = done;
-  if (dE_out && done > 0)
-    PG_CUDA(h, cudaMemcpy(dE_out, h->d_rp_dE + h->mc_first, sizeof(double) * (size_t)done, cudaMemcpyDeviceToHost));
-  if (accept_out && done > 0)
-    PG_CUDA(h, cudaMemcpy(accept_out, h->d_rp_acc + h->mc_first, (size_t)done, cudaMemcpyDeviceToHost));
+  if (dE_out && done > 0) memcpy(dE_out, h->h_mc_dE + h->mc_first, sizeof(double) * (size_t)done);
+  if (accept_out && done > 0) memcpy(accept_out, h->h_mc_acc + h->mc_first, (size_t)done);
   return PG_OK;
 }
 

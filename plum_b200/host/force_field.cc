@@ -67,6 +67,8 @@ struct McState {
   plum_mc::BatchSizer sizer;
   int n_mol_configured = -1;   // -1: (re)build the molecule tables (set by UpdateMolCounts after every GC move)
   bool sizer_ready = false;
+  int cooldown = 0;            // steps left to the driver's per-move path because batches kept stopping early
+  double avg_len = 256.0;      // smoothed steps per batch (GC steps / crankshafts cut batches short, too)
   vector<double> dE, xyz;
   vector<uint8_t> acc;
 };
@@ -443,17 +445,23 @@ void ForceField::FinalizeEnergies(vector<Molecule>& mols, bool accept, int moved
 
 
 // ------------------------------------------------- batched translational steps
-bool ForceField::BatchedMoves() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("PLUM_B200_BATCH"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1;
+// PLUM_B200_BATCH: unset / 1 = batches where they pay (see BatchSizer), 0 = never, 2 = always (tests).
+static int BatchMode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("PLUM_B200_BATCH"); mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
+  return mode;
 }
+bool ForceField::BatchedMoves() { return BatchMode() != 0; }
 
 int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, int max_steps, int first_step,
                                    double move_size, const double move_prob[5], int attempted[], int accepted[]) {
   if (max_steps <= 0) return 0;
   if (!mc_state) mc_state = new McState();
   McState& S = *static_cast<McState*>(mc_state);
+  // Where most steps end in an overlap (dE >= 1e8: dense systems, long pivots) a batch stops after a handful of
+  // steps and costs more than it saves: leave the next stretch to the driver's per-move path, then probe again.
+  if (BatchMode() == 2) S.cooldown = 0;
+  if (S.cooldown > 0) { S.cooldown--; return 0; }
   // the molecule list only changes through GC moves, which also change its length or leave it as it was
   if (S.n_mol_configured != (int)mols.size()) {
     plum_mc::Config cfg;
@@ -517,9 +525,15 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
       }
       if (stopped) steps_done = b.rewind_after_overlap(rand_gen, n_done);
       S.sizer.update(n_done, stopped);
+      if (!S.sizer.worthwhile()) { S.cooldown = 20000; S.sizer.run = 128.0; }   // probe again after the cool-down
+    }
+    if (budget >= 24) {   // (a short budget is the caller's choice — frequent sampling — not evidence)
+      S.avg_len = 0.9 * S.avg_len + 0.1 * steps_done;
+      if (S.avg_len < 24.0) { S.cooldown = 20000; S.avg_len = 64.0; }
     }
     executed += steps_done;
     if (!stopped && b.stop != plum_mc::STOP_FULL) break;   // the generator stands in front of a step the driver runs
+    if (S.cooldown > 0) break;
   }
   if (executed > 0) {
     // the device's coordinates are the accepted ones: bring the driver's beads (current and trial) up to date

@@ -18,6 +18,7 @@
 #ifndef PLUM_B200_MC_PROPOSE_H_
 #define PLUM_B200_MC_PROPOSE_H_
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <random>
@@ -61,22 +62,26 @@ struct Batch {
   }
 };
 
-// How many steps to hand to the device at once.  A batch that stops early (a dE >= 1e8 step) leaves the
-// kernels queued behind the stop as no-ops, so the batch length follows the observed distance between stops:
-// long batches where overlaps never happen (bulk WCA fluids at low density), short ones in dense / walled systems.
+// How many steps to hand to the device at once.  A batch that stops early (a dE >= 1e8 step) leaves the kernels
+// queued behind the stop as no-ops that still cost w ~ 3 us of device time each (measured, tools/mc_batch_probe.py),
+// and every batch costs C ~ 50 us of upload / launch / completion latency.  With a stop probability p per step the
+// overhead per done step, ~ C/B + w p B/2 for B << 1/p, is smallest at B = sqrt(2C/(w p)) ~ 6 sqrt(run), `run` = 1/p
+// being the smoothed number of steps between stops.  `worthwhile()` is false where even that optimum costs more
+// than the ~3 us round trip per step it saves (p above ~1.5 %: dense or walled systems, long pivots).
 struct BatchSizer {
   int cap = 1024;
-  double run = 1024.0;   // smoothed number of steps between stops
-  void reset(int max_batch) { cap = max_batch < 1 ? 1 : max_batch; run = cap; }
+  double run = 1024.0;
+  void reset(int max_batch) { cap = max_batch < 1 ? 1 : max_batch; run = 512.0; }
   void update(int n_done, bool stopped) {
-    if (stopped) run = 0.75 * run + 0.25 * n_done;
-    else run = 0.75 * run + 0.25 * (2.0 * n_done + 8.0);
-    if (run > cap) run = cap;
+    if (stopped) run = 0.8 * run + 0.2 * n_done;
+    else run = 0.8 * run + 0.2 * std::max(run, 2.0 * n_done + 8.0);   // no stop seen: at least this long, probably longer
+    if (run > 4096.0) run = 4096.0;
   }
   int next() const {
-    int b = (int)(1.5 * run) + 4;
+    int b = (int)(6.0 * std::sqrt(run));
     return b < 8 ? 8 : (b > cap ? cap : b);
   }
+  bool worthwhile() const { return run >= 64.0; }
 };
 
 class Proposer {

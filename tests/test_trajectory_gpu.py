@@ -47,10 +47,12 @@ def _parse(lines, n_steps):
     return init, kind, accept, mtype, mol, val, tot
 
 
-# batch "1": the driver hands stretches of translational steps to the device (ForceField::TranslationalBatch:
-# device-side proposals, Metropolis test and commit; the default); "0": every step through the driver's own
-# TranslationalMove -> EnergyDifference / FinalizeEnergies (pg_delta_e / pg_commit).
-@pytest.mark.parametrize("name,batch", [(n, "1") for n in EXAMPLES] + [("confined_nvt", "0"), ("confined_muvt", "0")])
+# PLUM_B200_BATCH "2": the driver hands every stretch of translational steps to the device
+# (ForceField::TranslationalBatch: device-side proposals, Metropolis test and commit); "1" (the default): only where
+# batches pay, falling back to the per-move path and probing again — both paths interleave on one trajectory;
+# "0": every step through the driver's own TranslationalMove -> EnergyDifference / FinalizeEnergies.
+@pytest.mark.parametrize("name,batch", [(n, "2") for n in EXAMPLES] + [("bulk_nvt", "1"), ("confined_nvt", "1"),
+                                                                        ("confined_nvt", "0"), ("confined_muvt", "0")])
 def test_accept_reject_sequence_identical_over_1e5_moves(name, batch):
     assert replay.have_plum_gpu(), "bin/plum_gpu missing: run __graft_entry__.build() where /root/reference exists"
     gold = replay.golden_long(name)
@@ -78,7 +80,7 @@ def test_accept_reject_sequence_identical_over_1e5_moves(name, batch):
     tidx = gold["tot_step"] - 1
     has = ~np.isnan(tot[tidx, 0])
     # (inside a device-side batch the totals are only materialised behind its last step — every 100th step here)
-    assert has.sum() >= 100, has.sum()
+    assert has.sum() >= 50, has.sum()
     err = np.abs(tot[tidx][has] - gold["tot"][has]) / np.maximum(1.0, np.abs(gold["tot"][has]))
     assert err.max() <= 1e-9, err.max()   # 10^5 accumulated += of 1e-16-level differences
     _compare_stat(name, files["output_stat.dat"])
