@@ -165,16 +165,19 @@ def write_inputs(directory: str, sysm: runin.System, n_steps: int = 1000, alpha:
                 f.write(f"{m} {sysm.symbol[i]} {x:.17g} {y:.17g} {z:.17g} {sysm.q[i]:g}\n")
 
 
-def load(n_chains: int = 200, chain_len: int = 100, alpha: float = 0.004, cache_dir: str = None):
-    """(RunIn, System, TypeTable, params) of the synthetic system; the configuration is cached as .npz."""
+def load(n_chains: int = 200, chain_len: int = 100, alpha: float = 0.004, cache_dir: str = None,
+         charged_every: int = 10, L: float = 200.0):
+    """(RunIn, System, TypeTable, params) of the synthetic system; the configuration is cached as .npz.
+    Defaults: S of SURVEY.md §8(d).  `load_full` gives the stress variant S-full."""
     r = runin.parse_run_in(make_run_in(alpha=alpha))
-    key = f"synth_S_{n_chains}x{chain_len}_seed{SEED}.npz"
+    key = f"synth_S_{n_chains}x{chain_len}_seed{SEED}.npz" if (charged_every == 10 and L == 200.0) else \
+        f"synth_S_{n_chains}x{chain_len}_q{charged_every}_L{L:g}_seed{SEED}.npz"
     path = os.path.join(cache_dir, key) if cache_dir else None
     if path and os.path.exists(path):
         z = np.load(path)
-        sysm = runin.System(z["xyz"], z["q"], ["P"] * int(z["q"].shape[0]), z["mol_first"], [200.0] * 3)
+        sysm = runin.System(z["xyz"], z["q"], ["P"] * int(z["q"].shape[0]), z["mol_first"], [L] * 3)
     else:
-        sysm = make_system(n_chains, chain_len)
+        sysm = make_system(n_chains, chain_len, charged_every=charged_every, L=L)
         if path:
             os.makedirs(cache_dir, exist_ok=True)
             tmp = f"{path}.{os.getpid()}.tmp.npz"   # atomic: several ranks may generate at once
@@ -182,3 +185,9 @@ def load(n_chains: int = 200, chain_len: int = 100, alpha: float = 0.004, cache_
             os.replace(tmp, path)
     types = runin.TypeTable(r, sysm.symbol)
     return r, sysm, types, runin.params_dict(r, sysm.box, types)
+
+
+def load_full(cache_dir: str = None):
+    """Stress variant S-full: every monomer charged => N = 40 000 (all charged), L = 250,
+    alpha = 0.003 => real_cutoff 60, repl_cell 10, K = 4138."""
+    return load(200, 100, alpha=0.003, cache_dir=cache_dir, charged_every=1, L=250.0)

@@ -17,7 +17,8 @@ local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local_rank)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-r, s, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
+FULL = "--full" in sys.argv   # stress variant S-full: 40 000 charged beads, K = 4138
+r, s, types, params = (synth.load_full if FULL else synth.load)(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
 eng = Engine(params, device=local_rank, capacity_beads=s.n)
 eng.upload(s.xyz, s.q, types.ids(s.symbol), s.mol_first)
 t_init = eng.init_energy()
