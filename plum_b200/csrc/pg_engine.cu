@@ -605,6 +605,31 @@ int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
   A.n_helpers = helpers;
   const long long room = std::max(1, slots - helpers);
   A.n_pair_ctas = (int)std::max(1LL, std::min(units, room));
+  // Throughput mode (several replicas share the device): a pair CTA takes whole partner tiles and walks all the
+  // moved beads, so the partner-side work (loads, box fractions, the warp's bounding extent) is done once per
+  // tile instead of once per (tile, bead chunk) — fewer instructions per move at the price of a longer single
+  // launch, which the other replicas' kernels hide.  A lone chain keeps the finest one-wave split.
+  {
+    static const int mode = [] { const char* e = getenv("PLUM_B200_TILE_CTAS"); return e ? atoi(e) : -1; }();
+    const int live = (h->device >= 0 && h->device < 64) ? g_live_engines[h->device].load(std::memory_order_relaxed) : 1;
+    const bool whole = (mode < 0) ? (live >= 4) : (mode != 0);
+    if (whole && big && glen > MV_GCHUNK && A.n_tiles > 0) {
+      static const int tiles_per_cta = [] { const char* e = getenv("PLUM_B200_TILES_PER_CTA"); return e ? std::max(1, atoi(e)) : 1; }();
+      // (measured, tools/sweep_tile_ctas.sh, 24 replicas: helpers n_sm/1 -> 412 k, /4 -> 460 k, /8 -> 461 k, /16 -> 464 k, /32 -> 446 k moves/s)
+      static const int helpers_div = [] { const char* e = getenv("PLUM_B200_HELPERS_DIV"); return e ? std::max(1, atoi(e)) : 8; }();
+      if (helpers_div > 1) {
+        helpers = std::max(1, n_sm / helpers_div);
+        int l = lanes_per_k(nq);
+        const int k_per_helper = (nk + helpers - 1) / helpers;
+        while (l > 2 && k_per_helper * l > MV_THREADS) l >>= 1;
+        A.lpk = l;
+        A.n_helpers = helpers;
+      }
+      const long long room2 = std::max(1, slots - helpers);
+      const long long per = std::max<long long>((A.n_tiles + room2 - 1) / room2, tiles_per_cta);
+      A.n_pair_ctas = (int)std::max(1LL, (A.n_tiles + per - 1) / per);
+    }
+  }
   return A.n_helpers + A.n_pair_ctas;
 }
 

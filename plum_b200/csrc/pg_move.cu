@@ -440,28 +440,67 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? MV_FAST_OCC : MV_GEN_OCC) k
     const int lane = tid & 31, warp = tid >> 5;
     int qn = 0;   // entries in this warp's queue (warp-uniform)
     bool first = true;
+    // Partner-side state: a function of the tile only, so consecutive segments of one tile (a CTA that owns a whole
+    // tile walks all the moved beads in chunks of MV_GCHUNK) load the partner, convert it to box fractions and
+    // measure the warp's extent once.
+    int cur_tile = -1, j = 0, sub = 0, pt = 0;
+    double px = 0, py = 0, pz = 0, pq = 0;
+    bool valid = false, pchg = false, anyq = false;
+    float psx = 0, psy = 0, psz = 0, cx = 0, cy = 0, cz = 0, hwx = 0, hwy = 0, hwz = 0;
+    unsigned vmask = 0u;
     while (u < u1) {
       const int tile = (int)(u / (unsigned)A.glen);
       const int gbeg = (int)(u - (unsigned)tile * (unsigned)A.glen);
       const int gcnt = min(min(A.glen - gbeg, MV_GCHUNK), (int)(u1 - u));
-      // partner first: its loads are the longest dependency chain of the segment
-      // FAST: one partner per thread.  Generic: img_split threads per partner, one (ix, iy) image column each.
-      const int slot = tile * MV_THREADS + tid;
-      const int j = FAST ? slot : slot / P.img_split;
-      const int sub = FAST ? 0 : slot - j * P.img_split;
-      double px = 0, py = 0, pz = 0, pq = 0;
-      int pt = 0;
-      if (j < A.n) {
-        const double2 c = A.zq[j];
-        const double2 a = A.xy[j];
-        pt = A.type[j];
-        pq = c.y;
-        px = a.x; py = a.y; pz = c.x;
-        if (j >= pg0 && j < pg1) {
-          px = ptrial[3 * (j - pg0)]; py = ptrial[3 * (j - pg0) + 1]; pz = ptrial[3 * (j - pg0) + 2];
+      if (tile != cur_tile) {
+        cur_tile = tile;
+        // partner first: its loads are the longest dependency chain of the segment
+        // FAST: one partner per thread.  Generic: img_split threads per partner, one (ix, iy) image column each.
+        const int slot = tile * MV_THREADS + tid;
+        j = FAST ? slot : slot / P.img_split;
+        sub = FAST ? 0 : slot - j * P.img_split;
+        px = 0; py = 0; pz = 0; pq = 0; pt = 0;
+        if (j < A.n) {
+          const double2 c = A.zq[j];
+          const double2 a = A.xy[j];
+          pt = A.type[j];
+          pq = c.y;
+          px = a.x; py = a.y; pz = c.x;
+          if (j >= pg0 && j < pg1) {
+            px = ptrial[3 * (j - pg0)]; py = ptrial[3 * (j - pg0) + 1]; pz = ptrial[3 * (j - pg0) + 2];
+          }
         }
-        if (gbeg == 0 && sub == 0) acc_mz += pq * pz;   // each partner's dipole moment is counted once: by the segment that starts its tile
+        // partners that are beads of the moved molecule itself were handled in (b)
+        valid = (j < A.n) && !((j >= A.g0) && (j < A.g0 + A.glen));
+        if (FAST) {
+          pchg = (pq != 0.0);
+          psx = mv_frac(px, iLx); psy = mv_frac(py, iLy); psz = mv_frac(pz, iLz);
+          // Warp-level culling, partner side.  The 32 partners of a warp are consecutive beads — a chain segment,
+          // i.e. a compact cloud.  Its extent around one reference partner (per-axis half widths, minimum image)
+          // gives a lower bound on the separation of ANY of them from a moved bead:
+          //   |wrap(g - p)| >= |wrap(g - c)| - hw   (triangle inequality on the circle, per axis).
+          vmask = __ballot_sync(0xffffffffu, valid);
+          if (vmask) {
+            const int ref = __ffs(vmask) - 1;
+            cx = __shfl_sync(0xffffffffu, psx, ref); cy = __shfl_sync(0xffffffffu, psy, ref);
+            cz = __shfl_sync(0xffffffffu, psz, ref);
+            float ex = psx - cx, ey = psy - cy, ez = psz - cz;
+            ex = valid ? fabsf(ex - mv_rintf(ex)) : 0.0f;
+            ey = valid ? fabsf(ey - mv_rintf(ey)) : 0.0f;
+            ez = valid ? fabsf(ez - mv_rintf(ez)) : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+              ey = fmaxf(ey, __shfl_xor_sync(0xffffffffu, ey, o));
+              ez = fmaxf(ez, __shfl_xor_sync(0xffffffffu, ez, o));
+            }
+            hwx = ex + 1e-6f; hwy = ey + 1e-6f; hwz = ez + 1e-6f;   // + FP32 slack in box fractions
+            anyq = __ballot_sync(0xffffffffu, valid && pchg) != 0u;
+          }
+        }
       }
+      // each partner's dipole moment is counted once: by the segment that starts its tile
+      if (gbeg == 0 && sub == 0 && j < A.n) acc_mz += pq * pz;
       if (!first) __syncthreads();   // previous segment's shared staging is still being read
       first = false;
       if (tid < gcnt) {
@@ -492,58 +531,32 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? MV_FAST_OCC : MV_GEN_OCC) k
       }
       __syncthreads();
       MV_STAMP(1);
-      // partners that are beads of the moved molecule itself were handled in (b)
-      const bool valid = (j < A.n) && !((j >= A.g0) && (j < A.g0 + A.glen));
       if (FAST) {
         // Every lane runs the filter (invalid lanes never hit) so the warp can vote: in-range
         // configurations are rare, so instead of evaluating erfc / LJ in a nearly empty diverged warp
         // they are compacted into this warp's queue and evaluated 32 at a time (mv_queue_flush).
-        const bool pchg = (pq != 0.0);
         const int csel = pchg ? 1 : 0;
-        const float psx = mv_frac(px, iLx), psy = mv_frac(py, iLy), psz = mv_frac(pz, iLz);
-        // Warp-level culling.  The 32 partners of a warp are consecutive beads — a chain segment, i.e. a
-        // compact cloud.  Its extent around one reference partner (per-axis half widths, minimum image)
-        // gives a lower bound on the separation of ANY of them from a moved bead:
-        //   |wrap(g - p)| >= |wrap(g - c)| - hw   (triangle inequality on the circle, per axis).
-        // Lane i applies the bound to moved bead i (a chunk has <= 32 beads); the warp then runs the
-        // per-partner filter only for the beads that survive.  It can only over-accept.
+        // Warp-level culling, moved-bead side: lane i applies the bound to moved bead i (a chunk has <= 32 beads);
+        // the warp then runs the per-partner filter only for the beads that survive.  It can only over-accept.
         unsigned keep = 0u;
-        {
-          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-          if (vmask) {
-            const int ref = __ffs(vmask) - 1;
-            const float cx = __shfl_sync(0xffffffffu, psx, ref), cy = __shfl_sync(0xffffffffu, psy, ref),
-                        cz = __shfl_sync(0xffffffffu, psz, ref);
-            float ex = psx - cx, ey = psy - cy, ez = psz - cz;
-            ex = valid ? fabsf(ex - mv_rintf(ex)) : 0.0f;
-            ey = valid ? fabsf(ey - mv_rintf(ey)) : 0.0f;
-            ez = valid ? fabsf(ez - mv_rintf(ez)) : 0.0f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
-              ey = fmaxf(ey, __shfl_xor_sync(0xffffffffu, ey, o));
-              ez = fmaxf(ez, __shfl_xor_sync(0xffffffffu, ez, o));
-            }
-            const float hwx = ex + 1e-6f, hwy = ey + 1e-6f, hwz = ez + 1e-6f;   // + FP32 slack in box fractions
-            const bool anyq = __ballot_sync(0xffffffffu, valid && pchg) != 0u;
-            bool k = false;
-            if (lane < gcnt && s_mv[lane]) {
-              const float4 fn = s_fn[lane], fo = s_fo[lane];
-              const float cutf = anyq ? fn.w : fo.w;
-              float bxn = fn.x - cx, byn = fn.y - cy, bzn = fn.z - cz;
-              float bxo = fo.x - cx, byo = fo.y - cy, bzo = fo.z - cz;
-              bxn = fmaxf(fabsf(bxn - mv_rintf(bxn)) - hwx, 0.0f) * fLx;
-              byn = fmaxf(fabsf(byn - mv_rintf(byn)) - hwy, 0.0f) * fLy;
-              bzn = fmaxf(fabsf(bzn - mv_rintf(bzn)) - hwz, 0.0f) * fLz;
-              bxo = fmaxf(fabsf(bxo - mv_rintf(bxo)) - hwx, 0.0f) * fLx;
-              byo = fmaxf(fabsf(byo - mv_rintf(byo)) - hwy, 0.0f) * fLy;
-              bzo = fmaxf(fabsf(bzo - mv_rintf(bzo)) - hwz, 0.0f) * fLz;
-              const float lbn = fmaf(bxn, bxn, fmaf(byn, byn, bzn * bzn));
-              const float lbo = fmaf(bxo, bxo, fmaf(byo, byo, bzo * bzo));
-              k = fminf(lbn, lbo) <= cutf;
-            }
-            keep = __ballot_sync(0xffffffffu, k);
+        if (vmask) {
+          bool k = false;
+          if (lane < gcnt && s_mv[lane]) {
+            const float4 fn = s_fn[lane], fo = s_fo[lane];
+            const float cutf = anyq ? fn.w : fo.w;
+            float bxn = fn.x - cx, byn = fn.y - cy, bzn = fn.z - cz;
+            float bxo = fo.x - cx, byo = fo.y - cy, bzo = fo.z - cz;
+            bxn = fmaxf(fabsf(bxn - mv_rintf(bxn)) - hwx, 0.0f) * fLx;
+            byn = fmaxf(fabsf(byn - mv_rintf(byn)) - hwy, 0.0f) * fLy;
+            bzn = fmaxf(fabsf(bzn - mv_rintf(bzn)) - hwz, 0.0f) * fLz;
+            bxo = fmaxf(fabsf(bxo - mv_rintf(bxo)) - hwx, 0.0f) * fLx;
+            byo = fmaxf(fabsf(byo - mv_rintf(byo)) - hwy, 0.0f) * fLy;
+            bzo = fmaxf(fabsf(bzo - mv_rintf(bzo)) - hwz, 0.0f) * fLz;
+            const float lbn = fmaf(bxn, bxn, fmaf(byn, byn, bzn * bzn));
+            const float lbo = fmaf(bxo, bxo, fmaf(byo, byo, bzo * bzo));
+            k = fminf(lbn, lbo) <= cutf;
           }
+          keep = __ballot_sync(0xffffffffu, k);
         }
         while (keep) {
           const int i = __ffs(keep) - 1;
