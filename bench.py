@@ -251,7 +251,7 @@ def run_ours(a):
 
     M, K, W = a.moves_per_step, a.steps, a.warmup
     # fixed per GPU whatever N is (weak scaling); each replica has one host thread in the e2e leg
-    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else 24
+    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else 30
     r, sysm, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
     ids = types.ids(sysm.symbol)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -671,7 +671,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-replica measurement")
     ap.add_argument("--replicas-per-gpu", type=int, default=0,
-                    help="independent Markov chains per GPU, each with its own engine/stream; 0 = 24 (fixed per GPU: weak scaling)")
+                    help="independent Markov chains per GPU, each with its own engine/stream; 0 = 30 (fixed per GPU: weak scaling; one stream each, below the 32 hardware queues)")
     ap.add_argument("--mc-batch", type=int, default=256, help="steps per uploaded batch in the batched (device-side proposal) leg")
     ap.add_argument("--host-threads", type=int, default=0,
                     help="host threads per GPU driving the replicas in the e2e leg (0 = host cores per GPU - 2, at most one per replica)")

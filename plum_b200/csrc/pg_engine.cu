@@ -628,6 +628,19 @@ int move_grid(pg_engine* h, int glen, int nq, PgMoveArgs& A) {
       const long long room2 = std::max(1, slots - helpers);
       const long long per = std::max<long long>((A.n_tiles + room2 - 1) / room2, tiles_per_cta);
       A.n_pair_ctas = (int)std::max(1LL, (A.n_tiles + per - 1) / per);
+    } else if (whole && h->fast && glen <= MV_GCHUNK) {
+      // small moves (every single-bead move): what limits the throughput of many co-running replicas is CTA-slot
+      // time, and a CTA of a small move is nearly all fixed latency — so fewer CTAs, each walking several tiles
+      // (measured, 24 replicas: 1 tile per CTA 465 k, 2 -> 491 k, 4 -> 500 k moves/s device-resident; the host-driven
+      // rate is flat to slightly lower beyond 2 because a single launch gets longer)
+      static const int small_tiles = [] { const char* e = getenv("PLUM_B200_SMALL_TILES"); return e ? std::max(1, atoi(e)) : 2; }();
+      static const int small_hdiv = [] { const char* e = getenv("PLUM_B200_SMALL_HELPERS_DIV"); return e ? std::max(1, atoi(e)) : 4; }();
+      if (small_hdiv > 1 && helpers > 1) {
+        helpers = std::max(1, (helpers + small_hdiv - 1) / small_hdiv);
+        A.n_helpers = helpers;
+      }
+      const long long u_per = (long long)small_tiles * std::max(glen, 1);
+      A.n_pair_ctas = (int)std::max(1LL, std::min<long long>((units + u_per - 1) / u_per, std::max(1, slots - helpers)));
     }
   }
   return A.n_helpers + A.n_pair_ctas;
