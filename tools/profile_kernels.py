@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Exercises every kernel of the path once or twice so that one ncu pass can capture them all:
    S (22 000 beads): init (k_tot_pairs, k_sk_slice, k_sk_reduce, k_tot_final), k_move<true> ion + chain,
-                     k_trials (30 trials), k_delta insert / delete (8-bead chain + 8 ions), k_commit
+                     k_trials (30 trials), k_delta insert / delete (8-bead chain + 8 ions), k_commit, k_propose (two 24-step batches)
    bulk_nvt / confined_nvt (reference examples): k_move<false> ion + chain (multi-image path), k_wall_force.
 Run:  ncu --set full --clock-control none --import-source on -k regex:'k_' -o gpurun_out/prof_<tag>_all python tools/profile_kernels.py   (tools/round_evidence.sh does it and keeps the raw-metric CSV)
 """
@@ -27,6 +27,19 @@ for rep in range(2):
         m = int(rng.choice(pool)); f, l = int(s.mol_first[m]), int(s.mol_first[m + 1])
         eng.delta_e(m, s.xyz[f:l] + rng.normal(scale=0.3, size=(l - f, 3)), np.ones(l - f, dtype=np.uint8))
         eng.commit(False)
+# k_propose (device-side proposals): two batches of 24 steps through pg_mc_* (bead, COM, pivot, reptation kinds)
+from plum_b200 import mcgen
+g = mcgen.Generator.for_run(r, s.mol_first, 4)
+for rep in range(2):
+    descs, rows, n_rows = [], [], 0
+    while len(descs) < 24:
+        kind, d, rv = g.next()
+        if kind < 0:
+            continue
+        d.rv_offset = n_rows
+        descs.append(d); rows.append(rv); n_rows += rv.shape[0]
+    eng.mc_upload(descs, np.concatenate(rows) if n_rows else None)
+    eng.mc_run(0, len(descs))
 tP = types.ids(["P"])[0]
 cl = 4
 cx = np.zeros((2 * cl, 3)); cq = np.zeros(2 * cl); ct = np.full(2 * cl, tP, dtype=np.int32)

@@ -74,10 +74,17 @@ if os.path.exists(allrep):
         u = units[ix[k]] if k in ix else "byte"
         return num(r, k) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
 
+    # last full instance per (kernel, grid): launches queued behind a stopped MC batch return at once (no-ops) and
+    # would otherwise stand in for the real kernel of that grid
+    most = {}
+    for r in data:
+        key = (r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), r[ix["Grid Size"]])
+        most[key] = max(most.get(key, 0.0), num(r, "smsp__inst_executed.sum"))
     last = {}
     for r in data:
         key = (r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), r[ix["Grid Size"]])
-        last[key] = r
+        if num(r, "smsp__inst_executed.sum") >= 0.5 * most[key]:
+            last[key] = r
     rows = []
     for (kname, grid), r in last.items():
         us = dur_us(r)
