@@ -611,6 +611,30 @@ def run_ours(a):
     e2e_launches, gpu_launches, roofline, clock_info = res["e2e_launches"], res["gpu_launches"], res["roofline"], res["clock_info"]
     replay_matches, t_wall_replay, t_flush, h2d, d2h = res["replay_matches"], res["wall_replay"], 0.0, res["h2d"], res["d2h"]
 
+    # ---------------- k-sharded full S(k) recompute: every rank holds the positions, fills its slice of
+    # the k list with k_sk_slice, NCCL all-gathers the slices; time per rank with the collective broken out, for S and for
+    # the stress variant S-full (where there is enough work per rank to be worth sharding).  Not part of `value`.
+    recompute = None
+    if not a.no_recompute:
+        recompute = {}
+        from plum_b200 import sharded
+        for name, loader in (("S", synth.load), ("S_full", synth.load_full)):
+            eng = None
+            try:
+                _, s2, ty2, par2 = loader(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
+                eng = Engine(par2, device=local_rank, capacity_beads=s2.n)
+                eng.upload(s2.xyz, s2.q, ty2.ids(s2.symbol), s2.mol_first)
+                t_init = eng.init_energy()
+                l0 = eng.launch_count()
+                recompute[name] = dict(n_charged=int(np.count_nonzero(s2.q)),
+                                       **sharded.time_sharded_recompute(eng, rank, world, t_init["recip"]))
+                recompute[name]["launches"] = int(eng.launch_count() - l0)
+            except Exception as e:   # noqa: BLE001
+                recompute[name] = {"error": repr(e)}
+            finally:
+                if eng is not None:
+                    eng.close()
+
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -649,6 +673,7 @@ def run_ours(a):
             "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
             "replay_matches_e2e": replay_matches, "wall_ms_per_step_replay": (t_wall_replay - t_flush) * 1e3 / K,
             "accept_ratio": res["accept"],
+            "sharded_recompute": recompute,
             "single_replica": None if single is None else {
                 "value": single["value"], "e2e": max(single["e2e_value"], single["mc_value"] if single["mc_close"] else 0.0),
                 "e2e_per_move": single["e2e_value"], "e2e_batched": single["mc_value"], "batched_same_chain": single["mc_close"], "unit": "moves/s", "roofline_frac": single["roofline"]["frac"],
@@ -670,6 +695,7 @@ def main():
     ap.add_argument("--moves-per-step", type=int, default=MOVES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-replica measurement")
+    ap.add_argument("--no-recompute", action="store_true", help="skip the k-sharded full S(k) recompute timing")
     ap.add_argument("--replicas-per-gpu", type=int, default=0,
                     help="independent Markov chains per GPU, each with its own engine/stream; 0 = 30 (fixed per GPU: weak scaling; one stream each, below the 32 hardware queues)")
     ap.add_argument("--mc-batch", type=int, default=256, help="steps per uploaded batch in the batched (device-side proposal) leg")

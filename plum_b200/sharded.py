@@ -86,3 +86,55 @@ def sharded_sk_recompute(engine, rank: int, world: int, group=None):
     if world > 1:
         dist.all_reduce(e_local, op=dist.ReduceOp.SUM, group=group)
     return sk, float(e_local.item())
+
+
+def time_sharded_recompute(engine, rank: int, world: int, e_recip_init: float, reps: int = 30, warm: int = 5, group=None) -> dict:
+    """Time the k-sharded full S(k) recompute of `engine`'s resident system (SURVEY.md §8e "Reported": recompute
+    time at 1/2/4/8 ranks with the NCCL part broken out).  Compute = host wall clock around the synchronous slice
+    kernel (`pg_sk_compute_slice`), collective = CUDA events around the NCCL all-gather on torch's current stream;
+    medians over `reps`, max over ranks.  Ends with one real `sharded_sk_recompute` whose all-reduced reciprocal
+    energy must reproduce `e_recip_init` (the energy initialisation's) within 1e-10."""
+    import time
+    import torch
+    import torch.distributed as dist
+    n_k = engine.ewald_info().n_k_half
+    first, count = k_slice(n_k, rank, world)
+    pad = padded_count(n_k, world)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    local = torch.zeros((pad, 2), dtype=torch.float64, device=dev)
+    full = torch.empty((world * pad, 2), dtype=torch.float64, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    t_comp, t_nccl, t_tot = [], [], []
+    for it in range(reps + warm):
+        if world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        if count:
+            engine.sk_compute_slice(first, count, local.data_ptr())
+        w1 = time.perf_counter()
+        nccl_ms = 0.0
+        if world > 1:
+            ev[0].record()
+            dist.all_gather_into_tensor(full, local, group=group)
+            ev[1].record()
+            torch.cuda.synchronize()
+            nccl_ms = ev[0].elapsed_time(ev[1])
+        w2 = time.perf_counter()
+        if it >= warm:
+            t_comp.append((w1 - w0) * 1e3)
+            t_nccl.append(nccl_ms)
+            t_tot.append((w2 - w0) * 1e3)
+    _, e = sharded_sk_recompute(engine, rank, world, group=group)
+    ok = abs(e - e_recip_init) <= 1e-10 * max(1.0, abs(e_recip_init))
+
+    def mx(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t.item())
+
+    return dict(n_gpus=int(world), n_k=int(n_k), k_per_rank=int(count), compute_ms=mx(float(np.median(t_comp))),
+                nccl_allgather_ms=mx(float(np.median(t_nccl))), total_ms=mx(float(np.median(t_tot))),
+                allgather_bytes=int(world * pad * 16) if world > 1 else 0, energy_matches_init=bool(ok),
+                timing=f"median of {reps}, max over ranks; compute = host wall around the synchronous slice kernel, NCCL = CUDA events")

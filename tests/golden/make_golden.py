@@ -11,7 +11,7 @@ container).  For each example of BASELINE.json's configs it
        short/<example>_seed<k>.trace.gz   full replayable trace (coordinates of every
                                           trial, every CBMC BeadsEnergy call) of the
                                           first SHORT_STEPS steps;
-       long/<example>_seed1.npz           the first 10^5 steps: accept/reject bits and
+       long/<example>_seed<k>.npz         (k = 1; 2 and 3 with --long-seed k) the first 10^5 steps: accept/reject bits and
                                           move kinds for every step, dE for the first
                                           2000 steps and every 25th step after, the
                                           four running totals every 1000 steps.
@@ -120,8 +120,21 @@ def synth_spring():
         print("short synth_spring", seed, len(lines), "lines")
 
 
+def long_seed(seed, examples=None):
+    """long/<example>_seed<seed>.{npz,stat.dat} for one more seed (the inputs are the committed copies)."""
+    for ex in (examples or EXAMPLES):
+        lines, files = replay.run_plum_ref(os.path.join(HERE, "examples", ex), LONG_STEPS, seed, xyz=False,
+                                           want_files=("output_stat.dat",))
+        compact_long(lines, os.path.join(HERE, "long", f"{ex}_seed{seed}.npz"), LONG_STEPS)
+        with open(os.path.join(HERE, "long", f"{ex}_seed{seed}.stat.dat"), "w") as f:
+            f.write(files["output_stat.dat"])
+        print("long", ex, "seed", seed, len(lines), "lines", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--long-seed", type=int, default=0, help="only long/<example>_seed<k>.{npz,stat.dat} for this extra seed")
+    ap.add_argument("--examples", default="", help="comma-separated subset for --long-seed")
     ap.add_argument("--long-from", default=None)
     ap.add_argument("--skip-long", action="store_true")
     ap.add_argument("--extras-only", action="store_true", help="only the sampler fixtures (extras())")
@@ -129,6 +142,9 @@ def main():
     a = ap.parse_args()
     if not replay.have_plum_ref():
         raise SystemExit("oracle/_ref/plum_ref missing: run python oracle/build_ref.py")
+    if a.long_seed:
+        long_seed(a.long_seed, [e for e in a.examples.split(",") if e] or None)
+        return
     if a.extras_only:
         os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
         extras()

@@ -278,5 +278,5 @@ class WallForceAverager:
                 self.cum[3] / (self.vp_z * a), self.cum[4] / (self.vp_z * a), self.cum[5] / a]
 
 
-def golden_long(name: str):
-    return np.load(os.path.join(GOLDEN, "long", f"{name}_seed1.npz"))
+def golden_long(name: str, seed: int = 1):
+    return np.load(os.path.join(GOLDEN, "long", f"{name}_seed{seed}.npz"))

@@ -95,3 +95,33 @@ def test_fresh_reference_run_agrees_with_oracle():
     rep = replay.replay(Oracle(params), r, s, types, lines)
     assert rep.n_moves == 200 and rep.sentinel_mismatch == 0
     assert rep.max_rel_dE < 1e-12, rep.worst
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("seed", [1, 2])
+def test_long_fixture_is_the_same_reference_trajectory_as_the_short_trace(name, seed):
+    """The 10^5-step fixtures (tests/golden/long, accept bits / move kinds / sampled dE) and the replayable short
+    traces were written by separate plum_ref runs with the same PLUM_SEED: the reference is deterministic for a
+    fixed seed, so the long fixture must start with exactly the short trace — same move kind,
+    molecule, accept bit and hex-float dE at every step.  Guards the fixtures themselves (a stale or mislabelled
+    file would otherwise only show up on the GPU box)."""
+    import numpy as np
+    gold = replay.golden_long(name, seed)
+    acc = np.unpackbits(gold["accept"])
+    dE_at = dict(zip(gold["dE_step"].tolist(), gold["dE"].tolist()))
+    n = 0
+    for ln in replay.golden_short_trace(name, seed):
+        f = ln.split()
+        if not f or f[0] not in ("T", "G"):
+            continue
+        step = int(f[1])
+        i = step - 1
+        if f[0] == "T":
+            assert gold["kind"][i] == 0 and gold["move_type"][i] == int(f[2]) and gold["mol"][i] == int(f[3]), ln
+            assert acc[i] == int(f[5]), ln
+        else:
+            assert gold["kind"][i] == (1 if f[2] == "I" else 2) and gold["mol"][i] == int(f[3]), ln
+        if step in dE_at:
+            assert dE_at[step] == replay.hx(f[4]), ln
+        n += 1
+    assert n >= 200

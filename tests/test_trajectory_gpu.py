@@ -4,7 +4,8 @@ real reference binary, same seed.
 BASELINE.json north_star: "for a fixed RNG seed, the accept/reject sequence must be identical over
 the first 10^5 moves of each example" and "per-move dE and total energies must agree with the
 reference within 1e-10 relative in FP64".  The reference side is the committed fixture
-tests/golden/long/<example>_seed1.npz, written by oracle/_ref/plum_ref (tests/golden/make_golden.py).
+tests/golden/long/<example>_seed<k>.npz (k = 1, 2, 3: SURVEY.md §8d), written by oracle/_ref/plum_ref
+(tests/golden/make_golden.py).
 """
 import numpy as np
 import pytest
@@ -51,12 +52,15 @@ def _parse(lines, n_steps):
 # (ForceField::TranslationalBatch: device-side proposals, Metropolis test and commit); "1" (the default): only where
 # batches pay, falling back to the per-move path and probing again — both paths interleave on one trajectory;
 # "0": every step through the driver's own TranslationalMove -> EnergyDifference / FinalizeEnergies.
-@pytest.mark.parametrize("name,batch", [(n, "2") for n in EXAMPLES] + [("bulk_nvt", "1"), ("confined_nvt", "1"),
-                                                                        ("confined_nvt", "0"), ("confined_muvt", "0")])
-def test_accept_reject_sequence_identical_over_1e5_moves(name, batch):
+# Seed 1: all four examples with batches forced, plus the other modes on a few; seed 2: the default mode; seed 3: the
+# per-move path.
+@pytest.mark.parametrize("name,batch,seed", [(n, "2", 1) for n in EXAMPLES] +
+                         [("bulk_nvt", "1", 1), ("confined_nvt", "1", 1), ("confined_nvt", "0", 1), ("confined_muvt", "0", 1)] +
+                         [(n, "1", 2) for n in EXAMPLES] + [(n, "0", 3) for n in EXAMPLES])
+def test_accept_reject_sequence_identical_over_1e5_moves(name, batch, seed):
     assert replay.have_plum_gpu(), "bin/plum_gpu missing: run __graft_entry__.build() where /root/reference exists"
-    gold = replay.golden_long(name)
-    lines, files = replay.run_plum_ref(replay.golden_example_dir(name), N_STEPS, 1, xyz=False, binary=replay.PLUM_GPU,
+    gold = replay.golden_long(name, seed)
+    lines, files = replay.run_plum_ref(replay.golden_example_dir(name), N_STEPS, seed, xyz=False, binary=replay.PLUM_GPU,
                                        want_files=("output_stat.dat",), extra_env={"PLUM_B200_BATCH": batch})
     init, kind, accept, mtype, mol, val, tot = _parse(lines, N_STEPS)
     # initial totals
@@ -83,17 +87,17 @@ def test_accept_reject_sequence_identical_over_1e5_moves(name, batch):
     assert has.sum() >= 50, has.sum()
     err = np.abs(tot[tidx][has] - gold["tot"][has]) / np.maximum(1.0, np.abs(gold["tot"][has]))
     assert err.max() <= 1e-9, err.max()   # 10^5 accumulated += of 1e-16-level differences
-    _compare_stat(name, files["output_stat.dat"])
+    _compare_stat(name, files["output_stat.dat"], seed)
 
 
-def _compare_stat(name, got_text):
+def _compare_stat(name, got_text, seed=1):
     """output_stat.dat (running averages of the energies, densities, Rg, acceptance ratios; written by the
     untouched driver from the façade's totals) against the reference's own file for the same seed.  Of the
     six wall-force pressure columns (pg_wall_force) the three electrostatic ones are
     compared; the LJ ones are not: the reference's PairForce reads an uninitialised r6
     (potential_truncated_lj.cc:94-100) and prints ~3.6e7 there.  The bulk "<P>" column is "nan" on both sides."""
     import os
-    with open(os.path.join(replay.GOLDEN, "long", f"{name}_seed1.stat.dat")) as f:
+    with open(os.path.join(replay.GOLDEN, "long", f"{name}_seed{seed}.stat.dat")) as f:
         ref = f.read().split("\n")
     got = got_text.split("\n")
     hdr = ref[0].split()
