@@ -240,8 +240,13 @@ __device__ __forceinline__ double2 mv_generic_column(const PgMoveDev& P, const P
 // Sum 5 values over the CTA with one barrier; result valid in thread 0.
 __device__ __forceinline__ void mv_block_sum5(double (&v)[5], double* smem /* [MV_WARPS][5] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < 5; i++) v[i] = warp_sum(v[i]);
+  // Most warps of a move have nothing but their partners' dipole moments (v[2]) to contribute: no pair of theirs was in
+  // range.  A warp whose other four accumulators are zero in every lane skips their shuffle trees (the sums are zero).
+  const bool any_nz = __any_sync(0xffffffffu, (v[0] != 0.0) | (v[1] != 0.0) | (v[3] != 0.0) | (v[4] != 0.0));
+  v[2] = warp_sum(v[2]);
+  if (any_nz) {
+    v[0] = warp_sum(v[0]); v[1] = warp_sum(v[1]); v[3] = warp_sum(v[3]); v[4] = warp_sum(v[4]);
+  }
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 5; i++) smem[warp * 5 + i] = v[i];
