@@ -167,6 +167,41 @@ def mix_rate(t_ion, t_chain, p_ion):
     return 1.0 / (p_ion * float(np.mean(t_ion)) + (1.0 - p_ion) * float(np.mean(t_chain)))
 
 
+def plum_ref_cut(n_chains=12, steps=40):
+    """The REAL reference binary (oracle/_ref/plum_ref: /root/reference/src compiled unmodified apart from the seed /
+    trace hooks, oracle/build_ref.py) on one core, on a cut of S it can hold: the same box, alpha and move mix (hence the
+    same cutoffs and K = 3574), 12 chains instead of 200 => N = 1320.  Its per-move cost is n_moved * N pair evaluations
+    of (27 images + 3574 cos), so t = a * sum(n_moved) * N is fitted on the run and carried to N = 22 000 — reported as
+    an EXTRAPOLATION next to the measured rate (profiles/r01d_cpu_scaling_plum_ref.jsonl holds N = 1320 / 2750 / 5500:
+    the fit is linear in N)."""
+    import tempfile
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import replay
+    from plum_b200 import synth
+    if not replay.have_plum_ref():
+        return {"unavailable": "oracle/_ref/plum_ref not built (python oracle/build_ref.py where /root/reference exists)"}
+    sysm = synth.make_system(n_chains=n_chains, chain_len=100, charged_every=10)
+    with tempfile.TemporaryDirectory(prefix="plum_ref_cut_") as d:
+        synth.write_inputs(d, sysm, n_steps=steps, alpha=0.004, spring=False)
+        t0 = time.perf_counter()
+        replay.run_plum_ref(d, 0, 1, xyz=False)                 # start-up + energy initialisation only
+        t_init = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        lines = replay.run_plum_ref(d, steps, 1, xyz=False)
+        t_run = max(time.perf_counter() - t0 - t_init, 1e-9)
+    T = [ln.split() for ln in lines if ln.startswith("T ")]
+    n_ion = sum(1 for t in T if t[2] == "0")
+    n_chain = len(T) - n_ion
+    a_fit = t_run / ((n_ion + 100.0 * n_chain) * sysm.n)
+    p_ion = MOVE_PROB[0]
+    t_move = a_fit * 22000 * (p_ion * 1 + (1 - p_ion) * 100)
+    return {"kind": "reference", "cores": 1, "N": int(sysm.n), "moves": len(T), "ion_moves": n_ion, "chain_moves": n_chain,
+            "init_s": t_init, "moves_s": t_run, "measured_moves_per_s_at_this_N": len(T) / t_run,
+            "extrapolated_moves_per_s_at_N22000": 1.0 / t_move,
+            "note": "plum_ref itself, one core, same box / alpha / K / move mix as the workload but 12 chains; the N = 22000 "
+                    "figure is EXTRAPOLATED (cost per move is linear in n_moved * N); plum_ref cannot hold N = 22000"}
+
+
 # ------------------------------------------------------------------- reference arm
 def run_reference(a):
     rank, _, world = dist_env()
@@ -196,6 +231,10 @@ def run_reference(a):
                 step_rates.append((rate, wall))
     value = float(np.mean([r for r, _ in step_rates]))
     ms_per_step = 1e3 * MOVES_PER_STEP * cores / value
+    try:
+        ref_cut = None if a.no_plum_ref else plum_ref_cut()
+    except Exception as e:   # noqa: BLE001
+        ref_cut = {"error": repr(e)}
     sample = (f"per step and core: {n_ion} ion move(s) + {n_chain} chain move(s) (100 beads flagged) of the same "
               f"22000-bead system evaluated with the reference's pairwise algorithm (oracle port, map-free, new-configuration "
               f"energies only like the reference); "
@@ -207,7 +246,7 @@ def run_reference(a):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "moves_per_step": MOVES_PER_STEP, "replicas": cores},
         "cpu_baseline": {"value": value, "unit": "moves/s", "cores": cores, "kind": "port", "sample": sample,
-                         "single_chain_value": value / cores},
+                         "single_chain_value": value / cores, "plum_ref_cut": ref_cut},
         "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0_all,
     }
@@ -696,6 +735,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="skip the extra single-replica measurement")
     ap.add_argument("--no-recompute", action="store_true", help="skip the k-sharded full S(k) recompute timing")
+    ap.add_argument("--no-plum-ref", action="store_true", help="reference arm: skip the real plum_ref binary's leg (1320-bead cut)")
     ap.add_argument("--replicas-per-gpu", type=int, default=0,
                     help="independent Markov chains per GPU, each with its own engine/stream; 0 = 30 (fixed per GPU: weak scaling; one stream each, below the 32 hardware queues)")
     ap.add_argument("--mc-batch", type=int, default=256, help="steps per uploaded batch in the batched (device-side proposal) leg")
