@@ -658,13 +658,22 @@ def run_ours(a):
         recompute = {}
         from plum_b200 import sharded
         for name, loader in (("S", synth.load), ("S_full", synth.load_full)):
-            eng = None
+            eng, setup_err = None, None
             try:
                 _, s2, ty2, par2 = loader(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
                 eng = Engine(par2, device=local_rank, capacity_beads=s2.n)
                 eng.upload(s2.xyz, s2.q, ty2.ids(s2.symbol), s2.mol_first)
                 t_init = eng.init_energy()
                 l0 = eng.launch_count()
+            except Exception as e:   # noqa: BLE001
+                setup_err = repr(e)
+            # a rank that failed to set up must not leave the others waiting in the all-gather
+            if max_over_ranks(1.0 if setup_err else 0.0) > 0.0:
+                recompute[name] = {"error": setup_err or "set-up failed on another rank"}
+                if eng is not None:
+                    eng.close()
+                continue
+            try:
                 recompute[name] = dict(n_charged=int(np.count_nonzero(s2.q)),
                                        **sharded.time_sharded_recompute(eng, rank, world, t_init["recip"]))
                 recompute[name]["launches"] = int(eng.launch_count() - l0)
