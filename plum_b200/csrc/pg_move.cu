@@ -493,11 +493,12 @@ __global__ void __launch_bounds__(MV_THREADS, FAST ? MV_FAST_OCC : MV_GEN_OCC) k
             ex = valid ? fabsf(ex - mv_rintf(ex)) : 0.0f;
             ey = valid ? fabsf(ey - mv_rintf(ey)) : 0.0f;
             ez = valid ? fabsf(ez - mv_rintf(ez)) : 0.0f;
-            // non-negative finite floats order like their bit patterns: one REDUX.MAX.U32 per axis instead of a
-            // five-step shuffle tree (15 SHFL + 15 FMNMX on the tile's critical path)
-            ex = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ex)));
-            ey = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ey)));
-            ez = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ez)));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              ex = fmaxf(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+              ey = fmaxf(ey, __shfl_xor_sync(0xffffffffu, ey, o));
+              ez = fmaxf(ez, __shfl_xor_sync(0xffffffffu, ez, o));
+            }
             hwx = ex + 1e-6f; hwy = ey + 1e-6f; hwz = ez + 1e-6f;   // + FP32 slack in box fractions
             anyq = __ballot_sync(0xffffffffu, valid && pchg) != 0u;
           }
