@@ -74,7 +74,7 @@ struct McState {
 };
 }  // namespace
 
-ForceField::ForceField() : engine(NULL), pending_mol(-1), mc_state(NULL), vp_z(0) {
+ForceField::ForceField() : vp_z(0), engine(NULL), pending_mol(-1), mc_state(NULL) {
   for (int i = 0; i < 12; i++) p_tensor[i] = 0;
 }
 
