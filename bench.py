@@ -649,6 +649,21 @@ def run_ours(a):
     value, e2e_value, dev_s, t_e2e, evals_total = res["value"], res["e2e_value"], res["dev_s"], res["t_e2e"], res["evals_total"]
     e2e_launches, gpu_launches, roofline, clock_info = res["e2e_launches"], res["gpu_launches"], res["roofline"], res["clock_info"]
     replay_matches, t_wall_replay, t_flush, h2d, d2h = res["replay_matches"], res["wall_replay"], 0.0, res["h2d"], res["d2h"]
+    # What the kernel EXECUTES next to what the reference's algorithm would (`achieved` prices every pair at the reference's
+    # 36 flop; the kernel culls most of them): executed FP64 flop per launch = dadd + dmul + 2 dfma thread instructions
+    # (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on) of the `ncu --set full` capture of this command,
+    # gpurun_out/prof_r01d_kmove.ncu-rep, summarised in profiles/r01_summary.md: 100-bead chain move 5.80e6, ion move 1.21e6.
+    try:
+        exe_per_launch = res["p_ion"] * 1.21e6 + (1.0 - res["p_ion"]) * 5.80e6
+        exe_tflops = roofline["achieved"] * exe_per_launch / roofline["algorithmic_flops_per_launch"]
+        roofline["executed_view"] = {
+            "achieved": exe_tflops, "peak": roofline["peak"], "unit": "TFLOP/s", "frac": exe_tflops / roofline["peak"],
+            "executed_flops_per_launch": exe_per_launch,
+            "note": "executed FP64 flop per launch from ncu (chain move 5.80e6, ion move 1.21e6, mixed with this run's ion "
+                    "fraction) over the same CUDA-event time: the kernel is bound by CTA-slot time and instruction issue, "
+                    "not by the FP64 pipe; `frac` above exceeds 1 because the algorithmic count includes the culled pairs"}
+    except Exception as e:   # noqa: BLE001
+        roofline["executed_view"] = {"error": repr(e)}
 
     # ---------------- k-sharded full S(k) recompute: every rank holds the positions, fills its slice of
     # the k list with k_sk_slice, NCCL all-gathers the slices; time per rank with the collective broken out, for S and for
