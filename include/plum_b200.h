@@ -242,6 +242,60 @@ int pg_mc_end(pg_engine* h, double* dE_out, uint8_t* accept_out, int* n_done, fl
 /* Trial coordinates the device built for step m of the batch ([len][3]; for tests). */
 int pg_mc_trial_xyz(pg_engine* h, int m, double* xyz);
 
+/* ---- device-resident Markov chain (whole translational steps, no host in the loop) ---- */
+/* Replaces the loop body of Simulation::Run for a stretch of translational steps
+ * (src/simulation/simulation.cc:216-355: the first draw of the step, TranslationalMove's pre-selection of a
+ * chain and an ion, the move type, the generator's own draws — Molecule::BeadTranslate / COMTranslate /
+ * Pivot / RandomReptation, src/molecules/molecule.cc:103-312, randSphere src/utilities/misc.cc:95-109 — the
+ * energy change, the Metropolis test :327-332 and FinalizeEnergies) by ONE kernel that keeps the driver's
+ * std::mt19937 stream on the device: the caller hands over the generator's 624 state words + position
+ * (what operator<< of std::mt19937 prints), the device consumes it draw for draw like the reference —
+ * including NOT drawing the acceptance variate when dE >= 1e8 — and hands the state back.  Nothing stops a
+ * chain except max_steps or a grand-canonical step (gc_freq > 0 and first draw % gc_freq == 0: the chain
+ * stops IN FRONT of it, the generator untouched, and the caller runs that step itself).
+ * Offered for single-image systems (3 periodic axes, one box for LJ and Ewald, real-space cutoff < L/2: what
+ * pg_create selects k_move<true> for) without crankshaft moves; pg_chain_configure says so otherwise and the
+ * caller stays on pg_mc_* / pg_delta_e.  Positions, S(k) and the running totals are the engine's own: the
+ * other entry points see the chain's result (pg_download_positions, pg_get_totals, pg_delta_e ...).     */
+typedef struct pg_chain_config {
+  int32_t phantom;        /* molecules [0, phantom) never move (simulation.cc:255)                       */
+  int32_t gc_freq;        /* > 0: ForceField::GCFrequency() of a grand-canonical run, else 0             */
+  int32_t vary_bond;      /* UseBondPot(): the generators vary the bond length (simulation.cc:293-296)   */
+  int32_t cluster_ctas;   /* CTAs (SMs) that share one chain: 1..16, 0 = 1                               */
+  int32_t keep_trials;    /* tests: keep every step's trial coordinates (pg_chain_trial_xyz)             */
+  int32_t _pad;
+  double move_size;       /* s1_MC_move_size                                                             */
+  double bond_len;        /* RigidBondLen() or EqBondLen() (simulation.cc:288-296)                       */
+  double move_prob[5];    /* bead, COM, pivot, crankshaft (must be 0), reptation (simulation.cc:46-50)   */
+} pg_chain_config;
+typedef struct pg_chain_step {
+  double dE;              /* what ForceField::EnergyDifference returned                                  */
+  int32_t mol;            /* moved molecule, -1: the step attempted nothing                              */
+  int8_t kind;            /* PG_MOVE_*, -1: the step attempted nothing                                   */
+  uint8_t accept;
+  uint8_t stage;          /* as pg_delta.stage                                                           */
+  uint8_t _pad;
+} pg_chain_step;
+int pg_chain_configure(pg_engine* h, const pg_chain_config* cfg);
+/* The generator: 624 state words and the position (0..624), libstdc++'s std::mt19937 layout.  get returns
+ * an EQUIVALENT state (same future outputs; a position of 624 comes back as 0 of the next generation). */
+int pg_chain_set_rng(pg_engine* h, const uint32_t* state624, int position);
+int pg_chain_get_rng(pg_engine* h, uint32_t* state624, int* position);
+/* Runs up to max_steps steps.  *n_done steps are over; *stop_kind 0: max_steps reached, 1: the next step is
+ * a grand-canonical step.  steps (may be NULL) receives n_done records; elapsed_ms is CUDA-event time.   */
+int pg_chain_run(pg_engine* h, int max_steps, int* n_done, int* stop_kind, pg_chain_step* steps, float* elapsed_ms);
+int pg_chain_begin(pg_engine* h, int max_steps);
+int pg_chain_end(pg_engine* h, int* n_done, int* stop_kind, pg_chain_step* steps, float* elapsed_ms);
+/* n independent replicas (one engine each, same device, same cluster size) in ONE launch on hs[0]'s stream;
+ * every replica continues from its own resident generator state.  n_done[n] may be NULL.                */
+int pg_chain_run_multi(pg_engine** hs, int n, int max_steps, int* n_done, float* elapsed_ms);
+/* Records [first, first+count) of the engine's last chain (also after pg_chain_run_multi).              */
+int pg_chain_steps(pg_engine* h, int first, int count, pg_chain_step* steps);
+/* tests: trial coordinates of step `step` of the last chain ([n_beads][3]; keep_trials), and a consistency
+ * check of the resident spatial structures against the resident coordinates (*n_bad inconsistencies).   */
+int pg_chain_trial_xyz(pg_engine* h, int step, double* xyz, int n_beads);
+int pg_chain_check(pg_engine* h, int* n_bad);
+
 /* ---- configurational-bias trial energies (ForceField::BeadsEnergy) ------- */
 /* One launch evaluates n_trials candidate (monomer, counter-ion) pairs against
  * every resident bead except molecules [skip_mol_first, skip_mol_last] (the

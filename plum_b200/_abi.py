@@ -60,6 +60,17 @@ class PgMoveDesc(C.Structure):
                 ("s", C.c_double), ("v", C.c_double * 3), ("vlen", C.c_double), ("u", C.c_double)]
 
 
+class PgChainConfig(C.Structure):
+    _fields_ = [("phantom", C.c_int32), ("gc_freq", C.c_int32), ("vary_bond", C.c_int32), ("cluster_ctas", C.c_int32),
+                ("keep_trials", C.c_int32), ("_pad", C.c_int32), ("move_size", C.c_double), ("bond_len", C.c_double),
+                ("move_prob", C.c_double * 5)]
+
+
+class PgChainStep(C.Structure):
+    _fields_ = [("dE", C.c_double), ("mol", C.c_int32), ("kind", C.c_int8), ("accept", C.c_uint8), ("stage", C.c_uint8),
+                ("_pad", C.c_uint8)]
+
+
 class PgTrialSet(C.Structure):
     _fields_ = [
         ("n_trials", C.c_int32), ("use_bead2", C.c_int32), ("type1", C.c_int32), ("type2", C.c_int32),

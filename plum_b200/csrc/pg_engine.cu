@@ -32,6 +32,7 @@
 #include "pg_trials.cu"
 #include "pg_pressure.cu"
 #include "pg_propose.cu"
+#include "pg_chain.cu"
 
 namespace {
 
@@ -162,6 +163,9 @@ struct pg_engine {
   std::vector<int> mc_mol;      // molecule of every step of the batch (wave construction)
   int mc_first = 0, mc_count = 0;
   bool mc_inflight = false;
+
+  // device-resident Markov chain (k_chain, pg_chain_*): resident spatial structures + io buffers
+  PgChainHost ch;
 };
 
 #define PG_CUDA(h, call)                                                                     \
@@ -787,7 +791,10 @@ int compute_totals(pg_engine* h, bool set_state, pg_totals* out) {
   return PG_OK;
 }
 
+void chain_free(pg_engine* h);
+
 void free_all(pg_engine* h) {
+  chain_free(h);
   cudaFree(h->xy); cudaFree(h->zq); cudaFree(h->type); cudaFree(h->mol);
   cudaFree(h->t_xy); cudaFree(h->t_zq); cudaFree(h->t_type); cudaFree(h->t_mol);
   cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_kvec); cudaFree(h->d_S); cudaFree(h->d_dS); cudaFree(h->d_Stmp);
@@ -1003,6 +1010,7 @@ int pg_upload_system(pg_engine* h, int n_beads, const double* xyz, const double*
   h->n_mol = n_mol;
   h->pending = false;
   h->pc.valid = false;
+  h->ch.valid = false;
   return PG_OK;
 }
 
@@ -1107,6 +1115,7 @@ int pg_commit(pg_engine* h, int accept) {
   if (!h) return PG_ERR_INVALID;
   if (!h->pending) { h->err = "no pending trial"; return PG_ERR_STATE; }
   h->pending = false;
+  if (accept) h->ch.valid = false;   // coordinates change outside the chain kernel: its resident structures are stale
   h->pc.valid = true;
   h->pc.accept = accept ? 1 : 0;
   h->pc.g0 = h->pend_g0; h->pc.glen = h->pend_glen; h->pc.d_group = h->pend_group; h->pc.cap = h->pend_cap;
@@ -1257,6 +1266,7 @@ int pg_replay_run(pg_engine* h, int first, int count, double* dE_out, uint8_t* a
   PG_CUDA(h, cudaSetDevice(h->device));
   int rc = flush_commit(h);
   if (rc) return rc;
+  h->ch.valid = false;
   cudaGraphExec_t exec = nullptr;
   rc = replay_graph(h, first, count, true, &exec);   // built outside the timed events
   if (rc) return rc;
@@ -1432,6 +1442,7 @@ int pg_mc_begin(pg_engine* h, int first, int count) {
   if (rc) return rc;
   rc = ensure_partials(h, h->move_slots + h->n_sm + 8);
   if (rc) return rc;
+  h->ch.valid = false;
   PG_CUDA(h, cudaMemsetAsync(h->d_stop, 0, sizeof(int), h->stream));
   PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   StageView base = stage_view(h->d_rp, (int)h->rp_beads);
@@ -1703,6 +1714,7 @@ int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, con
   h->h_type.insert(h->h_type.end(), type, type + n_add);
   h->n += n_add;
   h->n_mol += n_new_mol;
+  h->ch.valid = false;
   return PG_OK;
 }
 
@@ -1748,6 +1760,7 @@ int pg_delete_molecules(pg_engine* h, int mf, int ml, pg_totals* removed) {
   h->mol_first.swap(mfirst);
   h->n -= glen;
   h->n_mol -= nm;
+  h->ch.valid = false;
   return PG_OK;
 }
 
@@ -1874,3 +1887,4 @@ int pg_measure_fp64_peak(pg_engine* h, double* gflops) {
 }
 
 }  // extern "C"
+#include "pg_chain_host.cu"

@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from ._abi import (ParamBlock, PgDelta, PgEwaldInfo, PgMoveDesc, PgParams, PgProposal, PgTotals, PgTrialSet, bptr, c_double_p,
+from ._abi import (ParamBlock, PgChainConfig, PgChainStep, PgDelta, PgEwaldInfo, PgMoveDesc, PgParams, PgProposal, PgTotals, PgTrialSet, bptr, c_double_p,
                    c_int32_p, c_uint8_p, dptr, iptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -25,6 +25,8 @@ ABI_SYMBOLS = [
     "pg_delta_e_begin", "pg_delta_e_poll", "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_mc_upload", "pg_mc_run", "pg_mc_begin", "pg_mc_end", "pg_mc_trial_xyz", "pg_trial_energies", "pg_insert_molecules",
     "pg_delete_molecules", "pg_wall_force", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
     "pg_stream", "pg_measure_fp64_peak",
+    "pg_chain_configure", "pg_chain_set_rng", "pg_chain_get_rng", "pg_chain_run", "pg_chain_begin", "pg_chain_end",
+    "pg_chain_run_multi", "pg_chain_steps", "pg_chain_trial_xyz", "pg_chain_check",
 ]
 
 _LIB = None
@@ -81,6 +83,17 @@ def lib():
         L.pg_stream.restype = C.c_void_p
         L.pg_stream.argtypes = [vp]
         L.pg_measure_fp64_peak.argtypes = [vp, c_double_p]
+        u32p = C.POINTER(C.c_uint32)
+        L.pg_chain_configure.argtypes = [vp, C.POINTER(PgChainConfig)]
+        L.pg_chain_set_rng.argtypes = [vp, u32p, C.c_int]
+        L.pg_chain_get_rng.argtypes = [vp, u32p, C.POINTER(C.c_int)]
+        L.pg_chain_run.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(PgChainStep), C.POINTER(C.c_float)]
+        L.pg_chain_begin.argtypes = [vp, C.c_int]
+        L.pg_chain_end.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(PgChainStep), C.POINTER(C.c_float)]
+        L.pg_chain_run_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.pg_chain_steps.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PgChainStep)]
+        L.pg_chain_trial_xyz.argtypes = [vp, C.c_int, c_double_p, C.c_int]
+        L.pg_chain_check.argtypes = [vp, C.POINTER(C.c_int)]
         _LIB = L
     return _LIB
 
@@ -237,6 +250,53 @@ class Engine:
         out = np.zeros((length, 3))
         self._check(self.L.pg_mc_trial_xyz(self.h, int(m), dptr(out)), "pg_mc_trial_xyz")
         return out
+
+    # -- device-resident Markov chain (pg_chain_*) ---------------------------
+    def chain_configure(self, phantom, move_size, move_prob, bond_len, vary_bond=False, gc_freq=0, cluster=1,
+                        keep_trials=False):
+        c = PgChainConfig(phantom=int(phantom), gc_freq=int(gc_freq), vary_bond=int(bool(vary_bond)),
+                          cluster_ctas=int(cluster), keep_trials=int(bool(keep_trials)), move_size=float(move_size),
+                          bond_len=float(bond_len))
+        for i in range(5):
+            c.move_prob[i] = float(move_prob[i])
+        self._check(self.L.pg_chain_configure(self.h, C.byref(c)), "pg_chain_configure")
+
+    def chain_seed(self, seed: int):
+        """Generator state of std::mt19937(seed) (== numpy's legacy init_genrand seeding; position 624)."""
+        key = np.random.RandomState(int(seed)).get_state()[1].astype(np.uint32)
+        self.chain_set_rng(key, 624)
+
+    def chain_set_rng(self, state624, position: int):
+        st = np.ascontiguousarray(state624, dtype=np.uint32)
+        assert st.shape == (624,)
+        self._check(self.L.pg_chain_set_rng(self.h, st.ctypes.data_as(C.POINTER(C.c_uint32)), int(position)), "pg_chain_set_rng")
+
+    def chain_get_rng(self):
+        st = np.zeros(624, dtype=np.uint32)
+        pos = C.c_int(0)
+        self._check(self.L.pg_chain_get_rng(self.h, st.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos)), "pg_chain_get_rng")
+        return st, pos.value
+
+    def chain_run(self, max_steps: int):
+        """Returns (records as a structured array with dE / mol / kind / accept / stage, stop_kind, elapsed_ms)."""
+        arr = (PgChainStep * max(max_steps, 1))()
+        nd, stop, ms = C.c_int(0), C.c_int(0), C.c_float(0.0)
+        self._check(self.L.pg_chain_run(self.h, int(max_steps), C.byref(nd), C.byref(stop), arr, C.byref(ms)), "pg_chain_run")
+        dt = np.dtype([("dE", "<f8"), ("mol", "<i4"), ("kind", "i1"), ("accept", "u1"), ("stage", "u1"), ("_pad", "u1")])
+        rec = np.frombuffer(arr, dtype=dt, count=max(max_steps, 1))[:nd.value].copy()
+        return rec, stop.value, float(ms.value)
+
+    def chain_trial_xyz(self, step: int, n_beads: int) -> np.ndarray:
+        out = np.zeros((n_beads, 3))
+        self._check(self.L.pg_chain_trial_xyz(self.h, int(step), dptr(out), int(n_beads)), "pg_chain_trial_xyz")
+        return out
+
+    def chain_check(self) -> int:
+        nb = C.c_int(0)
+        self._check(self.L.pg_chain_check(self.h, C.byref(nb)), "pg_chain_check")
+        if nb.value:
+            raise EngineError(f"{nb.value} inconsistencies: {self.L.pg_last_error(self.h).decode()}")
+        return 0
 
     def trial_energies(self, b1, b2, t1, q1, t2, q2, use_bead2, chain_xyz, chain_q, chain_type, current_len,
                        skip_first=-1, skip_last=-1):

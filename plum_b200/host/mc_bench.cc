@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstring>
 #include <random>
+#include <sstream>
 #include <vector>
 
 #include "plum_b200.h"
@@ -339,6 +340,154 @@ int pb_run_mc(void** ps, int n_ctx, int n_moves, int batch_moves, double* wall_s
   }
   auto t1 = std::chrono::steady_clock::now();
   if (wall_seconds) *wall_seconds = std::chrono::duration<double>(t1 - t0).count();
+  return 0;
+}
+
+// ---- the device-resident chain (pg_chain_*): the host only carries the generator state across the boundary ----
+namespace {
+
+// std::mt19937 <-> (624 state words, position): the textual form operator<< / operator>> define.
+void mt_export(const std::mt19937& g, uint32_t* state, int* pos) {
+  std::stringstream ss;
+  ss << g;
+  for (int i = 0; i < 624; i++) { unsigned long v; ss >> v; state[i] = (uint32_t)v; }
+  unsigned long p; ss >> p;
+  *pos = (int)p;
+}
+void mt_import(std::mt19937& g, const uint32_t* state, int pos) {
+  std::stringstream ss;
+  for (int i = 0; i < 624; i++) ss << state[i] << ' ';
+  ss << pos;
+  ss >> g;
+}
+
+int chain_configure(Ctx* c, int cluster, int keep_trials) {
+  const plum_mc::Config& pc = c->prop.config();
+  pg_chain_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.phantom = pc.phantom; cfg.gc_freq = pc.gc_freq; cfg.vary_bond = pc.vary_bond ? 1 : 0;
+  cfg.cluster_ctas = cluster; cfg.keep_trials = keep_trials;
+  cfg.move_size = pc.move_size; cfg.bond_len = pc.bond_len;
+  for (int i = 0; i < 5; i++) cfg.move_prob[i] = pc.move_prob[i];
+  return pg_chain_configure(c->eng, &cfg);
+}
+
+// Books the records of n_steps finished steps of replica c; returns the moves among them.
+int chain_book(Ctx* c, const pg_chain_step* st, int n_steps) {
+  const int N = c->mol_first[c->n_mol];
+  int moves = 0;
+  for (int s = 0; s < n_steps; s++) {
+    if (st[s].kind < 0) continue;
+    const int mol = st[s].mol, len = c->mol_first[mol + 1] - c->mol_first[mol];
+    const double n_intra = (len > 1) ? 0.5 * len * (len - 1) : 0.0;
+    const double ev = (double)len * (double)(N - len) + n_intra;
+    c->evals += ev;
+    c->flops += 2.0 * ev * 36.0;
+    if (st[s].accept) c->acc_count++;
+    if (c->rec_mol) {
+      const int it = c->done + moves;
+      c->rec_mol[it] = mol; c->rec_off[it] = 0; c->rec_u[it] = 0.0; c->rec_dE[it] = st[s].dE; c->rec_acc[it] = st[s].accept;
+    }
+    moves++;
+  }
+  c->done += moves;
+  return moves;
+}
+
+}  // namespace
+
+// n_moves Metropolis steps of every replica through pg_chain_*: per batch the generator state goes down (2.5 KB), one
+// launch runs `batch` steps of ALL replicas (one cluster each), and the step log (16 B per step), the generator state
+// and — like ForceField::TranslationalBatch, whose driver reads Bead::current_pos afterwards — the accepted
+// coordinates come back.  One host thread drives everything.  (Systems without grand-canonical steps.)
+int pb_run_chain(void** ps, int n_ctx, int n_moves, int batch, int cluster, int keep_trials, int positions_every_batch,
+                 double* wall_seconds) {
+  std::vector<Ctx*> cs(n_ctx);
+  std::vector<pg_engine*> engs(n_ctx);
+  for (int i = 0; i < n_ctx; i++) {
+    cs[i] = static_cast<Ctx*>(ps[i]);
+    cs[i]->done = 0; cs[i]->used = 0; cs[i]->acc_count = 0; cs[i]->evals = 0; cs[i]->flops = 0;
+    engs[i] = cs[i]->eng;
+    int rc = chain_configure(cs[i], cluster, keep_trials);
+    if (rc) return rc;
+  }
+  if (batch <= 0) batch = 1024;
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<pg_chain_step> st((size_t)batch);
+  std::vector<int> n_done(n_ctx);
+  uint32_t state[624];
+  int pos = 0;
+  int left = n_moves;
+  while (left > 0) {
+    const int b = std::min(batch, left);
+    for (int i = 0; i < n_ctx; i++) {
+      mt_export(cs[i]->rng, state, &pos);
+      int rc = pg_chain_set_rng(engs[i], state, pos);
+      if (rc) return rc;
+    }
+    int rc = pg_chain_run_multi(engs.data(), n_ctx, b, n_done.data(), nullptr);
+    if (rc) return rc;
+    int moves0 = -1;
+    for (int i = 0; i < n_ctx; i++) {
+      if (n_done[i] != b) return PG_ERR_STATE;
+      rc = pg_chain_steps(engs[i], 0, b, st.data());
+      if (rc) return rc;
+      const int moves = chain_book(cs[i], st.data(), b);
+      if (i == 0) moves0 = moves;
+      rc = pg_chain_get_rng(engs[i], state, &pos);
+      if (rc) return rc;
+      mt_import(cs[i]->rng, state, pos);
+      if (positions_every_batch) {
+        rc = pg_download_positions(engs[i], cs[i]->pos.data());
+        if (rc) return rc;
+      }
+    }
+    // every step of these systems attempts a move; the loop counts replica 0's
+    left -= std::max(moves0, 1);
+  }
+  if (!positions_every_batch)
+    for (int i = 0; i < n_ctx; i++) {
+      int rc = pg_download_positions(engs[i], cs[i]->pos.data());
+      if (rc) return rc;
+    }
+  auto t1 = std::chrono::steady_clock::now();
+  if (wall_seconds) *wall_seconds = std::chrono::duration<double>(t1 - t0).count();
+  return 0;
+}
+
+// The same, device-resident: the generator state is already on the device (pb_chain_seed), nothing crosses the
+// boundary inside the call but the launch itself; returns the CUDA-event time of the launches.
+int pb_chain_seed(void** ps, int n_ctx, int cluster) {
+  uint32_t state[624];
+  int pos = 0;
+  for (int i = 0; i < n_ctx; i++) {
+    Ctx* c = static_cast<Ctx*>(ps[i]);
+    int rc = chain_configure(c, cluster, 0);
+    if (rc) return rc;
+    mt_export(c->rng, state, &pos);
+    rc = pg_chain_set_rng(c->eng, state, pos);
+    if (rc) return rc;
+  }
+  return 0;
+}
+int pb_chain_resident(void** ps, int n_ctx, int n_steps, int book, float* elapsed_ms) {
+  std::vector<pg_engine*> engs(n_ctx);
+  for (int i = 0; i < n_ctx; i++) engs[i] = static_cast<Ctx*>(ps[i])->eng;
+  std::vector<int> n_done(n_ctx);
+  int rc = pg_chain_run_multi(engs.data(), n_ctx, n_steps, n_done.data(), elapsed_ms);
+  if (rc) return rc;
+  for (int i = 0; i < n_ctx; i++)
+    if (n_done[i] != n_steps) return PG_ERR_STATE;
+  if (book) {
+    std::vector<pg_chain_step> st((size_t)n_steps);
+    for (int i = 0; i < n_ctx; i++) {
+      Ctx* c = static_cast<Ctx*>(ps[i]);
+      c->done = 0; c->acc_count = 0; c->evals = 0; c->flops = 0;
+      rc = pg_chain_steps(engs[i], 0, n_steps, st.data());
+      if (rc) return rc;
+      chain_book(c, st.data(), n_steps);
+    }
+  }
   return 0;
 }
 

@@ -116,6 +116,9 @@ def _bench_lib():
         L.pb_stats.restype = None
         L.pb_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp]
         L.pb_run_mc.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, dp]
+        L.pb_run_chain.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+        L.pb_chain_seed.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+        L.pb_chain_resident.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L._pb_ready = True
     return L
 
@@ -181,7 +184,24 @@ class NativeChain:
         """The same steps with device-side proposals, `batch_moves` per upload."""
         return self._run(self.L.pb_run_mc, int(n_moves), int(batch_moves))
 
+    def run_chain(self, n_moves, batch=1024, cluster=1, keep_trials=False):
+        """The same steps device-resident (pg_chain_*): the generator state crosses the boundary, nothing else."""
+        return self._run(self.L.pb_run_chain, int(n_moves), int(batch), int(cluster), int(bool(keep_trials)), 1)
+
     def positions(self):
         out = np.zeros((self.n, 3))
         self.L.pb_positions(self.ctx, dptr(out))
         return out
+
+
+def run_chain_multi(chains, n_moves, batch=1024, cluster=1):
+    """Several NativeChain replicas (one engine each, same device) through pg_chain_run_multi: one launch per batch
+    carries all of them, one host thread drives everything."""
+    L = _bench_lib()
+    arr = (C.c_void_p * len(chains))(*[c.ctx for c in chains])
+    wall = C.c_double(0.0)
+    rc = L.pb_run_chain(arr, len(chains), int(n_moves), int(batch), int(cluster), 0, 1, C.byref(wall))
+    if rc != 0:
+        msgs = [c.eng.L.pg_last_error(c.eng.h).decode() for c in chains]
+        raise RuntimeError(f"pb_run_chain failed ({rc}): {msgs}")
+    return wall.value

@@ -120,6 +120,48 @@ def synth_spring():
         print("short synth_spring", seed, len(lines), "lines")
 
 
+def compact_cut(lines, path, n_trials_kept):
+    """One npz per seed: every step's move kind / molecule / dE / accept bit / four running totals, and the trial
+    coordinates the reference built (X lines) for the first n_trials_kept steps."""
+    kind, mol, dE, acc, tot, t_off, t_xyz = [], [], [], [], [], [0], []
+    init = None
+    for i, ln in enumerate(lines):
+        f = ln.split()
+        if not f:
+            continue
+        if f[0] == "I":
+            init = [replay.hx(x) for x in f[2:6]]
+        if f[0] != "T":
+            continue
+        kind.append(int(f[2])); mol.append(int(f[3])); dE.append(replay.hx(f[4])); acc.append(int(f[5]))
+        tot.append([replay.hx(x) for x in f[6:10]])
+        if len(kind) <= n_trials_kept:
+            x = lines[i + 1].split()
+            assert x[0] == "X"
+            n = int(x[1])
+            t_xyz.append(np.array([[replay.hx(x[3 + 4 * k + a]) for a in range(3)] for k in range(n)]))
+            t_off.append(t_off[-1] + n)
+    np.savez_compressed(path, init=np.array(init), kind=np.array(kind, dtype=np.int8), mol=np.array(mol, dtype=np.int32),
+                        dE=np.array(dE), accept=np.array(acc, dtype=np.uint8), tot=np.array(tot),
+                        trial_off=np.array(t_off, dtype=np.int32), trial_xyz=np.concatenate(t_xyz))
+
+
+def synth_cut(steps=2000, seeds=(1, 2), n_trials_kept=300):
+    """examples/synth_cut + long/synth_cut_seed{1,2}.npz: the 1320-bead cut of the benchmark system S (plum_b200/synth.py:
+    12 chains x 100 beads, every 10th bead charged, + 120 counter-ions; SAME box L = 200, alpha = 0.004 — hence the same
+    cutoffs and K = 3574 — and the same move mix), the largest cut of S the reference walks in minutes.  It spans several
+    partner tiles / cells / charged-list chunks of the single-image kernels (k_move<true>, k_chain), which the 112-bead
+    synth_spring fixture does not."""
+    from plum_b200 import synth
+    sysm = synth.make_system(n_chains=12, chain_len=100, charged_every=10)
+    dst = os.path.join(HERE, "examples", "synth_cut")
+    synth.write_inputs(dst, sysm, n_steps=steps, alpha=0.004, spring=False)
+    for seed in seeds:
+        lines = replay.run_plum_ref(dst, steps, seed, xyz=True)
+        compact_cut(lines, os.path.join(HERE, "long", f"synth_cut_seed{seed}.npz"), n_trials_kept)
+        print("synth_cut seed", seed, len(lines), "lines", flush=True)
+
+
 def long_seed(seed, examples=None):
     """long/<example>_seed<seed>.{npz,stat.dat} for one more seed (the inputs are the committed copies)."""
     for ex in (examples or EXAMPLES):
@@ -139,6 +181,8 @@ def main():
     ap.add_argument("--skip-long", action="store_true")
     ap.add_argument("--extras-only", action="store_true", help="only the sampler fixtures (extras())")
     ap.add_argument("--synth-only", action="store_true", help="only the spring-bond fixture (synth_spring())")
+    ap.add_argument("--cut-seed", type=int, default=0, help="only the 1320-bead cut of S (synth_cut()) for this seed")
+    ap.add_argument("--cut-steps", type=int, default=2000)
     a = ap.parse_args()
     if not replay.have_plum_ref():
         raise SystemExit("oracle/_ref/plum_ref missing: run python oracle/build_ref.py")
@@ -151,6 +195,9 @@ def main():
         return
     if a.synth_only:
         synth_spring()
+        return
+    if a.cut_seed:
+        synth_cut(a.cut_steps, (a.cut_seed,))
         return
     os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
     os.makedirs(os.path.join(HERE, "long"), exist_ok=True)
@@ -176,6 +223,7 @@ def main():
         print("long", ex, len(lines), "lines")
     extras()
     synth_spring()
+    synth_cut()
 
 
 if __name__ == "__main__":
