@@ -263,7 +263,9 @@ typedef struct pg_chain_config {
   int32_t vary_bond;      /* UseBondPot(): the generators vary the bond length (simulation.cc:293-296)   */
   int32_t cluster_ctas;   /* CTAs (SMs) that share one chain: 1..16, 0 = 1                               */
   int32_t keep_trials;    /* tests: keep every step's trial coordinates (pg_chain_trial_xyz)             */
-  int32_t _pad;
+  int32_t pivot_mode;     /* 0: Molecule::Pivot in the reference's operation order (trial coordinates bit-identical
+                             to the reference's; one dependent step per bead of an arm); 1: the same arm as a prefix
+                             sum of independent bond vectors (coordinates equal to a few ulp, not bit for bit)  */
   double move_size;       /* s1_MC_move_size                                                             */
   double bond_len;        /* RigidBondLen() or EqBondLen() (simulation.cc:288-296)                       */
   double move_prob[5];    /* bead, COM, pivot, crankshaft (must be 0), reptation (simulation.cc:46-50)   */

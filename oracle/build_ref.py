@@ -47,7 +47,7 @@ def main():
         files = [os.path.join(src, "main.cc")]
         for d in ("simulation", "molecules", "utilities", "force_field"):
             files += sorted(os.path.join(src, d, f) for f in os.listdir(os.path.join(src, d)) if f.endswith(".cc"))
-        cmd = ["g++", "-std=c++11", "-O3", "-w", "-I", os.environ.get("EIGEN_INCLUDE", os.path.join(os.path.dirname(HERE), "plum_b200", "host", "eigen_standin")),
+        cmd = ["g++", "-std=c++11", "-O3", "-w", "-ffp-contract=off", "-I", os.environ.get("EIGEN_INCLUDE", os.path.join(os.path.dirname(HERE), "plum_b200", "host", "eigen_standin")),
                "-o", os.path.join(OUT, "plum_ref")] + files + ["-lm"]
         subprocess.check_call(cmd)
         print("build_ref: built", os.path.join(OUT, "plum_ref"))

@@ -62,7 +62,7 @@ class PgMoveDesc(C.Structure):
 
 class PgChainConfig(C.Structure):
     _fields_ = [("phantom", C.c_int32), ("gc_freq", C.c_int32), ("vary_bond", C.c_int32), ("cluster_ctas", C.c_int32),
-                ("keep_trials", C.c_int32), ("_pad", C.c_int32), ("move_size", C.c_double), ("bond_len", C.c_double),
+                ("keep_trials", C.c_int32), ("pivot_mode", C.c_int32), ("move_size", C.c_double), ("bond_len", C.c_double),
                 ("move_prob", C.c_double * 5)]
 
 

@@ -38,14 +38,18 @@ namespace cgx = cooperative_groups;
 #define CH_THREADS 512
 #define CH_WARPS (CH_THREADS / 32)
 #define CH_MAXLEN 256       // longest molecule the kernel moves (shared-memory staging)
-#define CH_CELL_CAP 8       // bead slots per cell (two 16-byte loads)
-#define CH_OVF_CAP 4096     // overflow list (cells that are full)
-#define CH_NC_MAX 32        // cells per axis at most
-#define CH_QCAP 128         // per-warp queue of in-range real-space configurations
+#define CH_CELL_CAP_MAX 32  // bead slots per cell: 4, 8, 16 or 32, chosen when the grid is built (16-byte loads)
+#define CH_OVF_CAP 4096     // overflow list (beads whose cell is full)
+#define CH_OVF_CHUNK 8      // overflow entries one work unit scans
+#define CH_NC_MAX 64        // cells per axis at most
+#define CH_CELLS_MAX (1 << 18)
+#define CH_QCAP 128         // per-warp queue of (partner, configuration) pairs that passed the FP32 filter
+#define CH_NEAR 256         // per-warp list of charged partners near the moved beads' bounding box
 #define CH_TAB 2048         // phase-table entries (double2)
 #define CH_GMAX 16          // largest cluster
 #define CH_NACC 8
 #define CH_KPT 8            // k vectors one thread owns at most
+#define CH_NPHASE 16
 
 enum { CH_ERR_NONE = 0, CH_ERR_RNG = 1, CH_ERR_LEN = 2, CH_ERR_KIND = 3, CH_ERR_OVERFLOW = 4, CH_ERR_K = 5 };
 
@@ -68,7 +72,7 @@ struct PgChainArgs {
   // charged beads
   int nq_tot; double2* qpos; float4* qfrac; const int* qslot;
   // cell grid
-  int nc[3]; int* cell_slots; int* ovf; int* ovf_n; int* bead_cell; int* bead_slot;
+  int nc[3]; int cell_cap; int* cell_slots; int* ovf; int* ovf_n; int* bead_cell; int* bead_slot;
   // in / out
   uint32_t* mt_io;          // [625] state words + position
   PgChainRec* log;          // [max_steps]
@@ -78,6 +82,13 @@ struct PgChainArgs {
   int* out;                 // [4] steps done, stop kind, error, overflow high-water
   int max_steps;
   int exact_pivot;
+  int specialize;           // clusters: run the four phases of the energy change on disjoint warp groups
+  int pad2_;
+  // instrumentation (tools/chain_probe.py): per-phase clock64 sums of thread 0 of rank 0 [5 kinds][CH_NPHASE], and a
+  // mask of phases to leave out (timing experiments only: the energies are then wrong)
+  unsigned long long* prof;
+  int dbg_skip;
+  int pad_;
 };
 
 struct ChSmem {
@@ -92,11 +103,19 @@ struct ChSmem {
   float4 fe[2 * CH_MAXLEN];
   double sq[2 * CH_MAXLEN];
   double2 tab[CH_TAB];
-  double q_r2[CH_WARPS][CH_QCAP], q_qq[CH_WARPS][CH_QCAP];
+  int q_near[CH_WARPS][CH_NEAR];
+  int2 q_hit[CH_WARPS][CH_QCAP];
+  int ovf_hw;                  // overflow list high-water mark (kept in step by rank 0 through DSMEM)
+  uint32_t pre_raw[32];        // the next 32 draws, tempered ...
+  double pre_u[32];            // ... and converted to uniforms by warp 0's lanes in parallel (a uniform is an FP64 division)
+  double uacc;                 // the draw behind the proposal as a uniform: the acceptance variate, if it gets drawn
+  int bcell[CH_MAXLEN], bslot[CH_MAXLEN];   // the moved beads' cell records (fetched with the coordinates, used by the commit)
+  long long wst[CH_NPHASE][CH_WARPS];   // instrumentation: per-warp clock at the end of each phase
   double red[CH_WARPS][CH_NACC];
   double part[2][CH_GMAX][CH_NACC];
   double tot[CH_NACC];
   int scan[CH_WARPS];
+  unsigned long long prof[5][CH_NPHASE];
 };
 
 // Cell coordinate of a position along one axis: the SAME function builds the grid on the host, files an accepted bead
@@ -135,23 +154,182 @@ __device__ __forceinline__ double ch_warp_sum(double v) {
   return v;
 }
 
+// phase stamp (instrumentation): every warp notes when it has finished phase `ph`; at the end of the step thread 0 of
+// the reporting rank charges each phase with the time from the previous phase's last warp to this phase's last warp
+#define CH_STAMP(ph)                                                            \
+  do {                                                                          \
+    if (A.prof && lane == 0) sm.wst[ph][warp] = clock64();                      \
+  } while (0)
+
+// Exact FP64 separation and the reference's real-space term for this warp's queued (partner, configuration) pairs, one
+// per lane: erfc runs in full warps.  Entries are in loop order and lane e takes entries e, e + 32, ...: deterministic.
 #define CH_QUEUE_FLUSH()                                                                  \
   do {                                                                                    \
     __syncwarp();                                                                         \
     for (int e_ = lane; e_ < qn; e_ += 32) {                                              \
-      const double r_ = sqrt(sm.q_r2[warp][e_]);                                          \
-      if (r_ > 0 && r_ <= P.real_cutoff) acc_real += P.lB * sm.q_qq[warp][e_] * erfc(P.sqrt_alpha * r_) / r_; \
+      const int2 h_ = sm.q_hit[warp][e_];                                                 \
+      const double2 a_ = __ldcg(&A.qpos[2 * h_.x]), c_ = __ldcg(&A.qpos[2 * h_.x + 1]);   \
+      const int g_ = sm.qidx[h_.y >> 1];                                                  \
+      double dx_, dy_, dz_;                                                               \
+      if (h_.y & 1) { dx_ = a_.x - sm.cur[0][g_]; dy_ = a_.y - sm.cur[1][g_]; dz_ = c_.x - sm.cur[2][g_]; } \
+      else { dx_ = a_.x - sm.trl[0][g_]; dy_ = a_.y - sm.trl[1][g_]; dz_ = c_.x - sm.trl[2][g_]; } \
+      dx_ -= Lx * mv_rint(dx_ * iLx); dy_ -= Ly * mv_rint(dy_ * iLy); dz_ -= Lz * mv_rint(dz_ * iLz); \
+      const double r2_ = dx_ * dx_ + dy_ * dy_ + dz_ * dz_;                               \
+      if (r2_ <= rc2) {                                                                   \
+        const double r_ = sqrt(r2_);                                                      \
+        if (r_ > 0 && r_ <= P.real_cutoff) acc_real += P.lB * (sm.sq[h_.y] * c_.y) * erfc(P.sqrt_alpha * r_) / r_; \
+      }                                                                                   \
     }                                                                                     \
     __syncwarp();                                                                         \
     qn = 0;                                                                               \
   } while (0)
+
+// FP32 pre-filter of this warp's near-partner list against every charged moved bead configuration; what passes goes
+// into the (partner, configuration) queue.
+#define CH_NEAR_PROCESS()                                                                 \
+  do {                                                                                    \
+    __syncwarp();                                                                         \
+    for (int b_ = 0; b_ < nn; b_ += 32) {                                                 \
+      const bool has_ = b_ + lane < nn;                                                   \
+      const int j_ = has_ ? sm.q_near[warp][b_ + lane] : 0;                               \
+      float4 pf_ = make_float4(0.f, 0.f, 0.f, 0.f);                                       \
+      if (has_) pf_ = __ldcg(&A.qfrac[j_]);                                               \
+      for (int e = 0; e < 2 * nq; e++) {                                                  \
+        const float4 f = sm.fe[e];                                                        \
+        float ax = pf_.x - f.x, ay = pf_.y - f.y, az = pf_.z - f.z;                       \
+        ax -= mv_rintf(ax); ay -= mv_rintf(ay); az -= mv_rintf(az);                       \
+        ax *= fLx; ay *= fLy; az *= fLz;                                                  \
+        const bool fhit = has_ && fmaf(ax, ax, fmaf(ay, ay, az * az)) <= cutf;            \
+        const unsigned mh = __ballot_sync(0xffffffffu, fhit);                             \
+        if (mh) {                                                                         \
+          if (fhit) sm.q_hit[warp][qn + __popc(mh & lt)] = make_int2(j_, e);              \
+          qn += __popc(mh);                                                               \
+          if (qn > CH_QCAP - 32) CH_QUEUE_FLUSH();                                        \
+        }                                                                                 \
+      }                                                                                   \
+    }                                                                                     \
+    __syncwarp();                                                                         \
+    nn = 0;                                                                               \
+  } while (0)
+
+// Bounding box (box fractions, minimum image around configuration 0) of the charged moved bead configurations, computed
+// by one warp for itself: centre bc[3] and half widths bh[3] in every lane.
+__device__ __forceinline__ void ch_bound_box(const ChSmem& sm, int n_e, int lane, float bc[3], float bh[3]) {
+  const float4 c = sm.fe[0];
+  float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f;
+  for (int e = lane; e < n_e; e += 32) {
+    const float4 f = sm.fe[e];
+    float dx = f.x - c.x, dy = f.y - c.y, dz = f.z - c.z;
+    dx -= mv_rintf(dx); dy -= mv_rintf(dy); dz -= mv_rintf(dz);
+    lox = fminf(lox, dx); hix = fmaxf(hix, dx); loy = fminf(loy, dy); hiy = fmaxf(hiy, dy); loz = fminf(loz, dz); hiz = fmaxf(hiz, dz);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+    loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+    loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+  }
+  // + slack for the FP32 rounding of the fractions; an extent of half a box or more bounds nothing
+  const float hx = 0.5f * (hix - lox) + 2e-6f, hy = 0.5f * (hiy - loy) + 2e-6f, hz = 0.5f * (hiz - loz) + 2e-6f;
+  bc[0] = c.x + 0.5f * (hix + lox); bc[1] = c.y + 0.5f * (hiy + loy); bc[2] = c.z + 0.5f * (hiz + loz);
+  bh[0] = hx < 0.25f ? hx : 0.5f; bh[1] = hy < 0.25f ? hy : 0.5f; bh[2] = hz < 0.25f ? hz : 0.5f;
+}
+
+// One arm of Molecule::Pivot (molecule.cc:170-198 forward, :203-231 backward) in the reference's operation order, one
+// warp: bead t of the arm (t = 1 .. La beads away from the pivot) is placed against the already placed bead t - 1 and the
+// rest of the arm is dragged along.  The dependency bead -> bead is sequential by construction; every lane computes it
+// redundantly, the dragged coordinates live in registers (lane l owns arm positions l + 1, l + 33, ...), so the only
+// traffic per step is three shuffles that are off the critical path.
+template <int DIR>
+__device__ __forceinline__ void ch_pivot_arm(ChSmem& sm, int p, int glen, double msr, int lane) {
+  const int La = DIR > 0 ? glen - 1 - p : p;
+  const int rowbase = DIR > 0 ? 0 : glen - 1 - p;
+  constexpr int NB = CH_MAXLEN / 32;
+  double ox[NB], oy[NB], oz[NB];
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    const int t = 32 * j + lane + 1;
+    const int i = t <= La ? p + DIR * t : p;
+    ox[j] = sm.cur[0][i]; oy[j] = sm.cur[1][i]; oz[j] = sm.cur[2][i];
+  }
+  double a[3] = {sm.cur[0][p], sm.cur[1][p], sm.cur[2][p]};
+  double b[3] = {sm.cur[0][p + DIR], sm.cur[1][p + DIR], sm.cur[2][p + DIR]};
+#pragma unroll
+  for (int jb = 0; jb < NB; jb++) {
+    if (32 * jb >= La) break;
+    for (int r = 0; r < 32; r++) {
+      const int t = 32 * jb + r + 1;
+      if (t > La) break;
+      const double4 row = sm.rv[rowbase + t - 1];
+      // arm position t + 1 before this step's translation: lane r + 1 of this register block, or lane 0 of the next
+      double n0, n1, n2;
+      {
+        constexpr int NXT = 0;   // (placeholder so that the block index below stays a compile-time constant)
+        (void)NXT;
+        const int jn = (jb + 1 < NB) ? jb + 1 : jb;
+        const double sx_ = (r < 31) ? ox[jb] : ox[jn];
+        const double sy_ = (r < 31) ? oy[jb] : oy[jn];
+        const double sz_ = (r < 31) ? oz[jb] : oz[jn];
+        const int src = (r + 1) & 31;
+        n0 = __shfl_sync(0xffffffffu, sx_, src); n1 = __shfl_sync(0xffffffffu, sy_, src); n2 = __shfl_sync(0xffffffffu, sz_, src);
+      }
+      const double v[3] = {row.x, row.y, row.z};
+      double m[3];
+      pp_pivot_step(a, b, msr, v, row.w, m);
+#pragma unroll
+      for (int j = 0; j < NB; j++)
+        if (j > jb || (j == jb && lane >= r)) { ox[j] = PP_ADD(ox[j], m[0]); oy[j] = PP_ADD(oy[j], m[1]); oz[j] = PP_ADD(oz[j], m[2]); }
+      a[0] = PP_ADD(b[0], m[0]); a[1] = PP_ADD(b[1], m[1]); a[2] = PP_ADD(b[2], m[2]);
+      b[0] = PP_ADD(n0, m[0]); b[1] = PP_ADD(n1, m[1]); b[2] = PP_ADD(n2, m[2]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    const int t = 32 * j + lane + 1;
+    if (t <= La) { const int i = p + DIR * t; sm.trl[0][i] = ox[j]; sm.trl[1][i] = oy[j]; sm.trl[2][i] = oz[j]; }
+  }
+}
+
+// The same arm as a prefix sum (pivot_mode 1): in exact arithmetic bead t sits at bead t - 1 + bond * unit(old_t -
+// old_{t-1} + msr * v_t) — the placed neighbour cancels out of the direction — so the bond vectors are independent and
+// the positions are their running sum.  Coordinates agree with the sequential form to a few ulp, not bit for bit.
+template <int DIR>
+__device__ __forceinline__ void ch_pivot_arm_prefix(ChSmem& sm, int p, int glen, double msr, int lane) {
+  const int La = DIR > 0 ? glen - 1 - p : p;
+  const int rowbase = DIR > 0 ? 0 : glen - 1 - p;
+  const int C = (La + 31) / 32;   // consecutive arm positions per lane
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int q = 0; q < C; q++) {
+    const int t = lane * C + q + 1;
+    if (t <= La) {
+      const int i = p + DIR * t;
+      const double4 row = sm.rv[rowbase + t - 1];
+      const double dx = (sm.cur[0][i] - sm.cur[0][i - DIR]) + msr * row.x, dy = (sm.cur[1][i] - sm.cur[1][i - DIR]) + msr * row.y,
+                   dz = (sm.cur[2][i] - sm.cur[2][i - DIR]) + msr * row.z;
+      const double nrm = row.w / sqrt(dx * dx + dy * dy + dz * dz);
+      sx += nrm * dx; sy += nrm * dy; sz += nrm * dz;
+      sm.trl[0][i] = sx; sm.trl[1][i] = sy; sm.trl[2][i] = sz;   // running sum inside the lane's stretch
+    }
+  }
+  // exclusive scan of the lanes' totals
+  double ex = sx, ey = sy, ez = sz;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double ux = __shfl_up_sync(0xffffffffu, ex, o), uy = __shfl_up_sync(0xffffffffu, ey, o), uz = __shfl_up_sync(0xffffffffu, ez, o);
+    if (lane >= o) { ex += ux; ey += uy; ez += uz; }
+  }
+  const double bx = sm.cur[0][p] + (ex - sx), by = sm.cur[1][p] + (ey - sy), bz = sm.cur[2][p] + (ez - sz);
+  for (int q = 0; q < C; q++) {
+    const int t = lane * C + q + 1;
+    if (t <= La) { const int i = p + DIR * t; sm.trl[0][i] += bx; sm.trl[1][i] += by; sm.trl[2][i] += bz; }
+  }
+}
 
 __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __restrict__ all) {
   cgx::cluster_group cluster = cgx::this_cluster();
   const int G = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gt = rank * CH_THREADS + tid, GT = G * CH_THREADS;
   const unsigned lt = (1u << lane) - 1u;
 
   extern __shared__ __align__(16) unsigned char ch_raw[];
@@ -181,7 +359,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
     E_pair = A.state->E_pair; E_ewald = A.state->E_ewald; E_bond = A.state->E_bond; E_ext = A.state->E_ext;
     E_real = A.state->E_real; E_recip = A.state->E_recip;
   }
-  int ovf_hw = __ldcg(A.ovf_n);   // overflow list high-water mark (changes only in rank 0 / warp 0, re-read behind a commit)
+  if (tid == 0) sm.ovf_hw = __ldcg(A.ovf_n);   // overflow list high-water mark (rank 0 keeps every CTA's copy in step)
 
   const double Lx = P.box[0], Ly = P.box[1], Lz = P.box[2];
   const double iLx = P.inv_box[0], iLy = P.inv_box[1], iLz = P.inv_box[2];
@@ -189,26 +367,56 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
   const double fdelta = 1e-6 * fmax(Lx, fmax(Ly, Lz));
   const float cutf = P.use_ewald ? mv_relax_f(P.rc2_relaxed, fdelta) : -1.0f;
   const int nk = P.use_ewald ? A.nk : 0;
-  unsigned k_lo, k_hi, q_lo, q_hi;
+  // Warp roles.  One CTA per chain (throughput): every warp takes its share of every phase in turn.  A cluster per chain
+  // (latency): the four independent phases of the energy change — reciprocal space, real space, cell-grid LJ,
+  // intra-molecular pairs — run side by side on disjoint warp groups of every CTA, so a step costs the longest of them
+  // instead of their sum.
+  const bool spec = (G > 1) && A.specialize;
+  const int rW0 = 0, rWn = spec ? 4 : CH_WARPS;
+  const int qW0 = spec ? 4 : 0, qWn = spec ? 7 : CH_WARPS;
+  const int cW0 = spec ? 11 : 0, cWn = spec ? 4 : CH_WARPS;
+  const int iW0 = spec ? 15 : 0, iWn = spec ? 1 : CH_WARPS;
+  const bool in_r = warp >= rW0 && warp < rW0 + rWn, in_q = warp >= qW0 && warp < qW0 + qWn;
+  const bool in_c = warp >= cW0 && warp < cW0 + cWn, in_i = warp >= iW0 && warp < iW0 + iWn;
+  const int rt = (warp - rW0) * 32 + lane, RT = rWn * 32;            // reciprocal space: thread of the CTA's k slice
+  const int gw = rank * qWn + (warp - qW0), GW = G * qWn;             // real space: warp over all charged partners
+  const int ct = (rank * cWn + (warp - cW0)) * 32 + lane, CT = G * cWn * 32;   // cell units
+  const int it = (rank * iWn + (warp - iW0)) * 32 + lane, IT = G * iWn * 32;   // intra-molecular pairs
+  unsigned k_lo, k_hi;
   mv_share((unsigned)nk, (unsigned)G, (unsigned)rank, k_lo, k_hi);
-  mv_share((unsigned)(P.use_ewald ? A.nq_tot : 0), (unsigned)G, (unsigned)rank, q_lo, q_hi);
-  const int nkt = ((int)(k_hi - k_lo) + CH_THREADS - 1) / CH_THREADS;
-  if (((nk + G - 1) / G + CH_THREADS - 1) / CH_THREADS > CH_KPT && tid == 0) sm.err = CH_ERR_K;   // (the host checks first)
+  const int nq_tot = P.use_ewald ? A.nq_tot : 0;
+  const int nkt = ((int)(k_hi - k_lo) + RT - 1) / RT;
+  if (((nk + G - 1) / G + RT - 1) / RT > CH_KPT && tid == 0) sm.err = CH_ERR_K;   // (the host checks first)
   const int ne0 = A.kmax[0] + 1, ne1 = A.kmax[1] + 1, ne2 = A.kmax[2] + 1, ne = ne0 + ne1 + ne2;
   const int EC = CH_TAB / ne;
   if (EC < 1 && tid == 0) sm.err = CH_ERR_K;
   const int nbx = A.nc[0] >= 3 ? 3 : 1, nby = A.nc[1] >= 3 ? 3 : 1, nbz = A.nc[2] >= 3 ? 3 : 1;
-  const int nnb = nbx * nby * nbz, per = nnb + 1;
+  const int nnb = nbx * nby * nbz;
+  const int ccap = A.cell_cap;
   __syncthreads();
 
   int step_i = 0;
   int par = 0;
+  long long t_prev = 0;
+  if (A.prof) {
+    for (int i = tid; i < 5 * CH_NPHASE; i += CH_THREADS) (&sm.prof[0][0])[i] = 0ull;
+    __syncthreads();
+    t_prev = clock64();
+  }
+  const int skip = A.dbg_skip & 0xff, prof_rank = (A.dbg_skip >> 8) & 0xff, pivot_mode = A.exact_pivot ? 0 : 1;
   for (; step_i < A.max_steps; step_i++) {
     // ------------------------------------------------------------------ (1) the step's head: which move, which molecule
+    if (warp == 0) {
+      const uint32_t rw = cg_raw(sm.mt, lane);
+      sm.pre_raw[lane] = rw;
+      sm.pre_u[lane] = cg_uniform_of(rw);
+      __syncwarp();
+    }
     if (tid == 0) {
       CgStep d;
       const int* mf = A.mol_first;
-      const int used = cg_step_header(sm.mt, A.cfg, A.chains, A.ions, [mf](int mol) { return mf[mol + 1] - mf[mol]; }, d);
+      const int used = cg_step_header(sm.mt, A.cfg, A.chains, A.ions, [mf](int mol) { return mf[mol + 1] - mf[mol]; }, d,
+                                      sm.pre_raw, sm.pre_u, 32);
       if (used > 560 && !sm.err) sm.err = CH_ERR_RNG;
       if (d.kind == CG_CRANK) sm.err = CH_ERR_KIND;
       if (d.kind == CG_STOP_GC) sm.stop = 1;
@@ -230,6 +438,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       continue;
     }
     const int g0 = sm.g0, glen = sm.glen;
+    int ovf_hw = sm.ovf_hw;
+    CH_STAMP(0);
 
     // ------------------------------------------------------------------ (2) the molecule's current coordinates
     for (int i = tid; i < glen; i += CH_THREADS) {
@@ -238,6 +448,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       sm.trl[0][i] = a.x; sm.trl[1][i] = a.y; sm.trl[2][i] = c.x;
       sm.gq[i] = c.y;
       sm.gtype[i] = A.type[g0 + i];
+      if (rank == 0 && P.pair_kind == 1) { sm.bcell[i] = __ldcg(&A.bead_cell[g0 + i]); sm.bslot[i] = __ldcg(&A.bead_slot[g0 + i]); }
     }
     // ------------------------------------------------------------------ (3) pivot rows: len - 1 x (randSphere, bond length)
     if (kind == CG_PIVOT) {
@@ -284,6 +495,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
     }
     __syncthreads();
     if (sm.err) break;
+    if (tid == 32) sm.uacc = cg_uniform_of(cg_raw(sm.mt, 0));   // off the critical path: read only behind the sums
+    CH_STAMP(1);
 
     // ------------------------------------------------------------------ (4) trial coordinates (pg_propose_math.h)
     {
@@ -301,47 +514,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
           const int a = i / glen, g = i - a * glen;
           sm.trl[a][g] = (g == end) ? pp_reptation_end(sm.cur[a][g], d.s, d.v[a], d.vlen) : sm.cur[a][g + dir];
         }
-      } else {   // CG_PIVOT: the two arms in two warps; an arm is sequential by construction (molecule.cc:170-231)
+      } else if (!(skip & 32)) {   // CG_PIVOT: the two arms in two warps
         const int p = d.i0;
-        const double msr = d.s;
-        double* sx = sm.trl[0]; double* sy = sm.trl[1]; double* sz = sm.trl[2];
-        if (warp == 0 && p + 1 < glen) {
-          double a[3] = {sx[p], sy[p], sz[p]};
-          double b[3] = {sx[p + 1], sy[p + 1], sz[p + 1]};
-          for (int i = p + 1; i < glen; i++) {
-            const double4 r = sm.rv[i - (p + 1)];
-            double nb[3] = {0.0, 0.0, 0.0};
-            if (i + 1 < glen) { nb[0] = sx[i + 1]; nb[1] = sy[i + 1]; nb[2] = sz[i + 1]; }
-            __syncwarp();
-            const double v[3] = {r.x, r.y, r.z};
-            double m[3];
-            pp_pivot_step(a, b, msr, v, r.w, m);
-            for (int j = i + lane; j < glen; j += 32) {
-              sx[j] = PP_ADD(sx[j], m[0]); sy[j] = PP_ADD(sy[j], m[1]); sz[j] = PP_ADD(sz[j], m[2]);
-            }
-            __syncwarp();
-            a[0] = PP_ADD(b[0], m[0]); a[1] = PP_ADD(b[1], m[1]); a[2] = PP_ADD(b[2], m[2]);
-            b[0] = PP_ADD(nb[0], m[0]); b[1] = PP_ADD(nb[1], m[1]); b[2] = PP_ADD(nb[2], m[2]);
-          }
-        } else if (warp == 1 && p > 0) {
-          const int row0 = glen - 1 - p;
-          double a[3] = {sx[p], sy[p], sz[p]};
-          double b[3] = {sx[p - 1], sy[p - 1], sz[p - 1]};
-          for (int i = p - 1; i >= 0; i--) {
-            const double4 r = sm.rv[row0 + (p - 1 - i)];
-            double nb[3] = {0.0, 0.0, 0.0};
-            if (i > 0) { nb[0] = sx[i - 1]; nb[1] = sy[i - 1]; nb[2] = sz[i - 1]; }
-            __syncwarp();
-            const double v[3] = {r.x, r.y, r.z};
-            double m[3];
-            pp_pivot_step(a, b, msr, v, r.w, m);
-            for (int j = i - lane; j >= 0; j -= 32) {
-              sx[j] = PP_ADD(sx[j], m[0]); sy[j] = PP_ADD(sy[j], m[1]); sz[j] = PP_ADD(sz[j], m[2]);
-            }
-            __syncwarp();
-            a[0] = PP_ADD(b[0], m[0]); a[1] = PP_ADD(b[1], m[1]); a[2] = PP_ADD(b[2], m[2]);
-            b[0] = PP_ADD(nb[0], m[0]); b[1] = PP_ADD(nb[1], m[1]); b[2] = PP_ADD(nb[2], m[2]);
-          }
+        if (pivot_mode == 0) {
+          if (warp == 0 && p + 1 < glen) ch_pivot_arm<1>(sm, p, glen, d.s, lane);
+          else if (warp == 1 && p > 0) ch_pivot_arm<-1>(sm, p, glen, d.s, lane);
+        } else {
+          if (warp == 0 && p + 1 < glen) ch_pivot_arm_prefix<1>(sm, p, glen, d.s, lane);
+          else if (warp == 1 && p > 0) ch_pivot_arm_prefix<-1>(sm, p, glen, d.s, lane);
         }
       }
     }
@@ -358,6 +538,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       if (lane == 0) sm.nq = cnt;
     }
     __syncthreads();
+    CH_STAMP(2);
     if (A.trial_log && rank == 0)
       for (int i = tid; i < 3 * glen; i += CH_THREADS) {
         const int g = i / 3, a = i - 3 * g;
@@ -370,18 +551,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       sm.fe[e] = make_float4(mv_frac(c[0][g], iLx), mv_frac(c[1][g], iLy), mv_frac(c[2][g], iLz), 0.0f);
       sm.sq[e] = (e & 1) ? -sm.gq[g] : sm.gq[g];
     }
+    __syncthreads();
 
     double acc_pair = 0.0, acc_real = 0.0, acc_rec = 0.0, acc_ov = 0.0, w_sum = 0.0, b_sum = 0.0, w_out = 0.0;
 
     // ------------------------------------------------------------------ (5) reciprocal space: this CTA's k slice
-    if (nq > 0 && nk > 0) {
+    if (in_r && nq > 0 && nk > 0 && !(skip & 1)) {
       double dre[CH_KPT], dim[CH_KPT];
 #pragma unroll
       for (int i = 0; i < CH_KPT; i++) { dre[i] = 0.0; dim[i] = 0.0; }
       for (int c0 = 0; c0 < 2 * nq; c0 += EC) {
         const int ec = min(EC, 2 * nq - c0);
-        __syncthreads();   // the previous chunk's tables are still being read (and sm.fe / sm.sq are now written)
-        for (int t = tid; t < 3 * ec; t += CH_THREADS) {
+        if (c0 > 0) { if (spec) asm volatile("bar.sync 1, %0;" ::"r"(RT)); else __syncthreads(); }   // the previous chunk's tables are still being read
+        for (int t = rt; t < 3 * ec; t += RT) {
           const int el = t / 3, ax = t - 3 * el, e = c0 + el;
           const int g = sm.qidx[e >> 1];
           double x = (e & 1) ? sm.cur[ax][g] : sm.trl[ax][g];
@@ -399,10 +581,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
             row[l] = make_double2(cr, sr);
           }
         }
-        __syncthreads();
+        if (spec) asm volatile("bar.sync 1, %0;" ::"r"(RT)); else __syncthreads();
 #pragma unroll
         for (int i = 0; i < CH_KPT; i++) {
-          const int k = (int)k_lo + tid + i * CH_THREADS;
+          const int k = (int)k_lo + rt + i * RT;
           if (i < nkt && k < (int)k_hi) {
             const int4 l = __ldg(&A.kl[k]);
             const int aly = abs(l.y), alz = abs(l.z);
@@ -424,7 +606,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       }
 #pragma unroll
       for (int i = 0; i < CH_KPT; i++) {
-        const int k = (int)k_lo + tid + i * CH_THREADS;
+        const int k = (int)k_lo + rt + i * RT;
         if (i < nkt && k < (int)k_hi) {
           const double2 S = __ldcg(&A.S[k]);
           const double ek2 = __ldg(&A.ek2[k]);
@@ -433,118 +615,125 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
           __stcg(&A.dS[k], make_double2(dre[i], dim[i]));
         }
       }
-    } else {
-      __syncthreads();   // sm.fe / sm.sq written above
+      __syncwarp();
     }
 
-    // ------------------------------------------------------------------ (6) real space: charged partners of this CTA's slice
-    if (nq > 0) {
-      int qn = 0;
+    CH_STAMP(3);
+    // ------------------------------------------------------------------ (6) real space: all charged partners, dealt to the warps
+    // of the whole cluster with a stride (consecutive partners are beads of one chain: near or far together)
+    if (in_q && nq > 0 && !(skip & 2)) {
+      int qn = 0, nn = 0;
       const double rc2 = P.rc2_relaxed;
-      for (unsigned jb = q_lo; jb < q_hi; jb += CH_THREADS) {
-        const unsigned j = jb + tid;
-        bool valid = j < q_hi;
-        float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          pf = __ldcg(&A.qfrac[j]);
+      float bc[3], bh[3];
+      ch_bound_box(sm, 2 * nq, lane, bc, bh);
+      // stage 1: partners whose distance from the moved beads' bounding box is within the cutoff (one test per partner);
+      // stage 2 (CH_NEAR_PROCESS): FP32 filter of those against every configuration; stage 3 (CH_QUEUE_FLUSH): FP64
+      for (int jb = 0; jb * GW < nq_tot; jb += 32) {
+        const int j = (jb + lane) * GW + gw;
+        bool near = false;
+        if (j < nq_tot) {
+          const float4 pf = __ldcg(&A.qfrac[j]);
           const int bead = __float_as_int(pf.w);
-          valid = !(bead >= g0 && bead < g0 + glen);   // beads of the moved molecule itself: (8)
+          float dx = pf.x - bc[0], dy = pf.y - bc[1], dz = pf.z - bc[2];
+          dx -= mv_rintf(dx); dy -= mv_rintf(dy); dz -= mv_rintf(dz);
+          dx = fmaxf(fabsf(dx) - bh[0], 0.0f) * fLx; dy = fmaxf(fabsf(dy) - bh[1], 0.0f) * fLy; dz = fmaxf(fabsf(dz) - bh[2], 0.0f) * fLz;
+          // beads of the moved molecule itself are handled with the intra-molecular pairs (8)
+          near = !(bead >= g0 && bead < g0 + glen) && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= cutf;
         }
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        bool have = false;
-        double px = 0, py = 0, pz = 0, pq = 0;
-        for (int e = 0; e < 2 * nq; e++) {
-          const float4 f = sm.fe[e];
-          float ax = pf.x - f.x, ay = pf.y - f.y, az = pf.z - f.z;
-          ax -= mv_rintf(ax); ay -= mv_rintf(ay); az -= mv_rintf(az);
-          ax *= fLx; ay *= fLy; az *= fLz;
-          const float f2 = fmaf(ax, ax, fmaf(ay, ay, az * az));
-          const bool fhit = valid && f2 <= cutf;
-          if (!__any_sync(0xffffffffu, fhit)) continue;
-          bool hit = false;
-          double r2 = 0.0;
-          if (fhit) {
-            if (!have) {
-              const double2 a = __ldcg(&A.qpos[2 * j]), c = __ldcg(&A.qpos[2 * j + 1]);
-              px = a.x; py = a.y; pz = c.x; pq = c.y;
-              have = true;
-            }
-            const int g = sm.qidx[e >> 1];
-            double dx, dy, dz;
-            if (e & 1) { dx = px - sm.cur[0][g]; dy = py - sm.cur[1][g]; dz = pz - sm.cur[2][g]; }
-            else { dx = px - sm.trl[0][g]; dy = py - sm.trl[1][g]; dz = pz - sm.trl[2][g]; }
-            dx -= Lx * mv_rint(dx * iLx); dy -= Ly * mv_rint(dy * iLy); dz -= Lz * mv_rint(dz * iLz);
-            r2 = dx * dx + dy * dy + dz * dz;
-            hit = r2 <= rc2;
-          }
-          const unsigned mh = __ballot_sync(0xffffffffu, hit);
-          if (mh) {
-            if (hit) {
-              const int pos = qn + __popc(mh & lt);
-              sm.q_r2[warp][pos] = r2; sm.q_qq[warp][pos] = sm.sq[e] * pq;
-            }
-            qn += __popc(mh);
-            if (qn > CH_QCAP - 32) CH_QUEUE_FLUSH();
-          }
-        }
+        const unsigned mn = __ballot_sync(0xffffffffu, near);
+        if (near) sm.q_near[warp][nn + __popc(mn & lt)] = j;
+        nn += __popc(mn);
+        if (nn > CH_NEAR - 32) CH_NEAR_PROCESS();
       }
+      if (nn > 0) CH_NEAR_PROCESS();
       if (qn > 0) CH_QUEUE_FLUSH();
     }
 
+    CH_STAMP(4);
     // ------------------------------------------------------------------ (7) LJ / WCA through the cell grid
-    if (P.pair_kind == 1) {
+    if (in_c && P.pair_kind == 1 && !(skip & 4)) {
       const int n_mv = (kind == CG_BEAD) ? 1 : glen;
+      // work units of one bead configuration: its 27 (or fewer) neighbour cells, then the overflow list in chunks
+      const int per = nnb + (ovf_hw + CH_OVF_CHUNK - 1) / CH_OVF_CHUNK;
       const int U = n_mv * 2 * per;
       const double ljc2max = P.ljc2max;
       const PgDev* __restrict__ Pg = A.Pg;
-      for (int u = gt; u < U; u += GT) {
-        const int mc = u / per, cc = u - mc * per;
-        const int m = mc >> 1, old = mc & 1;
-        const double x = old ? sm.cur[0][m] : sm.trl[0][m], y = old ? sm.cur[1][m] : sm.trl[1][m],
-                     z = old ? sm.cur[2][m] : sm.trl[2][m];
-        const int tm = sm.gtype[m];
-        // one candidate partner: exact FP64 minimum-image separation, the reference's r < rcut predicate
-        auto lj_eval = [&](int j) {
-          if (j < 0 || (j >= g0 && j < g0 + glen)) return;
-          const double2 a = __ldcg(&A.xy[j]), c = __ldcg(&A.zq[j]);
-          double dx = a.x - x, dy = a.y - y, dz = c.x - z;
-          dx -= Lx * mv_rint(dx * iLx); dy -= Ly * mv_rint(dy * iLy); dz -= Lz * mv_rint(dz * iLz);
-          const double r2 = dx * dx + dy * dy + dz * dz;
-          if (r2 > ljc2max) return;
-          const int tp = tm * PG_MAX_TYPES + A.type[j];
-          if (r2 > Pg->lj_rcut2_relaxed[tp]) return;
-          const double e = pg_pair_energy_r(*Pg, sqrt(r2), tp);
-          if (old) acc_pair -= e;
-          else { acc_pair += e; if (e >= PG_VLE) acc_ov += 1.0; }
-        };
-        if (cc < nnb) {
-          int ix = ch_cell1(x, iLx, A.nc[0]), iy = ch_cell1(y, iLy, A.nc[1]), iz = ch_cell1(z, iLz, A.nc[2]);
-          const int ox = (nbx == 3) ? (cc % 3) - 1 : 0;
-          const int r1 = (nbx == 3) ? cc / 3 : cc;
-          const int oy = (nby == 3) ? (r1 % 3) - 1 : 0;
-          const int r2_ = (nby == 3) ? r1 / 3 : r1;
-          const int oz = (nbz == 3) ? (r2_ % 3) - 1 : 0;
-          ix += ox; iy += oy; iz += oz;
-          if (ix < 0) ix += A.nc[0]; else if (ix >= A.nc[0]) ix -= A.nc[0];
-          if (iy < 0) iy += A.nc[1]; else if (iy >= A.nc[1]) iy -= A.nc[1];
-          if (iz < 0) iz += A.nc[2]; else if (iz >= A.nc[2]) iz -= A.nc[2];
-          const int cidx = (ix * A.nc[1] + iy) * A.nc[2] + iz;
-          const int4* cp = reinterpret_cast<const int4*>(A.cell_slots + (size_t)cidx * CH_CELL_CAP);
-          const int4 s0 = __ldcg(cp), s1 = __ldcg(cp + 1);
-          lj_eval(s0.x); lj_eval(s0.y); lj_eval(s0.z); lj_eval(s0.w);
-          lj_eval(s1.x); lj_eval(s1.y); lj_eval(s1.z); lj_eval(s1.w);
-        } else {
-          // last unit of a bead configuration: the overflow list (beads whose cell was full), normally empty
-          for (int o = 0; o < ovf_hw; o++) lj_eval(__ldcg(&A.ovf[o]));
+      // four units at a time: first their cell records (independent loads in flight together), then the candidates
+      for (int u0 = ct; u0 < U; u0 += 4 * CT) {
+        int4 rec[4];
+        int cix[4];
+#pragma unroll
+        for (int b_ = 0; b_ < 4; b_++) {
+          const int u = u0 + b_ * CT;
+          cix[b_] = -1;
+          rec[b_] = make_int4(-1, -1, -1, -1);
+          if (u < U) {
+            const int mc = u / per, cc = u - mc * per;
+            if (cc < nnb) {
+              const int m = mc >> 1, old = mc & 1;
+              const double x = old ? sm.cur[0][m] : sm.trl[0][m], y = old ? sm.cur[1][m] : sm.trl[1][m],
+                           z = old ? sm.cur[2][m] : sm.trl[2][m];
+              int ix = ch_cell1(x, iLx, A.nc[0]), iy = ch_cell1(y, iLy, A.nc[1]), iz = ch_cell1(z, iLz, A.nc[2]);
+              const int ox = (nbx == 3) ? (cc % 3) - 1 : 0;
+              const int r1 = (nbx == 3) ? cc / 3 : cc;
+              const int oy = (nby == 3) ? (r1 % 3) - 1 : 0;
+              const int r2_ = (nby == 3) ? r1 / 3 : r1;
+              const int oz = (nbz == 3) ? (r2_ % 3) - 1 : 0;
+              ix += ox; iy += oy; iz += oz;
+              if (ix < 0) ix += A.nc[0]; else if (ix >= A.nc[0]) ix -= A.nc[0];
+              if (iy < 0) iy += A.nc[1]; else if (iy >= A.nc[1]) iy -= A.nc[1];
+              if (iz < 0) iz += A.nc[2]; else if (iz >= A.nc[2]) iz -= A.nc[2];
+              cix[b_] = (ix * A.nc[1] + iy) * A.nc[2] + iz;
+              rec[b_] = __ldcg(reinterpret_cast<const int4*>(A.cell_slots + (size_t)cix[b_] * ccap));
+            }
+          }
+        }
+#pragma unroll
+        for (int b_ = 0; b_ < 4; b_++) {
+          const int u = u0 + b_ * CT;
+          if (u >= U) continue;
+          const int mc = u / per, cc = u - mc * per;
+          const int m = mc >> 1, old = mc & 1;
+          const double x = old ? sm.cur[0][m] : sm.trl[0][m], y = old ? sm.cur[1][m] : sm.trl[1][m],
+                       z = old ? sm.cur[2][m] : sm.trl[2][m];
+          const int tm = sm.gtype[m];
+          // one candidate partner: exact FP64 minimum-image separation, the reference's r < rcut predicate
+          auto lj_eval = [&](int j) {
+            if (j < 0 || (j >= g0 && j < g0 + glen)) return;
+            const double2 a = __ldcg(&A.xy[j]), c = __ldcg(&A.zq[j]);
+            double dx = a.x - x, dy = a.y - y, dz = c.x - z;
+            dx -= Lx * mv_rint(dx * iLx); dy -= Ly * mv_rint(dy * iLy); dz -= Lz * mv_rint(dz * iLz);
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 > ljc2max) return;
+            const int tp = tm * PG_MAX_TYPES + A.type[j];
+            if (r2 > Pg->lj_rcut2_relaxed[tp]) return;
+            const double e = pg_pair_energy_r(*Pg, sqrt(r2), tp);
+            if (old) acc_pair -= e;
+            else { acc_pair += e; if (e >= PG_VLE) acc_ov += 1.0; }
+          };
+          if (cc < nnb) {
+            lj_eval(rec[b_].x); lj_eval(rec[b_].y); lj_eval(rec[b_].z); lj_eval(rec[b_].w);
+            const int4* cp = reinterpret_cast<const int4*>(A.cell_slots + (size_t)cix[b_] * ccap);
+            for (int q4 = 4; q4 < ccap; q4 += 4) {
+              const int4 s0 = __ldcg(cp + (q4 >> 2));
+              lj_eval(s0.x); lj_eval(s0.y); lj_eval(s0.z); lj_eval(s0.w);
+            }
+          } else {
+            // the overflow list (beads whose cell was full when they arrived): normally a handful of entries
+            const int o0 = (cc - nnb) * CH_OVF_CHUNK, o1 = min(o0 + CH_OVF_CHUNK, ovf_hw);
+            for (int o = o0; o < o1; o++) lj_eval(__ldcg(&A.ovf[o]));
+          }
         }
       }
+      __syncwarp();   // the lanes of a warp leave this loop at different times: reconverge before the next phase
     }
 
     // ------------------------------------------------------------------ (8) intra-molecular pairs (potential_pair.cc:157-178,
     // potential_ewald.cc:436-477): every pair of a chain move has a moved bead
-    if (kind != CG_BEAD && glen > 1) {
+    CH_STAMP(5);
+    if (in_i && kind != CG_BEAD && glen > 1 && !(skip & 8)) {
       const int npairs = glen * (glen - 1) / 2;
-      for (int p = gt; p < npairs; p += GT) {
+      for (int p = it; p < npairs; p += IT) {
         int jj = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
         while (jj * (jj - 1) / 2 > p) jj--;
         while ((jj + 1) * jj / 2 <= p) jj++;
@@ -567,8 +756,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
           acc_pair -= eo.x; acc_real -= eo.y;
         }
       }
+      __syncwarp();
     }
 
+    CH_STAMP(6);
     // ------------------------------------------------------------------ (9) walls and bonds of the moved molecule (rank 0)
     if (rank == 0 && (P.ext_kind != 0 || P.bond_kind != 0)) {
       for (int g = tid; g < glen; g += CH_THREADS) {
@@ -584,6 +775,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       }
     }
 
+    CH_STAMP(7);
     // ------------------------------------------------------------------ (10) sums: warp -> CTA -> cluster, fixed order
     {
       double v[CH_NACC] = {acc_pair, acc_real, acc_rec, acc_ov, w_sum, b_sum, w_out, 0.0};
@@ -613,6 +805,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       __syncthreads();
     }
 
+    CH_STAMP(8);
     // ------------------------------------------------------------------ (11) ForceField::EnergyDifference's orchestration and
     // the Metropolis test, in every CTA alike (same sums, same stream)
     double d_pair = 0, d_real = 0, d_recip = 0, d_ext = 0, d_bond = 0, d_ewald = 0, dE = 0;
@@ -631,7 +824,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       }
       int accept = 0;
       if (dE < PG_VLE) {                     // simulation.cc:327-332: the variate is drawn only here
-        const double uacc = cg_uniform_of(cg_raw(sm.mt, 0));
+        const double uacc = sm.uacc;
         cg_advance(sm.mt, 1);
         accept = uacc < exp(-P.beta * dE);
       }
@@ -647,13 +840,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
     }
     __syncthreads();
     ch_mt_fix(sm.mt, tid);
+    CH_STAMP(9);
 
     // ------------------------------------------------------------------ (12) FinalizeEnergies: an accepted move becomes the state
-    if (sm.accept) {
-      if (nq > 0 && nk > 0) {
+    if (sm.accept && !(skip & 16)) {
+      if (in_r && nq > 0 && nk > 0) {
 #pragma unroll
         for (int i = 0; i < CH_KPT; i++) {
-          const int k = (int)k_lo + tid + i * CH_THREADS;
+          const int k = (int)k_lo + rt + i * RT;
           if (i < nkt && k < (int)k_hi) {
             double2 S = __ldcg(&A.S[k]);
             const double2 d = __ldcg(&A.dS[k]);
@@ -676,10 +870,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
             __stcg(&A.qfrac[s], make_float4(mv_frac(x, iLx), mv_frac(y, iLy), mv_frac(z, iLz), __int_as_float(jg)));
           }
         }
-        // cell grid: one warp, 32 beads at a time; beads that enter the same cell take its free slots in bead order
+        // cell grid: one warp, 32 beads at a time, every lane files its own bead: lanes that enter the same cell
+        // (__match_any_sync) take its free slots in bead order, whoever finds none goes to the overflow list
         if (warp == 0 && P.pair_kind == 1) {
           const int n_mv = (kind == CG_BEAD) ? 1 : glen;
           int hw = ovf_hw;
+          bool full = false;
           for (int base = 0; base < n_mv; base += 32) {
             const int i = base + lane;
             const bool active = i < n_mv;
@@ -688,62 +884,85 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
             if (active) {
               newc = (ch_cell1(sm.trl[0][i], iLx, A.nc[0]) * A.nc[1] + ch_cell1(sm.trl[1][i], iLy, A.nc[1])) * A.nc[2] +
                      ch_cell1(sm.trl[2][i], iLz, A.nc[2]);
-              oldc = __ldcg(&A.bead_cell[bead]);
+              oldc = sm.bcell[i];
             }
             const bool changed = active && newc != oldc;
             if (changed) {
-              const int os = __ldcg(&A.bead_slot[bead]);
-              if (os < CH_CELL_CAP) __stcg(&A.cell_slots[(size_t)oldc * CH_CELL_CAP + os], -1);
-              else __stcg(&A.ovf[os - CH_CELL_CAP], -1);
+              const int os = sm.bslot[i];
+              if (os < ccap) __stcg(&A.cell_slots[(size_t)oldc * ccap + os], -1);
+              else __stcg(&A.ovf[os - ccap], -1);
             }
-            __syncwarp();
-            unsigned todo = __ballot_sync(0xffffffffu, changed);
-            while (todo) {
-              const int leader = __ffs(todo) - 1;
-              const int c = __shfl_sync(0xffffffffu, newc, leader);
-              const unsigned grp = __ballot_sync(0xffffffffu, changed && newc == c) & todo;
-              int sv = 0;
-              if (lane < CH_CELL_CAP) sv = __ldcg(&A.cell_slots[(size_t)c * CH_CELL_CAP + lane]);
-              const unsigned empty = __ballot_sync(0xffffffffu, lane < CH_CELL_CAP && sv < 0);
-              const int n_empty = __popc(empty), n_grp = __popc(grp);
-              if ((grp >> lane) & 1u) {
-                const int r = __popc(grp & lt);
-                if (r < n_empty) {
-                  const int slot = __fns(empty, 0, r + 1);
-                  __stcg(&A.cell_slots[(size_t)c * CH_CELL_CAP + slot], bead);
-                  __stcg(&A.bead_slot[bead], slot);
-                } else {
-                  const int idx = hw + (r - n_empty);
-                  if (idx < CH_OVF_CAP) { __stcg(&A.ovf[idx], bead); __stcg(&A.bead_slot[bead], CH_CELL_CAP + idx); }
-                  else __stcg(&A.out[2], (int)CH_ERR_OVERFLOW);
-                }
-                __stcg(&A.bead_cell[bead], c);
+            __syncwarp();   // the freed slots are visible to the lanes that look for one
+            const unsigned grp = __match_any_sync(0xffffffffu, changed ? newc : -1 - lane);
+            unsigned empty = 0u;
+            if (changed) {
+              const int4* cp = reinterpret_cast<const int4*>(A.cell_slots + (size_t)newc * ccap);
+              for (int q4 = 0; q4 < ccap; q4 += 4) {
+                const int4 sv = __ldcg(cp + (q4 >> 2));
+                empty |= ((sv.x < 0 ? 1u : 0u) | (sv.y < 0 ? 2u : 0u) | (sv.z < 0 ? 4u : 0u) | (sv.w < 0 ? 8u : 0u)) << q4;
               }
-              if (n_grp > n_empty) hw = min(hw + (n_grp - n_empty), CH_OVF_CAP);
-              todo &= ~grp;
-              __syncwarp();
+            }
+            const int r = __popc(grp & lt), n_empty = __popc(empty);
+            const bool spill = changed && r >= n_empty;
+            const unsigned ms = __ballot_sync(0xffffffffu, spill);
+            if (changed) {
+              if (!spill) {
+                const int slot = __fns(empty, 0, r + 1);
+                __stcg(&A.cell_slots[(size_t)newc * ccap + slot], bead);
+                __stcg(&A.bead_slot[bead], slot);
+              } else {
+                const int idx = hw + __popc(ms & lt);
+                if (idx < CH_OVF_CAP) { __stcg(&A.ovf[idx], bead); __stcg(&A.bead_slot[bead], ccap + idx); }
+                else full = true;
+              }
+              __stcg(&A.bead_cell[bead], newc);
+            }
+            hw = min(hw + __popc(ms), CH_OVF_CAP);
+            __syncwarp();
+          }
+          full = __any_sync(0xffffffffu, full);
+          if (lane == 0) {
+            if (hw != ovf_hw) __stcg(A.ovf_n, hw);
+            for (int r = 0; r < G; r++) {
+              *cluster.map_shared_rank(&sm.ovf_hw, r) = hw;
+              if (full) *cluster.map_shared_rank(&sm.err, r) = (int)CH_ERR_OVERFLOW;
             }
           }
-          if (lane == 0 && hw != ovf_hw) __stcg(A.ovf_n, hw);
         }
       }
-      __threadfence();
+      // (the cluster barrier's release / acquire pair orders these global writes for the other CTAs)
       if (G > 1) cluster.sync(); else __syncthreads();
-      ovf_hw = __ldcg(A.ovf_n);
-      if (tid == 0 && __ldcg(&A.out[2]) != 0) sm.err = CH_ERR_OVERFLOW;   // raised by rank 0, seen by every CTA alike
     }
     __syncthreads();
+    CH_STAMP(10);
+    if (A.prof) {
+      __syncthreads();
+      if (tid == 0 && rank == prof_rank) {
+        long long prev = t_prev;
+        for (int ph = 0; ph <= 10; ph++) {
+          long long mx = prev;
+          for (int w = 0; w < CH_WARPS; w++) mx = sm.wst[ph][w] > mx ? sm.wst[ph][w] : mx;
+          sm.prof[kind][ph] += (unsigned long long)(mx - prev);
+          prev = mx;
+        }
+        sm.prof[kind][CH_NPHASE - 1] += 1ull;   // moves of this kind
+        t_prev = clock64();
+      }
+      __syncthreads();
+    }
   }
 
   // ------------------------------------------------------------------ epilogue
   __syncthreads();
+  if (A.prof && rank == prof_rank)
+    for (int i = tid; i < 5 * CH_NPHASE; i += CH_THREADS) A.prof[i] = (&sm.prof[0][0])[i];
   if (rank == 0) {
     for (int i = tid; i < CG_N; i += CH_THREADS) A.mt_io[i] = sm.mt.x[sm.mt.cur][i];
     if (tid == 0) {
       A.mt_io[CG_N] = (uint32_t)sm.mt.p;
       PgState* st = A.state;
       st->E_pair = E_pair; st->E_ewald = E_ewald; st->E_bond = E_bond; st->E_ext = E_ext; st->E_real = E_real; st->E_recip = E_recip;
-      A.out[0] = step_i; A.out[1] = sm.stop; A.out[3] = ovf_hw;
+      A.out[0] = step_i; A.out[1] = sm.stop; A.out[3] = sm.ovf_hw;
       if (sm.err) A.out[2] = sm.err;
     }
   }
@@ -762,12 +981,14 @@ struct PgChainHost {
   CgConfig cfg;
   int max_len = 1;
   bool want_trials = false;   // keep every step's trial coordinates (tests)
+  int pivot_mode = 0;
   // device
   int *d_mol_first = nullptr, *d_chains = nullptr, *d_ions = nullptr;
   size_t mol_cap = 0;
   int nc[3] = {1, 1, 1};
+  int cell_cap = 4;
   int *d_cell_slots = nullptr, *d_ovf = nullptr, *d_ovf_n = nullptr, *d_bead_cell = nullptr, *d_bead_slot = nullptr, *d_qslot = nullptr;
-  size_t cell_cap = 0, bead_cap = 0;
+  size_t cell_cap_words = 0, bead_cap = 0;
   int nq_tot = 0;
   double2* d_qpos = nullptr;
   float4* d_qfrac = nullptr;
@@ -783,4 +1004,6 @@ struct PgChainHost {
   int max_steps = 0;
   int kmax[3] = {0, 0, 0};
   double kunit[3] = {0, 0, 0};
+  unsigned long long* d_prof = nullptr;   // instrumentation
+  int dbg_skip = 0;
 };

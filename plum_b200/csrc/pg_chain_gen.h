@@ -86,12 +86,16 @@ PP_HD void cg_advance(PgMt& m, int n) {
   }
 }
 
-// A cursor over the look-ahead window: what one thread uses to walk the stream sequentially.
+// A cursor over the look-ahead window: what one thread uses to walk the stream sequentially.  The first `npre` draws may
+// have been tempered and converted ahead of time (by other lanes, in parallel: a uniform costs an FP64 division).
 struct CgCursor {
   const PgMt* m;
   int used;
-  PP_HD uint32_t raw() { return cg_raw(*m, used++); }
-  PP_HD double uniform() { return cg_uniform_of(raw()); }
+  const uint32_t* pre_raw;
+  const double* pre_u;
+  int npre;
+  PP_HD uint32_t raw() { const int i = used++; return (i < npre) ? pre_raw[i] : cg_raw(*m, i); }
+  PP_HD double uniform() { const int i = used++; return (i < npre) ? pre_u[i] : cg_uniform_of(cg_raw(*m, i)); }
 };
 
 // randSphere, misc.cc:95-109
@@ -155,8 +159,9 @@ struct CgConfig {
 // (everything except the pivot rows, which are bulk work).  `chains` / `ions` map the pre-selected counters to
 // molecule ids, `mol_len(mol)` is needed by the pivot.  Returns the draws consumed (not yet advanced).
 template <class LenFn>
-PP_HD int cg_step_header(const PgMt& mt, const CgConfig& c, const int* chains, const int* ions, LenFn mol_len, CgStep& d) {
-  CgCursor r{&mt, 0};
+PP_HD int cg_step_header(const PgMt& mt, const CgConfig& c, const int* chains, const int* ions, LenFn mol_len, CgStep& d,
+                         const uint32_t* pre_raw = nullptr, const double* pre_u = nullptr, int npre = 0) {
+  CgCursor r{&mt, 0, pre_raw, pre_u, npre};
   d.kind = CG_NONE; d.mol = -1; d.i0 = 0; d.n_rows = 0; d.s = 0.0; d.v[0] = d.v[1] = d.v[2] = 0.0; d.vlen = 0.0;
   const int rand_num = (int)r.raw();                                   // simulation.cc:221
   if (c.gc_freq > 0 && (rand_num % c.gc_freq == 0)) { d.kind = CG_STOP_GC; return 0; }
@@ -212,7 +217,7 @@ PP_HD int cg_step_header(const PgMt& mt, const CgConfig& c, const int* chains, c
 // behind every accepted pair shifts the pairing of everything that follows): rows [first, n_rows) are drawn until
 // `budget` draws are used up.  Returns the draws consumed; *next_row is where a later call continues.
 PP_HD int cg_pivot_rows_serial(const PgMt& mt, const CgConfig& c, int first, int n_rows, int budget, double* rows4, int* next_row) {
-  CgCursor r{&mt, 0};
+  CgCursor r{&mt, 0, nullptr, nullptr, 0};
   int row = first;
   while (row < n_rows && r.used < budget) {
     double v[3];

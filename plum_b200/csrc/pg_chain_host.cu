@@ -14,7 +14,7 @@ void chain_free(pg_engine* h) {
   cudaFree(c.d_mol_first); cudaFree(c.d_chains); cudaFree(c.d_ions);
   cudaFree(c.d_cell_slots); cudaFree(c.d_ovf); cudaFree(c.d_ovf_n); cudaFree(c.d_bead_cell); cudaFree(c.d_bead_slot);
   cudaFree(c.d_qslot); cudaFree(c.d_qpos); cudaFree(c.d_qfrac);
-  cudaFree(c.d_mt); cudaFree(c.d_log); cudaFree(c.d_trial_log); cudaFree(c.d_out); cudaFree(c.d_args);
+  cudaFree(c.d_mt); cudaFree(c.d_log); cudaFree(c.d_trial_log); cudaFree(c.d_out); cudaFree(c.d_args); cudaFree(c.d_prof);
   c = PgChainHost();
 }
 
@@ -78,25 +78,45 @@ int chain_build(pg_engine* h) {
   PG_CUDA(h, cudaMemcpyAsync(c.d_mol_first, h->mol_first.data(), sizeof(int) * (size_t)(n_mol + 1), cudaMemcpyHostToDevice, h->stream));
   if (!chains.empty()) PG_CUDA(h, cudaMemcpyAsync(c.d_chains, chains.data(), sizeof(int) * chains.size(), cudaMemcpyHostToDevice, h->stream));
   if (!ions.empty()) PG_CUDA(h, cudaMemcpyAsync(c.d_ions, ions.data(), sizeof(int) * ions.size(), cudaMemcpyHostToDevice, h->stream));
-  // cell grid
+  // cell grid: the finest split with cells no smaller than the largest LJ cutoff (<= 64 cells per axis, <= 2^18 cells);
+  // slots per cell: the smallest of 4 / 8 / 16 / 32 that leaves at most 0.1 % of the beads to the overflow list
   for (int a = 0; a < 3; a++) c.nc[a] = 1;
   if (P.pair_kind == PG_PAIR_TRUNCATED_LJ && P.lj_rcut2_relaxed_max > 0) {
     const double edge = sqrt(P.lj_rcut2_relaxed_max) * kChainCellMargin;
-    for (int a = 0; a < 3; a++) {
-      int k = (int)floor(P.box[a] / edge);
-      k = std::min(k, CH_NC_MAX);
-      c.nc[a] = (k >= 3) ? k : 1;   // fewer than 3 cells: the axis is not split (27 neighbours would alias)
+    int lim = CH_NC_MAX;
+    for (;;) {
+      for (int a = 0; a < 3; a++) {
+        int k = std::min((int)floor(P.box[a] / edge), lim);
+        c.nc[a] = (k >= 3) ? k : 1;   // fewer than 3 cells: the axis is not split (27 neighbours would alias)
+      }
+      if ((long long)c.nc[0] * c.nc[1] * c.nc[2] <= CH_CELLS_MAX || lim <= 3) break;
+      lim--;
     }
   }
   const size_t n_cells = (size_t)c.nc[0] * c.nc[1] * c.nc[2];
-  if (n_cells > c.cell_cap || !c.d_cell_slots) {
-    cudaFree(c.d_cell_slots); c.d_cell_slots = nullptr; c.cell_cap = 0;
-    PG_CUDA(h, cudaMalloc((void**)&c.d_cell_slots, sizeof(int) * CH_CELL_CAP * n_cells));
-    c.cell_cap = n_cells;
+  std::vector<int> cell_of(std::max(n, 1), 0), count(n_cells, 0);
+  if (P.pair_kind == PG_PAIR_TRUNCATED_LJ)
+    for (int i = 0; i < n; i++) {
+      cell_of[i] = chain_cell_of(c, P, hxy[i].x, hxy[i].y, hzq[i].x);
+      count[cell_of[i]]++;
+    }
+  int cap = 4;
+  for (; cap < CH_CELL_CAP_MAX; cap *= 2) {
+    long long over = 0;
+    for (size_t k = 0; k < n_cells; k++) over += std::max(0, count[k] - cap);
+    if (over * 1000 <= (long long)n) break;
+  }
+  c.cell_cap = cap;
+  if (n_cells * (size_t)cap > c.cell_cap_words || !c.d_cell_slots) {
+    cudaFree(c.d_cell_slots); c.d_cell_slots = nullptr; c.cell_cap_words = 0;
+    PG_CUDA(h, cudaMalloc((void**)&c.d_cell_slots, sizeof(int) * n_cells * (size_t)cap));
+    c.cell_cap_words = n_cells * (size_t)cap;
   }
   if (!c.d_ovf) {
     PG_CUDA(h, cudaMalloc((void**)&c.d_ovf, sizeof(int) * CH_OVF_CAP));
     PG_CUDA(h, cudaMalloc((void**)&c.d_ovf_n, sizeof(int)));
+  }
+  if (!c.d_mt) {
     PG_CUDA(h, cudaMalloc((void**)&c.d_mt, sizeof(uint32_t) * (CG_N + 8)));
     PG_CUDA(h, cudaMemset(c.d_mt, 0, sizeof(uint32_t) * (CG_N + 8)));
     PG_CUDA(h, cudaMalloc((void**)&c.d_out, sizeof(int) * 4));
@@ -111,19 +131,20 @@ int chain_build(pg_engine* h) {
     PG_CUDA(h, cudaMalloc((void**)&c.d_qslot, sizeof(int) * bead_need));
     c.bead_cap = bead_need;
   }
-  std::vector<int> slots(CH_CELL_CAP * n_cells, -1), count(n_cells, 0), ovf(CH_OVF_CAP, -1), bead_cell(std::max(n, 1), 0),
+  std::vector<int> slots((size_t)cap * n_cells, -1), ovf(CH_OVF_CAP, -1), bead_cell(std::max(n, 1), 0),
       bead_slot(std::max(n, 1), 0), qslot(std::max(n, 1), -1);
+  std::fill(count.begin(), count.end(), 0);
   int ovf_n = 0;
   if (P.pair_kind == PG_PAIR_TRUNCATED_LJ) {
     for (int i = 0; i < n; i++) {
-      const int cell = chain_cell_of(c, P, hxy[i].x, hxy[i].y, hzq[i].x);
+      const int cell = cell_of[i];
       bead_cell[i] = cell;
-      if (count[cell] < CH_CELL_CAP) {
+      if (count[cell] < cap) {
         bead_slot[i] = count[cell];
-        slots[(size_t)cell * CH_CELL_CAP + count[cell]++] = i;
+        slots[(size_t)cell * cap + count[cell]++] = i;
       } else {
         if (ovf_n >= CH_OVF_CAP) { h->err = "chain: cell overflow list is full (system too dense for the cell grid)"; return PG_ERR_CAPACITY; }
-        bead_slot[i] = CH_CELL_CAP + ovf_n;
+        bead_slot[i] = cap + ovf_n;
         ovf[ovf_n++] = i;
       }
     }
@@ -204,12 +225,21 @@ void chain_fill_args(pg_engine* h, int max_steps, PgChainArgs& A) {
   A.cfg = c.cfg;
   A.kl = reinterpret_cast<const int4*>(h->d_kl); A.ek2 = h->d_ek2; A.S = h->d_S; A.dS = h->d_dS; A.nk = h->P.use_ewald ? h->nk : 0;
   for (int a = 0; a < 3; a++) { A.kmax[a] = c.kmax[a]; A.kunit[a] = c.kunit[a]; A.nc[a] = c.nc[a]; }
+  A.cell_cap = c.cell_cap;
   A.nq_tot = c.nq_tot; A.qpos = c.d_qpos; A.qfrac = c.d_qfrac; A.qslot = c.d_qslot;
   A.cell_slots = c.d_cell_slots; A.ovf = c.d_ovf; A.ovf_n = c.d_ovf_n; A.bead_cell = c.d_bead_cell; A.bead_slot = c.d_bead_slot;
   A.mt_io = c.d_mt; A.log = c.d_log;
   A.trial_log = c.want_trials ? c.d_trial_log : nullptr;
   A.trial_stride = c.max_len;
-  A.state = h->d_state; A.out = c.d_out; A.max_steps = max_steps; A.exact_pivot = 1;
+  A.state = h->d_state; A.out = c.d_out; A.max_steps = max_steps; A.exact_pivot = (c.pivot_mode == 0) ? 1 : 0;
+  // side-by-side phases need the CTA's k slice to fit the four reciprocal-space warps
+  {
+    const int nkc = (A.nk + c.cluster - 1) / c.cluster;
+    static const bool no_spec = [] { const char* e = getenv("PLUM_B200_CHAIN_NO_SPEC"); return e && e[0] == '1'; }();
+    A.specialize = (c.cluster > 1 && !no_spec && (nkc + 127) / 128 <= CH_KPT) ? 1 : 0;
+  }
+  A.prof = c.d_prof;
+  A.dbg_skip = c.dbg_skip;
 }
 
 // What a chain launch needs from every engine it carries.
@@ -283,6 +313,8 @@ int pg_chain_configure(pg_engine* h, const pg_chain_config* cfg) {
   c.cfg.bond_len = cfg->bond_len;
   for (int i = 0; i < 5; i++) c.cfg.prob[i] = cfg->move_prob[i];
   c.want_trials = cfg->keep_trials != 0;
+  if (cfg->pivot_mode != 0 && cfg->pivot_mode != 1) { h->err = "pg_chain_*: pivot_mode must be 0 or 1"; return PG_ERR_INVALID; }
+  c.pivot_mode = cfg->pivot_mode;
   c.configured = true;
   return PG_OK;
 }
@@ -296,8 +328,6 @@ int pg_chain_set_rng(pg_engine* h, const uint32_t* state624, int position) {
     PG_CUDA(h, cudaMalloc((void**)&c.d_mt, sizeof(uint32_t) * (CG_N + 8)));
     PG_CUDA(h, cudaMalloc((void**)&c.d_out, sizeof(int) * 4));
     PG_CUDA(h, cudaMemset(c.d_out, 0, sizeof(int) * 4));
-    PG_CUDA(h, cudaMalloc((void**)&c.d_ovf, sizeof(int) * CH_OVF_CAP));
-    PG_CUDA(h, cudaMalloc((void**)&c.d_ovf_n, sizeof(int)));
   }
   uint32_t buf[CG_N + 1];
   memcpy(buf, state624, sizeof(uint32_t) * CG_N);
@@ -444,6 +474,28 @@ int pg_chain_trial_xyz(pg_engine* h, int step, double* xyz, int n_beads) {
   return PG_OK;
 }
 
+// Instrumentation (not part of the ABI header; tools/chain_probe.py): per-phase clock sums of the next chains of this
+// engine ([5 kinds][CH_NPHASE] unsigned 64-bit, read back with pgx_chain_prof_read) and a mask of phases to leave out.
+int pgx_chain_prof(pg_engine* h, int enable, int skip_mask) {
+  if (!h) return PG_ERR_INVALID;
+  PgChainHost& c = h->ch;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  if (enable && !c.d_prof) {
+    PG_CUDA(h, cudaMalloc((void**)&c.d_prof, sizeof(unsigned long long) * 5 * CH_NPHASE));
+    PG_CUDA(h, cudaMemset(c.d_prof, 0, sizeof(unsigned long long) * 5 * CH_NPHASE));
+  }
+  if (!enable && c.d_prof) { cudaFree(c.d_prof); c.d_prof = nullptr; }
+  c.dbg_skip = skip_mask;
+  return PG_OK;
+}
+int pgx_chain_prof_read(pg_engine* h, unsigned long long* out) {
+  if (!h || !out || !h->ch.d_prof) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  PG_CUDA(h, cudaMemcpy(out, h->ch.d_prof, sizeof(unsigned long long) * 5 * CH_NPHASE, cudaMemcpyDeviceToHost));
+  return PG_OK;
+}
+
 // Consistency of the resident structures with the resident coordinates (tests): every bead filed exactly once, in the
 // cell its coordinates map to; no stale entries; the compact charged records equal the bead arrays.
 int pg_chain_check(pg_engine* h, int* n_bad) {
@@ -458,7 +510,8 @@ int pg_chain_check(pg_engine* h, int* n_bad) {
   const size_t n_cells = (size_t)c.nc[0] * c.nc[1] * c.nc[2];
   std::vector<double2> hxy(std::max(n, 1)), hzq(std::max(n, 1)), qpos(2 * (size_t)std::max(c.nq_tot, 1));
   std::vector<float4> qfrac(std::max(c.nq_tot, 1));
-  std::vector<int> slots(CH_CELL_CAP * n_cells), ovf(CH_OVF_CAP), bead_cell(std::max(n, 1)), bead_slot(std::max(n, 1)), qslot(std::max(n, 1));
+  const int cap = c.cell_cap;
+  std::vector<int> slots((size_t)cap * n_cells), ovf(CH_OVF_CAP), bead_cell(std::max(n, 1)), bead_slot(std::max(n, 1)), qslot(std::max(n, 1));
   int ovf_n = 0;
   PG_CUDA(h, cudaStreamSynchronize(h->stream));
   if (n > 0) {
@@ -485,7 +538,7 @@ int pg_chain_check(pg_engine* h, int* n_bad) {
       if (b < 0) continue;
       if (b >= n) { flag("cell slot holds a bead index out of range"); continue; }
       seen[b]++;
-      if (bead_cell[b] != (int)(s / CH_CELL_CAP) || bead_slot[b] != (int)(s % CH_CELL_CAP)) flag("cell slot disagrees with the bead's own record, bead " + std::to_string(b));
+      if (bead_cell[b] != (int)(s / cap) || bead_slot[b] != (int)(s % cap)) flag("cell slot disagrees with the bead's own record, bead " + std::to_string(b));
     }
     if (ovf_n < 0 || ovf_n > CH_OVF_CAP) flag("overflow count out of range");
     for (int o = 0; o < std::min(std::max(ovf_n, 0), CH_OVF_CAP); o++) {
@@ -493,7 +546,7 @@ int pg_chain_check(pg_engine* h, int* n_bad) {
       if (b < 0) continue;
       if (b >= n) { flag("overflow entry out of range"); continue; }
       seen[b]++;
-      if (bead_slot[b] != CH_CELL_CAP + o) flag("overflow entry disagrees with the bead's own record");
+      if (bead_slot[b] != cap + o) flag("overflow entry disagrees with the bead's own record");
     }
     for (int i = 0; i < n; i++) {
       if (seen[i] != 1) flag("bead " + std::to_string(i) + " is filed " + std::to_string(seen[i]) + " times");

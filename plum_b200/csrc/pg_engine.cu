@@ -316,6 +316,9 @@ int build_params(pg_engine* h, const pg_params* p) {
     P.ebox[i] = p->box[i];
     P.inv_ebox[i] = 1.0 / p->box[i];
   }
+  if (p->pair_kind == PG_PAIR_TRUNCATED_LJ && (!p->lj_sigma || !p->lj_epsilon)) { g_create_err = "TruncatedLJ needs lj_sigma and lj_epsilon"; return PG_ERR_INVALID; }
+  if (p->pair_kind == PG_PAIR_HARD_SPHERE && !p->hs_radius) { g_create_err = "HardSphere needs hs_radius"; return PG_ERR_INVALID; }
+  if (p->pair_kind < PG_PAIR_NONE || p->pair_kind > PG_PAIR_HARD_SPHERE) { g_create_err = "unknown pair_kind"; return PG_ERR_INVALID; }
   P.n_types = p->n_types;
   P.beta = p->beta;
   P.pair_kind = p->pair_kind;
@@ -377,6 +380,20 @@ int build_params(pg_engine* h, const pg_params* p) {
 
 int flush_commit(pg_engine* h);
 
+// Cached replay / MC-batch state bakes device pointers (xy, zq, d_partial), bead ranges and grid shapes into CUDA graphs
+// and ReplayMove records.  Anything that reallocates those arrays drops the graphs; anything that changes the molecule
+// table (upload, insertion, deletion) also drops the recorded moves, so that a later pg_replay_run / pg_mc_begin reports
+// PG_ERR_INVALID instead of launching with stale ranges.
+void replay_invalidate(pg_engine* h, bool drop_moves) {
+  for (auto& g : h->rp_graphs) cudaGraphExecDestroy(g.exec);
+  h->rp_graphs.clear();
+  if (drop_moves) {
+    h->rp_moves.clear();
+    h->mc_mol.clear();
+    h->rp_mc = false;
+  }
+}
+
 int ensure_group(pg_engine* h, int glen) {
   if (glen <= h->gcap) return PG_OK;
   int rc = flush_commit(h);   // the pending trial's block is about to be freed
@@ -407,6 +424,7 @@ void next_slot(pg_engine* h) {
 int ensure_partials(pg_engine* h, int n_ctas) {
   if (n_ctas <= h->partial_cap) return PG_OK;
   int cap = std::max(4096, n_ctas * 2);
+  if (h->d_partial) { PG_CUDA(h, cudaStreamSynchronize(h->stream)); replay_invalidate(h, false); }
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_partial_i) cudaFree(h->d_partial_i);
   h->d_partial = nullptr; h->d_partial_i = nullptr;
@@ -436,6 +454,7 @@ int ensure_capacity(pg_engine* h, int n_need) {
     PG_CUDA(h, cudaMemcpyAsync(mol, h->mol, sizeof(int) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
     PG_CUDA(h, cudaStreamSynchronize(h->stream));
   }
+  replay_invalidate(h, false);
   cudaFree(h->xy); cudaFree(h->zq); cudaFree(h->type); cudaFree(h->mol);
   cudaFree(h->t_xy); cudaFree(h->t_zq); cudaFree(h->t_type); cudaFree(h->t_mol);
   h->xy = xy; h->zq = zq; h->type = type; h->mol = mol;
@@ -725,9 +744,11 @@ int wait_mail(pg_engine* h, unsigned int seq, pg_delta* o) {
   int aux[MV_NSLOT];
   for (int s = 0; s < MV_NSLOT; s++) {
     for (;;) {
-      if (m[s].seq == seq) {
+      if (__atomic_load_n(&h->h_mail[s].seq, __ATOMIC_ACQUIRE) == seq) {
+        // (acquire: on a weakly ordered host the payload loads must not be satisfied before the seq load)
         val[s] = m[s].value;
         aux[s] = m[s].aux;
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
         if (m[s].seq == seq) break;
       }
       int rc = w.step(h);
@@ -1011,6 +1032,7 @@ int pg_upload_system(pg_engine* h, int n_beads, const double* xyz, const double*
   h->pending = false;
   h->pc.valid = false;
   h->ch.valid = false;
+  replay_invalidate(h, true);
   return PG_OK;
 }
 
@@ -1059,6 +1081,7 @@ int pg_delta_e_begin(pg_engine* h, int mol, const double* trial_xyz, const uint8
   if (!h || !trial_xyz || !moved) return PG_ERR_INVALID;
   if (mol < 0 || mol >= h->n_mol) { h->err = "molecule index out of range"; return PG_ERR_INVALID; }
   if (h->pending || h->inflight) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  if (h->mc_inflight || h->ch.inflight) { h->err = "a batch is still in flight"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
   const int g0 = h->mol_first[mol], glen = h->mol_first[mol + 1] - g0;
   int rc = ensure_group(h, glen);
@@ -1088,9 +1111,8 @@ int pg_delta_e_begin(pg_engine* h, int mol, const double* trial_xyz, const uint8
 int pg_delta_e_poll(pg_engine* h, pg_delta* out) {
   if (!h || !out) return PG_ERR_INVALID;
   if (!h->inflight) { h->err = "no trial in flight"; return PG_ERR_STATE; }
-  volatile PgMailRec* m = h->h_mail;
   for (int s = MV_NSLOT - 1; s >= 0; s--)
-    if (m[s].seq != h->seq) return 1;
+    if (__atomic_load_n(&h->h_mail[s].seq, __ATOMIC_ACQUIRE) != h->seq) return 1;
   int rc = wait_mail(h, h->seq, out);
   if (rc) return rc;
   h->inflight = false;
@@ -1467,7 +1489,13 @@ int pg_mc_begin(pg_engine* h, int first, int count) {
       wave_hi = m + w;
     }
     rc = replay_launch(h, m, (m > first) ? m - 1 : -1, true);
-    if (rc) return rc;
+    if (rc) {
+      // kernels of this batch are already queued and the last decided step has no commit behind it: the engine's
+      // state can no longer be trusted — drain the stream and make every later batch call fail until a new upload
+      cudaStreamSynchronize(h->stream);
+      replay_invalidate(h, true);
+      return rc;
+    }
   }
   if (count > 0) {
     // the last step's decision (taken on the device) is applied by a stand-alone commit
@@ -1539,6 +1567,8 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
                       const double* chain_xyz, const double* chain_q, const int32_t* chain_type, double* out_energy,
                       double* out_pair, double* out_ewald) {
   if (!h || !set || !bead1_xyz || !out_energy) return PG_ERR_INVALID;
+  if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  if (h->inflight || h->mc_inflight || h->ch.inflight) { h->err = "a trial or batch is still in flight"; return PG_ERR_STATE; }
   const int nt = set->n_trials, cl = set->current_len, use2 = set->use_bead2 ? 1 : 0;
   if (nt <= 0 || cl < 0) return PG_ERR_INVALID;
   if (use2 && !bead2_xyz) return PG_ERR_INVALID;
@@ -1650,8 +1680,9 @@ int pg_trial_energies(pg_engine* h, const pg_trial_set* set, const double* bead1
     for (int r = 0; r < 3 * ntc; r++) {
       double v;
       for (;;) {
-        if (m[r].seq == A.seq) {
+        if (__atomic_load_n(&h->h_tmail[r].seq, __ATOMIC_ACQUIRE) == A.seq) {
           v = m[r].value;
+          __atomic_thread_fence(__ATOMIC_ACQUIRE);
           if (m[r].seq == A.seq) break;
         }
         int wrc = w.step(h);
@@ -1676,6 +1707,7 @@ int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, con
                         const int32_t* type, pg_totals* added) {
   if (!h || n_new_mol <= 0 || !mol_len || !xyz || !q || !type) return PG_ERR_INVALID;
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  if (h->inflight || h->mc_inflight || h->ch.inflight) { h->err = "a trial or batch is still in flight"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
   { int frc_ = flush_commit(h); if (frc_) return frc_; }
   int n_add = 0;
@@ -1715,12 +1747,14 @@ int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, con
   h->n += n_add;
   h->n_mol += n_new_mol;
   h->ch.valid = false;
+  replay_invalidate(h, true);
   return PG_OK;
 }
 
 int pg_delete_molecules(pg_engine* h, int mf, int ml, pg_totals* removed) {
   if (!h || mf < 0 || ml < mf || ml >= h->n_mol) return PG_ERR_INVALID;
   if (h->pending) { h->err = "previous trial not committed"; return PG_ERR_STATE; }
+  if (h->inflight || h->mc_inflight || h->ch.inflight) { h->err = "a trial or batch is still in flight"; return PG_ERR_STATE; }
   PG_CUDA(h, cudaSetDevice(h->device));
   { int frc_ = flush_commit(h); if (frc_) return frc_; }
   const int b0 = h->mol_first[mf], b1 = h->mol_first[ml + 1], glen = b1 - b0;
@@ -1761,6 +1795,7 @@ int pg_delete_molecules(pg_engine* h, int mf, int ml, pg_totals* removed) {
   h->n -= glen;
   h->n_mol -= nm;
   h->ch.valid = false;
+  replay_invalidate(h, true);
   return PG_OK;
 }
 

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(PP_THREADS) k_propose(const PgProposeArgs A) {
         const double4 r = srv[i - (p + 1)];
         double nb[3] = {0.0, 0.0, 0.0};
         if (i + 1 < len) { nb[0] = sx[i + 1]; nb[1] = sy[i + 1]; nb[2] = sz[i + 1]; }
+        __syncwarp();   // every lane has read its copy before any lane's update loop writes these rows
         const double v[3] = {r.x, r.y, r.z};
         double m[3];
         pp_pivot_step(a, b, msr, v, r.w, m);
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(PP_THREADS) k_propose(const PgProposeArgs A) {
         const double4 r = srv[row0 + (p - 1 - i)];
         double nb[3] = {0.0, 0.0, 0.0};
         if (i > 0) { nb[0] = sx[i - 1]; nb[1] = sy[i - 1]; nb[2] = sz[i - 1]; }
+        __syncwarp();
         const double v[3] = {r.x, r.y, r.z};
         double m[3];
         pp_pivot_step(a, b, msr, v, r.w, m);

@@ -253,10 +253,10 @@ class Engine:
 
     # -- device-resident Markov chain (pg_chain_*) ---------------------------
     def chain_configure(self, phantom, move_size, move_prob, bond_len, vary_bond=False, gc_freq=0, cluster=1,
-                        keep_trials=False):
+                        keep_trials=False, pivot_mode=0):
         c = PgChainConfig(phantom=int(phantom), gc_freq=int(gc_freq), vary_bond=int(bool(vary_bond)),
-                          cluster_ctas=int(cluster), keep_trials=int(bool(keep_trials)), move_size=float(move_size),
-                          bond_len=float(bond_len))
+                          cluster_ctas=int(cluster), keep_trials=int(bool(keep_trials)), pivot_mode=int(pivot_mode),
+                          move_size=float(move_size), bond_len=float(bond_len))
         for i in range(5):
             c.move_prob[i] = float(move_prob[i])
         self._check(self.L.pg_chain_configure(self.h, C.byref(c)), "pg_chain_configure")

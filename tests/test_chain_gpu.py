@@ -31,10 +31,10 @@ def _engine(name):
     return r, s, eng
 
 
-def _configure(eng, r, cluster, keep_trials=False):
+def _configure(eng, r, cluster, keep_trials=False, pivot_mode=0):
     bl, vary = mcgen.bond_settings(r)
     eng.chain_configure(r.phantom, r.move_size, r.move_prob, bl, vary_bond=vary, gc_freq=r.gc_freq if r.use_gc else 0,
-                        cluster=cluster, keep_trials=keep_trials)
+                        cluster=cluster, keep_trials=keep_trials, pivot_mode=pivot_mode)
 
 
 def _errors(got, ref):
@@ -99,20 +99,29 @@ def _cut_fixture(seed):
     return {k: z[k] for k in z.files}
 
 
-@pytest.mark.parametrize("seed,cluster", [(1, 1), (2, 8), (1, 4)])
-def test_chain_reproduces_reference_on_the_1320_bead_cut(seed, cluster):
-    """plum_ref itself, 2000 steps on 12 x 100-bead chains + 120 ions in S's box (same alpha, cutoffs and K = 3574)."""
+@pytest.mark.parametrize("seed,cluster,pivot_mode", [(1, 1, 0), (2, 8, 0), (1, 4, 0), (2, 1, 1), (1, 8, 1)])
+def test_chain_reproduces_reference_on_the_1320_bead_cut(seed, cluster, pivot_mode):
+    """plum_ref itself, 2000 steps on 12 x 100-bead chains + 120 ions in S's box (same alpha, cutoffs and K = 3574).
+    pivot_mode 0: the reference's operation order, trial coordinates bit-identical; pivot_mode 1: pivot arms as prefix
+    sums, trial coordinates equal to 1e-11, everything else held to the same bars."""
     r, s, eng = _engine("synth_cut")
     fx = _cut_fixture(seed)
     n = len(fx["kind"])
-    _configure(eng, r, cluster, keep_trials=True)
+    _configure(eng, r, cluster, keep_trials=True, pivot_mode=pivot_mode)
     eng.chain_seed(seed)
     n_tr = len(fx["trial_off"]) - 1
     rec, stop, ms = eng.chain_run(n_tr)
+    worst = 0.0
     for i in range(n_tr):
         trial = fx["trial_xyz"][fx["trial_off"][i]:fx["trial_off"][i + 1]]
         got = eng.chain_trial_xyz(i, trial.shape[0])
-        assert np.array_equal(got, trial), (i, int(fx["kind"][i]), np.abs(got - trial).max())
+        if pivot_mode == 0:
+            assert np.array_equal(got, trial), (i, int(fx["kind"][i]), np.abs(got - trial).max())
+        else:
+            worst = max(worst, float(np.abs(got - trial).max()))
+    if pivot_mode:
+        print(f"pivot_mode 1: max |trial - reference trial| over {n_tr} steps = {worst:.3e}")
+        assert worst <= 1e-11
     rec2, stop, ms = eng.chain_run(n - n_tr)
     rec = np.concatenate([rec, rec2])
     assert rec["kind"].tolist() == fx["kind"].tolist()
@@ -121,7 +130,7 @@ def test_chain_reproduces_reference_on_the_1320_bead_cut(seed, cluster):
     big = fx["dE"] >= VLE
     assert np.array_equal(rec["dE"] >= VLE, big)
     plain, scaled = _errors(rec["dE"], fx["dE"])
-    print(f"synth_cut seed {seed} cluster {cluster}: {n} steps, {int(big.sum())} overlap steps, accept ratio "
+    print(f"synth_cut seed {seed} cluster {cluster} pivot_mode {pivot_mode}: {n} steps, {int(big.sum())} overlap steps, accept ratio "
           f"{fx['accept'].mean():.3f}; max |dE - ref| / |ref| = {plain:.3e}, / max(1, |ref|) = {scaled:.3e}")
     assert scaled <= 1e-10
     eng.chain_check()

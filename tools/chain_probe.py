@@ -23,6 +23,10 @@ def main():
     ap.add_argument("--replicas", default="")
     ap.add_argument("--multi-cluster", default="1")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--prof", action="store_true", help="per-phase clock sums of thread 0 (pgx_chain_prof)")
+    ap.add_argument("--pivot-mode", type=int, default=0)
+    ap.add_argument("--prof-rank", type=int, default=0)
+    ap.add_argument("--skip", default="0", help="comma-separated phase-skip masks to time (1 R, 2 Q, 4 C, 8 intra, 16 commit, 32 pivot arms)")
     a = ap.parse_args()
     from plum_b200 import mcgen, synth
     from plum_b200.engine import Engine
@@ -38,16 +42,31 @@ def main():
         e = Engine(params, device=0, capacity_beads=s.n)
         e.upload(s.xyz, s.q, ids, s.mol_first)
         e.init_energy()
-        e.chain_configure(r.phantom, r.move_size, r.move_prob, bl, vary_bond=vary, cluster=cluster)
+        e.chain_configure(r.phantom, r.move_size, r.move_prob, bl, vary_bond=vary, cluster=cluster, pivot_mode=a.pivot_mode)
         return e
 
-    for g in [int(x) for x in a.clusters.split(",") if x]:
+    PHASES = ["header", "load+rows", "proposal", "lists+recip", "real", "cells", "intra", "walls", "reduce", "decide", "commit"]
+    for g, skip in [(int(x), int(k)) for x in a.clusters.split(",") if x for k in a.skip.split(",")]:
         e = make(g)
         e.chain_seed(11)
         e.chain_run(200)                      # warm-up (builds the structures)
+        if a.prof or skip:
+            e.L.pgx_chain_prof.argtypes = [C.c_void_p, C.c_int, C.c_int]
+            e.L.pgx_chain_prof_read.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+            assert e.L.pgx_chain_prof(e.h, 1 if a.prof else 0, skip | (min(a.prof_rank, g - 1) << 8)) == 0
         rec, stop, ms = e.chain_run(a.steps)
+        if a.prof:
+            buf = (C.c_uint64 * 80)()
+            assert e.L.pgx_chain_prof_read(e.h, buf) == 0
+            pr = np.array(buf[:], dtype=np.float64).reshape(5, 16)
+            tot_cyc = pr[:, :11].sum()
+            for k, name in enumerate(["bead", "com", "pivot", "crank", "rept"]):
+                if pr[k, 15] > 0:
+                    us = pr[k, :11] / tot_cyc * ms * 1e3 / pr[k, 15]
+                    print(json.dumps({"prof_kind": name, "cluster": g, "skip": skip, "moves": int(pr[k, 15]),
+                                      "us_per_move": float(us.sum()), "phases_us": {p_: round(float(u), 2) for p_, u in zip(PHASES, us)}}), flush=True)
         kinds = rec["kind"]
-        out = {"system": a.system, "cluster": g, "steps": int(len(rec)), "ms": ms, "us_per_step": 1e3 * ms / max(len(rec), 1),
+        out = {"system": a.system, "cluster": g, "skip": skip, "steps": int(len(rec)), "ms": ms, "us_per_step": 1e3 * ms / max(len(rec), 1),
                "moves_per_s": len(rec) / (ms * 1e-3), "accept": float(rec["accept"].mean()),
                "overlap_frac": float((rec["dE"] >= 1e8).mean()), "kind_frac": [float((kinds == k).mean()) for k in range(5)]}
         if a.check:
