@@ -1,40 +1,45 @@
 #!/usr/bin/env python3
-"""bench.py — MC moves/s of the per-trial-move energy path on the synthetic 22k-bead
-polyelectrolyte (BASELINE.json configs[4], SURVEY.md §8(d) "S").
+"""bench.py — MC moves/s of the per-trial-move energy path on the synthetic 22k-bead polyelectrolyte
+(BASELINE.json configs[4], SURVEY.md §8(d) "S").
 
   python bench.py --gpus N --steps K --warmup W            this repo (CUDA engine via the C ABI)
-  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU algorithm
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU algorithm on the host cores
 
-One *step* = MOVES_PER_STEP sequential Metropolis moves (move mix 0.5 ion translation /
-0.1 COM / 0.3 pivot / 0.1 reptation) of one replica.  One replica per GPU, no communication
-(SURVEY.md §8(e)): `value` is the aggregate over all ranks, scaling "weak".
+One *step* = MOVES_PER_STEP sequential Metropolis steps (move mix 0.5 ion translation / 0.1 COM / 0.3 pivot /
+0.1 reptation) of EVERY replica of the GPU.  Replicas are independent Markov chains (own engine, own random stream);
+there is no communication: scaling "weak", `value` is the aggregate over all ranks.
 
-  e2e    the loop a driver runs: host-generated trial coordinates -> pg_delta_e (H2D copy,
-         fused kernel, D2H result) -> Metropolis test on the host -> pg_commit; native C++
-         caller (plum_b200/host/mc_bench.cc) so no interpreter is inside the timed region.
-  value  the SAME move sequence replayed device-resident (pg_replay_run): proposals already in
-         HBM, acceptance taken on the device from the recorded variates, CUDA-event time.
-  roofline  dominant kernel k_move: algorithmic FP64 flops (SURVEY.md §8(d) formula) over its
-         CUDA-event time, against an FP64 FMA peak measured in this run (MEASURED_PEAKS.json
-         carries no FP64 figure); the byte view against MEASURED_PEAKS.json's hbm_gbs is added.
-  cpu_baseline  the CPU oracle port (pairwise reciprocal form = the reference's algorithm,
-         oracle/plum_oracle.c) on 1 host core, bounded sample.
+  value   THROUGHPUT mode: `replicas_per_gpu` chains per GPU (default one per SM, one CTA each), all of them in ONE launch
+          of the device-resident chain kernel k_chain per step (pg_chain_run_multi); generator state, coordinates, S(k),
+          cell grid already resident; CUDA-event time of the launches.  The rate ONE Markov chain sees is in
+          `single_chain` (a 16-CTA cluster per chain), next to `value`, for both pivot modes.
+  e2e     the same chains through the reference-facing call sequence with HOST buffers, one host thread per GPU: per
+          batch the std::mt19937 state goes down, one launch, and the step log, the generator state and the accepted
+          coordinates (what ForceField::TranslationalBatch hands back to the driver's beads) come back; wall clock.
+  per_move   the round-1 path for comparison: pg_delta_e / pg_commit with host-built trial coordinates (k_move).
+  roofline   dominant kernel k_chain.  `frac` = EXECUTED FP64 flop (dfma x2 + dadd + dmul thread instructions of the tracked
+          ncu capture profiles/r02_ncu_summary.json, per step) x measured steps/s / the FP64 FMA peak measured in this
+          run.  Also: issue-slot fraction (warp instructions/s over SMs x 4 x clock), an L2 view against an L2 streaming
+          peak measured in this run, the "necessary work" count (pair configurations inside a cutoff, counted by the
+          kernel) and the SURVEY §8(d) algorithmic figure, labelled as such.
+  cpu_baseline   the CPU oracle port (the reference's pairwise algorithm, oracle/plum_oracle.c) on 1 host core, bounded sample.
+  examples   bin/plum_gpu (the unchanged reference driver over the façade) on the four reference examples, 10^4 steps.
 """
 import argparse
 import ctypes as C
+import glob
 import json
 import multiprocessing as mp
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
-# more replica streams than the default 8 hardware work queues would alias onto shared queues and
-# serialise falsely; must be set before the CUDA context exists
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 # keep stdout to the one JSON line: NCCL's version / debug lines go to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 
@@ -48,6 +53,9 @@ WORKLOAD = ("synthetic_S: 200 chains x 100 beads (every 10th q=-1) + 2000 counte
             "lB=2.5, alpha=0.004 (real_cutoff 52, 3574 k-vectors), WCA sigma=2.227, "
             "moves 0.5 ion-translate/0.1 COM/0.3 pivot/0.1 reptation")
 MOVE_PROB = [0.5, 0.1, 0.3, 0.0, 0.1]
+EXAMPLES = ["bulk_nvt", "confined_nvt", "bulk_muvt", "confined_muvt"]
+EXAMPLE_STEPS = 10000          # the reference binary: 30-70 s per example on one core
+EXAMPLE_STEPS_GPU = 100000     # bin/plum_gpu: long enough to stand out from the process start-up
 
 
 def dist_env():
@@ -101,45 +109,45 @@ def mcbench_lib():
         raise RuntimeError(f"{path} missing: run __graft_entry__.build()")
     L = C.CDLL(path)
     dp, ip, bp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    vpp = C.POINTER(C.c_void_p)
     L.pb_create.restype = C.c_void_p
     L.pb_create.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, C.c_double, C.c_double, C.c_double, dp, C.c_int, C.c_uint]
     L.pb_destroy.argtypes = [C.c_void_p]
-    L.pb_run.argtypes = [C.c_void_p, C.c_int, ip, ip, dp, dp, bp, dp, bp, C.c_int, ip, dp, dp, dp, ip, C.c_int]
     L.pb_set_records.argtypes = [C.c_void_p, ip, ip, dp, dp, bp, dp, bp, C.c_int]
     L.pb_set_records.restype = None
     L.pb_stats.argtypes = [C.c_void_p, ip, dp, dp, ip]
     L.pb_stats.restype = None
-    L.pb_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp]
-    L.pb_run_mc.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, dp]
+    L.pb_run_multi.argtypes = [vpp, C.c_int, C.c_int, dp]
+    L.pb_run_chain.argtypes = [vpp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+    L.pb_chain_seed.argtypes = [vpp, C.c_int, C.c_int]
+    L.pb_chain_resident.argtypes = [vpp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.pb_set_pivot_mode.argtypes = [C.c_void_p, C.c_int]
+    L.pb_set_pivot_mode.restype = None
     return L
 
 
-def alg_flops_per_move(sysm, mols):
+def alg_flops_per_move(n, first, q, mols):
     """flops = 2*evals*F_pair + 2*n_moved_q*K*16 + 12*K; bytes = 40*N + 40*K + 48*n_moved."""
-    first = sysm.mol_first
-    N = sysm.n
     length = (first[mols + 1] - first[mols]).astype(np.float64)
-    cs = np.concatenate([[0.0], np.cumsum(sysm.q != 0)])
+    cs = np.concatenate([[0.0], np.cumsum(q != 0)])
     nq = cs[first[mols + 1]] - cs[first[mols]]
-    evals = length * (N - length) + 0.5 * length * (length - 1)
+    evals = length * (n - length) + 0.5 * length * (length - 1)
     flops = 2 * evals * F_PAIR + 2 * nq * K_FULL * 16 + 12 * K_FULL
-    bytes_ = 40.0 * N + 40.0 * K_FULL + 48.0 * length
-    return evals, flops, bytes_
+    return evals, flops, nq
 
 
 # ----------------------------------------------------------------------- CPU sample
 def cpu_sample(args):
-    """Times the reference algorithm (pairwise reciprocal form, map-free port) on ion and chain moves."""
+    """Times the reference algorithm (pairwise reciprocal form, map-free port) on ion and chain moves of S."""
     seed, n_ion, n_chain = args
     from oracle.oracle_py import Oracle
     from plum_b200 import synth
     r, sysm, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
     o = Oracle(params, repl_mode=0)
     o.upload(sysm.xyz, sysm.q, types.ids(sysm.symbol), sysm.mol_first)
-    # The reference evaluates only the NEW pair energies of a trial (the old ones come from its N^2
-    # std::map caches), so the port is timed in that mode: same arithmetic, same pair count, none of
-    # the map overhead (measured on a 1320-bead cut of this system the real plum_ref is 2.7x slower
-    # than this, DESIGN.md §6) — the most favourable stand-in for the reference.
+    # The reference evaluates only the NEW pair energies of a trial (the old ones come from its N^2 std::map caches), so
+    # the port is timed in that mode: same arithmetic, same pair count, none of the map overhead (on a 1320-bead cut the
+    # real plum_ref is 2.7x slower than this) — the most favourable stand-in for the reference.
     o.set_timing_new_only(True)
     rng = np.random.default_rng(seed)
     chains = [m for m in range(sysm.n_mol) if sysm.mol_first[m + 1] - sysm.mol_first[m] > 1]
@@ -167,19 +175,24 @@ def mix_rate(t_ion, t_chain, p_ion):
     return 1.0 / (p_ion * float(np.mean(t_ion)) + (1.0 - p_ion) * float(np.mean(t_chain)))
 
 
-def plum_ref_cut(n_chains=12, steps=40):
-    """The REAL reference binary (oracle/_ref/plum_ref: /root/reference/src compiled unmodified apart from the seed /
-    trace hooks, oracle/build_ref.py) on one core, on a cut of S it can hold: the same box, alpha and move mix (hence the
-    same cutoffs and K = 3574), 12 chains instead of 200 => N = 1320.  Its per-move cost is n_moved * N pair evaluations
-    of (27 images + 3574 cos), so t = a * sum(n_moved) * N is fitted on the run and carried to N = 22 000 — reported as
-    an EXTRAPOLATION next to the measured rate (profiles/r01d_cpu_scaling_plum_ref.jsonl holds N = 1320 / 2750 / 5500:
-    the fit is linear in N)."""
-    import tempfile
+# ------------------------------------------------------------------ the real reference binary
+def _replay():
     sys.path.insert(0, os.path.join(REPO, "tests"))
     import replay
+    return replay
+
+
+def plum_ref_cut(args):
+    """oracle/_ref/plum_ref ITSELF on a cut of S it can hold (same box, alpha, move mix, K = 3574; fewer chains), one core:
+    (N, moves, ion moves, chain moves, init seconds, move seconds)."""
+    n_chains, steps, core = args
+    replay = _replay()
     from plum_b200 import synth
-    if not replay.have_plum_ref():
-        return {"unavailable": "oracle/_ref/plum_ref not built (python oracle/build_ref.py where /root/reference exists)"}
+    if core is not None:
+        try:
+            os.sched_setaffinity(0, {core})
+        except Exception:
+            pass
     sysm = synth.make_system(n_chains=n_chains, chain_len=100, charged_every=10)
     with tempfile.TemporaryDirectory(prefix="plum_ref_cut_") as d:
         synth.write_inputs(d, sysm, n_steps=steps, alpha=0.004, spring=False)
@@ -191,75 +204,143 @@ def plum_ref_cut(n_chains=12, steps=40):
         t_run = max(time.perf_counter() - t0 - t_init, 1e-9)
     T = [ln.split() for ln in lines if ln.startswith("T ")]
     n_ion = sum(1 for t in T if t[2] == "0")
-    n_chain = len(T) - n_ion
-    a_fit = t_run / ((n_ion + 100.0 * n_chain) * sysm.n)
-    p_ion = MOVE_PROB[0]
-    t_move = a_fit * 22000 * (p_ion * 1 + (1 - p_ion) * 100)
-    return {"kind": "reference", "cores": 1, "N": int(sysm.n), "moves": len(T), "ion_moves": n_ion, "chain_moves": n_chain,
-            "init_s": t_init, "moves_s": t_run, "measured_moves_per_s_at_this_N": len(T) / t_run,
-            "extrapolated_moves_per_s_at_N22000": 1.0 / t_move,
-            "note": "plum_ref itself, one core, same box / alpha / K / move mix as the workload but 12 chains; the N = 22000 "
-                    "figure is EXTRAPOLATED (cost per move is linear in n_moved * N); plum_ref cannot hold N = 22000"}
+    return {"N": int(sysm.n), "moves": len(T), "ion_moves": n_ion, "chain_moves": len(T) - n_ion, "init_s": t_init, "moves_s": t_run}
+
+
+def run_example(args):
+    """One reference example through a driver binary (plum_ref or bin/plum_gpu): wall seconds of `steps` steps with the
+    sampling / output frequencies pushed beyond the run (only the move path is timed), minus the start-up of a 0-step run."""
+    name, binary, steps, core, extra_env = args
+    replay = _replay()
+    if core is not None:
+        try:
+            os.sched_setaffinity(0, {core})
+        except Exception:
+            pass
+    d = os.path.join(replay.GOLDEN, "examples", name)
+    off = {"s1_equilibrium_steps": 1000000000, "s1_sampling_frequency": 1000000000, "s1_sampling_print_frequency": 1000000000,
+           "s1_trajectory_print_frequency": 1000000000}
+    # start-up (process, CUDA context, energy initialisation) is taken out with a short run of the same binary: the
+    # difference of a `base`-step run and a `base + steps`-step run is the time of `steps` steps
+    base = steps // 10
+    t_init = float("inf")
+    for _ in range(2):   # (the first start of a CUDA process on a box is slower: take the faster of two)
+        t0 = time.perf_counter()
+        replay.run_plum_ref(d, base, 1, xyz=False, binary=binary, overrides=off, extra_env=extra_env)
+        t_init = min(t_init, time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    lines = replay.run_plum_ref(d, base + steps, 1, xyz=False, binary=binary, overrides=off, extra_env=extra_env)
+    t_all = time.perf_counter() - t0
+    n_gc = sum(1 for ln in lines if ln.startswith("G ")) * steps // (base + steps)
+    n_t = sum(1 for ln in lines if ln.startswith("T ")) * steps // (base + steps)
+    t_run = max(t_all - t_init, 1e-9)
+    return {"example": name, "steps": steps, "translational_steps": n_t, "gc_steps": n_gc, "startup_s": t_init, "run_s": t_run,
+            "steps_per_s": steps / t_run}
+
+
+def examples_block(binary, cores, extra_env=None, parallel=True, steps=EXAMPLE_STEPS):
+    replay = _replay()
+    if not os.path.exists(binary):
+        return {"unavailable": f"{os.path.relpath(binary, REPO)} not built"}
+    jobs = [(name, binary, steps, (cores[i % len(cores)] if cores else None), extra_env) for i, name in enumerate(EXAMPLES)]
+    try:
+        if parallel:
+            with mp.get_context("fork").Pool(len(jobs)) as pool:
+                res = pool.map(run_example, jobs)
+        else:
+            res = [run_example(j) for j in jobs]
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)}
+    return {r["example"]: {k: v for k, v in r.items() if k != "example"} for r in res}
 
 
 # ------------------------------------------------------------------- reference arm
 def run_reference(a):
+    """The reference's own CPU implementation of the path on this box's host cores.  plum_ref cannot hold S (70-115 GB of
+    std::map nodes, SURVEY.md §0.8), so the line's `value` is what was actually MEASURED per step: every host core evaluates
+    one ion move and one chain move (the workload's 50/50 mix) of the 22 000-bead system with the oracle port of the
+    reference's pairwise algorithm; value = moves evaluated / wall time of the step.  Beside it: plum_ref itself on three
+    cuts of S (1320 / 2750 / 5500 beads) with the per-core extrapolation to N = 22 000 (labelled), and plum_ref on the four
+    reference examples (10^4 steps each, one core each)."""
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    cores = max(1, min(os.cpu_count() or 1, 64))
+    t0_all = time.perf_counter()
+    cores_avail = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    cores = max(1, min(len(cores_avail), 64))
     p_ion = MOVE_PROB[0]
-    budget = 150.0 / max(1, a.steps + a.warmup)           # seconds of CPU work per step and worker
-    # one cheap calibration of both move kinds (also the warm-up's first step)
-    t_ion0, t_chain0 = cpu_sample((1, 1, 1))
-    n_ion = max(1, min(4, int(0.25 * budget / max(t_ion0[0], 1e-3))))
-    n_chain = 1 if budget >= 1.2 * t_chain0[0] else 0
-    t_chain_all = list(t_chain0)
-    step_rates, t0_all = [], time.perf_counter()
+    step_walls, t_ion_all, t_chain_all = [], [], []
     with mp.get_context("fork").Pool(cores) as pool:
         for s in range(a.warmup + a.steps):
             t0 = time.perf_counter()
-            res = pool.map(cpu_sample, [(1000 * s + w, n_ion, n_chain) for w in range(cores)])
+            res = pool.map(cpu_sample, [(1000 * s + w, 1, 1) for w in range(cores)])
             wall = time.perf_counter() - t0
-            ti = [x for r in res for x in r[0]]
-            tc = [x for r in res for x in r[1]]
-            t_chain_all += tc
             if s >= a.warmup:
-                # `cores` independent replicas advance concurrently; per-replica rate from the mix of
-                # measured per-move costs (chain-move cost from this step, or the running mean)
-                rate = cores * mix_rate(ti, tc if tc else t_chain_all, p_ion)
-                step_rates.append((rate, wall))
-    value = float(np.mean([r for r, _ in step_rates]))
-    ms_per_step = 1e3 * MOVES_PER_STEP * cores / value
-    try:
-        ref_cut = None if a.no_plum_ref else plum_ref_cut()
-    except Exception as e:   # noqa: BLE001
-        ref_cut = {"error": repr(e)}
-    sample = (f"per step and core: {n_ion} ion move(s) + {n_chain} chain move(s) (100 beads flagged) of the same "
-              f"22000-bead system evaluated with the reference's pairwise algorithm (oracle port, map-free, new-configuration "
-              f"energies only like the reference); "
-              f"moves/s = cores / (0.5 t_ion + 0.5 t_chain); plum_ref itself cannot hold N=22000 "
-              f"(70-115 GB of std::map nodes, SURVEY.md §0.8)")
+                step_walls.append(wall)
+                t_ion_all += [x for r_ in res for x in r_[0]]
+                t_chain_all += [x for r_ in res for x in r_[1]]
+    moves_per_step = 2 * cores
+    ms_per_step = 1e3 * float(np.mean(step_walls)) if step_walls else float("nan")
+    value = moves_per_step / (ms_per_step * 1e-3)
+    per_core = mix_rate(t_ion_all, t_chain_all, p_ion) if t_ion_all else float("nan")
+    ref_cuts, ex = None, None
+    replay = _replay()
+    if not a.no_plum_ref and replay.have_plum_ref():
+        try:
+            jobs = [(12, 40, cores_avail[0 % cores]), (25, 30, cores_avail[1 % cores]), (50, 24, cores_avail[2 % cores])]
+            with mp.get_context("fork").Pool(len(jobs)) as pool:
+                cuts = pool.map(plum_ref_cut, jobs)
+            # cost per move is linear in n_moved * N (pair evaluations of 27 images + 3574 cos): fit t = a * sum(n_moved) * N
+            num = sum(c["moves_s"] * (c["ion_moves"] + 100.0 * c["chain_moves"]) * c["N"] for c in cuts)
+            den = sum(((c["ion_moves"] + 100.0 * c["chain_moves"]) * c["N"]) ** 2 for c in cuts)
+            a_fit = num / den
+            t_move = a_fit * 22000 * (p_ion * 1 + (1 - p_ion) * 100)
+            ref_cuts = {"kind": "reference", "cores_per_run": 1, "cuts": cuts,
+                        "fit_seconds_per_moved_bead_and_partner": a_fit,
+                        "extrapolated_moves_per_s_per_core_at_N22000": 1.0 / t_move,
+                        "note": "oracle/_ref/plum_ref itself on cuts of S with the same box / alpha / K / move mix; the N = 22000 "
+                                "figure is EXTRAPOLATED (least-squares fit linear in n_moved x N over the cuts) and is per core; the "
+                                "N = 11000 cut (29 GB of map nodes, 4 min of initialisation) is in profiles/r02_cpu_scaling_plum_ref.jsonl"}
+        except Exception as e:   # noqa: BLE001
+            ref_cuts = {"error": repr(e)}
+        if not a.no_examples:
+            ex = examples_block(replay.PLUM_REF, cores_avail)
+    sample = (f"per step, each of {cores} host cores evaluates 1 ion move + 1 chain move (100 beads flagged) of the same 22000-bead "
+              f"system with the reference's pairwise algorithm (oracle port, map-free, new-configuration energies only like the "
+              f"reference): {moves_per_step} moves per step, value = moves / measured wall time of the step")
     line = {
         "impl": "reference", "metric": "MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "moves_per_step": MOVES_PER_STEP, "replicas": cores},
+        "config": {"workload": WORKLOAD, "moves_per_step": moves_per_step, "replicas": cores},
         "cpu_baseline": {"value": value, "unit": "moves/s", "cores": cores, "kind": "port", "sample": sample,
-                         "single_chain_value": value / cores, "plum_ref_cut": ref_cut},
+                         "per_core_moves_per_s": per_core, "plum_ref_cuts": ref_cuts},
         "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t0_all,
+        "examples": ex, "gpu_launches": 0, "wall_s": time.perf_counter() - t0_all,
     }
     print(json.dumps(line))
     return 0
 
 
 # ------------------------------------------------------------------------- our arm
+def load_profile_summary():
+    """Executed-work counters of k_chain from the tracked ncu capture (profiles/r*_ncu_summary.json, newest round)."""
+    files = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_summary.json")))
+    for f in reversed(files):
+        try:
+            with open(f) as fh:
+                j = json.load(fh)
+            if "k_chain" in j:
+                return os.path.basename(f), j["k_chain"]
+        except Exception:
+            continue
+    return None, None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
     from plum_b200 import synth
-    from plum_b200._abi import PgDelta  # noqa: F401
     from plum_b200.engine import Engine
 
     rank, local_rank, world = dist_env()
@@ -289,8 +370,8 @@ def run_ours(a):
         return float(t.item())
 
     M, K, W = a.moves_per_step, a.steps, a.warmup
-    # fixed per GPU whatever N is (weak scaling); each replica has one host thread in the e2e leg
-    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else 30
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else n_sm
     r, sysm, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
     ids = types.ids(sysm.symbol)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -307,367 +388,253 @@ def run_ours(a):
     mf = np.ascontiguousarray(sysm.mol_first, dtype=np.int32)
     n_total = (W + K) * M
 
-    def measure(R):
-        class Replica:
-            """One independent Markov chain: its own engine (stream, resident state) and random stream."""
+    class Fleet:
+        """R independent Markov chains on this GPU: one engine (resident state) and one std::mt19937 each."""
 
-            def __init__(self, idx):
-                self.eng = Engine(params, device=local_rank, capacity_beads=sysm.n)
-                self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
-                self.eng.init_energy()
-                self.stream = torch.cuda.ExternalStream(self.eng.stream(), device=torch.device("cuda", local_rank))
-                self.seed = 12345 + 1000 * rank + 17 * idx
-                self.ctx = self.new_ctx()
-                self.cap_beads = n_total * 100
-                self.rec_mol = np.zeros(n_total, dtype=np.int32)
-                self.rec_off = np.zeros(n_total, dtype=np.int32)
-                self.rec_u = np.zeros(n_total)
-                self.rec_dE = np.zeros(n_total)
-                self.rec_acc = np.zeros(n_total, dtype=np.uint8)
-                self.rec_trial = np.zeros((self.cap_beads, 3))
-                self.rec_moved = np.zeros(self.cap_beads, dtype=np.uint8)
-                self.used_total = 0
-                self.replay_dE = []
-                self.replay_ms = []
-                self.kd_ms = 0.0
+        def __init__(self, R, record=True):
+            self.R = R
+            self.engs, self.ctxs, self.rec = [], [], []
+            for i in range(R):
+                e = Engine(params, device=local_rank, capacity_beads=sysm.n)
+                self.engs.append(e)
+                self.rec.append(dict(mol=np.zeros(n_total, dtype=np.int32), off=np.zeros(n_total, dtype=np.int32), u=np.zeros(n_total),
+                                     dE=np.zeros(n_total), acc=np.zeros(n_total, dtype=np.uint8)) if record else None)
+            self.reset()
 
-            def new_ctx(self):
-                return L.pb_create(self.eng.h, sysm.n_mol, mf.ctypes.data_as(ip), xyz0.ctypes.data_as(dp),
-                                   box.ctypes.data_as(dp), C.c_double(r.beta), C.c_double(r.move_size),
-                                   C.c_double(r.rigid_bond), prob.ctypes.data_as(dp), 0, C.c_uint(self.seed))
+        def seed(self, i):
+            return 12345 + 1000 * rank + 17 * i
 
-            def reset_for_mc(self):
-                """Back to the initial configuration and the initial random stream: the batched leg must walk the
-                very same Markov chain as the per-move leg."""
-                self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
-                self.eng.init_energy()
-                self.ctx = self.new_ctx()
-                self.mc_mol = np.zeros(n_total, dtype=np.int32)
-                self.mc_off = np.zeros(n_total, dtype=np.int32)
-                self.mc_u = np.zeros(n_total)
-                self.mc_dE = np.zeros(n_total)
-                self.mc_acc = np.zeros(n_total, dtype=np.uint8)
+        def reset(self, pivot_mode=0):
+            """Back to the initial configuration and the initial random streams."""
+            for c in self.ctxs:
+                L.pb_destroy(c)
+            self.ctxs = []
+            for i, e in enumerate(self.engs):
+                e.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
+                e.init_energy()
+                c = L.pb_create(e.h, sysm.n_mol, mf.ctypes.data_as(ip), xyz0.ctypes.data_as(dp), box.ctypes.data_as(dp),
+                                C.c_double(r.beta), C.c_double(r.move_size), C.c_double(r.rigid_bond), prob.ctypes.data_as(dp), 0,
+                                C.c_uint(self.seed(i)))
+                L.pb_set_pivot_mode(c, pivot_mode)
+                self.ctxs.append(c)
+            self.arr = (C.c_void_p * self.R)(*self.ctxs)
 
-            def set_mc_records(self, s):
-                sl = slice(s * M, (s + 1) * M)
-                L.pb_set_records(self.ctx, self.mc_mol[sl].ctypes.data_as(ip), self.mc_off[sl].ctypes.data_as(ip),
-                                 self.mc_u[sl].ctypes.data_as(dp), self.mc_dE[sl].ctypes.data_as(dp),
-                                 self.mc_acc[sl].ctypes.data_as(bp), None, None, 0)
+        def set_records(self, s, which="rec"):
+            sl = slice(s * M, (s + 1) * M)
+            for c, rc in zip(self.ctxs, getattr(self, which)):
+                if rc is None:
+                    L.pb_set_records(c, None, None, None, None, None, None, None, 0)
+                else:
+                    L.pb_set_records(c, rc["mol"][sl].ctypes.data_as(ip), rc["off"][sl].ctypes.data_as(ip), rc["u"][sl].ctypes.data_as(dp),
+                                     rc["dE"][sl].ctypes.data_as(dp), rc["acc"][sl].ctypes.data_as(bp), None, None, 0)
 
-            def set_records(self, s):
-                sl = slice(s * M, (s + 1) * M)
-                L.pb_set_records(self.ctx, self.rec_mol[sl].ctypes.data_as(ip), self.rec_off[sl].ctypes.data_as(ip),
-                                 self.rec_u[sl].ctypes.data_as(dp), self.rec_dE[sl].ctypes.data_as(dp),
-                                 self.rec_acc[sl].ctypes.data_as(bp), self.rec_trial[self.used_total:].ctypes.data_as(dp),
-                                 self.rec_moved[self.used_total:].ctypes.data_as(bp), self.cap_beads - self.used_total)
+        def check(self, rc, what):
+            if rc != 0:
+                msgs = sorted({e.L.pg_last_error(e.h).decode() for e in self.engs})
+                raise RuntimeError(f"{what} failed ({rc}): {msgs}")
 
-            def collect(self, s):
-                used = C.c_int32()
-                L.pb_stats(self.ctx, C.byref(used), None, None, None)
-                self.rec_off[s * M:(s + 1) * M] += self.used_total
-                self.used_total += used.value
+        def e2e_step(self, s, cluster, batch):
+            self.set_records(s)
+            wall = C.c_double()
+            self.check(L.pb_run_chain(self.arr, self.R, M, batch, cluster, 0, 1, C.byref(wall)), "pb_run_chain")
+            return wall.value
 
-            def reset_for_replay(self):
-                L.pb_destroy(self.ctx)
-                self.final_e2e = self.eng.totals()
-                self.eng.upload(sysm.xyz, sysm.q, ids, sysm.mol_first)
-                self.eng.init_energy()
-                self.eng.replay_upload(self.rec_mol, self.rec_off, self.rec_u, self.rec_trial[:self.used_total],
-                                       self.rec_moved[:self.used_total])
+        def resident_seed(self, cluster):
+            self.check(L.pb_chain_seed(self.arr, self.R, cluster), "pb_chain_seed")
 
-            def replay_step(self, s, keep):
-                dE, acc, ms = self.eng.replay_run(s * M, M)
-                if keep:
-                    self.replay_dE.append(dE)
-                    self.replay_ms.append(ms)
+        def resident_step(self, s, book):
+            if book:
+                self.set_records(s, "rec2")
+            ms = C.c_float()
+            self.check(L.pb_chain_resident(self.arr, self.R, M, 1 if book else 0, C.byref(ms)), "pb_chain_resident")
+            return ms.value
 
-            def time_delta(self):
-                self.kd_ms = self.eng.replay_time_delta(W * M, K * M)
+        def launches(self):
+            return sum(e.launch_count() for e in self.engs)
 
-        reps = [Replica(i) for i in range(R)]
+        def close(self):
+            for c in self.ctxs:
+                L.pb_destroy(c)
+            for e in self.engs:
+                e.close()
 
-        def run_all(fn):
-            """Run fn(replica) for every replica concurrently (ctypes releases the GIL inside the C ABI)."""
-            if R == 1:
-                fn(reps[0])
-                return
-            errs = []
-
-            def wrap(rp):
-                try:
-                    fn(rp)
-                except Exception as e:   # noqa: BLE001
-                    errs.append(e)
-            ths = [threading.Thread(target=wrap, args=(rp,)) for rp in reps]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
-            if errs:
-                raise errs[0]
-
-        def device_ms(fn):
-            """Device time of `fn` run on every replica concurrently: every replica stream first waits on a start
-            event, the end event is recorded after all of them have joined — robust against replicas that do
-            not overlap (queueing, launch skew), unlike a max over per-replica event times."""
-            cur = torch.cuda.current_stream()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(cur)
-            for rp in reps:
-                rp.stream.wait_event(e0)
-            run_all(fn)
-            for rp in reps:
-                ej = torch.cuda.Event()
-                ej.record(rp.stream)
-                cur.wait_event(ej)
-            e1.record(cur)
-            e1.synchronize()
-            return e0.elapsed_time(e1)
-
-        # ---------------- e2e leg: host-driven Metropolis loops through the C ABI (native callers).
-        # T host threads, each driving its share of the replicas through pg_delta_e_begin / _poll so that
-        # their round trips overlap; every chain stays strictly sequential.
-        T = max(1, min(R, a.host_threads if a.host_threads > 0 else max(1, (os.cpu_count() or 2) // world - 2)))
-        groups = [reps[i::T] for i in range(T)]
-
-        def e2e_step(s):
-            errs = []
-
-            def drive(group):
-                try:
-                    for rp in group:
-                        rp.set_records(s)
-                    arr = (C.c_void_p * len(group))(*[rp.ctx for rp in group])
-                    wall = C.c_double()
-                    rc = L.pb_run_multi(arr, len(group), M, C.byref(wall))
-                    if rc != 0:
-                        msgs = [rp.eng.L.pg_last_error(rp.eng.h).decode() for rp in group]
-                        raise RuntimeError(f"pb_run_multi failed ({rc}): {msgs}")
-                    for rp in group:
-                        rp.collect(s)
-                except Exception as e:   # noqa: BLE001
-                    errs.append(e)
-            if T == 1:
-                drive(groups[0])
-            else:
-                ths = [threading.Thread(target=drive, args=(g_,)) for g_ in groups]
-                for t in ths:
-                    t.start()
-                for t in ths:
-                    t.join()
-            if errs:
-                raise errs[0]
-
+    def chain_legs(R, cluster, pivot_mode, batch, clocks=None):
+        """e2e and device-resident legs of R chains with `cluster` CTAs each."""
+        fl = Fleet(R)
+        fl.reset(pivot_mode)
         for s in range(W):
-            e2e_step(s)
+            fl.e2e_step(s, cluster, batch)
             flush_l2()
-        launches0 = sum(rp.eng.launch_count() for rp in reps)
-        clocks = ClockSampler(local_rank)
-        clocks.start()
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(W, W + K):
-            e2e_step(s)
-            flush_l2()
-        barrier()
-        t_e2e = time.perf_counter() - t0
-        e2e_launches = sum(rp.eng.launch_count() for rp in reps) - launches0
-        t_e2e = max_over_ranks(t_e2e)
-
-        # ---------------- value leg: the same sequences, device-resident replay (one CUDA graph per step)
-        run_all(lambda rp: rp.reset_for_replay())
-        for s in range(W):
-            run_all(lambda rp: rp.replay_step(s, False))
-            flush_l2()
-        for s in range(W, W + K):   # instantiate the timed steps' graphs outside the timed region
-            for rp in reps:
-                rp.eng.replay_prepare(s * M, M, True)
-        launches0 = sum(rp.eng.launch_count() for rp in reps)
+        if clocks:
+            clocks.start()
         barrier()
         t0 = time.perf_counter()
         t_flush = 0.0
-        step_ms = []
         for s in range(W, W + K):
-            step_ms.append(device_ms(lambda rp: rp.replay_step(s, True)))
+            fl.e2e_step(s, cluster, batch)
             tf = time.perf_counter()
             flush_l2()
             t_flush += time.perf_counter() - tf
         barrier()
-        t_wall_replay = time.perf_counter() - t0
-        gpu_launches = sum(rp.eng.launch_count() for rp in reps) - launches0
-        clock_info = clocks.stop()
-        dev_ms = float(sum(step_ms))   # fork/join CUDA events around all replicas of a step
-        dev_s = max_over_ranks(dev_ms * 1e-3)
-        replay_matches = all(bool(np.array_equal(np.concatenate(rp.replay_dE), rp.rec_dE[W * M:]) and
-                                  rp.eng.totals() == rp.final_e2e) for rp in reps)
-
-
-        # ---------------- roofline of the dominant kernel (k_move), timed alone, same proposals
-        timed = np.arange(W * M, (W + K) * M)
-        evals = flops = bytes_ = 0.0
-        for rp in reps:
-            e_, f_, b_ = alg_flops_per_move(sysm, rp.rec_mol[timed])
-            evals += float(e_.sum()); flops += float(f_.sum()); bytes_ += float(b_.sum())
-            rp.eng.replay_time_delta(W * M, min(M, 256))   # warm + instantiate
-            rp.eng.replay_prepare(W * M, K * M, False)
-        torch.cuda.synchronize()
-        kd_ms = device_ms(lambda rp: rp.time_delta())
-        fp64_peak_gflops = reps[0].eng.measure_fp64_peak()
-        peaks = {}
-        try:
-            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # traffic: dram bytes per k_move launch from the committed `ncu --set full` capture of this command
-        traffic = None
-        try:
-            import glob
-            prof_file = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_summary.json")))[-1]
-            with open(prof_file) as f:
-                prof = json.load(f)["k_move_full"]
-            vals = []
-            for p_ in prof:
-                rd, wr = p_["dram__bytes_read.sum"].split(), p_["dram__bytes_write.sum"].split()
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-                vals.append(float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]])
-            traffic = float(np.mean(vals))
-        except Exception:
-            traffic = None
-        n_launch = R * K * M
-        achieved_tflops = flops / (kd_ms * 1e-3) / 1e12
-        roofline = {
-            "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_gflops / 1e3, "unit": "TFLOP/s",
-            "frac": achieved_tflops / (fp64_peak_gflops / 1e3), "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write per k_move launch, ncu --set full (cold cache), profiles/" + (os.path.basename(prof_file) if traffic is not None else "-"),
-            "kernel": "k_move", "launches": int(n_launch), "avg_launch_us": kd_ms * 1e3 / (K * M),
-            "avg_launch_note": f"CUDA-event time (fork/join over the {R} replica stream(s)) of {K * M} back-to-back k_move launches "
-                               f"per replica / {K * M}; achieved = algorithmic flops of all replicas / that time",
-            "peak_source": "FP64 FMA microbenchmark measured in this run (pg_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-            "algorithmic_flops_per_launch": flops / n_launch,
-            "bytes_view": {"bound": "hbm", "achieved": bytes_ / (kd_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                           "unit": "GB/s", "frac": bytes_ / (kd_ms * 1e-3) / 1e9 / hbm_peak,
-                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                           "note": "the 0.9 MB working set per replica is L2-resident by design; HBM is the conservative denominator"},
-        }
-
-        # ---------------- batched leg: the same chains once more, now with device-side proposals (pg_mc_*): the host
-        # only draws the random stream ahead (native caller, plum_b200/host/mc_propose.h) and uploads one descriptor
-        # block per batch; trial coordinates, dE, the Metropolis test and the commit never leave the device.
-        mc_error = None
-        try:
-            run_all(lambda rp: rp.reset_for_mc())
-
-            def mc_step(s):
-                errs = []
-
-                def drive(group):
-                    try:
-                        for rp in group:
-                            rp.set_mc_records(s)
-                        arr = (C.c_void_p * len(group))(*[rp.ctx for rp in group])
-                        wall = C.c_double()
-                        rc = L.pb_run_mc(arr, len(group), M, a.mc_batch, C.byref(wall))
-                        if rc != 0:
-                            msgs = [rp.eng.L.pg_last_error(rp.eng.h).decode() for rp in group]
-                            raise RuntimeError(f"pb_run_mc failed ({rc}): {msgs}")
-                    except Exception as e:   # noqa: BLE001
-                        errs.append(e)
-                if T == 1:
-                    drive(groups[0])
-                else:
-                    ths = [threading.Thread(target=drive, args=(g_,)) for g_ in groups]
-                    for t in ths:
-                        t.start()
-                    for t in ths:
-                        t.join()
-                if errs:
-                    raise errs[0]
-
-            for s in range(W):
-                mc_step(s)
-                flush_l2()
-        except Exception as e:   # noqa: BLE001 — keep the other legs' numbers
-            mc_error = repr(e)
-        launches0 = sum(rp.eng.launch_count() for rp in reps)
-        barrier()   # collectives stay outside the try blocks: a rank that failed still takes part
-        t0 = time.perf_counter()
-        try:
-            if mc_error is None:
-                for s in range(W, W + K):
-                    mc_step(s)
-                    flush_l2()
-        except Exception as e:   # noqa: BLE001
-            mc_error = repr(e)
-        t_mc = (time.perf_counter() - t0) if mc_error is None else float("inf")
+        t_e2e = max_over_ranks(time.perf_counter() - t0 - t_flush)
+        final_e2e = [e.totals() for e in fl.engs]
+        # device-resident: same seeds, same chains
+        fl.rec2 = [dict(mol=np.zeros(n_total, dtype=np.int32), off=np.zeros(n_total, dtype=np.int32), u=np.zeros(n_total),
+                        dE=np.zeros(n_total), acc=np.zeros(n_total, dtype=np.uint8)) for _ in range(R)]
+        fl.reset(pivot_mode)
+        fl.resident_seed(cluster)
+        for s in range(W):
+            fl.resident_step(s, True)
+            flush_l2()
+        for e in fl.engs:
+            e.chain_counters(reset=True)
+        l0 = fl.launches()
         barrier()
-        t_mc = max_over_ranks(t_mc)
-        mc_launches, mc_matches, mc_close = 0, False, False
-        try:
-            if mc_error is not None:
-                raise RuntimeError(mc_error)
-            mc_launches = sum(rp.eng.launch_count() for rp in reps) - launches0
-            mc_matches = all(bool(np.array_equal(rp.mc_mol, rp.rec_mol) and np.array_equal(rp.mc_acc, rp.rec_acc) and
-                                  np.array_equal(rp.mc_dE, rp.rec_dE) and rp.eng.totals() == rp.final_e2e) for rp in reps)
-            mc_close = all(bool(np.array_equal(rp.mc_mol, rp.rec_mol) and np.array_equal(rp.mc_acc, rp.rec_acc) and
-                                np.all(np.abs(rp.mc_dE - rp.rec_dE) <= 1e-10 * np.maximum(1.0, np.abs(rp.rec_dE)))) for rp in reps)
-            for rp in reps:
-                L.pb_destroy(rp.ctx)
-        except Exception as e:   # noqa: BLE001
-            mc_error = mc_error or repr(e)
+        step_ms = []
+        t0 = time.perf_counter()
+        for s in range(W, W + K):
+            step_ms.append(fl.resident_step(s, True))
+            flush_l2()
+        barrier()
+        wall_res = time.perf_counter() - t0
+        launches = fl.launches() - l0
+        dev_s = max_over_ranks(float(sum(step_ms)) * 1e-3)
+        cnt = np.array([e.chain_counters() for e in fl.engs], dtype=np.float64).sum(axis=0)
+        same = all(bool(np.array_equal(a_["mol"], b_["mol"]) and np.array_equal(a_["acc"], b_["acc"]) and np.array_equal(a_["dE"], b_["dE"]))
+                   for a_, b_ in zip(fl.rec, fl.rec2)) and all(e.totals() == f_ for e, f_ in zip(fl.engs, final_e2e))
+        timed = slice(W * M, (W + K) * M)
+        mols = np.concatenate([rc["mol"][timed] for rc in fl.rec])
+        evals, flops, nq = alg_flops_per_move(sysm.n, sysm.mol_first, sysm.q, mols)
+        lens = (sysm.mol_first[mols + 1] - sysm.mol_first[mols])
+        acc = float(np.concatenate([rc["acc"][timed] for rc in fl.rec]).mean())
+        out = dict(R=R, cluster=cluster, pivot_mode=pivot_mode, dev_s=dev_s, t_e2e=t_e2e, launches=launches, same=same,
+                   evals=float(evals.sum()), alg_flops=float(flops.sum()), counters=cnt.tolist(), accept=acc,
+                   p_ion=float(np.mean(lens == 1)), wall_res=wall_res, rec0=fl.rec[0], step_ms=step_ms,
+                   batches_per_step=(M + batch - 1) // batch)
+        out["peaks"] = None
+        if clocks is not None:
+            out["peaks"] = (fl.engs[0].measure_fp64_peak(), fl.engs[0].measure_l2_peak())
+        fl.close()
+        return out
 
-        # ---------------- totals over ranks
-        moves_total = sum_over_ranks(float(R * K * M))
-        evals_total = sum_over_ranks(evals)
-        value = moves_total / dev_s
-        e2e_value = moves_total / t_e2e
-        # bytes crossing PCIe per step: staged group block H2D (trial xyz + q + type + index + moved) and the mailbox D2H
-        lens = np.concatenate([(sysm.mol_first[rp.rec_mol[timed] + 1] - sysm.mol_first[rp.rec_mol[timed]]) for rp in reps]).astype(np.float64)
-        h2d = float((lens * (24 + 8 + 4 + 4 + 1)).sum() / K)
-        d2h = float(R * M * 128)
-        rec_acc_all = np.concatenate([rp.rec_acc[W * M:] for rp in reps])
-        # batched path: 72 B descriptor per move + 21 B per bead of the moved molecule (charge, type, index, flag)
-        # + 32 B per pivot step H2D; 9 B per move (dE, accept bit) + the stop word per batch D2H
-        chain_moves = lens > 1
-        p_piv = MOVE_PROB[2] / max(MOVE_PROB[1] + MOVE_PROB[2] + MOVE_PROB[4], 1e-12)   # pivots among the chain moves (rows are not recorded)
-        mc_h2d = float((72.0 * lens.size + 21.0 * lens.sum() + p_piv * 32.0 * (lens[chain_moves] - 1).sum()) / K)
-        mc_d2h = float(R * M * 9 + R * (M // max(a.mc_batch, 1) + 1) * 4)
+    def per_move_legs(R):
+        """The round-1 path for comparison: host-built trials through pg_delta_e_begin/_poll/pg_commit (k_move), one thread."""
+        fl = Fleet(R)
+        wall = C.c_double()
+        for s in range(W):
+            fl.set_records(s)
+            fl.check(L.pb_run_multi(fl.arr, R, M, C.byref(wall)), "pb_run_multi")
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(W, W + K):
+            fl.set_records(s)
+            fl.check(L.pb_run_multi(fl.arr, R, M, C.byref(wall)), "pb_run_multi")
+        barrier()
+        t = max_over_ranks(time.perf_counter() - t0)
+        rec0 = fl.rec[0]
+        fl.close()
+        return dict(t=t, rec0=rec0)
 
-        for rp in reps:
-            rp.eng.close()
-        return dict(R=R, T=T, value=value, e2e_value=e2e_value, dev_s=dev_s, t_e2e=t_e2e, evals_total=evals_total,
-                    e2e_launches=e2e_launches, gpu_launches=gpu_launches, roofline=roofline, clock_info=clock_info,
-                    replay_matches=replay_matches, wall_replay=(t_wall_replay - t_flush), h2d=h2d, d2h=d2h,
-                    accept=float(rec_acc_all.mean()), p_ion=float(np.mean(lens == 1)),
-                    mc_value=moves_total / t_mc, t_mc=t_mc, mc_launches=mc_launches, mc_matches=mc_matches, mc_close=mc_close,
-                    mc_h2d=mc_h2d, mc_d2h=mc_d2h, mc_error=mc_error)
+    # ---------------- throughput mode (the headline) and one chain per GPU
+    clocks = ClockSampler(local_rank)
+    main = chain_legs(R_auto, a.cluster, a.pivot_mode, a.batch, clocks)
+    clock_info = clocks.stop()
+    R = main["R"]
+    moves_total = sum_over_ranks(float(R * K * M))
+    value = moves_total / main["dev_s"]
+    e2e_value = moves_total / main["t_e2e"]
 
-    single = measure(1) if (R_auto > 1 and not a.no_single) else None
-    res = measure(R_auto)
-    R = res["R"]
-    value, e2e_value, dev_s, t_e2e, evals_total = res["value"], res["e2e_value"], res["dev_s"], res["t_e2e"], res["evals_total"]
-    e2e_launches, gpu_launches, roofline, clock_info = res["e2e_launches"], res["gpu_launches"], res["roofline"], res["clock_info"]
-    replay_matches, t_wall_replay, t_flush, h2d, d2h = res["replay_matches"], res["wall_replay"], 0.0, res["h2d"], res["d2h"]
-    # What the kernel EXECUTES next to what the reference's algorithm would (`achieved` prices every pair at the reference's
-    # 36 flop; the kernel culls most of them): executed FP64 flop per launch = dadd + dmul + 2 dfma thread instructions
-    # (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on) of the `ncu --set full` capture of this command,
-    # gpurun_out/prof_r01d_kmove.ncu-rep, summarised in profiles/r01_summary.md: 100-bead chain move 5.80e6, ion move 1.21e6.
+    single = None
+    if not a.no_single:
+        single = {}
+        for pm in (0, 1):
+            sc = chain_legs(1, a.single_cluster, pm, a.batch)
+            single[f"pivot_mode_{pm}"] = {
+                "value": float(K * M) / sc["dev_s"], "e2e": float(K * M) / sc["t_e2e"], "us_per_step": sc["dev_s"] * 1e6 / (K * M),
+                "resident_matches_e2e": sc["same"], "accept_ratio": sc["accept"]}
+            if pm == 0:
+                sc0 = sc
+        pmv = per_move_legs(1)
+        n_cmp = min(len(sc0["rec0"]["mol"]), len(pmv["rec0"]["mol"]))
+        a_, b_ = sc0["rec0"], pmv["rec0"]
+        big = b_["dE"][:n_cmp] >= 1e8
+        same_chain = bool(np.array_equal(a_["mol"][:n_cmp], b_["mol"][:n_cmp]) and np.array_equal(a_["acc"][:n_cmp], b_["acc"][:n_cmp]) and
+                          np.array_equal(a_["dE"][:n_cmp] >= 1e8, big))
+        ddE = np.abs(a_["dE"][:n_cmp][~big] - b_["dE"][:n_cmp][~big]) / np.maximum(1.0, np.abs(b_["dE"][:n_cmp][~big]))
+        single["per_move_path"] = {"e2e": float(K * M) / pmv["t"], "unit": "moves/s",
+                                   "note": "round-1 path: pg_delta_e / pg_commit round trip per move, host-built trial coordinates (k_move)"}
+        single["chain_vs_per_move_same_chain"] = {"moves_compared": int(n_cmp), "molecule_and_accept_identical": same_chain,
+                                                  "max_ddE_over_max1_dE": float(ddE.max()) if ddE.size else 0.0}
+        single["unit"] = "moves/s"
+        single["cluster_ctas"] = a.single_cluster
+        single["note"] = ("ONE Markov chain per GPU (what a single Plum run sees), a cluster of CTAs sharing the chain; pivot_mode 0 builds "
+                          "pivot arms in the reference's operation order (trial coordinates bit-identical to the reference's, one "
+                          "dependent step per bead), pivot_mode 1 as a prefix sum (coordinates equal to ~1e-13)")
+
+    # ---------------- roofline of the dominant kernel (k_chain): executed work from the tracked ncu capture
+    peaks = {}
     try:
-        exe_per_launch = res["p_ion"] * 1.21e6 + (1.0 - res["p_ion"]) * 5.80e6
-        exe_tflops = roofline["achieved"] * exe_per_launch / roofline["algorithmic_flops_per_launch"]
-        roofline["executed_view"] = {
-            "achieved": exe_tflops, "peak": roofline["peak"], "unit": "TFLOP/s", "frac": exe_tflops / roofline["peak"],
-            "executed_flops_per_launch": exe_per_launch,
-            "note": "executed FP64 flop per launch from ncu (chain move 5.80e6, ion move 1.21e6, mixed with this run's ion "
-                    "fraction) over the same CUDA-event time: the kernel is bound by CTA-slot time and instruction issue, "
-                    "not by the FP64 pipe; `frac` above exceeds 1 because the algorithmic count includes the culled pairs"}
-    except Exception as e:   # noqa: BLE001
-        roofline["executed_view"] = {"error": repr(e)}
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    fp64_peak_gflops, l2_peak_gbs = main["peaks"]
+    steps_per_s = R * K * M / main["dev_s"]             # this rank's chains
+    prof_file, prof = load_profile_summary()
+    n_in, n_eval, n_acc = main["counters"]
+    kernel_us = main["dev_s"] * 1e6 / max(main["launches"], 1)
+    roofline = {"bound": "fp64", "kernel": "k_chain", "unit": "TFLOP/s", "peak": fp64_peak_gflops / 1e3,
+                "peak_source": "FP64 FMA microbenchmark measured in this run (pg_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                "launches": int(main["launches"]), "avg_launch_us": kernel_us,
+                "avg_launch_note": f"one launch = {M} steps of each of the {R} chains of this GPU (CUDA events around the launch)"}
+    if prof:
+        fl_step = prof["executed_fp64_flop_per_step"]
+        wi_step = prof["warp_instructions_per_step"]
+        l2_step = prof.get("l2_bytes_per_step")
+        ach = fl_step * steps_per_s / 1e12
+        clk = (clock_info.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+        roofline.update({
+            "achieved": ach, "frac": ach / (fp64_peak_gflops / 1e3),
+            "achieved_note": "EXECUTED FP64 flop per step (2 x dfma + dadd + dmul thread instructions of the tracked ncu capture) x the "
+                             "steps/s measured here with CUDA events",
+            "executed_fp64_flop_per_step": fl_step, "profile": "profiles/" + prof_file,
+            "traffic": prof.get("dram_bytes_per_step"),
+            "traffic_note": "dram__bytes_read + dram__bytes_write per step from the same capture (one chain, cold caches): the working "
+                            "set is L2-resident by design",
+            "issue_slots": {"warp_instructions_per_step": wi_step, "achieved_per_s": wi_step * steps_per_s,
+                            "peak_per_s": n_sm * 4 * clk, "frac": wi_step * steps_per_s / (n_sm * 4 * clk),
+                            "note": "warp instructions/s over SMs x 4 schedulers x the SM clock sampled during the timed region"},
+            "l2_view": None if not l2_step else {"achieved": l2_step * steps_per_s / 1e9, "peak": l2_peak_gbs, "unit": "GB/s",
+                                                 "frac": l2_step * steps_per_s / 1e9 / l2_peak_gbs,
+                                                 "peak_source": "L2 streaming-read microbenchmark measured in this run (pg_measure_l2_peak)"},
+        })
+    else:
+        roofline.update({"achieved": None, "frac": None, "traffic": None,
+                         "note": "profiles/r*_ncu_summary.json with a k_chain section not found: executed counters unavailable"})
+    # what had to be computed: pair configurations inside a cutoff (counted by the kernel) + the reciprocal-space update
+    nec_flops = n_in * F_PAIR + main["alg_flops"] - 2 * main["evals"] * F_PAIR
+    roofline["necessary_work_view"] = {
+        "pair_configurations_in_range_per_step": n_in / max(n_eval, 1), "flops_per_step": nec_flops / max(n_eval, 1),
+        "achieved": nec_flops / main["dev_s"] / 1e12, "frac": nec_flops / main["dev_s"] / 1e12 / (fp64_peak_gflops / 1e3),
+        "note": "SURVEY §8(d) prices (36 flop per pair configuration, 2 n_q K 16 + 12 K for the reciprocal update) applied only to the pair "
+                "configurations that lie inside a cutoff, as counted by the kernel itself"}
+    roofline["algorithmic_view"] = {
+        "flops_per_step": main["alg_flops"] / (R * K * M), "achieved": main["alg_flops"] / main["dev_s"] / 1e12,
+        "speedup_equivalent": main["alg_flops"] / main["dev_s"] / 1e12 / (fp64_peak_gflops / 1e3),
+        "note": "SURVEY §8(d) formula: EVERY moved-bead x partner pair priced at 36 flop although all but ~0.1 % lie outside both cutoffs "
+                "and are never evaluated (cell grid, charged list) — not a utilisation figure, only how many reference-style pair "
+                "evaluations per second the path stands for"}
+    roofline["hbm_view"] = {"peak": float(peaks.get("hbm_gbs", 6650.0)),
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                            "note": "not the bound: DRAM is touched on first use only"}
 
-    # ---------------- k-sharded full S(k) recompute (SURVEY.md §8e): every rank holds the positions, fills its slice of
-    # the k list with k_sk_slice, NCCL all-gathers the slices; time per rank with the collective broken out, for S and for
-    # the stress variant S-full (where there is enough work per rank to be worth sharding).  Not part of `value`.
+    # ---------------- examples through the unchanged driver
+    examples = None
+    if rank == 0 and not a.no_examples:
+        replay = _replay()
+        examples = examples_block(replay.PLUM_GPU, None, parallel=False, steps=EXAMPLE_STEPS_GPU)
+
+    # ---------------- k-sharded full S(k) recompute (SURVEY.md §8e)
     recompute = None
     if not a.no_recompute:
         recompute = {}
@@ -682,16 +649,19 @@ def run_ours(a):
                 l0 = eng.launch_count()
             except Exception as e:   # noqa: BLE001
                 setup_err = repr(e)
-            # a rank that failed to set up must not leave the others waiting in the all-gather
             if max_over_ranks(1.0 if setup_err else 0.0) > 0.0:
                 recompute[name] = {"error": setup_err or "set-up failed on another rank"}
                 if eng is not None:
                     eng.close()
                 continue
             try:
+                sharded.attach_peers(eng, rank, world)
                 recompute[name] = dict(n_charged=int(np.count_nonzero(s2.q)),
-                                       **sharded.time_sharded_recompute(eng, rank, world, t_init["recip"]))
+                                       **sharded.time_fused_recompute(eng, rank, world, t_init["recip"]))
                 recompute[name]["launches"] = int(eng.launch_count() - l0)
+                if world > 1:
+                    eng.sk_detach()
+                    recompute[name]["nccl_allgather_baseline"] = sharded.time_sharded_recompute(eng, rank, world, t_init["recip"], reps=10)
             except Exception as e:   # noqa: BLE001
                 recompute[name] = {"error": repr(e)}
             finally:
@@ -702,46 +672,37 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         t_ion, t_chain = cpu_sample((7, 6, 2))
-        p_ion = res["p_ion"]
-        v = mix_rate(t_ion, t_chain, p_ion)
+        v = mix_rate(t_ion, t_chain, main["p_ion"])
         cpu = {"value": v, "unit": "moves/s", "cores": 1, "kind": "port",
-               "sample": f"6 ion moves ({np.mean(t_ion):.3f} s each) + 2 chain moves of 100 flagged beads "
-                         f"({np.mean(t_chain):.3f} s each) on the same 22000-bead system, reference pairwise algorithm "
-                         f"(oracle port, map-free, new-configuration energies only like the reference), mixed with the realised ion fraction {p_ion:.3f}; plum_ref cannot "
-                         f"hold N=22000 (SURVEY.md §0.8)"}
+               "sample": f"6 ion moves ({np.mean(t_ion):.3f} s each) + 2 chain moves of 100 flagged beads ({np.mean(t_chain):.3f} s each) on "
+                         f"the same 22000-bead system, reference pairwise algorithm (oracle port, map-free, new-configuration energies only "
+                         f"like the reference), mixed with the realised ion fraction {main['p_ion']:.3f}; plum_ref cannot hold N=22000 "
+                         f"(SURVEY.md §0.8)"}
 
-    e2e_per_move = {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": t_e2e * 1e3 / K, "pair_dE_evals_per_s": evals_total / t_e2e,
-                    "caller": f"native C++ Metropolis loops over pg_delta_e_begin/_poll/pg_commit (plum_b200/host/mc_bench.cc): {res['T']} host thread(s) per GPU driving {R} replicas; trial coordinates built on the host",
-                    "launches": int(e2e_launches)}
-    e2e_batched = {"value": res["mc_value"], "unit": "moves/s", "h2d_bytes_per_step": res["mc_h2d"], "d2h_bytes_per_step": res["mc_d2h"],
-                   "ms_per_step": res["t_mc"] * 1e3 / K, "pair_dE_evals_per_s": evals_total / res["t_mc"],
-                   "caller": f"native C++ caller over pg_mc_upload/_begin/_end (plum_b200/host/mc_bench.cc), batches of {a.mc_batch} steps: the host draws the "
-                             f"std::mt19937 stream ahead in the reference's order and uploads descriptors; proposals (k_propose), dE (k_move), Metropolis test and "
-                             f"commit stay on the device; {res['T']} host thread(s) per GPU driving {R} replicas; wall clock incl. generation, uploads and result downloads",
-                   "launches": int(res["mc_launches"]),
-                   "same_chain_as_per_move": {"bit_identical": res["mc_matches"], "within_1e-10": res["mc_close"]}, "error": res["mc_error"]}
-    e2e_best = e2e_batched if (res["mc_close"] and res["mc_value"] > e2e_value) else e2e_per_move
+    # bytes crossing PCIe per step in the e2e leg (per GPU): generator state + launch arguments down; step log, generator
+    # state, status words and the accepted coordinates (2 x double2 per bead) up — per batch and replica
+    nb = main["batches_per_step"]
+    h2d = float(R * nb * (625 * 4 + 768))
+    d2h = float(R * (16 * M + nb * (625 * 4 + 16 + 32 * sysm.n)))
     if rank == 0:
         line = {
             "metric": "MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_s * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": main["dev_s"] * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "moves_per_step": M, "replicas_per_gpu": R,
-                       "l2": "flushed between steps (256 MiB fill, inside the timed region); within a step the "
-                             "0.9 MB working set stays L2-resident by design (north_star)"},
-            "pair_dE_evals_per_s": evals_total / dev_s,
-            "e2e": e2e_best,
-            "e2e_per_move": e2e_per_move, "e2e_batched": e2e_batched,
-            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
-            "replay_matches_e2e": replay_matches, "wall_ms_per_step_replay": (t_wall_replay - t_flush) * 1e3 / K,
-            "accept_ratio": res["accept"],
-            "sharded_recompute": recompute,
-            "single_replica": None if single is None else {
-                "value": single["value"], "e2e": max(single["e2e_value"], single["mc_value"] if single["mc_close"] else 0.0),
-                "e2e_per_move": single["e2e_value"], "e2e_batched": single["mc_value"], "batched_same_chain": single["mc_close"], "unit": "moves/s", "roofline_frac": single["roofline"]["frac"],
-                "avg_launch_us": single["roofline"]["avg_launch_us"], "replay_matches_e2e": single["replay_matches"],
-                "note": "one Markov chain on the GPU (latency-bound): the rate a single Plum run sees"},
+            "config": {"workload": WORKLOAD, "moves_per_step": M, "replicas_per_gpu": R, "cluster_ctas_per_chain": main["cluster"],
+                       "pivot_mode": main["pivot_mode"],
+                       "mode": f"throughput: {R} independent Markov chains per GPU, all in one k_chain launch per step; the rate of ONE chain is in single_chain",
+                       "l2": "flushed between steps (256 MiB fill); within a step each chain's working set stays L2-resident by design (north_star)"},
+            "pair_dE_evals_per_s": sum_over_ranks(main["evals"]) / main["dev_s"],
+            "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": main["t_e2e"] * 1e3 / K,
+                    "caller": f"native C++ caller (plum_b200/host/mc_bench.cc pb_run_chain), ONE host thread per GPU driving {R} chains: per batch of "
+                              f"{a.batch} steps pg_chain_set_rng (std::mt19937 state down), pg_chain_run_multi (one launch), pg_chain_steps (log up), "
+                              f"pg_chain_get_rng, pg_download_positions (accepted coordinates up, as ForceField::TranslationalBatch does)"},
+            "gpu_launches": int(main["launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
+            "resident_matches_e2e": main["same"], "accept_ratio": main["accept"],
+            "wall_ms_per_step_resident": main["wall_res"] * 1e3 / K,
+            "single_chain": single, "examples": examples, "sharded_recompute": recompute,
         }
         print(json.dumps(line))
     if world > 1:
@@ -757,14 +718,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--moves-per-step", type=int, default=MOVES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-single", action="store_true", help="skip the extra single-replica measurement")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-chain measurements")
     ap.add_argument("--no-recompute", action="store_true", help="skip the k-sharded full S(k) recompute timing")
-    ap.add_argument("--no-plum-ref", action="store_true", help="reference arm: skip the real plum_ref binary's leg (1320-bead cut)")
-    ap.add_argument("--replicas-per-gpu", type=int, default=0,
-                    help="independent Markov chains per GPU, each with its own engine/stream; 0 = 30 (fixed per GPU: weak scaling; one stream each, below the 32 hardware queues)")
-    ap.add_argument("--mc-batch", type=int, default=256, help="steps per uploaded batch in the batched (device-side proposal) leg")
-    ap.add_argument("--host-threads", type=int, default=0,
-                    help="host threads per GPU driving the replicas in the e2e leg (0 = host cores per GPU - 2, at most one per replica)")
+    ap.add_argument("--no-examples", action="store_true", help="skip the four reference examples")
+    ap.add_argument("--no-plum-ref", action="store_true", help="reference arm: skip the real plum_ref binary's legs")
+    ap.add_argument("--replicas-per-gpu", type=int, default=0, help="independent Markov chains per GPU; 0 = one per SM")
+    ap.add_argument("--cluster", type=int, default=1, help="CTAs per chain in throughput mode")
+    ap.add_argument("--single-cluster", type=int, default=16, help="CTAs per chain in the single-chain measurement")
+    ap.add_argument("--pivot-mode", type=int, default=0, help="0: pivot arms in the reference's operation order; 1: prefix sums")
+    ap.add_argument("--batch", type=int, default=MOVES_PER_STEP, help="steps per host round trip in the e2e leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

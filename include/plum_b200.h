@@ -291,12 +291,22 @@ int pg_chain_end(pg_engine* h, int* n_done, int* stop_kind, pg_chain_step* steps
 /* n independent replicas (one engine each, same device, same cluster size) in ONE launch on hs[0]'s stream;
  * every replica continues from its own resident generator state.  n_done[n] may be NULL.                */
 int pg_chain_run_multi(pg_engine** hs, int n, int max_steps, int* n_done, float* elapsed_ms);
+/* The same with the whole boundary crossing in one call and one synchronisation: rng_io [n][625] (624 state words +
+ * position per replica, in and out); rng_up [n] (may be NULL = all) 0: replica i continues from the generator state
+ * resident on the device (the caller has not drawn since the last call handed it back); steps [n][max_steps] (may be
+ * NULL); xyz [n] pointers to [n_beads][3] accepted coordinates (may be NULL; all engines then hold the same number
+ * of beads).                                                                                             */
+int pg_chain_run_multi_io(pg_engine** hs, int n, int max_steps, uint32_t* rng_io, const uint8_t* rng_up,
+                          pg_chain_step* steps, double* const* xyz, int* n_done, float* elapsed_ms);
 /* Records [first, first+count) of the engine's last chain (also after pg_chain_run_multi).              */
 int pg_chain_steps(pg_engine* h, int first, int count, pg_chain_step* steps);
 /* tests: trial coordinates of step `step` of the last chain ([n_beads][3]; keep_trials), and a consistency
  * check of the resident spatial structures against the resident coordinates (*n_bad inconsistencies).   */
 int pg_chain_trial_xyz(pg_engine* h, int step, double* xyz, int n_beads);
 int pg_chain_check(pg_engine* h, int* n_bad);
+/* Work counters of this engine's chains since the last reset: out3 = {pair configurations evaluated inside a cutoff
+ * (LJ, real space, intra-molecular), steps that evaluated an energy change, accepted steps}.              */
+int pg_chain_counters(pg_engine* h, uint64_t* out3, int reset);
 
 /* ---- configurational-bias trial energies (ForceField::BeadsEnergy) ------- */
 /* One launch evaluates n_trials candidate (monomer, counter-ion) pairs against
@@ -358,6 +368,24 @@ int pg_sk_set(pg_engine* h, const double* sk_dev);
 /* Reciprocal energy of the k slice from the engine's S(k). */
 int pg_sk_energy(pg_engine* h, int k_first, int k_count, double* e_out);
 int pg_sk_download(pg_engine* h, double* sk_host /* [n_k_half][2] */);
+/* Full recompute of S(k) from the resident coordinates into the engine's own S(k) — the drift reset of the incrementally
+ * updated structure factor (the reference's counterpart of a full recompute is PotentialEwald::EnergyInitialization,
+ * src/force_field/potential_ewald.cc:176-230).  The running energy totals are NOT touched (the reference accumulates
+ * them, src/force_field/force_field.cc:436-451); *recip_energy (may be NULL) receives the reciprocal energy of the fresh
+ * S(k).  When peers are attached the recompute is k-sharded: this rank computes a contiguous slice of the k list and
+ * the reduction epilogue stores it into every peer's S(k) through peer-mapped memory (NVLink) and handshakes with flags
+ * — a collective: every attached rank must call it.  _begin / _end let one thread drive several ranks.             */
+int pg_recompute_sk(pg_engine* h, double* recip_energy);
+int pg_recompute_sk_begin(pg_engine* h);
+int pg_recompute_sk_end(pg_engine* h, double* recip_energy, float* elapsed_ms);
+/* Peers of the k-sharded recompute.  Every rank exports a 64-byte handle (cudaIpcMemHandle_t) of its exchange block
+ * [S(k) | flags]; the caller exchanges the handles (any transport) and attaches all of them: handles is [world][64],
+ * the entry of `rank` itself is ignored.  _attach_local is the same for engines of ONE process (other GPUs with peer
+ * access, or the same GPU).  world <= 16; all ranks hold the same k list (same force field and box).               */
+int pg_sk_export(pg_engine* h, void* handle64);
+int pg_sk_attach(pg_engine* h, int rank, int world, const void* handles);
+int pg_sk_attach_local(pg_engine* h, int rank, int world, pg_engine* const* peers);
+int pg_sk_detach(pg_engine* h);
 
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this engine has launched since creation. */
@@ -367,6 +395,8 @@ void* pg_stream(const pg_engine* h);
 /* FP64 FMA throughput microbenchmark (GFLOP/s, FMA = 2 flop) used as the
  * roofline denominator the driver's MEASURED_PEAKS.json does not carry. */
 int pg_measure_fp64_peak(pg_engine* h, double* gflops);
+/* L2 streaming-read bandwidth microbenchmark (GB/s, 32 MiB L2-resident buffer). */
+int pg_measure_l2_peak(pg_engine* h, double* gbs);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,9 @@ struct PgChainArgs {
   unsigned long long* prof;
   int dbg_skip;
   int pad_;
+  // work counters, accumulated over the launches of this engine: [0] pair configurations evaluated inside a cutoff
+  // (LJ + real space + intra-molecular), [1] steps that evaluated an energy change, [2] accepted steps
+  unsigned long long* counters;
 };
 
 struct ChSmem {
@@ -109,7 +112,6 @@ struct ChSmem {
   uint32_t pre_raw[32];        // the next 32 draws, tempered ...
   double pre_u[32];            // ... and converted to uniforms by warp 0's lanes in parallel (a uniform is an FP64 division)
   double uacc;                 // the draw behind the proposal as a uniform: the acceptance variate, if it gets drawn
-  int bcell[CH_MAXLEN], bslot[CH_MAXLEN];   // the moved beads' cell records (fetched with the coordinates, used by the commit)
   long long wst[CH_NPHASE][CH_WARPS];   // instrumentation: per-warp clock at the end of each phase
   double red[CH_WARPS][CH_NACC];
   double part[2][CH_GMAX][CH_NACC];
@@ -177,7 +179,7 @@ __device__ __forceinline__ double ch_warp_sum(double v) {
       const double r2_ = dx_ * dx_ + dy_ * dy_ + dz_ * dz_;                               \
       if (r2_ <= rc2) {                                                                   \
         const double r_ = sqrt(r2_);                                                      \
-        if (r_ > 0 && r_ <= P.real_cutoff) acc_real += P.lB * (sm.sq[h_.y] * c_.y) * erfc(P.sqrt_alpha * r_) / r_; \
+        if (r_ > 0 && r_ <= P.real_cutoff) { acc_real += P.lB * (sm.sq[h_.y] * c_.y) * erfc(P.sqrt_alpha * r_) / r_; acc_cnt += 1.0; } \
       }                                                                                   \
     }                                                                                     \
     __syncwarp();                                                                         \
@@ -355,6 +357,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
 
   // running totals (rank 0, thread 0): the reference's E_tot members
   double E_pair = 0, E_ewald = 0, E_bond = 0, E_ext = 0, E_real = 0, E_recip = 0;
+  double n_inrange = 0.0;
+  unsigned long long n_eval = 0ull, n_acc = 0ull;
   if (rank == 0 && tid == 0) {
     E_pair = A.state->E_pair; E_ewald = A.state->E_ewald; E_bond = A.state->E_bond; E_ext = A.state->E_ext;
     E_real = A.state->E_real; E_recip = A.state->E_recip;
@@ -448,7 +452,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       sm.trl[0][i] = a.x; sm.trl[1][i] = a.y; sm.trl[2][i] = c.x;
       sm.gq[i] = c.y;
       sm.gtype[i] = A.type[g0 + i];
-      if (rank == 0 && P.pair_kind == 1) { sm.bcell[i] = __ldcg(&A.bead_cell[g0 + i]); sm.bslot[i] = __ldcg(&A.bead_slot[g0 + i]); }
     }
     // ------------------------------------------------------------------ (3) pivot rows: len - 1 x (randSphere, bond length)
     if (kind == CG_PIVOT) {
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
     }
     __syncthreads();
 
-    double acc_pair = 0.0, acc_real = 0.0, acc_rec = 0.0, acc_ov = 0.0, w_sum = 0.0, b_sum = 0.0, w_out = 0.0;
+    double acc_pair = 0.0, acc_real = 0.0, acc_rec = 0.0, acc_ov = 0.0, w_sum = 0.0, b_sum = 0.0, w_out = 0.0, acc_cnt = 0.0;
 
     // ------------------------------------------------------------------ (5) reciprocal space: this CTA's k slice
     if (in_r && nq > 0 && nk > 0 && !(skip & 1)) {
@@ -658,71 +661,48 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       const int U = n_mv * 2 * per;
       const double ljc2max = P.ljc2max;
       const PgDev* __restrict__ Pg = A.Pg;
-      // four units at a time: first their cell records (independent loads in flight together), then the candidates
-      for (int u0 = ct; u0 < U; u0 += 4 * CT) {
-        int4 rec[4];
-        int cix[4];
-#pragma unroll
-        for (int b_ = 0; b_ < 4; b_++) {
-          const int u = u0 + b_ * CT;
-          cix[b_] = -1;
-          rec[b_] = make_int4(-1, -1, -1, -1);
-          if (u < U) {
-            const int mc = u / per, cc = u - mc * per;
-            if (cc < nnb) {
-              const int m = mc >> 1, old = mc & 1;
-              const double x = old ? sm.cur[0][m] : sm.trl[0][m], y = old ? sm.cur[1][m] : sm.trl[1][m],
-                           z = old ? sm.cur[2][m] : sm.trl[2][m];
-              int ix = ch_cell1(x, iLx, A.nc[0]), iy = ch_cell1(y, iLy, A.nc[1]), iz = ch_cell1(z, iLz, A.nc[2]);
-              const int ox = (nbx == 3) ? (cc % 3) - 1 : 0;
-              const int r1 = (nbx == 3) ? cc / 3 : cc;
-              const int oy = (nby == 3) ? (r1 % 3) - 1 : 0;
-              const int r2_ = (nby == 3) ? r1 / 3 : r1;
-              const int oz = (nbz == 3) ? (r2_ % 3) - 1 : 0;
-              ix += ox; iy += oy; iz += oz;
-              if (ix < 0) ix += A.nc[0]; else if (ix >= A.nc[0]) ix -= A.nc[0];
-              if (iy < 0) iy += A.nc[1]; else if (iy >= A.nc[1]) iy -= A.nc[1];
-              if (iz < 0) iz += A.nc[2]; else if (iz >= A.nc[2]) iz -= A.nc[2];
-              cix[b_] = (ix * A.nc[1] + iy) * A.nc[2] + iz;
-              rec[b_] = __ldcg(reinterpret_cast<const int4*>(A.cell_slots + (size_t)cix[b_] * ccap));
-            }
+      for (int u = ct; u < U; u += CT) {
+        const int mc = u / per, cc = u - mc * per;
+        const int m = mc >> 1, old = mc & 1;
+        const double x = old ? sm.cur[0][m] : sm.trl[0][m], y = old ? sm.cur[1][m] : sm.trl[1][m],
+                     z = old ? sm.cur[2][m] : sm.trl[2][m];
+        const int tm = sm.gtype[m];
+        // one candidate partner: exact FP64 minimum-image separation, the reference's r < rcut predicate
+        auto lj_eval = [&](int j) {
+          if (j < 0 || (j >= g0 && j < g0 + glen)) return;
+          const double2 a = __ldcg(&A.xy[j]), c = __ldcg(&A.zq[j]);
+          double dx = a.x - x, dy = a.y - y, dz = c.x - z;
+          dx -= Lx * mv_rint(dx * iLx); dy -= Ly * mv_rint(dy * iLy); dz -= Lz * mv_rint(dz * iLz);
+          const double r2 = dx * dx + dy * dy + dz * dz;
+          if (r2 > ljc2max) return;
+          const int tp = tm * PG_MAX_TYPES + A.type[j];
+          if (r2 > Pg->lj_rcut2_relaxed[tp]) return;
+          const double e = pg_pair_energy_r(*Pg, sqrt(r2), tp);
+          acc_cnt += 1.0;
+          if (old) acc_pair -= e;
+          else { acc_pair += e; if (e >= PG_VLE) acc_ov += 1.0; }
+        };
+        if (cc < nnb) {
+          int ix = ch_cell1(x, iLx, A.nc[0]), iy = ch_cell1(y, iLy, A.nc[1]), iz = ch_cell1(z, iLz, A.nc[2]);
+          const int ox = (nbx == 3) ? (cc % 3) - 1 : 0;
+          const int r1 = (nbx == 3) ? cc / 3 : cc;
+          const int oy = (nby == 3) ? (r1 % 3) - 1 : 0;
+          const int r2_ = (nby == 3) ? r1 / 3 : r1;
+          const int oz = (nbz == 3) ? (r2_ % 3) - 1 : 0;
+          ix += ox; iy += oy; iz += oz;
+          if (ix < 0) ix += A.nc[0]; else if (ix >= A.nc[0]) ix -= A.nc[0];
+          if (iy < 0) iy += A.nc[1]; else if (iy >= A.nc[1]) iy -= A.nc[1];
+          if (iz < 0) iz += A.nc[2]; else if (iz >= A.nc[2]) iz -= A.nc[2];
+          const int cidx = (ix * A.nc[1] + iy) * A.nc[2] + iz;
+          const int4* cp = reinterpret_cast<const int4*>(A.cell_slots + (size_t)cidx * ccap);
+          for (int q4 = 0; q4 < ccap; q4 += 4) {
+            const int4 s0 = __ldcg(cp + (q4 >> 2));
+            lj_eval(s0.x); lj_eval(s0.y); lj_eval(s0.z); lj_eval(s0.w);
           }
-        }
-#pragma unroll
-        for (int b_ = 0; b_ < 4; b_++) {
-          const int u = u0 + b_ * CT;
-          if (u >= U) continue;
-          const int mc = u / per, cc = u - mc * per;
-          const int m = mc >> 1, old = mc & 1;
-          const double x = old ? sm.cur[0][m] : sm.trl[0][m], y = old ? sm.cur[1][m] : sm.trl[1][m],
-                       z = old ? sm.cur[2][m] : sm.trl[2][m];
-          const int tm = sm.gtype[m];
-          // one candidate partner: exact FP64 minimum-image separation, the reference's r < rcut predicate
-          auto lj_eval = [&](int j) {
-            if (j < 0 || (j >= g0 && j < g0 + glen)) return;
-            const double2 a = __ldcg(&A.xy[j]), c = __ldcg(&A.zq[j]);
-            double dx = a.x - x, dy = a.y - y, dz = c.x - z;
-            dx -= Lx * mv_rint(dx * iLx); dy -= Ly * mv_rint(dy * iLy); dz -= Lz * mv_rint(dz * iLz);
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            if (r2 > ljc2max) return;
-            const int tp = tm * PG_MAX_TYPES + A.type[j];
-            if (r2 > Pg->lj_rcut2_relaxed[tp]) return;
-            const double e = pg_pair_energy_r(*Pg, sqrt(r2), tp);
-            if (old) acc_pair -= e;
-            else { acc_pair += e; if (e >= PG_VLE) acc_ov += 1.0; }
-          };
-          if (cc < nnb) {
-            lj_eval(rec[b_].x); lj_eval(rec[b_].y); lj_eval(rec[b_].z); lj_eval(rec[b_].w);
-            const int4* cp = reinterpret_cast<const int4*>(A.cell_slots + (size_t)cix[b_] * ccap);
-            for (int q4 = 4; q4 < ccap; q4 += 4) {
-              const int4 s0 = __ldcg(cp + (q4 >> 2));
-              lj_eval(s0.x); lj_eval(s0.y); lj_eval(s0.z); lj_eval(s0.w);
-            }
-          } else {
-            // the overflow list (beads whose cell was full when they arrived): normally a handful of entries
-            const int o0 = (cc - nnb) * CH_OVF_CHUNK, o1 = min(o0 + CH_OVF_CHUNK, ovf_hw);
-            for (int o = o0; o < o1; o++) lj_eval(__ldcg(&A.ovf[o]));
-          }
+        } else {
+          // the overflow list (beads whose cell was full when they arrived): normally a handful of entries
+          const int o0 = (cc - nnb) * CH_OVF_CHUNK, o1 = min(o0 + CH_OVF_CHUNK, ovf_hw);
+          for (int o = o0; o < o1; o++) lj_eval(__ldcg(&A.ovf[o]));
         }
       }
       __syncwarp();   // the lanes of a warp leave this loop at different times: reconverge before the next phase
@@ -747,11 +727,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
         const double qq = P.use_ewald ? sm.gq[g] * sm.gq[jj] : 0.0;
         const double lim = fmax(P.pair_kind == 1 ? P.ljc2max : -1.0, (qq != 0.0) ? P.rc2_relaxed : -1.0);
         if (r2n <= lim) {
+          acc_cnt += 1.0;
           const double2 en = mv_pair_inrange(A.Pg, r2n, qq, tp);
           if (en.x >= PG_VLE) acc_ov += 1.0;
           acc_pair += en.x; acc_real += en.y;
         }
         if (r2o <= lim) {
+          acc_cnt += 1.0;
           const double2 eo = mv_pair_inrange(A.Pg, r2o, qq, tp);
           acc_pair -= eo.x; acc_real -= eo.y;
         }
@@ -778,9 +760,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
     CH_STAMP(7);
     // ------------------------------------------------------------------ (10) sums: warp -> CTA -> cluster, fixed order
     {
-      double v[CH_NACC] = {acc_pair, acc_real, acc_rec, acc_ov, w_sum, b_sum, w_out, 0.0};
+      double v[CH_NACC] = {acc_pair, acc_real, acc_rec, acc_ov, w_sum, b_sum, w_out, acc_cnt};
 #pragma unroll
-      for (int i = 0; i < 7; i++) v[i] = ch_warp_sum(v[i]);
+      for (int i = 0; i < CH_NACC; i++) v[i] = ch_warp_sum(v[i]);
       if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < CH_NACC; i++) sm.red[warp][i] = v[i];
@@ -833,6 +815,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       if (rank == 0) {
         PgChainRec r; r.dE = dE; r.mol = sm.step.mol; r.info = (kind & 0xff) | (accept << 8) | (stage << 16);
         A.log[step_i] = r;
+        n_inrange += sm.tot[7]; n_eval++; n_acc += (unsigned long long)accept;
         if (accept) {
           E_pair += d_pair; E_ewald += d_ewald; E_bond += d_bond; E_ext += d_ext; E_real += d_real; E_recip += d_recip;
         }
@@ -884,11 +867,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
             if (active) {
               newc = (ch_cell1(sm.trl[0][i], iLx, A.nc[0]) * A.nc[1] + ch_cell1(sm.trl[1][i], iLy, A.nc[1])) * A.nc[2] +
                      ch_cell1(sm.trl[2][i], iLz, A.nc[2]);
-              oldc = sm.bcell[i];
+              oldc = __ldcg(&A.bead_cell[bead]);
             }
             const bool changed = active && newc != oldc;
             if (changed) {
-              const int os = sm.bslot[i];
+              const int os = __ldcg(&A.bead_slot[bead]);
               if (os < ccap) __stcg(&A.cell_slots[(size_t)oldc * ccap + os], -1);
               else __stcg(&A.ovf[os - ccap], -1);
             }
@@ -963,6 +946,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       PgState* st = A.state;
       st->E_pair = E_pair; st->E_ewald = E_ewald; st->E_bond = E_bond; st->E_ext = E_ext; st->E_real = E_real; st->E_recip = E_recip;
       A.out[0] = step_i; A.out[1] = sm.stop; A.out[3] = sm.ovf_hw;
+      if (A.counters) { A.counters[0] += (unsigned long long)n_inrange; A.counters[1] += n_eval; A.counters[2] += n_acc; }
       if (sm.err) A.out[2] = sm.err;
     }
   }
@@ -1005,5 +989,8 @@ struct PgChainHost {
   int kmax[3] = {0, 0, 0};
   double kunit[3] = {0, 0, 0};
   unsigned long long* d_prof = nullptr;   // instrumentation
+  unsigned long long* d_counters = nullptr;
+  char* h_pin = nullptr;                  // pinned staging of pg_chain_run_multi_io
+  size_t pin_cap = 0;
   int dbg_skip = 0;
 };

@@ -14,7 +14,8 @@ void chain_free(pg_engine* h) {
   cudaFree(c.d_mol_first); cudaFree(c.d_chains); cudaFree(c.d_ions);
   cudaFree(c.d_cell_slots); cudaFree(c.d_ovf); cudaFree(c.d_ovf_n); cudaFree(c.d_bead_cell); cudaFree(c.d_bead_slot);
   cudaFree(c.d_qslot); cudaFree(c.d_qpos); cudaFree(c.d_qfrac);
-  cudaFree(c.d_mt); cudaFree(c.d_log); cudaFree(c.d_trial_log); cudaFree(c.d_out); cudaFree(c.d_args); cudaFree(c.d_prof);
+  if (c.h_pin) cudaFreeHost(c.h_pin);
+  cudaFree(c.d_mt); cudaFree(c.d_log); cudaFree(c.d_trial_log); cudaFree(c.d_out); cudaFree(c.d_args); cudaFree(c.d_prof); cudaFree(c.d_counters);
   c = PgChainHost();
 }
 
@@ -115,6 +116,10 @@ int chain_build(pg_engine* h) {
   if (!c.d_ovf) {
     PG_CUDA(h, cudaMalloc((void**)&c.d_ovf, sizeof(int) * CH_OVF_CAP));
     PG_CUDA(h, cudaMalloc((void**)&c.d_ovf_n, sizeof(int)));
+  }
+  if (!c.d_counters) {
+    PG_CUDA(h, cudaMalloc((void**)&c.d_counters, sizeof(unsigned long long) * 4));
+    PG_CUDA(h, cudaMemset(c.d_counters, 0, sizeof(unsigned long long) * 4));
   }
   if (!c.d_mt) {
     PG_CUDA(h, cudaMalloc((void**)&c.d_mt, sizeof(uint32_t) * (CG_N + 8)));
@@ -240,6 +245,7 @@ void chain_fill_args(pg_engine* h, int max_steps, PgChainArgs& A) {
   }
   A.prof = c.d_prof;
   A.dbg_skip = c.dbg_skip;
+  A.counters = c.d_counters;
 }
 
 // What a chain launch needs from every engine it carries.
@@ -453,6 +459,96 @@ int pg_chain_run_multi(pg_engine** hs, int n, int max_steps, int* n_done, float*
   return PG_OK;
 }
 
+// The whole boundary crossing of a batch in ONE call and ONE synchronisation (the end-to-end path of a driver that keeps
+// the generators and the beads on the host): generator states down, one launch, step logs, generator states and (if xyz
+// is not NULL) the accepted coordinates up — all through one pinned staging block of the first engine.
+//   rng_io   [n][625]  in: state words + position of every replica's std::mt19937; out: the state behind the last step
+//   rng_up   [n] (may be NULL = all): 0 = replica i continues from the state resident on the device (the caller's
+//            generator has not been touched since the last call handed it back)
+//   steps    [n][max_steps] records (may be NULL);  xyz [n] pointers to [n_beads][3] (may be NULL, entries may be NULL)
+int pg_chain_run_multi_io(pg_engine** hs, int n, int max_steps, uint32_t* rng_io, const uint8_t* rng_up, pg_chain_step* steps,
+                          double* const* xyz, int* n_done, float* elapsed_ms) {
+  if (!hs || n <= 0 || !hs[0] || !rng_io) return PG_ERR_INVALID;
+  pg_engine* lead = hs[0];
+  const int cluster = lead->ch.cluster;
+  const int nb = lead->n;
+  for (int i = 0; i < n; i++) {
+    if (!hs[i]) return PG_ERR_INVALID;
+    if (hs[i]->device != lead->device || hs[i]->ch.cluster != cluster) { lead->err = "pg_chain_run_multi_io: engines must share device and cluster size"; return PG_ERR_INVALID; }
+    if (xyz && hs[i]->n != nb) { lead->err = "pg_chain_run_multi_io: engines must hold the same number of beads"; return PG_ERR_INVALID; }
+    if ((!rng_up || rng_up[i]) && rng_io[(size_t)i * 625 + 624] > CG_N) { lead->err = "pg_chain_run_multi_io: generator position out of range"; return PG_ERR_INVALID; }
+    int rc = chain_prepare(hs[i], max_steps);
+    if (rc) { if (hs[i] != lead) lead->err = hs[i]->err; return rc; }
+  }
+  PgChainHost& c = lead->ch;
+  // pinned staging: [n] x { rng 625 u32 (pad to 640) | out 4 int | log max_steps x 16 B | xy nb x 16 B | zq nb x 16 B }
+  const size_t rng_b = 640 * sizeof(uint32_t), out_b = 16, log_b = steps ? sizeof(PgChainRec) * (size_t)std::max(max_steps, 1) : 0;
+  const size_t pos_b = xyz ? sizeof(double2) * (size_t)std::max(nb, 1) : 0;
+  const size_t per = rng_b + out_b + log_b + 2 * pos_b;
+  if (per * (size_t)n > c.pin_cap) {
+    if (c.h_pin) cudaFreeHost(c.h_pin);
+    c.h_pin = nullptr; c.pin_cap = 0;
+    PG_CUDA(lead, cudaHostAlloc((void**)&c.h_pin, per * (size_t)n, cudaHostAllocDefault));
+    c.pin_cap = per * (size_t)n;
+  }
+  if (c.args_cap < (size_t)n) {
+    cudaFree(c.d_args); c.d_args = nullptr; c.args_cap = 0;
+    PG_CUDA(lead, cudaMalloc((void**)&c.d_args, sizeof(PgChainArgs) * (size_t)n));
+    c.args_cap = (size_t)n;
+  }
+  std::vector<PgChainArgs> args((size_t)n);
+  for (int i = 0; i < n; i++) {
+    char* base = c.h_pin + per * (size_t)i;
+    chain_fill_args(hs[i], max_steps, args[i]);
+    if (hs[i] != lead) PG_CUDA(lead, cudaStreamSynchronize(hs[i]->stream));
+    if (!rng_up || rng_up[i]) {
+      memcpy(base, rng_io + (size_t)i * 625, 625 * sizeof(uint32_t));
+      PG_CUDA(lead, cudaMemcpyAsync(hs[i]->ch.d_mt, base, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, lead->stream));
+    }
+    PG_CUDA(lead, cudaMemsetAsync(hs[i]->ch.d_out, 0, sizeof(int) * 4, lead->stream));
+  }
+  PG_CUDA(lead, cudaMemcpyAsync(c.d_args, args.data(), sizeof(PgChainArgs) * (size_t)n, cudaMemcpyHostToDevice, lead->stream));
+  PG_CUDA(lead, cudaEventRecord(lead->ev0, lead->stream));
+  int rc = chain_launch(lead, c.d_args, n, cluster);
+  if (rc) return rc;
+  PG_CUDA(lead, cudaEventRecord(lead->ev1, lead->stream));
+  for (int i = 0; i < n; i++) {
+    char* base = c.h_pin + per * (size_t)i;
+    PG_CUDA(lead, cudaMemcpyAsync(base, hs[i]->ch.d_mt, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, lead->stream));
+    PG_CUDA(lead, cudaMemcpyAsync(base + rng_b, hs[i]->ch.d_out, sizeof(int) * 4, cudaMemcpyDeviceToHost, lead->stream));
+    if (steps && max_steps > 0)
+      PG_CUDA(lead, cudaMemcpyAsync(base + rng_b + out_b, hs[i]->ch.d_log, sizeof(PgChainRec) * (size_t)max_steps, cudaMemcpyDeviceToHost, lead->stream));
+    if (xyz && nb > 0) {
+      PG_CUDA(lead, cudaMemcpyAsync(base + rng_b + out_b + log_b, hs[i]->xy, pos_b, cudaMemcpyDeviceToHost, lead->stream));
+      PG_CUDA(lead, cudaMemcpyAsync(base + rng_b + out_b + log_b + pos_b, hs[i]->zq, pos_b, cudaMemcpyDeviceToHost, lead->stream));
+    }
+  }
+  PG_CUDA(lead, cudaStreamSynchronize(lead->stream));
+  if (elapsed_ms) PG_CUDA(lead, cudaEventElapsedTime(elapsed_ms, lead->ev0, lead->ev1));
+  for (int i = 0; i < n; i++) {
+    const char* base = c.h_pin + per * (size_t)i;
+    const int* out = reinterpret_cast<const int*>(base + rng_b);
+    hs[i]->ch.max_steps = max_steps;
+    if (out[2] != 0) {
+      hs[i]->err = chain_err_text(out[2]);
+      hs[i]->ch.valid = false;
+      lead->err = hs[i]->err;
+      return PG_ERR_STATE;
+    }
+    if (out[0] < 0 || out[0] > max_steps) { lead->err = "chain: inconsistent step count"; return PG_ERR_STATE; }
+    if (n_done) n_done[i] = out[0];
+    memcpy(rng_io + (size_t)i * 625, base, 625 * sizeof(uint32_t));
+    if (steps && out[0] > 0) memcpy(steps + (size_t)i * max_steps, base + rng_b + out_b, sizeof(PgChainRec) * (size_t)out[0]);
+    if (xyz && xyz[i]) {
+      const double2* hxy = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b);
+      const double2* hzq = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b + pos_b);
+      double* dst = xyz[i];
+      for (int b = 0; b < nb; b++) { dst[3 * b] = hxy[b].x; dst[3 * b + 1] = hxy[b].y; dst[3 * b + 2] = hzq[b].x; }
+    }
+  }
+  return PG_OK;
+}
+
 // The log of the last chain of this engine (also after pg_chain_run_multi).
 int pg_chain_steps(pg_engine* h, int first, int count, pg_chain_step* steps) {
   if (!h || !steps || first < 0 || count < 0) return PG_ERR_INVALID;
@@ -493,6 +589,22 @@ int pgx_chain_prof_read(pg_engine* h, unsigned long long* out) {
   PG_CUDA(h, cudaSetDevice(h->device));
   PG_CUDA(h, cudaStreamSynchronize(h->stream));
   PG_CUDA(h, cudaMemcpy(out, h->ch.d_prof, sizeof(unsigned long long) * 5 * CH_NPHASE, cudaMemcpyDeviceToHost));
+  return PG_OK;
+}
+
+// Work counters of this engine's chains since the last reset: pair configurations evaluated inside a cutoff, steps that
+// evaluated an energy change, accepted steps.
+int pg_chain_counters(pg_engine* h, uint64_t* out3, int reset) {
+  if (!h || !out3) return PG_ERR_INVALID;
+  PgChainHost& c = h->ch;
+  out3[0] = out3[1] = out3[2] = 0;
+  if (c.inflight) { h->err = "a chain is in flight"; return PG_ERR_STATE; }
+  if (!c.d_counters) return PG_OK;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  unsigned long long v[4];
+  PG_CUDA(h, cudaMemcpy(v, c.d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+  out3[0] = v[0]; out3[1] = v[1]; out3[2] = v[2];
+  if (reset) PG_CUDA(h, cudaMemset(c.d_counters, 0, sizeof(unsigned long long) * 4));
   return PG_OK;
 }
 

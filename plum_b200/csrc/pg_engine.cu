@@ -33,6 +33,7 @@
 #include "pg_pressure.cu"
 #include "pg_propose.cu"
 #include "pg_chain.cu"
+#include "pg_sk.cu"
 
 namespace {
 
@@ -166,6 +167,22 @@ struct pg_engine {
 
   // device-resident Markov chain (k_chain, pg_chain_*): resident spatial structures + io buffers
   PgChainHost ch;
+
+  // full S(k) recompute (pg_sk.cu): compact list of the charged beads (rebuilt from the host mirror of the charges when
+  // the bead set changes), the exchange block [S(k) | flags] other ranks map, the peers of a k-sharded recompute
+  int* d_qidx = nullptr; size_t qidx_cap = 0; int nq_tot = 0; bool qidx_valid = false;
+  char* d_xchg = nullptr;              // one allocation: nk_alloc double2 (d_S points here) + 2 * SK_MAX_PEERS flags
+  unsigned int* d_flags = nullptr;
+  unsigned int* d_sk_counter = nullptr;
+  int sk_kmax[3] = {0, 0, 0};
+  double sk_kunit[3] = {0, 0, 0};
+  std::vector<PgSkItem> h_sk_items;     // k columns in segments of <= SK_SEG consecutive lz (pg_sk.cu)
+  std::vector<int> h_sk_item_n;
+  PgSkItem* d_sk_items = nullptr;
+  int* d_sk_item_n = nullptr;
+  PgSkPeers peers;                      // world <= 1: not sharded
+  void* ipc_opened[SK_MAX_PEERS] = {nullptr};
+  bool sk_inflight = false;
 };
 
 #define PG_CUDA(h, call)                                                                     \
@@ -762,23 +779,76 @@ int wait_mail(pg_engine* h, unsigned int seq, pg_delta* o) {
 }
 
 
-// S(k) of the k slice [k_first, k_first + k_count) into `out` (device): bead chunks x k tiles, then the
-// ordered reduction over the chunks.  At most 128 chunks, whole 256-bead tiles each.
-int launch_sk_slice(pg_engine* h, int k_first, int k_count, double2* out) {
-  if (k_count <= 0) return PG_OK;
-  int chunk = PG_TILE * std::max(1, ((h->n + 127) / 128 + PG_TILE - 1) / PG_TILE);
-  const int n_chunks = std::max(1, (h->n + chunk - 1) / chunk);
-  const size_t need = (size_t)n_chunks * (size_t)k_count;
+// Compact list of the charged beads, from the host mirror of the charges.
+int ensure_qidx(pg_engine* h) {
+  if (h->qidx_valid) return PG_OK;
+  std::vector<int> idx;
+  for (int i = 0; i < h->n; i++)
+    if (h->h_q[i] != 0.0) idx.push_back(i);
+  if (idx.size() > h->qidx_cap || !h->d_qidx) {
+    cudaFree(h->d_qidx); h->d_qidx = nullptr; h->qidx_cap = 0;
+    const size_t cap = std::max<size_t>(idx.size() * 2, 1024);
+    PG_CUDA(h, cudaMalloc((void**)&h->d_qidx, sizeof(int) * cap));
+    h->qidx_cap = cap;
+  }
+  if (!idx.empty()) {
+    PG_CUDA(h, cudaMemcpyAsync(h->d_qidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->nq_tot = (int)idx.size();
+  h->qidx_valid = true;
+  return PG_OK;
+}
+
+// S(k) of the k slice [k_first, k_first + k_count) into `out` (device): k tiles x chunks of the charged list, then the
+// ordered reduction over the chunks (pg_sk.cu).  The chunking is a function of the number of charged beads only, so a
+// slice computed alone is bit-identical to the same rows of the full result.  With `exchange` the reduction also stores
+// the slice into the attached peers' S(k) and handshakes with them.
+int launch_sk_slice(pg_engine* h, int k_first, int k_count, double2* out, bool exchange = false) {
+  if (k_count <= 0 && !exchange) return PG_OK;
+  int rc = ensure_qidx(h);
+  if (rc) return rc;
+  const int nq = h->nq_tot;
+  const int chunk = SK_BEADS * std::max(1, (nq + SK_BEADS * 256 - 1) / (SK_BEADS * 256));
+  const int n_chunks = std::max(1, (nq + chunk - 1) / chunk);
+  const size_t need = (size_t)n_chunks * (size_t)std::max(k_count, 1);
   if (need > h->sk_partial_cap) {
     cudaFree(h->d_sk_partial); h->d_sk_partial = nullptr; h->sk_partial_cap = 0;
     PG_CUDA(h, cudaMalloc((void**)&h->d_sk_partial, sizeof(double2) * need));
     h->sk_partial_cap = need;
   }
-  const int kt = (k_count + PG_TILE - 1) / PG_TILE;
-  k_sk_slice<<<dim3(kt, n_chunks), PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->n, h->d_kvec, k_first, k_count, chunk,
-                                                          h->d_sk_partial);
-  k_sk_reduce<<<kt, PG_TILE, 0, h->stream>>>(h->d_sk_partial, n_chunks, k_count, out);
-  h->launches += 2;
+  PgSkArgs A;
+  memset(&A, 0, sizeof(A));
+  A.xy = h->xy; A.zq = h->zq; A.qidx = h->d_qidx; A.nq = nq;
+  A.k_first = k_first; A.k_count = k_count;
+  // the items that overlap the slice (items are sorted by their first k)
+  int i0 = 0, i1 = (int)h->h_sk_items.size();
+  while (i0 < i1 && h->h_sk_items[i0].k0 + h->h_sk_item_n[i0] <= k_first) i0++;
+  while (i1 > i0 && h->h_sk_items[i1 - 1].k0 >= k_first + k_count) i1--;
+  A.items = h->d_sk_items; A.item_n = h->d_sk_item_n; A.item_first = i0; A.item_count = i1 - i0;
+  for (int a = 0; a < 3; a++) {
+    A.kmax[a] = h->sk_kmax[a]; A.kunit[a] = h->sk_kunit[a];
+    A.ebox[a] = h->P.ebox[a]; A.inv_ebox[a] = h->P.inv_ebox[a]; A.pbc[a] = h->P.pbc[a];
+  }
+  A.chunk = chunk; A.partial = h->d_sk_partial;
+  const int ne = (h->sk_kmax[0] + 1) + (2 * h->sk_kmax[1] + 1) + (2 * h->sk_kmax[2] + 1);
+  const size_t smem = sizeof(double2) * (size_t)SK_BEADS * ne;
+  if (smem > 200 * 1024) { h->err = "S(k) recompute: k table does not fit shared memory"; return PG_ERR_CAPACITY; }
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    PG_CUDA(h, cudaFuncSetAttribute(k_sk_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  if (k_count > 0 && A.item_count > 0) {
+    const int kt = (A.item_count + SK_ITHREADS - 1) / SK_ITHREADS;
+    k_sk_block<<<dim3(kt, n_chunks), SK_ITHREADS, smem, h->stream>>>(A);
+    h->launches++;
+  }
+  PgSkPeers Pe = h->peers;
+  if (!exchange) Pe.world = 0;
+  k_sk_finish<<<std::max(1, (k_count + SK_THREADS - 1) / SK_THREADS), SK_THREADS, 0, h->stream>>>(
+      h->d_sk_partial, n_chunks, k_count, k_first, out, Pe, h->d_sk_counter);
+  h->launches++;
   PG_CUDA(h, cudaGetLastError());
   return PG_OK;
 }
@@ -818,7 +888,10 @@ void free_all(pg_engine* h) {
   chain_free(h);
   cudaFree(h->xy); cudaFree(h->zq); cudaFree(h->type); cudaFree(h->mol);
   cudaFree(h->t_xy); cudaFree(h->t_zq); cudaFree(h->t_type); cudaFree(h->t_mol);
-  cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_kvec); cudaFree(h->d_S); cudaFree(h->d_dS); cudaFree(h->d_Stmp);
+  for (int r = 0; r < SK_MAX_PEERS; r++)
+    if (h->ipc_opened[r]) cudaIpcCloseMemHandle(h->ipc_opened[r]);
+  cudaFree(h->d_kl); cudaFree(h->d_ek2); cudaFree(h->d_kvec); cudaFree(h->d_xchg); cudaFree(h->d_dS); cudaFree(h->d_Stmp);
+  cudaFree(h->d_qidx); cudaFree(h->d_sk_counter); cudaFree(h->d_sk_items); cudaFree(h->d_sk_item_n);
   for (int s = 0; s < 2; s++) {
     if (h->h_stage2[s]) cudaFreeHost(h->h_stage2[s]);
     cudaFree(h->d_stage2[s]);
@@ -940,7 +1013,37 @@ int pg_create(const pg_params* params, int device, int capacity_beads, pg_engine
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_kl, sizeof(int) * 4 * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_ek2, sizeof(double) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_kvec, sizeof(double4) * (size_t)nk_alloc));
-  PG_CREATE_CUDA(cudaMalloc((void**)&h->d_S, sizeof(double2) * (size_t)nk_alloc));
+  {
+    const size_t s_bytes = sizeof(double2) * (size_t)nk_alloc;
+    PG_CREATE_CUDA(cudaMalloc((void**)&h->d_xchg, s_bytes + sizeof(unsigned int) * 2 * SK_MAX_PEERS));
+    PG_CREATE_CUDA(cudaMemset(h->d_xchg, 0, s_bytes + sizeof(unsigned int) * 2 * SK_MAX_PEERS));
+    h->d_S = reinterpret_cast<double2*>(h->d_xchg);
+    h->d_flags = reinterpret_cast<unsigned int*>(h->d_xchg + s_bytes);
+    PG_CREATE_CUDA(cudaMalloc((void**)&h->d_sk_counter, sizeof(unsigned int) * 4));
+    PG_CREATE_CUDA(cudaMemset(h->d_sk_counter, 0, sizeof(unsigned int) * 4));
+    memset(&h->peers, 0, sizeof(h->peers));
+    for (int a = 0; a < 3; a++) { h->sk_kmax[a] = 0; h->sk_kunit[a] = 1 * 2 * kPi / h->P.ebox[a]; }
+    for (int k = 0; k < h->nk; k++)
+      for (int a = 0; a < 3; a++) h->sk_kmax[a] = std::max(h->sk_kmax[a], std::abs(h->h_kl[4 * k + a]));
+    // work items of the full recompute: runs of the k list with equal (lx, ly) and consecutive lz, at most SK_SEG long
+    for (int k = 0; k < h->nk;) {
+      const int lx = h->h_kl[4 * k], ly = h->h_kl[4 * k + 1], lz0 = h->h_kl[4 * k + 2];
+      int n = 1;
+      while (k + n < h->nk && n < SK_SEG && h->h_kl[4 * (k + n)] == lx && h->h_kl[4 * (k + n) + 1] == ly &&
+             h->h_kl[4 * (k + n) + 2] == lz0 + n) n++;
+      PgSkItem it; it.lx = lx; it.ly = ly; it.lz0 = lz0; it.k0 = k;
+      h->h_sk_items.push_back(it);
+      h->h_sk_item_n.push_back(n);
+      k += n;
+    }
+    const size_t ni = std::max<size_t>(h->h_sk_items.size(), 1);
+    PG_CREATE_CUDA(cudaMalloc((void**)&h->d_sk_items, sizeof(PgSkItem) * ni));
+    PG_CREATE_CUDA(cudaMalloc((void**)&h->d_sk_item_n, sizeof(int) * ni));
+    if (!h->h_sk_items.empty()) {
+      PG_CREATE_CUDA(cudaMemcpy(h->d_sk_items, h->h_sk_items.data(), sizeof(PgSkItem) * h->h_sk_items.size(), cudaMemcpyHostToDevice));
+      PG_CREATE_CUDA(cudaMemcpy(h->d_sk_item_n, h->h_sk_item_n.data(), sizeof(int) * h->h_sk_item_n.size(), cudaMemcpyHostToDevice));
+    }
+  }
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_dS, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMalloc((void**)&h->d_Stmp, sizeof(double2) * (size_t)nk_alloc));
   PG_CREATE_CUDA(cudaMemset(h->d_S, 0, sizeof(double2) * (size_t)nk_alloc));
@@ -1032,6 +1135,7 @@ int pg_upload_system(pg_engine* h, int n_beads, const double* xyz, const double*
   h->pending = false;
   h->pc.valid = false;
   h->ch.valid = false;
+  h->qidx_valid = false;
   replay_invalidate(h, true);
   return PG_OK;
 }
@@ -1747,6 +1851,7 @@ int pg_insert_molecules(pg_engine* h, int n_new_mol, const int32_t* mol_len, con
   h->n += n_add;
   h->n_mol += n_new_mol;
   h->ch.valid = false;
+  h->qidx_valid = false;
   replay_invalidate(h, true);
   return PG_OK;
 }
@@ -1795,6 +1900,7 @@ int pg_delete_molecules(pg_engine* h, int mf, int ml, pg_totals* removed) {
   h->n -= glen;
   h->n_mol -= nm;
   h->ch.valid = false;
+  h->qidx_valid = false;
   replay_invalidate(h, true);
   return PG_OK;
 }
@@ -1889,6 +1995,166 @@ int pg_sk_download(pg_engine* h, double* sk_host) {
   return PG_OK;
 }
 
+// ---- full S(k) recompute: drift reset, k-sharded over GPUs through peer-mapped memory (pg_sk.cu)
+int pg_sk_export(pg_engine* h, void* handle64) {
+  if (!h || !handle64) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t hd;
+  PG_CUDA(h, cudaIpcGetMemHandle(&hd, h->d_xchg));
+  memcpy(handle64, &hd, 64);
+  return PG_OK;
+}
+
+static int sk_set_peers(pg_engine* h, int rank, int world, char* const* blocks) {
+  const size_t s_bytes = sizeof(double2) * (size_t)std::max(h->nk, 1);
+  {
+    // nothing may allocate (an implicit device synchronisation) while a peer's kernel spins on a flag: size the
+    // scratch of a recompute now, and make the driver load the kernels of the recompute (with lazy module loading the
+    // FIRST launch of a kernel waits for the device to drain — behind a spinning kernel of the same process: forever)
+    cudaFuncAttributes fa;
+    PG_CUDA(h, cudaFuncGetAttributes(&fa, k_sk_ready));
+    PG_CUDA(h, cudaFuncGetAttributes(&fa, k_sk_block));
+    PG_CUDA(h, cudaFuncGetAttributes(&fa, k_sk_finish));
+    PG_CUDA(h, cudaFuncGetAttributes(&fa, k_sk_energy));
+    int rc = ensure_qidx(h);
+    if (rc) return rc;
+    const int chunk = SK_BEADS * std::max(1, (h->nq_tot + SK_BEADS * 256 - 1) / (SK_BEADS * 256));
+    const size_t need = (size_t)std::max(1, (h->nq_tot + chunk - 1) / chunk) * (size_t)std::max(h->nk, 1);
+    if (need > h->sk_partial_cap) {
+      cudaFree(h->d_sk_partial); h->d_sk_partial = nullptr; h->sk_partial_cap = 0;
+      PG_CUDA(h, cudaMalloc((void**)&h->d_sk_partial, sizeof(double2) * need));
+      h->sk_partial_cap = need;
+    }
+  }
+  memset(&h->peers, 0, sizeof(h->peers));
+  h->peers.world = world; h->peers.rank = rank; h->peers.seq = 0;
+  for (int r = 0; r < world; r++) {
+    h->peers.S[r] = reinterpret_cast<double2*>(blocks[r]);
+    h->peers.flags[r] = reinterpret_cast<unsigned int*>(blocks[r] + s_bytes);
+  }
+  return PG_OK;
+}
+
+int pg_sk_detach(pg_engine* h) {
+  if (!h) return PG_ERR_INVALID;
+  if (h->sk_inflight) { h->err = "a recompute is in flight"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < SK_MAX_PEERS; r++)
+    if (h->ipc_opened[r]) { cudaIpcCloseMemHandle(h->ipc_opened[r]); h->ipc_opened[r] = nullptr; }
+  memset(&h->peers, 0, sizeof(h->peers));
+  PG_CUDA(h, cudaMemset(h->d_flags, 0, sizeof(unsigned int) * 2 * SK_MAX_PEERS));
+  return PG_OK;
+}
+
+int pg_sk_attach(pg_engine* h, int rank, int world, const void* handles) {
+  if (!h || !handles || world < 1 || world > SK_MAX_PEERS || rank < 0 || rank >= world) return PG_ERR_INVALID;
+  int rc = pg_sk_detach(h);
+  if (rc) return rc;
+  char* blocks[SK_MAX_PEERS];
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { blocks[r] = h->d_xchg; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const char*>(handles) + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    PG_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened[r] = p;
+    blocks[r] = static_cast<char*>(p);
+  }
+  return sk_set_peers(h, rank, world, blocks);
+}
+
+int pg_sk_attach_local(pg_engine* h, int rank, int world, pg_engine* const* peers) {
+  if (!h || !peers || world < 1 || world > SK_MAX_PEERS || rank < 0 || rank >= world) return PG_ERR_INVALID;
+  int rc = pg_sk_detach(h);
+  if (rc) return rc;
+  char* blocks[SK_MAX_PEERS];
+  for (int r = 0; r < world; r++) {
+    if (!peers[r] || peers[r]->nk != h->nk) { h->err = "pg_sk_attach_local: peers must share the k list"; return PG_ERR_INVALID; }
+    if (peers[r]->device != h->device) {
+      int can = 0;
+      PG_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, peers[r]->device));
+      if (!can) { h->err = "pg_sk_attach_local: no peer access between the devices"; return PG_ERR_INVALID; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = cudaGetErrorString(e); return PG_ERR_CUDA; }
+      cudaGetLastError();
+    }
+    blocks[r] = peers[r]->d_xchg;
+  }
+  return sk_set_peers(h, rank, world, blocks);
+}
+
+int pg_recompute_sk_begin(pg_engine* h) {
+  if (!h) return PG_ERR_INVALID;
+  if (h->sk_inflight) { h->err = "a recompute is in flight"; return PG_ERR_STATE; }
+  if (h->pending || h->inflight || h->mc_inflight || h->ch.inflight) { h->err = "a trial or batch is still in flight"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  int rc = flush_commit(h);
+  if (rc) return rc;
+  PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  if (h->P.use_ewald && h->nk > 0) {
+    if (h->peers.world > 1) {
+      h->peers.seq++;
+      k_sk_ready<<<1, 32, 0, h->stream>>>(h->peers);
+      h->launches++;
+      const int q = h->nk / h->peers.world, r = h->nk % h->peers.world;
+      const int first = q * h->peers.rank + std::min(h->peers.rank, r), count = q + (h->peers.rank < r ? 1 : 0);
+      rc = launch_sk_slice(h, first, count, h->d_S + first, true);
+    } else {
+      rc = launch_sk_slice(h, 0, h->nk, h->d_S, false);
+    }
+    if (rc) return rc;
+    k_sk_energy<<<1, 256, 0, h->stream>>>(h->P, h->d_S, h->d_ek2, 0, h->nk, h->d_out8);
+    h->launches++;
+    PG_CUDA(h, cudaGetLastError());
+    PG_CUDA(h, cudaMemcpyAsync(h->h_out8, h->d_out8, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PG_CUDA(h, cudaMemcpyAsync(h->h_out8 + 1, h->d_sk_counter, sizeof(unsigned int) * 2, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    h->h_out8[0] = 0.0;
+    h->h_out8[1] = 0.0;
+  }
+  PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  h->sk_inflight = true;
+  return PG_OK;
+}
+
+int pg_recompute_sk_end(pg_engine* h, double* recip_energy, float* elapsed_ms) {
+  if (!h) return PG_ERR_INVALID;
+  if (!h->sk_inflight) { h->err = "no recompute in flight"; return PG_ERR_STATE; }
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->sk_inflight = false;
+  PG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (recip_energy) *recip_energy = h->h_out8[0];
+  if (elapsed_ms) PG_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  {
+    unsigned int w[2];
+    memcpy(w, h->h_out8 + 1, sizeof(w));
+    if (w[1] != 0u) {
+      h->err = std::string("k-sharded recompute: rank ") + std::to_string(w[1] > 100u ? w[1] - 101u : w[1] - 1u) +
+               (w[1] > 100u ? " never finished its slice" : " never entered the recompute") + " (every attached rank must call it)";
+      cudaMemsetAsync(h->d_sk_counter, 0, sizeof(unsigned int) * 4, h->stream);
+      return PG_ERR_TIMEOUT;
+    }
+  }
+  return PG_OK;
+}
+
+int pg_recompute_sk(pg_engine* h, double* recip_energy) {
+  int rc = pg_recompute_sk_begin(h);
+  if (rc) return rc;
+  return pg_recompute_sk_end(h, recip_energy, nullptr);
+}
+
+// Debug only (not part of the ABI header): the flag block of the k-sharded recompute ([0..16) ready, [16..32) done) + seq.
+int pgx_sk_flags(pg_engine* h, unsigned int* out33) {
+  if (!h || !out33) return PG_ERR_INVALID;
+  cudaSetDevice(h->device);
+  cudaMemcpy(out33, h->d_flags, sizeof(unsigned int) * 2 * SK_MAX_PEERS, cudaMemcpyDeviceToHost);
+  out33[32] = h->peers.seq;
+  return PG_OK;
+}
+
 // Debug only (not part of the ABI header): per-CTA %globaltimer stamps of the last k_move launch.
 int pgx_read_timing(pg_engine* h, unsigned long long* out, int max_ctas) {
   if (!h || !h->d_timing) return 0;
@@ -1918,6 +2184,34 @@ int pg_measure_fp64_peak(pg_engine* h, double* gflops) {
     if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e9);
   }
   *gflops = best;
+  return PG_OK;
+}
+
+// L2 streaming-read bandwidth (GB/s): 32 MiB buffer (a quarter of the 126 MB L2, resident after the first sweep),
+// best of 5 timed launches of 16 sweeps each.
+int pg_measure_l2_peak(pg_engine* h, double* gbs) {
+  if (!h || !gbs) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  const size_t bytes = (size_t)32 << 20, n16 = bytes / 16;
+  int4* buf = nullptr;
+  PG_CUDA(h, cudaMalloc((void**)&buf, bytes));
+  PG_CUDA(h, cudaMemsetAsync(buf, 1, bytes, h->stream));
+  cudaDeviceProp prop;
+  PG_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+  const int blocks = prop.multiProcessorCount * 8, reps = 16;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    PG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    k_l2_read<<<blocks, 256, 0, h->stream>>>(buf, n16, reps, reinterpret_cast<int*>(h->d_out8));
+    h->launches++;
+    PG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    PG_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    PG_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (rep > 0) best = std::max(best, (double)bytes * reps / (ms * 1e-3) / 1e9);
+  }
+  cudaFree(buf);
+  *gbs = best;
   return PG_OK;
 }
 

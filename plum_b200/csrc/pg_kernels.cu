@@ -592,3 +592,16 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
   double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
   if (s == 12345.678) out[0] = s;   // never true; keeps the loop alive
 }
+
+
+// L2 streaming-read microbenchmark (roofline denominator next to k_fp64_peak): every thread block sweeps an L2-resident
+// buffer with 16-byte loads, `reps` times; the sum keeps the loads alive.
+__global__ void __launch_bounds__(256) k_l2_read(const int4* __restrict__ buf, size_t n16, int reps, int* sink) {
+  int acc = 0;
+  for (int r = 0; r < reps; r++)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+      const int4 v = __ldcg(buf + i);
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x7fffffff) *sink = acc;
+}

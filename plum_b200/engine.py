@@ -26,7 +26,9 @@ ABI_SYMBOLS = [
     "pg_delete_molecules", "pg_wall_force", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
     "pg_stream", "pg_measure_fp64_peak",
     "pg_chain_configure", "pg_chain_set_rng", "pg_chain_get_rng", "pg_chain_run", "pg_chain_begin", "pg_chain_end",
-    "pg_chain_run_multi", "pg_chain_steps", "pg_chain_trial_xyz", "pg_chain_check",
+    "pg_chain_run_multi", "pg_chain_steps", "pg_chain_trial_xyz", "pg_chain_check", "pg_chain_counters",
+    "pg_chain_run_multi_io", "pg_measure_l2_peak",
+    "pg_recompute_sk", "pg_recompute_sk_begin", "pg_recompute_sk_end", "pg_sk_export", "pg_sk_attach", "pg_sk_attach_local", "pg_sk_detach",
 ]
 
 _LIB = None
@@ -94,6 +96,17 @@ def lib():
         L.pg_chain_steps.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PgChainStep)]
         L.pg_chain_trial_xyz.argtypes = [vp, C.c_int, c_double_p, C.c_int]
         L.pg_chain_check.argtypes = [vp, C.POINTER(C.c_int)]
+        L.pg_chain_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
+        L.pg_chain_run_multi_io.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(C.c_uint32), c_uint8_p, C.POINTER(PgChainStep),
+                                            C.POINTER(c_double_p), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.pg_measure_l2_peak.argtypes = [vp, c_double_p]
+        L.pg_recompute_sk.argtypes = [vp, c_double_p]
+        L.pg_recompute_sk_begin.argtypes = [vp]
+        L.pg_recompute_sk_end.argtypes = [vp, c_double_p, C.POINTER(C.c_float)]
+        L.pg_sk_export.argtypes = [vp, C.c_void_p]
+        L.pg_sk_attach.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+        L.pg_sk_attach_local.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+        L.pg_sk_detach.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -369,12 +382,53 @@ class Engine:
         self._check(self.L.pg_sk_download(self.h, dptr(out)), "pg_sk_download")
         return out[:nk]
 
+    def recompute_sk(self) -> float:
+        """Full S(k) recompute into the engine's own S(k) (k-sharded when peers are attached); returns the reciprocal energy."""
+        e = C.c_double()
+        self._check(self.L.pg_recompute_sk(self.h, C.cast(C.byref(e), c_double_p)), "pg_recompute_sk")
+        return e.value
+
+    def recompute_sk_begin(self):
+        self._check(self.L.pg_recompute_sk_begin(self.h), "pg_recompute_sk_begin")
+
+    def recompute_sk_end(self):
+        e, ms = C.c_double(), C.c_float()
+        self._check(self.L.pg_recompute_sk_end(self.h, C.cast(C.byref(e), c_double_p), C.byref(ms)), "pg_recompute_sk_end")
+        return e.value, float(ms.value)
+
+    def sk_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.L.pg_sk_export(self.h, buf), "pg_sk_export")
+        return buf.raw
+
+    def sk_attach(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == 64 * world
+        self._check(self.L.pg_sk_attach(self.h, int(rank), int(world), handles), "pg_sk_attach")
+
+    def sk_attach_local(self, rank: int, peers):
+        arr = (C.c_void_p * len(peers))(*[p.h for p in peers])
+        self._check(self.L.pg_sk_attach_local(self.h, int(rank), len(peers), arr), "pg_sk_attach_local")
+
+    def sk_detach(self):
+        self._check(self.L.pg_sk_detach(self.h), "pg_sk_detach")
+
     # -- instrumentation ---------------------------------------------------
     def launch_count(self) -> int:
         return int(self.L.pg_launch_count(self.h))
 
     def stream(self) -> int:
         return int(self.L.pg_stream(self.h) or 0)
+
+    def chain_counters(self, reset=False):
+        """(pair configurations evaluated inside a cutoff, evaluated steps, accepted steps) since the last reset."""
+        out = (C.c_uint64 * 3)()
+        self._check(self.L.pg_chain_counters(self.h, out, int(bool(reset))), "pg_chain_counters")
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def measure_l2_peak(self) -> float:
+        g = C.c_double()
+        self._check(self.L.pg_measure_l2_peak(self.h, C.cast(C.byref(g), c_double_p)), "pg_measure_l2_peak")
+        return g.value
 
     def measure_fp64_peak(self) -> float:
         g = C.c_double()

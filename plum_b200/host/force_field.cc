@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
@@ -71,7 +72,27 @@ struct McState {
   double avg_len = 256.0;      // smoothed steps per batch (GC steps / crankshafts cut batches short, too)
   vector<double> dE, xyz;
   vector<uint8_t> acc;
+  // device-resident chain (pg_chain_*): -1 not tried yet, 0 not offered for this system (the pg_mc_* path is used), 1 on
+  int chain = -1;
+  vector<pg_chain_step> steps;
+  mt19937 rng_handed;          // the driver's generator as the device handed it back last time
+  bool rng_resident = false;   // ... the device still holds that state: no upload unless the driver has drawn since
 };
+
+// std::mt19937 <-> 624 state words + position: the textual form operator<< / operator>> define.
+void MtExport(const mt19937& g, uint32_t* state, int* pos) {
+  std::stringstream ss;
+  ss << g;
+  for (int i = 0; i < 624; i++) { unsigned long v; ss >> v; state[i] = (uint32_t)v; }
+  unsigned long p; ss >> p;
+  *pos = (int)p;
+}
+void MtImport(mt19937& g, const uint32_t* state, int pos) {
+  std::stringstream ss;
+  for (int i = 0; i < 624; i++) ss << state[i] << ' ';
+  ss << pos;
+  ss >> g;
+}
 }  // namespace
 
 ForceField::ForceField() : vp_z(0), engine(NULL), pending_mol(-1), mc_state(NULL) {
@@ -441,6 +462,7 @@ void ForceField::FinalizeEnergies(vector<Molecule>& mols, bool accept, int moved
   { SiteTimer st_(kTCommit); rc = pg_commit(engine, accept ? 1 : 0); }
   if (rc) Fail("pg_commit", rc);
   pending_mol = -1;
+  SkDriftReset(1);
 }
 
 
@@ -452,6 +474,19 @@ static int BatchMode() {
   return mode;
 }
 bool ForceField::BatchedMoves() { return BatchMode() != 0; }
+
+// S(k) is carried incrementally (S += dS on every accepted move), so rounding drift grows with the number of updates;
+// every PLUM_B200_SK_RESET steps (default 2^20, 0 = never) it is recomputed from the resident coordinates
+// (pg_recompute_sk: the totals the driver prints are accumulated like the reference's and are not touched).
+void ForceField::SkDriftReset(int steps_done) {
+  static const long long every = [] { const char* e = getenv("PLUM_B200_SK_RESET"); return e ? atoll(e) : (1LL << 20); }();
+  if (every <= 0 || !use_ewald_pot) return;
+  sk_steps += steps_done;
+  if (sk_steps < every) return;
+  sk_steps = 0;
+  int rc = pg_recompute_sk(engine, NULL);
+  if (rc) Fail("pg_recompute_sk", rc);
+}
 
 int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, int max_steps, int first_step,
                                    double move_size, const double move_prob[5], int attempted[], int accepted[]) {
@@ -479,7 +514,75 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
   FILE* tf = plum_trace_file ? plum_trace_file() : NULL;
   FILE* tx = plum_trace_xyz_file ? plum_trace_xyz_file() : NULL;
   int executed = 0;
-  while (executed < max_steps) {
+  // ---- the device-resident chain: the generator itself goes to the device, nothing stops a stretch but a GC step.
+  // Offered for single-image systems without crankshaft moves (pg_chain_configure says so otherwise); PLUM_B200_CHAIN=0
+  // keeps the descriptor path below, PLUM_B200_CLUSTER sets the CTAs that share the chain (default 16),
+  // PLUM_B200_PIVOT_MODE=1 the prefix-sum pivot arms.
+  if (S.chain != 0) {
+    static const bool chain_off = [] { const char* e = getenv("PLUM_B200_CHAIN"); return e && e[0] == '0'; }();
+    if (S.chain < 0 || S.n_mol_configured < 0) {
+      pg_chain_config cc;
+      memset(&cc, 0, sizeof(cc));
+      cc.phantom = phantom;
+      cc.gc_freq = use_gc ? gc_freq : 0;
+      cc.vary_bond = use_bond_pot ? 1 : 0;
+      const char* ec = getenv("PLUM_B200_CLUSTER");
+      cc.cluster_ctas = ec ? atoi(ec) : 16;
+      const char* ep = getenv("PLUM_B200_PIVOT_MODE");
+      cc.pivot_mode = (ep && ep[0] == '1') ? 1 : 0;
+      cc.keep_trials = tx ? 1 : 0;
+      cc.move_size = move_size;
+      cc.bond_len = use_bond_pot ? bond_r0 : (use_bond_rigid ? rigid_bond : 0.0);
+      for (int i = 0; i < 5; i++) cc.move_prob[i] = move_prob[i];
+      S.chain = (!chain_off && pg_chain_configure(engine, &cc) == PG_OK) ? 1 : 0;
+    }
+  }
+  if (S.chain == 1) {
+    uint32_t state[624];
+    int pos = 0;
+    S.steps.resize(max_steps);
+    int rc = 0, n_done = 0, stop = 0;
+    { SiteTimer st_(kTDelta);
+      if (!(S.rng_resident && rand_gen == S.rng_handed)) {
+        MtExport(rand_gen, state, &pos);
+        rc = pg_chain_set_rng(engine, state, pos);
+        if (rc) Fail("pg_chain_set_rng", rc);
+      }
+      rc = pg_chain_run(engine, max_steps, &n_done, &stop, S.steps.data(), NULL);
+      if (rc) Fail("pg_chain_run", rc);
+      rc = pg_chain_get_rng(engine, state, &pos);
+      if (rc) Fail("pg_chain_get_rng", rc); }
+    MtImport(rand_gen, state, pos);
+    S.rng_handed = rand_gen;
+    S.rng_resident = true;
+    for (int m = 0; m < n_done; m++) {
+      const pg_chain_step& d = S.steps[m];
+      if (d.kind < 0) continue;
+      attempted[d.kind]++;
+      if (d.accept) accepted[d.kind]++;
+      if (tf) {
+        fprintf(tf, "T %d %d %d %a %d", first_step + m, (int)d.kind, d.mol, d.dE, (int)d.accept);
+        if (m == n_done - 1) {
+          fprintf(tf, " %a %a %a %a\n", use_pair_pot ? TotPairEnergy() : 0.0, use_ewald_pot ? TotEwaldEnergy() : 0.0,
+                  use_bond_pot ? TotBondEnergy() : 0.0, use_ext_pot ? TotExtEnergy() : 0.0);
+        } else {
+          fprintf(tf, " nan nan nan nan\n");
+        }
+        if (tx) {
+          const int len = mols[d.mol].Size();
+          vector<double> t(3 * len);
+          rc = pg_chain_trial_xyz(engine, m, t.data(), len);
+          if (rc) Fail("pg_chain_trial_xyz", rc);
+          fprintf(tx, "X %d", len);
+          for (int i = 0; i < len; i++)
+            fprintf(tx, " %d %a %a %a", (d.kind == PG_MOVE_BEAD) ? (i == 0) : 1, t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+          fprintf(tx, "\n");
+        }
+      }
+    }
+    executed = n_done;
+  }
+  while (S.chain != 1 && executed < max_steps) {
     const int budget = min(S.sizer.next(), max_steps - executed);
     const int n_steps = S.prop.generate(rand_gen, budget, S.batch);
     if (n_steps == 0) break;   // a GC step or a crankshaft is next
@@ -535,6 +638,7 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
     if (!stopped && b.stop != plum_mc::STOP_FULL) break;   // the generator stands in front of a step the driver runs
     if (S.cooldown > 0) break;
   }
+  SkDriftReset(executed);
   if (executed > 0) {
     // the device's coordinates are the accepted ones: bring the driver's beads (current and trial) up to date
     int n = 0;

@@ -78,6 +78,7 @@ class ForceField {
   map<string, int> type_of;        // bead symbol -> dense type id
   vector<string> type_symbols;
   int pending_mol;                  // molecule of the trial awaiting FinalizeEnergies (-1: none)
+  long long sk_steps = 0;           // steps since the last full S(k) recompute (SkDriftReset)
   void* mc_state;                   // batched translational steps: generator, batch buffers (force_field.cc)
 
   int TypeId(const string& symbol);
@@ -110,6 +111,8 @@ class ForceField {
                          const double move_prob[5], int attempted[], int accepted[]);
   /** PLUM_B200_BATCH=0 turns the batched steps off (the driver then runs every step itself). */
   bool BatchedMoves();
+  /** Periodic full recompute of the structure factor (drift reset); called with the steps just executed. */
+  void SkDriftReset(int steps_done);
 
   // Pressure samplers: SURVEY.md §8(f) "next" #1 — not on the per-move path.  They
   // consume no random numbers, so leaving them out does not change the trajectory.

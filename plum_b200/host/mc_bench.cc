@@ -49,6 +49,9 @@ struct Ctx {
   double *rec_u = nullptr, *rec_dE = nullptr, *rec_trial = nullptr;
   uint8_t *rec_acc = nullptr, *rec_moved = nullptr;
   int rec_cap_beads = 0;
+  int pivot_mode = 0;        // pg_chain_config.pivot_mode of the chain path
+  std::mt19937 rng_handed;   // the generator as the device handed it back last time
+  bool rng_resident = false; // ... and whether that hand-back happened (the device then still holds the state)
 };
 
 // One proposal, drawn in the reference's order (mc_propose.h) and built on the host; false when the
@@ -216,6 +219,9 @@ int pb_run(void* p, int n_moves, int32_t* rec_mol, int32_t* rec_off, double* rec
 }
 
 
+// Chain path: 0 builds pivot arms in the reference's operation order, 1 as prefix sums (include/plum_b200.h).
+void pb_set_pivot_mode(void* p, int mode) { static_cast<Ctx*>(p)->pivot_mode = mode; }
+
 // Spring-bond variant: the generators vary the bond length by +-10 % (simulation.cc:293-296).
 void pb_set_vary_bond(void* p, int vary) {
   Ctx* c = static_cast<Ctx*>(p);
@@ -362,11 +368,12 @@ void mt_import(std::mt19937& g, const uint32_t* state, int pos) {
 }
 
 int chain_configure(Ctx* c, int cluster, int keep_trials) {
+
   const plum_mc::Config& pc = c->prop.config();
   pg_chain_config cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.phantom = pc.phantom; cfg.gc_freq = pc.gc_freq; cfg.vary_bond = pc.vary_bond ? 1 : 0;
-  cfg.cluster_ctas = cluster; cfg.keep_trials = keep_trials;
+  cfg.cluster_ctas = cluster; cfg.keep_trials = keep_trials; cfg.pivot_mode = c->pivot_mode;
   cfg.move_size = pc.move_size; cfg.bond_len = pc.bond_len;
   for (int i = 0; i < 5; i++) cfg.move_prob[i] = pc.move_prob[i];
   return pg_chain_configure(c->eng, &cfg);
@@ -413,34 +420,38 @@ int pb_run_chain(void** ps, int n_ctx, int n_moves, int batch, int cluster, int 
   }
   if (batch <= 0) batch = 1024;
   auto t0 = std::chrono::steady_clock::now();
-  std::vector<pg_chain_step> st((size_t)batch);
+  // (buffers of the call live across calls: a fresh 100 MB vector per step would cost more than the transfers)
+  static thread_local std::vector<pg_chain_step> st;
+  static thread_local std::vector<uint32_t> rng;
+  static thread_local std::vector<uint8_t> up;
+  static thread_local std::vector<double*> xyz;
+  if (st.size() < (size_t)batch * n_ctx) st.resize((size_t)batch * n_ctx);
+  rng.resize((size_t)625 * n_ctx); up.resize(n_ctx); xyz.resize(n_ctx);
   std::vector<int> n_done(n_ctx);
-  uint32_t state[624];
-  int pos = 0;
   int left = n_moves;
   while (left > 0) {
     const int b = std::min(batch, left);
     for (int i = 0; i < n_ctx; i++) {
-      mt_export(cs[i]->rng, state, &pos);
-      int rc = pg_chain_set_rng(engs[i], state, pos);
-      if (rc) return rc;
+      // the generator goes down only if the host has drawn from it since the device handed it back
+      up[i] = !(cs[i]->rng_resident && cs[i]->rng == cs[i]->rng_handed);
+      if (up[i]) {
+        int pos = 0;
+        mt_export(cs[i]->rng, rng.data() + (size_t)625 * i, &pos);
+        rng[(size_t)625 * i + 624] = (uint32_t)pos;
+      }
+      xyz[i] = positions_every_batch ? cs[i]->pos.data() : nullptr;
     }
-    int rc = pg_chain_run_multi(engs.data(), n_ctx, b, n_done.data(), nullptr);
+    int rc = pg_chain_run_multi_io(engs.data(), n_ctx, b, rng.data(), up.data(), st.data(), positions_every_batch ? xyz.data() : nullptr,
+                                   n_done.data(), nullptr);
     if (rc) return rc;
     int moves0 = -1;
     for (int i = 0; i < n_ctx; i++) {
       if (n_done[i] != b) return PG_ERR_STATE;
-      rc = pg_chain_steps(engs[i], 0, b, st.data());
-      if (rc) return rc;
-      const int moves = chain_book(cs[i], st.data(), b);
+      const int moves = chain_book(cs[i], st.data() + (size_t)b * i, b);
       if (i == 0) moves0 = moves;
-      rc = pg_chain_get_rng(engs[i], state, &pos);
-      if (rc) return rc;
-      mt_import(cs[i]->rng, state, pos);
-      if (positions_every_batch) {
-        rc = pg_download_positions(engs[i], cs[i]->pos.data());
-        if (rc) return rc;
-      }
+      mt_import(cs[i]->rng, rng.data() + (size_t)625 * i, (int)rng[(size_t)625 * i + 624]);
+      cs[i]->rng_handed = cs[i]->rng;
+      cs[i]->rng_resident = true;
     }
     // every step of these systems attempts a move; the loop counts replica 0's
     left -= std::max(moves0, 1);

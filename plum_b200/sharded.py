@@ -8,8 +8,14 @@
    which every rank holds the full S(k) and adopts it.  The reciprocal energy is the all-reduced
    sum of the per-slice energies.
 
-The collective is `torch.distributed` plumbing; the compute is the engine's k_sk_slice kernel
-(`pg_sk_compute_slice`).  Nothing here is on the per-move path.
+Two forms of the exchange:
+  * fused (the product path, `attach_peers` + `engine.recompute_sk()`): the ranks swap 64-byte handles of their exchange
+    blocks once (torch.distributed, any backend); afterwards a recompute is three kernels per rank and no collective call —
+    the reduction epilogue of every rank stores its slice into every peer's S(k) through peer-mapped memory and handshakes
+    with flags (plum_b200/csrc/pg_sk.cu);
+  * all-gather (`sharded_sk_recompute`): slices computed into a torch buffer, `all_gather_into_tensor`, adopted with
+    `pg_sk_set` — kept as the plain-collective baseline the fused form is measured against, and for the gloo CPU tests.
+Nothing here is on the per-move path.
 """
 from __future__ import annotations
 
@@ -138,3 +144,41 @@ def time_sharded_recompute(engine, rank: int, world: int, e_recip_init: float, r
                 nccl_allgather_ms=mx(float(np.median(t_nccl))), total_ms=mx(float(np.median(t_tot))),
                 allgather_bytes=int(world * pad * 16) if world > 1 else 0, energy_matches_init=bool(ok),
                 timing=f"median of {reps}, max over ranks; compute = host wall around the synchronous slice kernel, NCCL = CUDA events")
+
+
+def attach_peers(engine, rank: int, world: int, group=None) -> None:
+    """Exchange the ranks' exchange-block handles and attach them: afterwards `engine.recompute_sk()` is k-sharded."""
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    mine = engine.sk_export()
+    got = [None] * world
+    dist.all_gather_object(got, mine, group=group)
+    engine.sk_attach(rank, world, b"".join(got))
+
+
+def time_fused_recompute(engine, rank: int, world: int, e_recip_init: float, reps: int = 30, warm: int = 5, group=None) -> dict:
+    """Time the (k-sharded when world > 1) full S(k) recompute with the exchange fused into the reduction epilogue:
+    CUDA-event time from the first kernel to the last (the waits for the peers' flags included), median over `reps`, max
+    over ranks.  The reciprocal energy of the result must reproduce `e_recip_init` within 1e-10."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device())
+    times, e = [], 0.0
+    for it in range(reps + warm):
+        if world > 1:
+            dist.barrier(group=group)
+        engine.recompute_sk_begin()
+        e, ms = engine.recompute_sk_end()
+        if it >= warm:
+            times.append(ms)
+    ok = abs(e - e_recip_init) <= 1e-10 * max(1.0, abs(e_recip_init))
+    t = torch.tensor([float(np.median(times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    n_k = engine.ewald_info().n_k_half
+    return dict(n_gpus=int(world), n_k=int(n_k), k_per_rank=int(k_slice(n_k, rank, world)[1]), total_ms=float(t.item()),
+                exchange="slice stored into the peers' S(k) by the reduction epilogue over peer-mapped memory + flag handshake (no NCCL call)"
+                if world > 1 else "none (one rank)",
+                bytes_stored_to_peers=int(k_slice(n_k, rank, world)[1] * 16 * (world - 1)), energy_matches_init=bool(ok),
+                timing=f"CUDA events around the rank's kernels (ready flag, k_sk_block, k_sk_finish incl. waits, energy), median of {reps}, max over ranks")

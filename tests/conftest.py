@@ -1,6 +1,10 @@
 import os
 import sys
 
+# engines of one process that stand in for the ranks of a collective (k-sharded recompute) spin on each other's flags:
+# every stream needs a hardware queue of its own (the default 8 would alias 7 engine streams + the default stream)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (REPO, os.path.join(REPO, "tests")):
     if p not in sys.path:

@@ -704,3 +704,53 @@ def test_stress_variant_s_full_parity():
     assert ca.rec_mol.tolist() == cb.rec_mol.tolist() and ca.rec_acc.tolist() == cb.rec_acc.tolist()
     assert np.array_equal(ca.positions(), cb.positions())
     eng.close(); eng2.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 7])
+def test_fused_k_sharded_recompute_with_emulated_ranks(world):
+    """pg_recompute_sk with peers (pg_sk_attach_local: `world` engines of this process on one GPU stand in for the ranks): every
+    rank computes its k slice, the reduction epilogue stores it into every peer's S(k) and handshakes with flags.  Every
+    rank's S(k) must equal, bit for bit, the S(k) a single engine computes alone (the chunking of the charged list does not
+    depend on the slicing), and the reciprocal energy the initialisation's."""
+    r, s, types, params = replay.load_golden("synth_cut")
+    ids = types.ids(s.symbol)
+    engs = []
+    for _ in range(world):
+        e = _engine(params, s.n)
+        e.upload(s.xyz, s.q, ids, s.mol_first)
+        engs.append(e)
+    t0 = engs[0].init_energy()
+    want = engs[0].sk_download()
+    for rk, e in enumerate(engs):
+        e.sk_attach_local(rk, engs)
+    for rep in range(3):                      # flags are sequence numbers: the collective can be repeated
+        for e in engs:
+            e.recompute_sk_begin()
+        for e in engs:
+            en, ms = e.recompute_sk_end()
+            assert abs(en - t0["recip"]) <= 1e-12 * max(1.0, abs(t0["recip"]))
+        for e in engs:
+            assert np.array_equal(e.sk_download(), want)
+    for e in engs:
+        e.sk_detach()
+        assert abs(e.recompute_sk() - t0["recip"]) <= 1e-12 * max(1.0, abs(t0["recip"]))
+        e.close()
+
+
+def test_recompute_sk_resets_drift_without_touching_totals():
+    """After a stretch of accepted moves the incrementally updated S(k) equals the recomputed one to rounding; pg_recompute_sk
+    replaces it and leaves the accumulated totals alone."""
+    from plum_b200 import mcgen
+    r, s, types, params = replay.load_golden("synth_cut")
+    e = _engine(params, s.n)
+    e.upload(s.xyz, s.q, types.ids(s.symbol), s.mol_first)
+    e.init_energy()
+    c = mcgen.NativeChain(e, r, s, 9, record_moves=400)
+    c.run_chain(400, batch=400, cluster=4)
+    before, tot = e.sk_download(), e.totals()
+    en = e.recompute_sk()
+    after = e.sk_download()
+    assert np.abs(after - before).max() <= 1e-10
+    assert e.totals() == tot
+    assert abs(en - e.recompute_totals()["recip"]) <= 1e-12 * max(1.0, abs(en))
+    e.close()

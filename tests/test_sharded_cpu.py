@@ -78,3 +78,38 @@ def test_world2_allgather_reproduces_full_structure_factor(name, tmp_path):
         assert np.array_equal(got, ref)          # slices are moved, never recomputed: bit identical
         e = np.load(os.path.join(str(tmp_path), f"e_{rank}.npy"))
         assert abs(e[0] - e[1]) <= 1e-12 * abs(e[1])
+
+
+def _attach_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from plum_b200 import sharded
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    class FakeEngine:
+        """Stands in for Engine: records what attach_peers hands to pg_sk_attach."""
+        def sk_export(self):
+            return bytes([rank]) * 64
+
+        def sk_attach(self, rk, w, handles):
+            out.put((rank, rk, w, handles))
+
+    sharded.attach_peers(FakeEngine(), rank, world)
+    dist.destroy_process_group()
+
+
+def test_attach_peers_exchanges_every_ranks_handle_in_rank_order():
+    """Host plumbing of the fused k-sharded recompute (world_size 2, gloo): every rank receives all 64-byte handles,
+    concatenated in rank order, together with its own rank and the world size."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29731
+    ps = [ctx.Process(target=_attach_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = bytes([0]) * 64 + bytes([1]) * 64
+    assert got == [(0, 0, 2, want), (1, 1, 2, want)]

@@ -168,3 +168,31 @@ def test_chemical_potential_sampler_on_trajectory():
     # mu column (6th) of the step-200 line
     mu_got, mu_ref = float(got_stat[1][5]), float(ref_stat[1][5])
     assert abs(mu_got - mu_ref) <= 1e-6 * abs(mu_ref), (mu_got, mu_ref)
+
+
+@pytest.mark.parametrize("seed,env", [(1, {}), (2, {"PLUM_B200_CLUSTER": "8"}), (1, {"PLUM_B200_PIVOT_MODE": "1"}),
+                                      (2, {"PLUM_B200_CHAIN": "0", "PLUM_B200_BATCH": "2"}), (1, {"PLUM_B200_BATCH": "0"})])
+def test_driver_over_the_device_resident_chain_reproduces_the_reference_on_the_cut_of_S(seed, env):
+    """bin/plum_gpu (the reference's unchanged driver + façade) on the 1320-bead cut of the benchmark system: the
+    translational steps run as device-resident chains (ForceField::TranslationalBatch -> pg_chain_*: the driver's own
+    std::mt19937 state travels to the device and back), as descriptor batches (pg_mc_*) or move by move — always the
+    trajectory plum_ref itself walked (tests/golden/long/synth_cut_seed<k>.npz: 2000 steps)."""
+    import os
+    assert replay.have_plum_gpu(), "bin/plum_gpu missing: run __graft_entry__.build() where /root/reference exists"
+    z = np.load(os.path.join(replay.GOLDEN, "long", f"synth_cut_seed{seed}.npz"))
+    n = len(z["kind"])
+    lines = replay.run_plum_ref(replay.golden_example_dir("synth_cut"), n, seed, xyz=False, binary=replay.PLUM_GPU,
+                                overrides={"s1_sampling_frequency": 250, "s1_sampling_print_frequency": 500}, extra_env=env)
+    init, kind, accept, mtype, mol, val, tot = _parse(lines, n)
+    assert np.all(np.abs(init - z["init"]) <= TOL * np.maximum(1.0, np.abs(z["init"])))
+    assert mtype.tolist() == z["kind"].tolist()
+    assert mol.tolist() == z["mol"].tolist()
+    assert accept.tolist() == z["accept"].tolist()
+    big = z["dE"] >= 1e8
+    assert np.array_equal(val >= 1e8, big)
+    err = np.abs(val[~big] - z["dE"][~big]) / np.maximum(1.0, np.abs(z["dE"][~big]))
+    assert err.max() <= TOL, err.max()
+    has = ~np.isnan(tot[:, 0])
+    assert has.sum() >= 4
+    terr = np.abs(tot[has] - z["tot"][has]) / np.maximum(1.0, np.abs(z["tot"][has]))
+    assert terr.max() <= 1e-9, terr.max()
