@@ -348,7 +348,9 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must take the job down in minutes, not after NCCL's default 10 min watchdog
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
 
     def barrier():
         if world > 1:
@@ -684,6 +686,7 @@ def run_ours(a):
     nb = main["batches_per_step"]
     h2d = float(R * nb * (625 * 4 + 768))
     d2h = float(R * (16 * M + nb * (625 * 4 + 16 + 32 * sysm.n)))
+    evals_total = sum_over_ranks(main["evals"])     # a collective: every rank takes part
     if rank == 0:
         line = {
             "metric": "MC moves/sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -693,7 +696,7 @@ def run_ours(a):
                        "pivot_mode": main["pivot_mode"],
                        "mode": f"throughput: {R} independent Markov chains per GPU, all in one k_chain launch per step; the rate of ONE chain is in single_chain",
                        "l2": "flushed between steps (256 MiB fill); within a step each chain's working set stays L2-resident by design (north_star)"},
-            "pair_dE_evals_per_s": sum_over_ranks(main["evals"]) / main["dev_s"],
+            "pair_dE_evals_per_s": evals_total / main["dev_s"],
             "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": main["t_e2e"] * 1e3 / K,
                     "caller": f"native C++ caller (plum_b200/host/mc_bench.cc pb_run_chain), ONE host thread per GPU driving {R} chains: per batch of "

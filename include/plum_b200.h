@@ -358,6 +358,26 @@ int pg_delete_molecules(pg_engine* h, int mol_first, int mol_last, pg_totals* re
  * behaviour in the reference. */
 int pg_wall_force(pg_engine* h, int n_phantom, double* out6);
 
+/* One sample of the volume-perturbation pressure estimator: the energy change of the resident
+ * configuration under a virtual stretch of the box along z by dz, split by species pair —
+ * the loops of ForceField::CalcPressureVolScalingHSELSlit (src/force_field/pressure.cc:187-338;
+ * the reference fixes dz = kDz = 1e-5, src/utilities/constants.h:55).  Species: 0 cation,
+ * 1 anion, 2 polymer bead, 3 surface site (the first n_phantom molecules); tables are indexed
+ * i*4+j with i <= j like p_tensor_el / p_tensor_hs.  The caller keeps the running sums and the
+ * Yethiraj / de Miguel averages (pressure.cc:346-384).  The pairwise reciprocal-space sum of
+ * PairEnergyReplForP (potential_ewald_coul.cc:228-250) is evaluated through per-species
+ * structure factors of both geometries; see plum_b200/csrc/pg_volscale.cu. */
+typedef struct pg_vol_sample {
+  double el[16];   /* electrostatic dU per species pair (p_tensor_el increments)        */
+  double hs[16];   /* LJ / hard-sphere and wall dU per species pair (p_tensor_hs)      */
+  double bond;     /* bond-potential dU (p_tensor[5] increment)                        */
+  double dipole;   /* dipole-correction dU (p_tensor[4] increment)                     */
+  double dU;       /* everything above                                                 */
+  int32_t n_free;  /* n_mol - n_phantom                                                */
+  int32_t _pad;
+} pg_vol_sample;
+int pg_vol_scaling_sample(pg_engine* h, int n_phantom, double dz, pg_vol_sample* out);
+
 /* Full S(k) over all charged beads for the k slice [k_first, k_first+k_count)
  * of the half-space list; writes interleaved (re,im) to sk_dev (device pointer,
  * may alias a torch tensor) or, if NULL, into the engine's own S(k).  Used by

@@ -5,7 +5,7 @@ Compiles /root/reference/src (nuwapi/Plum, unmodified arithmetic) into
 ``oracle/_ref/plum_ref`` so the restatement in ``oracle/plum_oracle.c`` and the
 CUDA path can be pinned against the real thing.  Nothing from the reference is
 copied into the repository: the sources are copied to a throw-away directory
-under /tmp, two hooks are applied to that copy, and only the binary lands in
+under /tmp, observation hooks are applied to that copy, and only the binary lands in
 ``oracle/_ref/`` (git-ignored).
 
 Differences from the reference's own ``src/Makefile:1-25``:
@@ -15,7 +15,9 @@ Differences from the reference's own ``src/Makefile:1-25``:
     ``src/simulation/simulation.cc:134``;
   * hook 2 (trace): when ``PLUM_TRACE`` names a file, one line per MC step is
     appended with the move, dE (hex float), the accept decision and the four
-    running energy totals.  The hooks only *observe*; no arithmetic changes.
+    running energy totals, and one per volume-perturbation pressure sample (the
+    accumulators of src/force_field/pressure.cc:187-387, which the reference never
+    prints for bulk systems).  The hooks only *observe*; no arithmetic changes.
 
 Trace format: see plum_b200/host/driver_hooks.py.
 """
@@ -44,6 +46,7 @@ def main():
         shutil.copytree(os.path.join(REF, "src"), src)
         driver_hooks.apply_sim_hooks(src)
         driver_hooks.apply_cbmc_hooks(src)
+        driver_hooks.apply_pressure_hook(src)
         files = [os.path.join(src, "main.cc")]
         for d in ("simulation", "molecules", "utilities", "force_field"):
             files += sorted(os.path.join(src, d, f) for f in os.listdir(os.path.join(src, d)) if f.endswith(".cc"))

@@ -46,6 +46,8 @@ def lib():
         L.po_commit.argtypes = [C.c_void_p, C.c_int]
         L.po_mz_current.restype = C.c_double
         L.po_mz_current.argtypes = [C.c_void_p]
+        L.po_vol_scaling.restype = C.c_int
+        L.po_vol_scaling.argtypes = [C.c_void_p, C.c_int, C.c_double, c_double_p]
         L.po_wall_force.restype = C.c_int
         L.po_wall_force.argtypes = [C.c_void_p, C.c_int, c_double_p]
         L.po_beads_energy.restype = C.c_double
@@ -148,6 +150,15 @@ class Oracle:
     def commit(self, accept: bool):
         rc = self.L.po_commit(self.h, int(bool(accept)))
         assert rc == 0, rc
+
+    def vol_scaling_sample(self, phantom: int, dz: float = 1e-5) -> dict:
+        """One sample of CalcPressureVolScalingHSELSlit's dU terms (pressure.cc:187-338), pairwise like the reference."""
+        out = np.zeros(36)
+        rc = self.L.po_vol_scaling(self.h, int(phantom), float(dz), dptr(out))
+        if rc != 0:
+            raise RuntimeError("po_vol_scaling failed")
+        return {"el": out[:16].copy(), "hs": out[16:32].copy(), "bond": float(out[32]), "dipole": float(out[33]),
+                "dU": float(out[34]), "n_free": int(out[35])}
 
     def wall_force(self, phantom: int) -> np.ndarray:
         """One sample of CalcPressureForceLJELSlit (pressure.cc:404-469): the six force sums

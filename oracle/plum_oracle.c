@@ -1174,6 +1174,184 @@ int po_wall_force(const po_system *s, int phantom, double out[6]) {
   return 0;
 }
 
+/* ------------------------------------------ volume-perturbation pressure -- */
+/* src/force_field/potential_ewald_coul.cc:167-196 — PairEnergyRealForP: distance vector wrapped in the cell
+ * stretched along z by dz, images stepped by the stretched edge; no zero-charge shortcut. */
+static double pair_real_forp(const po_system *s, double dz, const double *b1, double q1, const double *b2, double q2) {
+  double energy = 0;
+  double dist[3];
+  double box_l_scaled[3] = {s->ebox[0], s->ebox[1], s->ebox[2] + dz};
+  for (int i = 0; i < 3; i++) {
+    double di = b2[i] - b1[i];
+    if (i < s->npbc) di -= box_l_scaled[i] * round(di / box_l_scaled[i]);
+    dist[i] = di;
+  }
+  double prefactor = s->lB * q1 * q2;
+  for (int i = -s->real_cell[0]; i <= s->real_cell[0]; i++)
+    for (int j = -s->real_cell[1]; j <= s->real_cell[1]; j++)
+      for (int k = -s->real_cell[2]; k <= s->real_cell[2]; k++) {
+        double rx = dist[0] + i * s->ebox[0];
+        double ry = dist[1] + j * s->ebox[1];
+        double rz = dist[2] + k * (s->ebox[2] + dz);
+        double r = sqrt(rx * rx + ry * ry + rz * rz);
+        if (r > 0 && r <= s->real_cutoff) energy += prefactor * erfc(sqrt(s->alpha) * r) / r;
+      }
+  return energy;
+}
+
+/* src/force_field/potential_ewald_coul.cc:228-250 — PairEnergyReplForP with the k_z, k^2 and ek2 tables of
+ * the stretched cell (potential_ewald_coul.cc:86-112) and its volume. */
+static double pair_repl_forp(const po_system *s, double dz, const double *kz_forp, const double *k2_forp,
+                             const double *ek2_forp, const double *b1, double q1, const double *b2, double q2) {
+  double energy = 0;
+  double r[3];
+  double box_l_scaled[3] = {s->ebox[0], s->ebox[1], s->ebox[2] + dz};
+  for (int i = 0; i < 3; i++) {
+    double di = b2[i] - b1[i];
+    if (i < s->npbc) di -= box_l_scaled[i] * round(di / box_l_scaled[i]);
+    r[i] = di;
+  }
+  double box_vol_forp = s->ebox[0] * s->ebox[1] * (s->ebox[2] + dz);
+  double prefactor = s->lB * q1 * q2 / (kPi * box_vol_forp) * (4 * kPi * kPi);
+  for (int lx = 0; lx < s->repl_ceto[0]; lx++)
+    for (int ly = 0; ly < s->repl_ceto[1]; ly++)
+      for (int lz = 0; lz < s->repl_ceto[2]; lz++) {
+        size_t idx = (size_t)s->repl_ceto[1] * s->repl_ceto[2] * lx + (size_t)s->repl_ceto[2] * ly + lz;
+        if (k2_forp[idx] > 0 && k2_forp[idx] <= s->repl_cutoff)
+          energy += prefactor * ek2_forp[idx] * cos(s->kx[lx] * r[0] + s->ky[ly] * r[1] + kz_forp[lz] * r[2]);
+      }
+  return energy;
+}
+
+/* One sample of ForceField::CalcPressureVolScalingHSELSlit, src/force_field/pressure.cc:187-338 (the
+ * accumulation into averages, :340-384, is the caller's): out[0..15] electrostatic dU per species pair
+ * (index i*4+j, i <= j; 0 cation, 1 anion, 2 polymer, 3 surface), out[16..31] LJ/HS + wall dU, out[32] bond
+ * dU, out[33] dipole dU, out[34] total dU, out[35] n_mol - phantom.  "Stored" pair energies of the
+ * reference's maps are recomputed from the current coordinates (they are functions of those). */
+int po_vol_scaling(const po_system *s, int phantom, double dz, double out[36]) {
+  for (int i = 0; i < 36; i++) out[i] = 0;
+  if (phantom < 0 || phantom > s->n_mol) return -1;
+  const int n_mol = s->n_mol;
+  double dU = 0, oldE, newE;
+  po_system sz = *s; /* shallow: the same tables, the slab box stretched (box_l_scaled, pressure.cc:195) */
+  sz.box[2] = s->box[2] + dz;
+  double *kz_forp = NULL, *k2_forp = NULL, *ek2_forp = NULL;
+  if (s->use_ewald) {
+    size_t cube = (size_t)s->repl_ceto[0] * s->repl_ceto[1] * s->repl_ceto[2];
+    kz_forp = (double *)malloc(sizeof(double) * s->repl_ceto[2]);
+    k2_forp = (double *)malloc(sizeof(double) * cube);
+    ek2_forp = (double *)malloc(sizeof(double) * cube);
+    for (int lz = -s->repl_cell[2]; lz <= s->repl_cell[2]; lz++)
+      kz_forp[lz + s->repl_cell[2]] = lz * 2 * kPi / (s->ebox[2] + dz);
+    for (int ix = 0; ix < s->repl_ceto[0]; ix++)
+      for (int iy = 0; iy < s->repl_ceto[1]; iy++)
+        for (int iz = 0; iz < s->repl_ceto[2]; iz++) {
+          size_t idx = (size_t)s->repl_ceto[1] * s->repl_ceto[2] * ix + (size_t)s->repl_ceto[2] * iy + iz;
+          k2_forp[idx] = s->kx[ix] * s->kx[ix] + s->ky[iy] * s->ky[iy] + kz_forp[iz] * kz_forp[iz];
+          ek2_forp[idx] = exp(-k2_forp[idx] / (4 * s->alpha)) / k2_forp[idx];
+        }
+  }
+  double *d_com_z = (double *)calloc((size_t)(n_mol > 0 ? n_mol : 1), sizeof(double));
+  double *tz = (double *)malloc(sizeof(double) * 3 * (size_t)(s->n > 0 ? s->n : 1)); /* scaled (trial) coordinates */
+  /* 2. displacements */
+  for (int i = 0; i < n_mol; i++) {
+    int first = s->mol_first[i], len = s->mol_first[i + 1] - first;
+    double com_z = 0;
+    for (int j = 0; j < len; j++) com_z += s->cur[3 * (first + j) + 2];
+    com_z /= len;
+    d_com_z[i] = dz * (com_z / s->box[2]);
+    int g = s->graft_kind[s->type[first]];
+    if (g == PG_GRAFT_RIGHT) d_com_z[i] = dz;
+    else if (g == PG_GRAFT_LEFT) d_com_z[i] = 0;
+  }
+  /* 3. scaled coordinates */
+  for (int i = 0; i < n_mol; i++)
+    for (int b = s->mol_first[i]; b < s->mol_first[i + 1]; b++) {
+      tz[3 * b] = s->cur[3 * b]; tz[3 * b + 1] = s->cur[3 * b + 1];
+      if (s->bond_kind != PG_BOND_NONE && s->graft_kind[s->type[b]] == PG_GRAFT_NONE)
+        tz[3 * b + 2] = s->cur[3 * b + 2] * (1.0 + dz / s->box[2]);
+      else
+        tz[3 * b + 2] = s->cur[3 * b + 2] + d_com_z[i];
+    }
+  for (int i = 0; i < n_mol; i++) {
+    int len_i = s->mol_first[i + 1] - s->mol_first[i];
+    int id_i;
+    if (i < phantom) id_i = 3;
+    else if (len_i > 1) id_i = 2;
+    else if (s->q[s->mol_first[i]] >= 0) id_i = 0;
+    else id_i = 1;
+    for (int j = 0; j < len_i; j++) {
+      int bi = s->mol_first[i] + j;
+      for (int k = i; k < n_mol; k++) {
+        int len_k = s->mol_first[k + 1] - s->mol_first[k];
+        int id_k;
+        if (k < phantom) id_k = 3;
+        else if (len_k > 1) id_k = 2;
+        else if (s->q[s->mol_first[k]] >= 0) id_k = 0;
+        else id_k = 1;
+        for (int l = 0; l < len_k; l++) {
+          int bk = s->mol_first[k] + l;
+          if ((k > i || (k == i && l >= j)) && (i >= phantom || (i < phantom / 2 && k >= phantom / 2))) {
+            int index1 = (id_i < id_k) ? id_i : id_k;
+            int index2 = (id_i > id_k) ? id_i : id_k;
+            int index = index1 * 4 + index2;
+            if (s->use_ewald) {
+              /* GetERealRepl(0, ., .): the stored real + reciprocal pair energy, half for a bead with itself
+               * (potential_ewald.cc EnergyInitialization) */
+              oldE = pair_real(s, s->cur + 3 * bi, s->q[bi], s->cur + 3 * bk, s->q[bk]) +
+                     pair_repl(s, s->cur + 3 * bi, s->q[bi], s->cur + 3 * bk, s->q[bk]);
+              if (bi == bk) oldE *= 0.5;
+              newE = pair_real_forp(s, dz, tz + 3 * bi, s->q[bi], tz + 3 * bk, s->q[bk]);
+              newE += pair_repl_forp(s, dz, kz_forp, k2_forp, ek2_forp, tz + 3 * bi, s->q[bi], tz + 3 * bk, s->q[bk]);
+              if (bi == bk) newE *= 0.5;
+              dU += newE - oldE;
+              out[index] += newE - oldE;
+            }
+            if (s->pair_kind != PG_PAIR_NONE && i >= phantom && k >= phantom && bi != bk) {
+              /* stored energy: 0 for bonded hard-sphere neighbours (potential_pair.cc:64-67) */
+              if (s->pair_kind == PG_PAIR_HARD_SPHERE && k == i && l == j + 1) oldE = 0;
+              else oldE = pair_energy(s, s->cur + 3 * bi, s->type[bi], s->cur + 3 * bk, s->type[bk]);
+              newE = pair_energy(&sz, tz + 3 * bi, s->type[bi], tz + 3 * bk, s->type[bk]);
+              dU += newE - oldE;
+              out[16 + index] += newE - oldE;
+            }
+          }
+        }
+      }
+      if (s->ext_kind != PG_EXT_NONE && i >= phantom) {
+        int index1 = (id_i < 3) ? id_i : 3;
+        int index2 = (id_i > 3) ? id_i : 3;
+        int index = index1 * 4 + index2;
+        oldE = wall_energy(s, s->cur + 3 * bi, s->type[bi]);
+        newE = wall_energy(&sz, tz + 3 * bi, s->type[bi]);
+        dU += newE - oldE;
+        out[16 + index] += newE - oldE;
+      }
+    }
+    if (s->bond_kind != PG_BOND_NONE) {
+      oldE = molecule_bond_energy(s, s->cur, s->mol_first[i], s->mol_first[i + 1]);
+      newE = molecule_bond_energy(&sz, tz, s->mol_first[i], s->mol_first[i + 1]);
+      dU += newE - oldE;
+      out[32] += newE - oldE;
+    }
+  }
+  if (s->use_ewald && s->dipole_correction) {
+    double Mz_old = 0, Mz_new = 0;
+    for (int b = 0; b < s->n; b++) {
+      Mz_old += s->q[b] * s->cur[3 * b + 2];
+      Mz_new += s->q[b] * tz[3 * b + 2];
+    }
+    double vol = s->box[0] * s->box[1] * s->box[2];
+    double d_di = (s->lB * 2 * kPi) * (Mz_new * Mz_new / (s->box[0] * s->box[1] * (s->box[2] + dz)) - Mz_old * Mz_old / vol);
+    dU += d_di;
+    out[33] += d_di;
+  }
+  out[34] = dU;
+  out[35] = n_mol - phantom;
+  free(d_com_z); free(tz); free(kz_forp); free(k2_forp); free(ek2_forp);
+  return 0;
+}
+
 /* --------------------------------------------------- standalone helpers -- */
 /* Single-pair entry points for unit tests of the primitives. */
 double po_pair_energy(const po_system *s, const double *a, int ta, const double *b, int tb) {

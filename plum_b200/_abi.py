@@ -71,6 +71,11 @@ class PgChainStep(C.Structure):
                 ("_pad", C.c_uint8)]
 
 
+class PgVolSample(C.Structure):
+    _fields_ = [("el", C.c_double * 16), ("hs", C.c_double * 16), ("bond", C.c_double), ("dipole", C.c_double),
+                ("dU", C.c_double), ("n_free", C.c_int32), ("_pad", C.c_int32)]
+
+
 class PgTrialSet(C.Structure):
     _fields_ = [
         ("n_trials", C.c_int32), ("use_bead2", C.c_int32), ("type1", C.c_int32), ("type2", C.c_int32),

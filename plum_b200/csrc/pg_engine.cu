@@ -31,6 +31,7 @@
 #include "pg_move.cu"
 #include "pg_trials.cu"
 #include "pg_pressure.cu"
+#include "pg_volscale.cu"
 #include "pg_propose.cu"
 #include "pg_chain.cu"
 #include "pg_sk.cu"
@@ -56,6 +57,7 @@ struct pg_engine {
   cudaStream_t stream = nullptr;
   PgDev P;
   pg_ewald_info info;
+  double alpha = 0.0;           // Ewald alpha as given (tables of the stretched box, pg_vol_scaling_sample)
   std::string err;
   uint64_t launches = 0;
 
@@ -247,6 +249,7 @@ void ewald_setup(pg_engine* h, const pg_params* p) {
   }
   double box_vol = box_l[0] * box_l[1] * box_l[2];
   double lB = p->lB, alpha = p->alpha;
+  h->alpha = alpha;
   double real_cutoff = 1;
   while (0.5 * lB * 1 * 1 * erfc(sqrt(alpha) * real_cutoff) / real_cutoff > kEwaldCutoff) real_cutoff += 1;
   int real_cell[3], repl_cell[3], ceto[3];
@@ -1947,6 +1950,92 @@ int pg_wall_force(pg_engine* h, int n_phantom, double* out6) {
   if (e != cudaSuccess) { h->err = std::string("pg_wall_force: ") + cudaGetErrorString(e); return PG_ERR_CUDA; }
   for (long long b = 0; b < blocks; b++)
     for (int k = 0; k < 6; k++) out6[k] += part[(size_t)b * 6 + k];
+  return PG_OK;
+}
+
+// ------------------------------------------- volume-perturbation pressure
+int pg_vol_scaling_sample(pg_engine* h, int n_phantom, double dz, pg_vol_sample* out) {
+  if (!h || !out || n_phantom < 0 || n_phantom > h->n_mol || !(dz > 0)) return PG_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  PG_CUDA(h, cudaSetDevice(h->device));
+  { int frc_ = flush_commit(h); if (frc_) return frc_; }
+  const int n = h->n, n_mol = h->n_mol;
+  out->n_free = n_mol - n_phantom;
+  if (n == 0) return PG_OK;
+  // parameter block of the box stretched along z (pressure.cc:195, potential_ewald_coul.cc:51-54, :98-100)
+  PgDev Pz = h->P;
+  Pz.box[2] = h->P.box[2] + dz;
+  Pz.inv_box[2] = 1.0 / Pz.box[2];
+  Pz.half_box[2] = 0.5 * Pz.box[2];
+  std::vector<int> kl;
+  std::vector<double> kw;
+  if (h->P.use_ewald) {
+    Pz.ebox[2] = h->P.ebox[2] + dz;
+    Pz.inv_ebox[2] = 1.0 / Pz.ebox[2];
+    Pz.recip_pref = 2 * kPi * h->P.lB / (h->P.ebox[0] * h->P.ebox[1] * (h->P.ebox[2] + dz));
+    bool single = (h->P.pbc[2] != 0);
+    for (int i = 0; i < 3; i++)
+      if (!(Pz.rc_relaxed < 0.5 * Pz.ebox[i] * (1.0 - 1e-9))) single = false;
+    Pz.single_image = single ? 1 : 0;
+    Pz.real_self_unit = 0.5 * pg_pair_real_d(Pz, 0.0, 0.0, 0.0, 1.0);
+    // k vectors inside the cutoff sphere of either geometry (half space), with ek2 of each
+    const int* rc = h->info.repl_cell;
+    const double cut = h->info.repl_cutoff, alpha = h->alpha;
+    for (int ax = -rc[0]; ax <= rc[0]; ax++)
+      for (int ay = -rc[1]; ay <= rc[1]; ay++)
+        for (int az = -rc[2]; az <= rc[2]; az++) {
+          const bool pos = (ax > 0) || (ax == 0 && ay > 0) || (ax == 0 && ay == 0 && az > 0);
+          if (!pos) continue;
+          const double kx = ax * 2 * kPi / h->P.ebox[0], ky = ay * 2 * kPi / h->P.ebox[1];
+          const double kz_o = az * 2 * kPi / h->P.ebox[2], kz_n = az * 2 * kPi / (h->P.ebox[2] + dz);
+          const double k2_o = kx * kx + ky * ky + kz_o * kz_o, k2_n = kx * kx + ky * ky + kz_n * kz_n;
+          const bool in_o = (k2_o > 0 && k2_o <= cut), in_n = (k2_n > 0 && k2_n <= cut);
+          if (!in_o && !in_n) continue;
+          kl.push_back(ax); kl.push_back(ay); kl.push_back(az); kl.push_back(0);
+          kw.push_back(in_o ? exp(-k2_o / (4 * alpha)) / k2_o : 0.0);
+          kw.push_back(in_n ? exp(-k2_n / (4 * alpha)) / k2_n : 0.0);
+        }
+  }
+  for (int i = 0; i < 3; i++) Pz.same_box[i] = (Pz.ebox[i] == Pz.box[i]) ? 1 : 0;
+  const int nku = (int)(kw.size() / 2);
+  PgVolArgs A;
+  memset(&A, 0, sizeof(A));
+  A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.mol = h->mol;
+  A.n = n; A.n_mol = n_mol; A.phantom = n_phantom; A.dz = dz; A.nku = nku;
+  // one scratch block: Pz | mol_first | z_new | mol_part | row_part | k_part | kw | kl | out | grp
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_P = take(sizeof(PgDev)), o_mf = take(sizeof(int) * (size_t)(n_mol + 1)), o_zn = take(sizeof(double) * (size_t)n),
+               o_mp = take(sizeof(double) * 4 * (size_t)n_mol), o_rp = take(sizeof(double) * 8 * (size_t)n),
+               o_kp = take(sizeof(double) * 16 * (size_t)(nku > 0 ? nku : 1)), o_kw = take(sizeof(double) * 2 * (size_t)(nku > 0 ? nku : 1)),
+               o_kl = take(sizeof(int) * 4 * (size_t)(nku > 0 ? nku : 1)), o_out = take(sizeof(double) * 36), o_g = take((size_t)n);
+  char* d = nullptr;
+  double res[36];
+  cudaError_t e = cudaMalloc((void**)&d, off);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_P, &Pz, sizeof(PgDev), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_mf, h->mol_first.data(), sizeof(int) * (size_t)(n_mol + 1), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && nku > 0) e = cudaMemcpyAsync(d + o_kw, kw.data(), sizeof(double) * kw.size(), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && nku > 0) e = cudaMemcpyAsync(d + o_kl, kl.data(), sizeof(int) * kl.size(), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    A.Pz = reinterpret_cast<const PgDev*>(d + o_P); A.mol_first = reinterpret_cast<const int*>(d + o_mf);
+    A.z_new = reinterpret_cast<double*>(d + o_zn); A.mol_part = reinterpret_cast<double*>(d + o_mp);
+    A.row_part = reinterpret_cast<double*>(d + o_rp); A.k_part = reinterpret_cast<double*>(d + o_kp);
+    A.kw = reinterpret_cast<const double*>(d + o_kw); A.kl = reinterpret_cast<const int*>(d + o_kl);
+    A.out = reinterpret_cast<double*>(d + o_out); A.grp = reinterpret_cast<unsigned char*>(d + o_g);
+    k_vol_prep<<<(n_mol + 127) / 128, 128, 0, h->stream>>>(h->P, A);
+    k_vol_pairs<<<(n + PG_TILE - 1) / PG_TILE, PG_TILE, 0, h->stream>>>(h->P, A);
+    h->launches += 2;
+    if (nku > 0) { k_vol_recip<<<(nku + 63) / 64, 64, 0, h->stream>>>(h->P, A); h->launches++; }
+    k_vol_final<<<1, VS_FINAL_THREADS, 0, h->stream>>>(h->P, A);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(res, d + o_out, sizeof(res), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) { h->err = std::string("pg_vol_scaling_sample: ") + cudaGetErrorString(e); return PG_ERR_CUDA; }
+  for (int c = 0; c < 16; c++) { out->el[c] = res[c]; out->hs[c] = res[16 + c]; }
+  out->bond = res[32]; out->dipole = res[33]; out->dU = res[34];
   return PG_OK;
 }
 

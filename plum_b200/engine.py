@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from ._abi import (ParamBlock, PgChainConfig, PgChainStep, PgDelta, PgEwaldInfo, PgMoveDesc, PgParams, PgProposal, PgTotals, PgTrialSet, bptr, c_double_p,
+from ._abi import (ParamBlock, PgChainConfig, PgChainStep, PgDelta, PgEwaldInfo, PgMoveDesc, PgParams, PgProposal, PgTotals, PgTrialSet, PgVolSample, bptr, c_double_p,
                    c_int32_p, c_uint8_p, dptr, iptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "pg_create", "pg_destroy", "pg_last_error", "pg_abi_version", "pg_get_ewald_info", "pg_upload_system",
     "pg_init_energy", "pg_recompute_totals", "pg_get_totals", "pg_download_positions", "pg_num_beads", "pg_delta_e",
     "pg_delta_e_begin", "pg_delta_e_poll", "pg_commit", "pg_replay_upload", "pg_replay_run", "pg_replay_time_delta", "pg_replay_prepare", "pg_mc_upload", "pg_mc_run", "pg_mc_begin", "pg_mc_end", "pg_mc_trial_xyz", "pg_trial_energies", "pg_insert_molecules",
-    "pg_delete_molecules", "pg_wall_force", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
+    "pg_delete_molecules", "pg_wall_force", "pg_vol_scaling_sample", "pg_sk_compute_slice", "pg_sk_set", "pg_sk_energy", "pg_sk_download", "pg_launch_count",
     "pg_stream", "pg_measure_fp64_peak",
     "pg_chain_configure", "pg_chain_set_rng", "pg_chain_get_rng", "pg_chain_run", "pg_chain_begin", "pg_chain_end",
     "pg_chain_run_multi", "pg_chain_steps", "pg_chain_trial_xyz", "pg_chain_check", "pg_chain_counters",
@@ -59,6 +59,7 @@ def lib():
         L.pg_num_beads.argtypes = [vp]
         L.pg_delta_e.argtypes = [vp, C.c_int, c_double_p, c_uint8_p, C.POINTER(PgDelta)]
         L.pg_wall_force.argtypes = [vp, C.c_int, c_double_p]
+        L.pg_vol_scaling_sample.argtypes = [vp, C.c_int, C.c_double, C.POINTER(PgVolSample)]
         L.pg_delta_e_begin.argtypes = [vp, C.c_int, c_double_p, c_uint8_p]
         L.pg_delta_e_poll.argtypes = [vp, C.POINTER(PgDelta)]
         L.pg_commit.argtypes = [vp, C.c_int]
@@ -341,6 +342,14 @@ class Engine:
         out = np.zeros(6)
         self._check(self.L.pg_wall_force(self.h, int(phantom), dptr(out)), "pg_wall_force")
         return out
+
+    def vol_scaling_sample(self, phantom: int, dz: float = 1e-5) -> dict:
+        """One sample of the volume-perturbation pressure estimator (pg_vol_scaling_sample): dU of a virtual
+        stretch of the box along z by dz, per species pair."""
+        o = PgVolSample()
+        self._check(self.L.pg_vol_scaling_sample(self.h, int(phantom), float(dz), C.byref(o)), "pg_vol_scaling_sample")
+        return {"el": np.array(o.el[:]), "hs": np.array(o.hs[:]), "bond": o.bond, "dipole": o.dipole, "dU": o.dU,
+                "n_free": o.n_free}
 
     # -- GC ----------------------------------------------------------------
     def insert_molecules(self, mol_len, xyz, q, type_ids) -> dict:

@@ -18,6 +18,9 @@ Trace format (space separated, doubles as C99 %a):
   G <step> <I|D> <result> <weight> <n_mol> <Epair> <Eewald> <Ebond> <Eext>
      (result: insertion 0/1, deletion = deleted molecule index or -1;
       weight = Rosenbluth weight at the acceptance test, -1 if never reached)
+  V <n_samples> <p_tensor[0..5]> <p_tensor_el[0..15]> <p_tensor_hs[0..15]>
+     after every ForceField::CalcPressureVolScalingHSELSlit call (src/force_field/pressure.cc:187-387; the
+     reference itself never prints these for systems without walls)
 With PLUM_TRACE_XYZ=1 additionally:
   X <n> then n x (<moved> <x> <y> <z>)      trial coordinates of the molecule just tried
   A <n_beads> then n x (<mol> <symbol> <q> <x> <y> <z>)   beads appended by an accepted insertion
@@ -130,6 +133,20 @@ def apply_batch_hook(src):
           "      }\n"
           "    }\n"
           "    int rand_num = rand_gen();\n")
+
+
+def apply_pressure_hook(src):
+    """Reference binary only: one V line per volume-perturbation pressure sample (pressure.cc:187-387)."""
+    prs = os.path.join(src, "force_field", "pressure.cc")
+    patch(prs, '#include "../utilities/constants.h"\n',
+          '#include "../utilities/constants.h"\n#include <cstdio>\nFILE* plum_trace_file();\n')
+    patch(prs, "  delete [] d_com_z;\n",
+          "  if (plum_trace_file()) { FILE* tf = plum_trace_file(); fprintf(tf, \"V %d\", (int)vp_z);\n"
+          "    for (int ti = 0; ti < 6; ti++) fprintf(tf, \" %a\", p_tensor[ti]);\n"
+          "    for (int ti = 0; ti < 16; ti++) fprintf(tf, \" %a\", p_tensor_el[ti]);\n"
+          "    for (int ti = 0; ti < 16; ti++) fprintf(tf, \" %a\", p_tensor_hs[ti]);\n"
+          "    fprintf(tf, \"\\n\"); }\n"
+          "  delete [] d_com_z;\n")
 
 
 def apply_cbmc_hooks(src):

@@ -41,9 +41,9 @@ namespace {
 double Uniform(mt19937& g) { return (double)g() / g.max(); }
 
 // PLUM_B200_PROFILE=1: wall time spent inside each ABI entry point, printed to stderr at exit.
-enum { kTDelta, kTCommit, kTTrials, kTInsert, kTDelete, kTTotals, kTWallForce, kTSites };
+enum { kTDelta, kTCommit, kTTrials, kTInsert, kTDelete, kTTotals, kTWallForce, kTVolScale, kTSites };
 const char* const kSiteName[kTSites] = {"pg_delta_e", "pg_commit", "pg_trial_energies", "pg_insert_molecules",
-                                        "pg_delete_molecules", "pg_get_totals", "pg_wall_force"};
+                                        "pg_delete_molecules", "pg_get_totals", "pg_wall_force", "pg_vol_scaling_sample"};
 bool prof_on = getenv("PLUM_B200_PROFILE") != NULL;
 double prof_s[kTSites];
 long prof_n[kTSites];
@@ -97,6 +97,7 @@ void MtImport(mt19937& g, const uint32_t* state, int pos) {
 
 ForceField::ForceField() : vp_z(0), engine(NULL), pending_mol(-1), mc_state(NULL) {
   for (int i = 0; i < 12; i++) p_tensor[i] = 0;
+  for (int i = 0; i < 20; i++) p_tensor2[i] = p_tensor3[i] = p_tensor_hs[i] = p_tensor_el[i] = 0;
 }
 
 ForceField::~ForceField() {
@@ -989,9 +990,51 @@ double ForceField::CalcChemicalPotentialF(vector<Molecule>& mols, mt19937& rand_
 }
 
 // ------------------------------------------------------------------ samplers
-// Bulk volume-perturbation sampler (pressure.cc:187-387): its results are never printed for systems
-// without walls (GetPressure returns "nan", pressure.cc:490-500) and it draws no random numbers.
-void ForceField::CalcPressureVolScalingHSELSlit(vector<Molecule>& mols) { (void)mols; }
+// Bulk volume-perturbation sampler, src/force_field/pressure.cc:187-387.  The energy change of the virtual
+// stretch (all pair loops, wall, bond and dipole terms, pressure.cc:208-338) is one pg_vol_scaling_sample call on
+// the resident configuration; the accumulation and the Yethiraj / de Miguel averages below are the reference's
+// (pressure.cc:340-384).  The reference never prints them for systems without walls (GetPressure returns "nan",
+// pressure.cc:490-500); with PLUM_TRACE set both binaries write them as a "V" line (driver_hooks.py).
+void ForceField::CalcPressureVolScalingHSELSlit(vector<Molecule>& mols) {
+  (void)mols;
+  vp_z++;
+  const double dz = kDz;
+  pg_vol_sample smp;
+  int rc;
+  { SiteTimer st_(kTVolScale); rc = pg_vol_scaling_sample(engine, phantom, dz, &smp); }
+  if (rc) Fail("pg_vol_scaling_sample", rc);
+  for (int i = 0; i < 16; i++) { p_tensor_el[i] += smp.el[i]; p_tensor_hs[i] += smp.hs[i]; }
+  p_tensor[5] += smp.bond;
+  p_tensor[4] += smp.dipole;
+  const double dU = smp.dU;
+  const double vol = box_l[0] * box_l[1] * box_l[2];
+  p_tensor[2] += (n_mol - phantom) / vol;
+  p_tensor[3] += pow(1.0 + dz / box_l[2], n_mol - phantom) * exp(-beta * dU);
+  p_tensor[0] = 0;
+  for (int i = 0; i < 4; i++)
+    for (int j = i; j < 4; j++) p_tensor[0] += p_tensor_el[i * 4 + j] + p_tensor_hs[i * 4 + j];
+  p_tensor[0] += p_tensor[4] + p_tensor[5];
+  p_tensor[0] /= (box_l[0] * box_l[1] * dz);
+  p_tensor[0] = (beta * p_tensor[2] - p_tensor[0]) / vp_z;
+  for (int i = 0; i < 4; i++)
+    for (int j = i; j < 4; j++) {
+      const int index = i * 4 + j;
+      p_tensor2[index] = -p_tensor_hs[index] / (box_l[0] * box_l[1] * dz * vp_z);
+      p_tensor3[index] = -p_tensor_el[index] / (box_l[0] * box_l[1] * dz * vp_z);
+    }
+  p_tensor2[17] = -p_tensor[5] / (box_l[0] * box_l[1] * dz * vp_z);
+  p_tensor2[18] = -p_tensor[4] / (box_l[0] * box_l[1] * dz * vp_z);
+  p_tensor2[19] = beta * p_tensor[2] / vp_z;
+  p_tensor[1] = beta / (box_l[0] * box_l[1] * dz) * log(p_tensor[3] / vp_z);
+  if (plum_trace_file && plum_trace_file()) {
+    FILE* tf = plum_trace_file();
+    fprintf(tf, "V %d", vp_z);
+    for (int i = 0; i < 6; i++) fprintf(tf, " %a", p_tensor[i]);
+    for (int i = 0; i < 16; i++) fprintf(tf, " %a", p_tensor_el[i]);
+    for (int i = 0; i < 16; i++) fprintf(tf, " %a", p_tensor_hs[i]);
+    fprintf(tf, "\n");
+  }
+}
 // Slab wall-force pressure, src/force_field/pressure.cc:404-484.  The six force sums of the current
 // configuration come from one pg_wall_force launch (site-site LJ + Ewald real/reciprocal z-forces between
 // the wall sites and everything else, plus the plate LJ force); the running averages below are the

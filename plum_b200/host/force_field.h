@@ -43,7 +43,9 @@ class ForceField {
   double beta;
   int npbc;
   double box_l[3];
-  double p_tensor[12];   // wall-force pressure: [0..5] running averages, [6..11] cumulative sums (pressure.cc:389-403)
+  double p_tensor[12];   // wall-force pressure: [0..5] running averages, [6..11] cumulative sums (pressure.cc:389-403);
+                         // volume-perturbation pressure (no walls): the six entries of pressure.cc:176-186
+  double p_tensor2[20], p_tensor3[20], p_tensor_hs[20], p_tensor_el[20];   // per-species tables of pressure.cc:184-185, :366-377
   int vp_z;              // pressure samples taken
   int n_mol, phantom, coion, grafted, grafted_counterion;
   int chain_len, n_chain, n_cion, n_aion;

@@ -104,6 +104,21 @@ def extras():
         print("extra", name, len(lines), "lines")
 
 
+def vol_pressure():
+    """short/{bulk_nvt,synth_spring}_volp_seed1.trace.gz: 330 steps with coordinates and sampling every 10 steps, so
+    that ForceField::CalcPressureVolScalingHSELSlit (pressure.cc:187-387) runs at steps 200 and 300; the V lines
+    carry its accumulators (oracle/build_ref.py pressure hook).  bulk_nvt: rigid bonds; synth_spring: the Spring
+    bond potential (per-bead scaling branch, bond term)."""
+    over = {"s1_sampling_frequency": 10, "s1_equilibrium_steps": 100}
+    for ex_dir, name in ((os.path.join(HERE, "examples", "bulk_nvt"), "bulk_nvt_volp_seed1"),
+                         (os.path.join(HERE, "examples", "synth_spring"), "synth_spring_volp_seed1")):
+        lines = replay.run_plum_ref(ex_dir, 330, 1, xyz=True, overrides=over)
+        assert sum(1 for ln in lines if ln.startswith("V ")) == 2
+        with gzip.open(os.path.join(HERE, "short", name + ".trace.gz"), "wt") as f:
+            f.write("\n".join(lines))
+        print("vol_pressure", name, len(lines), "lines")
+
+
 def synth_spring():
     """examples/synth_spring + short/synth_spring_seed{1,2}.trace.gz: a small cut of the synthetic polyelectrolyte
     (plum_b200/synth.py: 4 chains x 24 beads + counter-ions, same box / alpha / move mix as the benchmark system S)
@@ -180,6 +195,7 @@ def main():
     ap.add_argument("--long-from", default=None)
     ap.add_argument("--skip-long", action="store_true")
     ap.add_argument("--extras-only", action="store_true", help="only the sampler fixtures (extras())")
+    ap.add_argument("--volp-only", action="store_true", help="only the volume-perturbation pressure fixtures (vol_pressure())")
     ap.add_argument("--synth-only", action="store_true", help="only the spring-bond fixture (synth_spring())")
     ap.add_argument("--cut-seed", type=int, default=0, help="only the 1320-bead cut of S (synth_cut()) for this seed")
     ap.add_argument("--cut-steps", type=int, default=2000)
@@ -195,6 +211,9 @@ def main():
         return
     if a.synth_only:
         synth_spring()
+        return
+    if a.volp_only:
+        vol_pressure()
         return
     if a.cut_seed:
         synth_cut(a.cut_steps, (a.cut_seed,))
@@ -223,6 +242,7 @@ def main():
         print("long", ex, len(lines), "lines")
     extras()
     synth_spring()
+    vol_pressure()
     synth_cut()
 
 

@@ -254,6 +254,56 @@ def golden_pressure_fixture():
     return lines, cols
 
 
+def golden_vol_pressure_fixture(name):
+    """short/<name>_volp_seed1.trace.gz (make_golden.py vol_pressure()): (trace lines, {step: V-line values}) —
+    the reference's accumulators after each CalcPressureVolScalingHSELSlit call: p_tensor[0..5], p_tensor_el[16],
+    p_tensor_hs[16]."""
+    import gzip
+    with gzip.open(os.path.join(GOLDEN, "short", f"{name}_volp_seed1.trace.gz"), "rt") as f:
+        lines = f.read().split("\n")
+    ref, step = {}, 0
+    for ln in lines:
+        t = ln.split()
+        if not t:
+            continue
+        if t[0] == "T":
+            step = int(t[1])
+        elif t[0] == "V":
+            v = [hx(x) for x in t[2:]]
+            ref[step] = {"n": int(t[1]), "p": np.array(v[:6]), "el": np.array(v[6:22]), "hs": np.array(v[22:38])}
+    return [ln for ln in lines if not ln.startswith("V ")], ref
+
+
+class VolScalingAverager:
+    """Host-side bookkeeping of ForceField::CalcPressureVolScalingHSELSlit (pressure.cc:340-384) around an engine
+    that returns the dU terms of one virtual stretch (mirrors plum_b200/host/force_field.cc)."""
+
+    def __init__(self, box, beta, dz=1e-5):
+        self.box, self.beta, self.dz = [float(x) for x in box], float(beta), float(dz)
+        self.vp_z = 0
+        self.p = np.zeros(6)
+        self.el = np.zeros(16)
+        self.hs = np.zeros(16)
+
+    def add(self, smp):
+        import math
+        b, dz = self.box, self.dz
+        self.vp_z += 1
+        self.el += smp["el"]; self.hs += smp["hs"]
+        self.p[5] += smp["bond"]; self.p[4] += smp["dipole"]
+        vol = b[0] * b[1] * b[2]
+        self.p[2] += smp["n_free"] / vol
+        self.p[3] += math.pow(1.0 + dz / b[2], smp["n_free"]) * math.exp(-self.beta * smp["dU"])
+        tot = 0.0
+        for i in range(4):
+            for j in range(i, 4):
+                tot += self.el[i * 4 + j] + self.hs[i * 4 + j]
+        tot += self.p[4] + self.p[5]
+        tot /= (b[0] * b[1] * dz)
+        self.p[0] = (self.beta * self.p[2] - tot) / self.vp_z
+        self.p[1] = self.beta / (b[0] * b[1] * dz) * math.log(self.p[3] / self.vp_z)
+
+
 class WallForceAverager:
     """Host-side bookkeeping of ForceField::CalcPressureForceLJELSlit (pressure.cc:404-484) around an
     engine that returns the six force sums of one configuration: wall-wall terms only from the first

@@ -36,14 +36,14 @@ def test_struct_layout_matches_header_sizes(tmp_path):
     import subprocess
     from plum_b200 import _abi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
                    'sizeof(pg_params),sizeof(pg_ewald_info),sizeof(pg_delta),sizeof(pg_totals),sizeof(pg_trial_set),'
-                   'sizeof(pg_proposal),sizeof(pg_move_desc),sizeof(pg_chain_config),sizeof(pg_chain_step));return 0;}\n' % os.path.join(REPO, "include", "plum_b200.h"))
+                   'sizeof(pg_proposal),sizeof(pg_move_desc),sizeof(pg_chain_config),sizeof(pg_chain_step),sizeof(pg_vol_sample));return 0;}\n' % os.path.join(REPO, "include", "plum_b200.h"))
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     mirror = [C.sizeof(t) for t in (_abi.PgParams, _abi.PgEwaldInfo, _abi.PgDelta, _abi.PgTotals, _abi.PgTrialSet,
-                                    _abi.PgProposal, _abi.PgMoveDesc, _abi.PgChainConfig, _abi.PgChainStep)]
+                                    _abi.PgProposal, _abi.PgMoveDesc, _abi.PgChainConfig, _abi.PgChainStep, _abi.PgVolSample)]
     assert sizes == mirror
 
 

@@ -497,6 +497,108 @@ def test_wall_force_plate_term_matches_oracle(case):
     eng.close()
 
 
+def _vol_close(g, o, scale):
+    """dU tables of one virtual stretch: every entry is a sum of (stretched - current) energies, so the bar is
+    1e-10 of the energy being differenced (TOL * scale); entries the oracle leaves at zero must be zero."""
+    for k in ("el", "hs"):
+        assert np.max(np.abs(g[k] - o[k])) <= TOL * scale, (k, g[k], o[k])
+        assert not g[k][o[k] == 0.0].any(), (k, g[k], o[k])
+    for k in ("bond", "dipole", "dU"):
+        assert abs(g[k] - o[k]) <= TOL * max(scale, abs(o[k]) * 1e-2), (k, g[k], o[k])
+    assert g["n_free"] == o["n_free"]
+
+
+@pytest.mark.parametrize("name", ["bulk_nvt", "synth_spring"])
+def test_vol_scaling_sample_matches_reference_accumulators(name):
+    """pg_vol_scaling_sample (CalcPressureVolScalingHSELSlit, pressure.cc:187-387) on the reference's own trace: the
+    accumulators the reference holds after its samples at steps 200 and 300 (V lines of the fixture) from the GPU
+    samples, and every sample against the oracle's pairwise evaluation."""
+    r, s, types, params = replay.load_golden(name)
+    lines, ref = replay.golden_vol_pressure_fixture(name)
+    eng, orc = _engine(params, s.n + 64), _oracle(params)
+    avg = replay.VolScalingAverager(s.box, r.beta)
+    seen = []
+
+    def check(step):
+        if step in ref:
+            g, o = eng.vol_scaling_sample(r.phantom), orc.vol_scaling_sample(r.phantom)
+            tot = orc.totals()
+            scale = max(1.0, abs(tot["ewald"]), abs(tot["pair"]), abs(tot["bond"]))
+            _vol_close(g, o, scale)
+            avg.add(g)
+            w = ref[step]
+            assert np.max(np.abs(avg.el - w["el"])) <= TOL * scale and np.max(np.abs(avg.hs - w["hs"])) <= TOL * scale
+            assert np.max(np.abs(avg.p[4:6] - w["p"][4:6])) <= TOL * scale
+            for k in (0, 1):
+                assert abs(avg.p[k] - w["p"][k]) <= 1e-6 * abs(w["p"][k]), (step, k, avg.p[k], w["p"][k])
+            print(f"{name} step {step}: P_yethiraj {avg.p[0]:.9e} (ref {w['p'][0]:.9e}), rel err "
+                  f"{abs(avg.p[0] - w['p'][0]) / abs(w['p'][0]):.2e}; max |d el| / scale "
+                  f"{np.max(np.abs(avg.el - w['el'])) / scale:.2e}")
+            seen.append(step)
+
+    class Both:
+        def upload(self, *a): eng.upload(*a); orc.upload(*a)
+        def init_energy(self): orc.init_energy(); return eng.init_energy()
+        def delta_e(self, *a): orc.delta_e(*a); return eng.delta_e(*a)
+        def commit(self, acc): orc.commit(acc); eng.commit(acc)
+        def totals(self): return eng.totals()
+
+    replay.replay(Both(), r, s, types, lines, check_totals_every=0, beads_energy=False, on_step=check)
+    assert seen == [200, 300]
+    eng.close()
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3, 4, 5, 8, 9])
+def test_vol_scaling_sample_matches_oracle_on_random_systems(case):
+    """Multi-image and single-image real space, slab + dipole term + walls (the wall branch of pressure.cc:300-309,
+    never reached by the reference's own call site but part of the function), springs, attractive LJ, hard spheres
+    (stored energy 0 for bonded neighbours), grafted L/R beads; then with four ions promoted to surface sites so that
+    the first-plate / second-plate restriction of pressure.cc:264-265 is exercised."""
+    c = dict(CASES[case])
+    rng = np.random.default_rng(1200 + case)
+    box = c.pop("box")
+    sysm = _random_system(rng, c.pop("n_chain"), c.pop("chain_len"), c.pop("n_ion"), np.array(box),
+                          c.pop("charged_every", 1), c.pop("slab", False))
+    r, types, params = _params(box, **c)
+    if c.get("graft"):
+        for m in range(4):
+            f = int(sysm.mol_first[m])
+            sysm.symbol[f] = "L" if m % 2 == 0 else "R"
+            sysm.xyz[f, 2] = 1.3 if m % 2 == 0 else box[2] - 1.3
+    eng, orc = _engine(params, sysm.n), _oracle(params)
+
+    def both(xyz, q, ids, mf, phantom):
+        eng.upload(xyz, q, ids, mf); orc.upload(xyz, q, ids, mf)
+        eng.init_energy(); to = orc.init_energy()
+        g, o = eng.vol_scaling_sample(phantom), orc.vol_scaling_sample(phantom)
+        pair = abs(to["pair"]) if abs(to["pair"]) < 1e7 else 1.0      # hard-sphere overlaps: 1e8 sentinels
+        scale = max(1.0, abs(to["ewald"]), abs(to["real"]), abs(to["recip"]), pair, abs(to["bond"]), abs(to["ext"]) if abs(to["ext"]) < 1e7 else 1.0)
+        big = np.abs(o["hs"]) >= 1e7
+        if big.any():    # sentinel differences: exact multiples of 1e8
+            assert np.array_equal(np.round(g["hs"][big] / 1e8), np.round(o["hs"][big] / 1e8))
+            g["hs"][big] = o["hs"][big] = 0.0
+            g["dU"] = o["dU"] = 0.0
+        _vol_close(g, o, scale)
+        return o
+
+    o0 = both(sysm.xyz, sysm.q, types.ids(sysm.symbol), sysm.mol_first, 0)
+    assert np.count_nonzero(o0["el"]) >= 3
+    if params["bond_kind"]:
+        assert o0["bond"] != 0.0
+    if params["dipole_correction"]:
+        assert o0["dipole"] != 0.0
+    perm_first = list(range(sysm.n_mol - 4, sysm.n_mol)) + list(range(sysm.n_mol - 4))
+    xyz = np.concatenate([sysm.xyz[sysm.mol_first[m]:sysm.mol_first[m + 1]] for m in perm_first])
+    q = np.concatenate([sysm.q[sysm.mol_first[m]:sysm.mol_first[m + 1]] for m in perm_first])
+    sym = [sysm.symbol[b] for m in perm_first for b in range(sysm.mol_first[m], sysm.mol_first[m + 1])]
+    lens = [int(sysm.mol_first[m + 1] - sysm.mol_first[m]) for m in perm_first]
+    mf = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    o4 = both(xyz, q, types.ids(sym), mf, 4)
+    assert o4["el"][15] != 0.0 and o4["n_free"] == sysm.n_mol - 4      # plate-plate term, surface x mobile terms
+    assert any(o4["el"][i] != 0.0 for i in (3, 7, 11))
+    eng.close()
+
+
 def test_full_size_synthetic_system_parity():
     """BASELINE.json configs[4] at FULL size (22 000 beads, K = 3574): the FAST k_move path and k_trials
     against the oracle on a bounded sample — init totals, three ion moves, one 100-bead chain move

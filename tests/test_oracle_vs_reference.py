@@ -8,6 +8,7 @@ energy totals.  Tolerance: 1e-12 relative (floor 1.0) for the pairwise
 reciprocal form, which follows the reference's loop order; 1e-11 for the S(k)
 form the CUDA path uses (truncated kPi makes the two forms differ by O(1e-13)).
 """
+import numpy as np
 import pytest
 
 import replay
@@ -65,6 +66,45 @@ def test_oracle_wall_force_matches_reference_pressure_columns():
     assert checked == [1000, 2000, 3000]
     # plate LJ force: the site-site LJ sums vanish (wall sites have epsilon 0), what is left is BeadForceOnWall
     assert avg.cum[2] == 0.0 and abs(avg.cum[0]) > 0.0
+
+
+@pytest.mark.parametrize("name", ["bulk_nvt", "synth_spring"])
+def test_oracle_vol_scaling_matches_reference_accumulators(name):
+    """CalcPressureVolScalingHSELSlit (pressure.cc:187-387): replay the reference's own trace and sample the oracle
+    where the reference samples (steps 200 and 300 of the fixture); the per-species accumulators p_tensor_el /
+    p_tensor_hs, the bond and dipole sums and both pressure estimates of the reference's V lines must come out.
+    Every entry is a sum of (stretched - current) pair energies, i.e. differences ~1e-7 of the energies themselves:
+    the tolerance is 1e-10 of the energy being differenced (the total Ewald / pair energy), which is what a
+    relative 1e-10 on the two terms allows; the plain relative error is asserted at 1e-6."""
+    r, s, types, params = replay.load_golden(name)
+    lines, ref = replay.golden_vol_pressure_fixture(name)
+    o = Oracle(params)
+    avg = replay.VolScalingAverager(s.box, r.beta)
+    checked = []
+
+    def on_step(step):
+        if step in ref:
+            avg.add(o.vol_scaling_sample(r.phantom))
+            tot = o.totals()
+            scale = max(1.0, abs(tot["ewald"]), abs(tot["pair"]), abs(tot["bond"]))
+            g = ref[step]
+            assert avg.vp_z == g["n"]
+            for got, want in ((avg.el, g["el"]), (avg.hs, g["hs"]), (avg.p[4:6], g["p"][4:6])):
+                assert np.max(np.abs(got - want)) <= 1e-10 * scale, (step, got, want)
+                nz = np.abs(want) > 0
+                assert np.all(np.abs(got[nz] - want[nz]) <= 1e-6 * np.abs(want[nz])), (step, got, want)
+                assert not got[~nz].any()
+            assert abs(avg.p[2] - g["p"][2]) <= 1e-14 * abs(g["p"][2])
+            assert abs(avg.p[3] - g["p"][3]) <= 1e-12 * abs(g["p"][3])
+            for k in (0, 1):   # the two pressure estimates: dU / (A dz) amplifies the error of dU by 1 / (A dz)
+                assert abs(avg.p[k] - g["p"][k]) <= 1e-6 * abs(g["p"][k]), (step, k, avg.p[k], g["p"][k])
+            checked.append(step)
+
+    replay.replay(o, r, s, types, lines, check_totals_every=0, beads_energy=False, on_step=on_step)
+    assert checked == [200, 300]
+    assert np.count_nonzero(avg.el) >= 2 and np.count_nonzero(avg.hs) >= 1
+    if name == "synth_spring":
+        assert avg.p[5] != 0.0
 
 
 def test_ewald_setup_matches_reference_logs():

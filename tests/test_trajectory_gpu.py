@@ -170,6 +170,35 @@ def test_chemical_potential_sampler_on_trajectory():
     assert abs(mu_got - mu_ref) <= 1e-6 * abs(mu_ref), (mu_got, mu_ref)
 
 
+@pytest.mark.parametrize("name", ["bulk_nvt", "synth_spring"])
+def test_volume_perturbation_pressure_sampler_on_trajectory(name):
+    """bin/plum_gpu with sampling every 10 steps: ForceField::CalcPressureVolScalingHSELSlit (façade ->
+    pg_vol_scaling_sample) runs at steps 200 and 300 of the same trajectory; its accumulators (V lines) against the
+    ones plum_ref wrote (tests/golden/short/<name>_volp_seed1.trace.gz).  Entries are sums of energy differences
+    ~1e-7 of the energies: 1e-9 of the largest accumulator entry absolute, 1e-6 relative on the two pressures."""
+    assert replay.have_plum_gpu()
+    _, ref = replay.golden_vol_pressure_fixture(name)
+    lines = replay.run_plum_ref(replay.golden_example_dir(name), 330, 1, xyz=False, binary=replay.PLUM_GPU,
+                                overrides={"s1_sampling_frequency": 10, "s1_equilibrium_steps": 100})
+    got, step = {}, 0
+    for ln in lines:
+        t = ln.split()
+        if t and t[0] == "T":
+            step = int(t[1])
+        elif t and t[0] == "V":
+            v = [replay.hx(x) for x in t[2:]]
+            got[step] = (int(t[1]), np.array(v[:6]), np.array(v[6:22]), np.array(v[22:38]))
+    assert sorted(got) == sorted(ref) == [200, 300]
+    for step, w in ref.items():
+        n, p, el, hs = got[step]
+        assert n == w["n"]
+        scale = max(1e-30, float(np.max(np.abs(np.concatenate([w["el"], w["hs"]])))))
+        assert np.max(np.abs(el - w["el"])) <= 1e-6 * scale and np.max(np.abs(hs - w["hs"])) <= 1e-6 * scale
+        assert not el[w["el"] == 0].any() and not hs[w["hs"] == 0].any()
+        for k in range(6):
+            assert abs(p[k] - w["p"][k]) <= 1e-6 * abs(w["p"][k]) + 1e-300, (step, k, p[k], w["p"][k])
+
+
 @pytest.mark.parametrize("seed,env", [(1, {}), (2, {"PLUM_B200_CLUSTER": "8"}), (1, {"PLUM_B200_PIVOT_MODE": "1"}),
                                       (2, {"PLUM_B200_CHAIN": "0", "PLUM_B200_BATCH": "2"}), (1, {"PLUM_B200_BATCH": "0"})])
 def test_driver_over_the_device_resident_chain_reproduces_the_reference_on_the_cut_of_S(seed, env):
