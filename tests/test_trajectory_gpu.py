@@ -175,7 +175,7 @@ def test_volume_perturbation_pressure_sampler_on_trajectory(name):
     """bin/plum_gpu with sampling every 10 steps: ForceField::CalcPressureVolScalingHSELSlit (façade ->
     pg_vol_scaling_sample) runs at steps 200 and 300 of the same trajectory; its accumulators (V lines) against the
     ones plum_ref wrote (tests/golden/short/<name>_volp_seed1.trace.gz).  Entries are sums of energy differences
-    ~1e-7 of the energies: 1e-9 of the largest accumulator entry absolute, 1e-6 relative on the two pressures."""
+    ~1e-7 of the energies: 1e-6 of the largest accumulator entry absolute, 1e-6 relative on the two pressures."""
     assert replay.have_plum_gpu()
     _, ref = replay.golden_vol_pressure_fixture(name)
     lines = replay.run_plum_ref(replay.golden_example_dir(name), 330, 1, xyz=False, binary=replay.PLUM_GPU,
