@@ -1,10 +1,16 @@
 #!/bin/bash
 # Round-2 evidence, ONE gpurun call on one GPU:  bash tools/round2_evidence.sh r02
-# GPU suite, smoke, bench (both arms), the ncu launch list of the bench command, one `ncu --set full` capture of k_chain
-# (single chain, one CTA, 300 steps of S) and its summary -> gpurun_out/<tag>_* ; copy what is to be judged into profiles/.
+# One `ncu --set full` capture of k_chain (single chain, one CTA, 300 steps of S) and its summary (copied to
+# profiles/<tag>_ncu_summary.json on the box so that the bench run below reads the counters of THIS build), the GPU suite,
+# smoke, bench (both arms) and the ncu launch list of the bench command -> gpurun_out/<tag>_* ; copy what is to be judged
+# into profiles/.
 tag=${1:-r02}
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:k_chain -s 1 -c 1 -f -o gpurun_out/prof_${tag}_kchain \
+    python tools/chain_probe.py --system S --steps 300 --clusters 1 > gpurun_out/${tag}_ncu.log 2>&1
+python tools/ncu_chain_summary.py gpurun_out/prof_${tag}_kchain.ncu-rep 300 gpurun_out/${tag}_ncu_summary.json | head -c 400
+cp gpurun_out/${tag}_ncu_summary.json profiles/${tag}_ncu_summary.json
 timeout -k 10 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/${tag}_pytest_gpu.txt
 cat gpurun_out/${tag}_pytest_gpu.txt
 timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.txt 2>&1; tail -2 gpurun_out/${tag}_smoke.txt
@@ -12,6 +18,3 @@ timeout -k 10 900 python bench.py > gpurun_out/${tag}_bench_n1.json 2> gpurun_ou
 timeout -k 10 900 python bench.py --impl reference > gpurun_out/${tag}_bench_ref_n1.json 2> gpurun_out/${tag}_bench_ref_n1.err; tail -c 400 gpurun_out/${tag}_bench_ref_n1.json
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --moves-per-step 128 --no-cpu-baseline --no-single --no-recompute --no-examples --replicas-per-gpu 16 > gpurun_out/${tag}_launches_bench.log 2>&1
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:k_chain -s 1 -c 1 -o gpurun_out/prof_${tag}_kchain \
-    python tools/chain_probe.py --system S --steps 300 --clusters 1 > gpurun_out/${tag}_ncu.log 2>&1
-python tools/ncu_chain_summary.py gpurun_out/prof_${tag}_kchain.ncu-rep 300 gpurun_out/${tag}_ncu_summary.json | head -c 400
