@@ -214,16 +214,22 @@ int pg_replay_prepare(pg_engine* h, int first, int count, int with_commit);
  * dE >= 1e8 (simulation.cc:327-332), which shifts every later draw: a batch
  * therefore stops after such a step (`n_done`), and the caller rewinds its
  * generator to that point and continues with a new batch.
- * Crankshaft (molecule.cc:239-265) needs Eigen's rotation and is not offered:
- * the caller runs such a step through pg_delta_e.                              */
+ * Crankshaft (molecule.cc:239-265): the descriptor carries the axis beads, the
+ * angle and its sine / cosine (the caller's libm, i.e. the reference's); the
+ * device normalises the axis and builds the rotation in the operation order of
+ * Eigen's AngleAxisd::toRotationMatrix.                         */
 enum { PG_MOVE_BEAD = 0, PG_MOVE_COM = 1, PG_MOVE_PIVOT = 2, PG_MOVE_CRANKSHAFT = 3, PG_MOVE_REPTATION = 4 };
 typedef struct pg_move_desc {
   int32_t mol;        /* moved molecule                                                        */
-  int32_t kind;       /* PG_MOVE_* (not CRANKSHAFT)                                            */
-  int32_t i0;         /* PIVOT: the pivot bead; REPTATION: direction (+1 forward, -1 backward) */
-  int32_t rv_offset;  /* PIVOT: first of its len-1 rows in `rvec`, in draw order               */
-  double s;           /* BEAD: 3*move_size/|v| (0-length v: |v|); PIVOT: move_size_rand; REPTATION: bond_len */
-  double v[3];        /* BEAD: randSphere vector; COM: displacement; REPTATION: randSphere vector */
+  int32_t kind;       /* PG_MOVE_*                                                             */
+  int32_t i0;         /* PIVOT: the pivot bead; REPTATION: direction (+1 forward, -1 backward);
+                         CRANKSHAFT: first bead of the axis                                    */
+  int32_t rv_offset;  /* PIVOT: first of its len-1 rows in `rvec`, in draw order;
+                         CRANKSHAFT: last bead of the axis                                     */
+  double s;           /* BEAD: 3*move_size/|v| (0-length v: |v|); PIVOT: move_size_rand; REPTATION: bond_len;
+                         CRANKSHAFT: the angle                                                 */
+  double v[3];        /* BEAD: randSphere vector; COM: displacement; REPTATION: randSphere vector;
+                         CRANKSHAFT: v[0] = sin(angle), v[1] = cos(angle)                      */
   double vlen;        /* REPTATION: |v|                                                        */
   double u;           /* uniform variate of the acceptance test                                */
 } pg_move_desc;
@@ -254,8 +260,9 @@ int pg_mc_trial_xyz(pg_engine* h, int m, double* xyz);
  * chain except max_steps or a grand-canonical step (gc_freq > 0 and first draw % gc_freq == 0: the chain
  * stops IN FRONT of it, the generator untouched, and the caller runs that step itself).
  * Offered for single-image systems (3 periodic axes, one box for LJ and Ewald, real-space cutoff < L/2: what
- * pg_create selects k_move<true> for) without crankshaft moves; pg_chain_configure says so otherwise and the
- * caller stays on pg_mc_* / pg_delta_e.  Positions, S(k) and the running totals are the engine's own: the
+ * pg_create selects k_move<true> for); pg_chain_configure says so otherwise and the caller stays on
+ * pg_mc_* / pg_delta_e.  A crankshaft's sine and cosine come from the device's sincos (<= 2 ulp from the host
+ * libm's): its trial coordinates agree with the reference's to ~1e-15 instead of bit for bit.  Positions, S(k) and the running totals are the engine's own: the
  * other entry points see the chain's result (pg_download_positions, pg_get_totals, pg_delta_e ...).     */
 typedef struct pg_chain_config {
   int32_t phantom;        /* molecules [0, phantom) never move (simulation.cc:255)                       */
@@ -268,7 +275,7 @@ typedef struct pg_chain_config {
                              sum of independent bond vectors (coordinates equal to a few ulp, not bit for bit)  */
   double move_size;       /* s1_MC_move_size                                                             */
   double bond_len;        /* RigidBondLen() or EqBondLen() (simulation.cc:288-296)                       */
-  double move_prob[5];    /* bead, COM, pivot, crankshaft (must be 0), reptation (simulation.cc:46-50)   */
+  double move_prob[5];    /* bead, COM, pivot, crankshaft, reptation (simulation.cc:46-50)               */
 } pg_chain_config;
 typedef struct pg_chain_step {
   double dE;              /* what ForceField::EnergyDifference returned                                  */

@@ -422,7 +422,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
       const int used = cg_step_header(sm.mt, A.cfg, A.chains, A.ions, [mf](int mol) { return mf[mol + 1] - mf[mol]; }, d,
                                       sm.pre_raw, sm.pre_u, 32);
       if (used > 560 && !sm.err) sm.err = CH_ERR_RNG;
-      if (d.kind == CG_CRANK) sm.err = CH_ERR_KIND;
       if (d.kind == CG_STOP_GC) sm.stop = 1;
       else cg_advance(sm.mt, used);
       if (d.kind >= 0) {
@@ -516,6 +515,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain(const PgChainArgs* __re
         for (int i = tid; i < 3 * glen; i += CH_THREADS) {
           const int a = i / glen, g = i - a * glen;
           sm.trl[a][g] = (g == end) ? pp_reptation_end(sm.cur[a][g], d.s, d.v[a], d.vlen) : sm.cur[a][g + dir];
+        }
+      } else if (kind == CG_CRANK) {
+        // Molecule::Crankshaft, molecule.cc:239-265: beads strictly between the two axis beads turn about the axis.
+        // The untouched beads keep trial == current: their "moved" pair terms and structure-factor terms are the
+        // same arithmetic on the same numbers twice, i.e. exact zeros in every sum below.
+        const int first = d.i0, last = min(d.i1, glen - 1);
+        double* rot = reinterpret_cast<double*>(sm.rv);
+        if (tid == 0) {
+          const double pf[3] = {sm.cur[0][first], sm.cur[1][first], sm.cur[2][first]};
+          const double pl[3] = {sm.cur[0][last], sm.cur[1][last], sm.cur[2][last]};
+          double sn, cs;
+          sincos(d.s, &sn, &cs);
+          pp_crank_matrix(pf, pl, sn, cs, rot);
+        }
+        __syncthreads();
+        for (int i = first + 1 + tid; i < last; i += CH_THREADS) {
+          const double pf[3] = {sm.cur[0][first], sm.cur[1][first], sm.cur[2][first]};
+          const double pos[3] = {sm.cur[0][i], sm.cur[1][i], sm.cur[2][i]};
+          double out[3];
+          pp_crank_apply(rot, pf, pos, out);
+          sm.trl[0][i] = out[0]; sm.trl[1][i] = out[1]; sm.trl[2][i] = out[2];
         }
       } else if (!(skip & 32)) {   // CG_PIVOT: the two arms in two warps
         const int p = d.i0;

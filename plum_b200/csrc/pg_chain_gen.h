@@ -27,6 +27,7 @@
 #define CG_COM 1
 #define CG_PIVOT 2
 #define CG_CRANK 3
+#define CG_M_PI 3.14159265358979323846   // M_PI of <cmath>, molecule.cc:247 (not the truncated kPi)
 #define CG_REPT 4
 #define CG_NONE (-1)      // the step attempts nothing (simulation.cc:242,284,315)
 #define CG_STOP_GC (-2)   // the next step is a grand-canonical step: the chain stops IN FRONT of it
@@ -140,9 +141,10 @@ PP_HD double cg_varied_bond(CgCursor& r, double bond_len, int vary) {
 struct CgStep {
   int kind;        // CG_*
   int mol;
-  int i0;          // PIVOT: pivot bead; REPT: direction
+  int i0;          // PIVOT: pivot bead; REPT: direction; CRANK: first bead of the axis
+  int i1;          // CRANK: last bead of the axis
   int n_rows;      // PIVOT: len - 1 rows still to be drawn (by cg_pivot_rows_*)
-  double s;        // BEAD: 3*move_size/|v|; PIVOT: move_size_rand; REPT: bond_len
+  double s;        // BEAD: 3*move_size/|v|; PIVOT: move_size_rand; REPT: bond_len; CRANK: angle
   double v[3];
   double vlen;
 };
@@ -162,7 +164,7 @@ template <class LenFn>
 PP_HD int cg_step_header(const PgMt& mt, const CgConfig& c, const int* chains, const int* ions, LenFn mol_len, CgStep& d,
                          const uint32_t* pre_raw = nullptr, const double* pre_u = nullptr, int npre = 0) {
   CgCursor r{&mt, 0, pre_raw, pre_u, npre};
-  d.kind = CG_NONE; d.mol = -1; d.i0 = 0; d.n_rows = 0; d.s = 0.0; d.v[0] = d.v[1] = d.v[2] = 0.0; d.vlen = 0.0;
+  d.kind = CG_NONE; d.mol = -1; d.i0 = 0; d.i1 = 0; d.n_rows = 0; d.s = 0.0; d.v[0] = d.v[1] = d.v[2] = 0.0; d.vlen = 0.0;
   const int rand_num = (int)r.raw();                                   // simulation.cc:221
   if (c.gc_freq > 0 && (rand_num % c.gc_freq == 0)) { d.kind = CG_STOP_GC; return 0; }
   if (c.n_chain + c.n_ion <= 0) return r.used;                         // simulation.cc:242
@@ -201,8 +203,13 @@ PP_HD int cg_step_header(const PgMt& mt, const CgConfig& c, const int* chains, c
     d.s = PP_DIV(PP_MUL(c.move_size, (double)r.raw()), 4294967295.0);
     d.n_rows = len - 1;
     d.kind = CG_PIVOT;
-  } else if (move_type == 3) {
-    d.kind = CG_CRANK;                                                 // not offered: the caller never configures it
+  } else if (move_type == 3) {                                         // Crankshaft, molecule.cc:239-247
+    const int first = (int)floor(PP_DIV(PP_MUL((double)(len - 2), (double)r.raw()), 4294967295.0));
+    const int last = (int)floor(PP_DIV(PP_MUL((double)(len - first), (double)r.raw()), 4294967295.0)) + first;
+    d.i0 = first;
+    d.i1 = last;
+    d.s = PP_MUL(c.move_size, PP_SUB(PP_MUL(PP_MUL(r.uniform(), 2.0), CG_M_PI), CG_M_PI));
+    d.kind = CG_CRANK;
   } else {                                                             // RandomReptation, molecule.cc:268-312
     d.s = cg_varied_bond(r, c.bond_len, c.vary_bond);
     d.i0 = (r.raw() % 2 == 0) ? -1 : 1;

@@ -307,7 +307,6 @@ int pg_chain_configure(pg_engine* h, const pg_chain_config* cfg) {
     h->err = "pg_chain_*: needs a single-image system (3 periodic axes, one box, real-space cutoff < L/2); use pg_mc_* / pg_delta_e";
     return PG_ERR_INVALID;
   }
-  if (cfg->move_prob[3] != 0.0) { h->err = "pg_chain_*: crankshaft moves are not offered on the device"; return PG_ERR_INVALID; }
   if (cfg->cluster_ctas < 0 || cfg->cluster_ctas > CH_GMAX) { h->err = "pg_chain_*: cluster_ctas must be 0 (default) or 1..16"; return PG_ERR_INVALID; }
   if (cfg->phantom < 0 || cfg->gc_freq < 0) return PG_ERR_INVALID;
   c.cluster = cfg->cluster_ctas > 0 ? cfg->cluster_ctas : 1;

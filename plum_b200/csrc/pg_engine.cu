@@ -1492,8 +1492,10 @@ int pg_mc_upload(pg_engine* h, int n_moves, const pg_move_desc* moves, int n_rve
       if (d.i0 < 0 || d.i0 >= len || d.rv_offset < 0 || d.rv_offset + (len - 1) > n_rvec) { h->err = "mc: bad pivot descriptor"; return PG_ERR_INVALID; }
     } else if (d.kind == PG_MOVE_REPTATION) {
       if (d.i0 != 1 && d.i0 != -1) { h->err = "mc: reptation direction must be +1 or -1"; return PG_ERR_INVALID; }
+    } else if (d.kind == PG_MOVE_CRANKSHAFT) {
+      if (d.i0 < 0 || d.i0 >= len || d.rv_offset < d.i0 || d.rv_offset > len) { h->err = "mc: bad crankshaft descriptor"; return PG_ERR_INVALID; }
     } else if (d.kind != PG_MOVE_BEAD && d.kind != PG_MOVE_COM) {
-      h->err = "mc: move kind not offered on the device"; return PG_ERR_INVALID;
+      h->err = "mc: unknown move kind"; return PG_ERR_INVALID;
     }
     beads += (size_t)len;
   }
@@ -1541,9 +1543,12 @@ int pg_mc_upload(pg_engine* h, int n_moves, const pg_move_desc* moves, int n_rve
     const pg_move_desc& d = moves[m];
     ReplayMove r;
     r.mol = d.mol; r.g0 = h->mol_first[d.mol]; r.glen = h->mol_first[d.mol + 1] - r.g0; r.off = off; r.u = d.u;
+    // crankshaft: only the beads strictly between the axis beads are flagged (molecule.cc:251-253); when there are
+    // none the whole molecule is flagged with trial == current, which evaluates to the same dE = 0
+    const bool crank = (d.kind == PG_MOVE_CRANKSHAFT) && (std::min(d.rv_offset, r.glen - 1) - d.i0 > 1);
     for (int i = 0; i < r.glen; i++) {
       sv.gq[off + i] = h->h_q[r.g0 + i]; sv.gtype[off + i] = h->h_type[r.g0 + i];
-      sv.moved[off + i] = (d.kind == PG_MOVE_BEAD) ? (i == 0) : 1;
+      sv.moved[off + i] = (d.kind == PG_MOVE_BEAD) ? (i == 0) : (crank ? (i > d.i0 && i < std::min(d.rv_offset, r.glen - 1)) : 1);
     }
     r.nq = stage_fill_qidx(sv, off, r.glen);
     h->rp_moves.push_back(r);

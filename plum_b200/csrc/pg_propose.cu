@@ -15,6 +15,8 @@
 //               two arms are independent and run in two warps, every lane of a warp computes the
 //               same step and the lanes share the arm's translation)
 //   REPTATION   Molecule::RandomReptation :268-312
+//   CRANKSHAFT  Molecule::Crankshaft      :239-265   (Eigen's AngleAxisd::toRotationMatrix order; the sine and
+//               cosine of the angle are evaluated by the host generator's libm and travel in the descriptor)
 //
 // Arithmetic: pg_propose_math.h (separately rounded operations in the reference's order, so the
 // coordinates are bit-identical to the host generator's and to the reference's).
@@ -98,6 +100,22 @@ __global__ void __launch_bounds__(PP_THREADS) k_propose(const PgProposeArgs A) {
         x = sx[g + dir]; y = sy[g + dir]; z = sz[g + dir];
       }
       out[3 * g] = x; out[3 * g + 1] = y; out[3 * g + 2] = z;
+    }
+  } else if (d.kind == PP_CRANK) {
+    // Molecule::Crankshaft, molecule.cc:239-265: sin / cos of the angle come with the descriptor (vx, vy), the axis
+    // and the rotation matrix from the resident coordinates in Eigen's operation order (pg_propose_math.h)
+    const int first = d.i0, last = min(d.rv_off, len - 1);
+    const double pf[3] = {sx[first], sy[first], sz[first]};
+    const double pl[3] = {sx[last], sy[last], sz[last]};
+    double rot[9];
+    pp_crank_matrix(pf, pl, d.vx, d.vy, rot);
+    for (int g = tid; g < len; g += PP_THREADS) {
+      double o[3] = {sx[g], sy[g], sz[g]};
+      if (g > first && g < last) {
+        const double pos[3] = {sx[g], sy[g], sz[g]};
+        pp_crank_apply(rot, pf, pos, o);
+      }
+      out[3 * g] = o[0]; out[3 * g + 1] = o[1]; out[3 * g + 2] = o[2];
     }
   } else if (d.kind == PP_PIVOT) {
     const int p = d.i0;

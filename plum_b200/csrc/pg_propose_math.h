@@ -60,4 +60,42 @@ PP_HD void pp_pivot_step(const double a[3], const double b[3], double msr, const
   m[2] = PP_SUB(cz, b[2]);
 }
 
+// Molecule::Crankshaft, molecule.cc:242-250: the rotation about the axis bead `first` -> bead `last` by an angle
+// whose sine and cosine are s and c.  Vector3d::normalize (x / sqrt(x.x), skipped for a zero vector) and
+// AngleAxisd::toRotationMatrix in Eigen's operation order (plum_b200/host/eigen_standin):
+// sin_axis = s * axis, cos1_axis = (1 - c) * axis, off-diagonals tmp -/+ sin_axis, diagonal cos1_axis * axis + c.
+PP_HD void pp_crank_matrix(const double pf[3], const double pl[3], double s, double c, double rot[9]) {
+  double ax[3] = {PP_SUB(pl[0], pf[0]), PP_SUB(pl[1], pf[1]), PP_SUB(pl[2], pf[2])};
+  const double n2 = PP_ADD(PP_ADD(PP_MUL(ax[0], ax[0]), PP_MUL(ax[1], ax[1])), PP_MUL(ax[2], ax[2]));
+  if (n2 > 0) {
+    const double n = PP_SQRT(n2);
+    ax[0] = PP_DIV(ax[0], n); ax[1] = PP_DIV(ax[1], n); ax[2] = PP_DIV(ax[2], n);
+  }
+  const double omc = PP_SUB(1.0, c);
+  const double sa[3] = {PP_MUL(s, ax[0]), PP_MUL(s, ax[1]), PP_MUL(s, ax[2])};
+  const double ca[3] = {PP_MUL(omc, ax[0]), PP_MUL(omc, ax[1]), PP_MUL(omc, ax[2])};
+  double tmp = PP_MUL(ca[0], ax[1]);
+  rot[1] = PP_SUB(tmp, sa[2]);
+  rot[3] = PP_ADD(tmp, sa[2]);
+  tmp = PP_MUL(ca[0], ax[2]);
+  rot[2] = PP_ADD(tmp, sa[1]);
+  rot[6] = PP_SUB(tmp, sa[1]);
+  tmp = PP_MUL(ca[1], ax[2]);
+  rot[5] = PP_SUB(tmp, sa[0]);
+  rot[7] = PP_ADD(tmp, sa[0]);
+  rot[0] = PP_ADD(PP_MUL(ca[0], ax[0]), c);
+  rot[4] = PP_ADD(PP_MUL(ca[1], ax[1]), c);
+  rot[8] = PP_ADD(PP_MUL(ca[2], ax[2]), c);
+}
+
+// molecule.cc:254-262: v = pos - first; v = rot * v (row times vector, summed left to right); trial = v + first.
+PP_HD void pp_crank_apply(const double rot[9], const double pf[3], const double pos[3], double out[3]) {
+  const double v[3] = {PP_SUB(pos[0], pf[0]), PP_SUB(pos[1], pf[1]), PP_SUB(pos[2], pf[2])};
+  for (int i = 0; i < 3; i++) {
+    const double r = PP_ADD(PP_ADD(PP_MUL(rot[3 * i], v[0]), PP_MUL(rot[3 * i + 1], v[1])), PP_MUL(rot[3 * i + 2], v[2]));
+    out[i] = PP_ADD(r, pf[i]);
+  }
+}
+
+
 #endif

@@ -69,7 +69,7 @@ struct McState {
   int n_mol_configured = -1;   // -1: (re)build the molecule tables (set by UpdateMolCounts after every GC move)
   bool sizer_ready = false;
   int cooldown = 0;            // steps left to the driver's per-move path because batches kept stopping early
-  double avg_len = 256.0;      // smoothed steps per batch (GC steps / crankshafts cut batches short, too)
+  double avg_len = 256.0;      // smoothed steps per batch (GC steps cut batches short, too)
   vector<double> dE, xyz;
   vector<uint8_t> acc;
   // device-resident chain (pg_chain_*): -1 not tried yet, 0 not offered for this system (the pg_mc_* path is used), 1 on
@@ -516,7 +516,7 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
   FILE* tx = plum_trace_xyz_file ? plum_trace_xyz_file() : NULL;
   int executed = 0;
   // ---- the device-resident chain: the generator itself goes to the device, nothing stops a stretch but a GC step.
-  // Offered for single-image systems without crankshaft moves (pg_chain_configure says so otherwise); PLUM_B200_CHAIN=0
+  // Offered for single-image systems (pg_chain_configure says so otherwise); PLUM_B200_CHAIN=0
   // keeps the descriptor path below, PLUM_B200_CLUSTER sets the CTAs that share the chain (default 16),
   // PLUM_B200_PIVOT_MODE=1 the prefix-sum pivot arms.
   if (S.chain != 0) {
@@ -586,7 +586,7 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
   while (S.chain != 1 && executed < max_steps) {
     const int budget = min(S.sizer.next(), max_steps - executed);
     const int n_steps = S.prop.generate(rand_gen, budget, S.batch);
-    if (n_steps == 0) break;   // a GC step or a crankshaft is next
+    if (n_steps == 0) break;   // a GC step is next
     plum_mc::Batch& b = S.batch;
     const int n_moves = (int)b.moves.size();
     int steps_done = n_steps;

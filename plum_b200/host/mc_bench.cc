@@ -55,7 +55,7 @@ struct Ctx {
 };
 
 // One proposal, drawn in the reference's order (mc_propose.h) and built on the host; false when the
-// system has nothing to move or the step is one the harness does not drive (GC, crankshaft).
+// system has nothing to move or the step is one the harness does not drive (GC).
 bool propose(Ctx* c) {
   for (;;) {
     if (c->prop.generate(c->rng, 1, c->one) != 1) return false;
@@ -66,6 +66,8 @@ bool propose(Ctx* c) {
   c->trial.resize(3 * (size_t)len);
   c->moved.assign(len, 1);
   if (d.kind == PG_MOVE_BEAD) for (int i = 1; i < len; i++) c->moved[i] = 0;
+  if (d.kind == PG_MOVE_CRANKSHAFT && std::min(d.rv_offset, len - 1) - d.i0 > 1)   // molecule.cc:251-253 (none moved: all, at rest)
+    for (int i = 0; i < len; i++) c->moved[i] = (i > d.i0 && i < std::min(d.rv_offset, len - 1)) ? 1 : 0;
   plum_mc::Proposer::apply(d, c->one.rvec.data(), len, c->pos.data() + 3 * (size_t)f, c->trial.data());
   c->cur_mol = mol; c->cur_f = f; c->cur_len = len;
   return true;

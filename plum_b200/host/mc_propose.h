@@ -110,11 +110,6 @@ class Proposer {
       }
       pg_move_desc d;
       const int kind = one_step(r, d, b.rvec);
-      if (kind == PG_MOVE_CRANKSHAFT) {
-        g = before; r.n = n_before; b.stop = STOP_UNSUPPORTED;
-        // rows a pivot-free crankshaft never adds: nothing to take back
-        break;
-      }
       b.kind.push_back(kind);
       if (kind >= 0) {
         b.pos_accept.push_back(r.n);
@@ -163,6 +158,13 @@ class Proposer {
           for (int j = i; j >= 0; j--)
             for (int k = 0; k < 3; k++) out[3 * j + k] = PP_ADD(out[3 * j + k], m[k]);
         }
+        break;
+      }
+      case PG_MOVE_CRANKSHAFT: {                             // molecule.cc:242-263
+        const int first = d.i0, last = d.rv_offset < len ? d.rv_offset : len - 1;
+        double rot[9];
+        pp_crank_matrix(cur + 3 * first, cur + 3 * last, d.v[0], d.v[1], rot);
+        for (int i = first + 1; i < last; i++) pp_crank_apply(rot, cur + 3 * first, cur + 3 * i, out + 3 * i);
         break;
       }
       default: break;
@@ -251,8 +253,17 @@ class Proposer {
         d.kind = PG_MOVE_PIVOT;
         return PG_MOVE_PIVOT;
       }
-      case 3:
+      case 3: {                                                // Crankshaft, molecule.cc:239-247
+        const int first = (int)std::floor((len - 2) * (double)r() / 4294967295.0);
+        const int last = (int)std::floor((len - first) * (double)r() / 4294967295.0) + first;
+        d.i0 = first;
+        d.rv_offset = last;
+        d.s = cfg.move_size * ((double)r() / 4294967295.0 * 2 * M_PI - M_PI);
+        d.v[0] = std::sin(d.s);                                // what AngleAxisd::toRotationMatrix takes of the angle:
+        d.v[1] = std::cos(d.s);                                // evaluated here by the same libm as the reference's
+        d.kind = PG_MOVE_CRANKSHAFT;
         return PG_MOVE_CRANKSHAFT;
+      }
       default: {                                               // RandomReptation, molecule.cc:268-312
         d.s = varied_bond(r);
         d.i0 = (r() % 2 == 0) ? -1 : 1;

@@ -94,7 +94,8 @@ def apply(desc: PgMoveDesc, rvec: np.ndarray, cur: np.ndarray) -> np.ndarray:
     rv = np.ascontiguousarray(rvec, dtype=np.float64).reshape(-1, 4)
     d = PgMoveDesc()
     C.memmove(C.byref(d), C.byref(desc), C.sizeof(PgMoveDesc))
-    d.rv_offset = 0
+    if d.kind == 2:      # PIVOT: the rows handed in start at 0 (CRANKSHAFT keeps its last-bead index there)
+        d.rv_offset = 0
     lib().pmc_apply(C.byref(d), dptr(rv) if rv.size else None, int(cur.shape[0]), dptr(cur), dptr(out))
     return out
 

@@ -23,7 +23,8 @@ SEED = 20261017
 SIGMA = 2.22724679535
 
 
-def make_run_in(n_steps: int = 1000, alpha: float = 0.004, spring: bool = False) -> str:
+def make_run_in(n_steps: int = 1000, alpha: float = 0.004, spring: bool = False,
+                move_prob=(0.5, 0.1, 0.3, 0.0, 0.1)) -> str:
     lines = [
         "s1_input_coordinate_file        input_crd.dat",
         "s1_input_topology_file          input_top.dat",
@@ -41,11 +42,11 @@ def make_run_in(n_steps: int = 1000, alpha: float = 0.004, spring: bool = False)
         "s1_number_of_surf_counterions   0",
         "s1_number_of_grafted_chains     0",
         "s1_number_of_grafted_counterion 0",
-        "s1_prob_b_bead_translation      0.5",
-        "s1_prob_p_COM_translation       0.1",
-        "s1_prob_p_pivot                 0.3",
-        "s1_prob_p_crankshaft            0.0",
-        "s1_prob_p_random_reptation      0.1",
+        f"s1_prob_b_bead_translation      {move_prob[0]}",
+        f"s1_prob_p_COM_translation       {move_prob[1]}",
+        f"s1_prob_p_pivot                 {move_prob[2]}",
+        f"s1_prob_p_crankshaft            {move_prob[3]}",
+        f"s1_prob_p_random_reptation      {move_prob[4]}",
         "s1_vp_bin_resolution_in_ul      10",
         "s1_bead_size_virial_pressure    2.5",
         "s2_use_short_range_potential    1",
@@ -149,10 +150,11 @@ def make_system(n_chains: int = 200, chain_len: int = 100, charged_every: int = 
                         np.array(first, dtype=np.int32), [L, L, L])
 
 
-def write_inputs(directory: str, sysm: runin.System, n_steps: int = 1000, alpha: float = 0.004, spring: bool = False):
+def write_inputs(directory: str, sysm: runin.System, n_steps: int = 1000, alpha: float = 0.004, spring: bool = False,
+                 move_prob=(0.5, 0.1, 0.3, 0.0, 0.1)):
     os.makedirs(directory, exist_ok=True)
     with open(os.path.join(directory, "run.in"), "w") as f:
-        f.write(make_run_in(n_steps, alpha, spring))
+        f.write(make_run_in(n_steps, alpha, spring, move_prob))
     with open(os.path.join(directory, "input_top.dat"), "w") as f:
         f.write(f"TotNoOfBeads: {sysm.n}\nTotNoOfMolec: {sysm.n_mol}\n")
         f.write(f"Box_Length_X: {sysm.box[0]!r}\nBox_Length_Y: {sysm.box[1]!r}\nBox_Length_Z: {sysm.box[2]!r}\n")

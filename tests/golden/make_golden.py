@@ -104,6 +104,22 @@ def extras():
         print("extra", name, len(lines), "lines")
 
 
+def synth_crank():
+    """examples/synth_crank + short/synth_crank_seed{1,2}.trace.gz: the small cut of synth_spring with rigid bonds
+    and crankshaft moves on (s1_prob_p_crankshaft 0.3 — zero in all four of the reference's examples), 400 steps
+    with trial coordinates.  The rotation is Eigen's AngleAxisd in the reference; plum_ref is built against the
+    stand-in of plum_b200/host/eigen_standin, which follows Eigen's operation order."""
+    from plum_b200 import synth
+    sysm = synth.make_system(n_chains=4, chain_len=24, charged_every=6)
+    dst = os.path.join(HERE, "examples", "synth_crank")
+    synth.write_inputs(dst, sysm, n_steps=400, alpha=0.004, move_prob=(0.3, 0.1, 0.2, 0.3, 0.1))
+    for seed in SHORT_SEEDS:
+        lines = replay.run_plum_ref(dst, 400, seed, xyz=True)
+        with gzip.open(os.path.join(HERE, "short", f"synth_crank_seed{seed}.trace.gz"), "wt") as f:
+            f.write("\n".join(lines))
+        print("short synth_crank", seed, len(lines), "lines")
+
+
 def vol_pressure():
     """short/{bulk_nvt,synth_spring}_volp_seed1.trace.gz: 330 steps with coordinates and sampling every 10 steps, so
     that ForceField::CalcPressureVolScalingHSELSlit (pressure.cc:187-387) runs at steps 200 and 300; the V lines
@@ -195,6 +211,7 @@ def main():
     ap.add_argument("--long-from", default=None)
     ap.add_argument("--skip-long", action="store_true")
     ap.add_argument("--extras-only", action="store_true", help="only the sampler fixtures (extras())")
+    ap.add_argument("--crank-only", action="store_true", help="only the crankshaft fixture (synth_crank())")
     ap.add_argument("--volp-only", action="store_true", help="only the volume-perturbation pressure fixtures (vol_pressure())")
     ap.add_argument("--synth-only", action="store_true", help="only the spring-bond fixture (synth_spring())")
     ap.add_argument("--cut-seed", type=int, default=0, help="only the 1320-bead cut of S (synth_cut()) for this seed")
@@ -211,6 +228,9 @@ def main():
         return
     if a.synth_only:
         synth_spring()
+        return
+    if a.crank_only:
+        synth_crank()
         return
     if a.volp_only:
         vol_pressure()
@@ -242,6 +262,7 @@ def main():
         print("long", ex, len(lines), "lines")
     extras()
     synth_spring()
+    synth_crank()
     vol_pressure()
     synth_cut()
 

@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
   std::vector<int> len = {1, 1, 1, 100, 1, 16, 1, 1, 7, 2, 1, 100, 1};
   cfg.mol_len = len;
   cfg.move_size = 2.0;
-  const double prob[5] = {0.5, 0.1, 0.3, 0.0, 0.1};
+  const double prob[5] = {0.4, 0.1, 0.25, 0.15, 0.1};   // crankshaft on (zero in the reference's own examples)
   for (int i = 0; i < 5; i++) cfg.move_prob[i] = prob[i];
   cfg.bond_len = 2.5; cfg.vary_bond = vary != 0; cfg.gc_freq = gc_freq;
   plum_mc::Proposer prop; prop.configure(cfg);
@@ -95,7 +95,12 @@ int main(int argc, char** argv) {
           printf("step %d: pivot rows differ\n", s); return 1;
         }
       }
-      if (r.mol != d.mol || r.kind != d.kind || r.i0 != d.i0 || memcmp(&r.s, &d.s, 8) || memcmp(r.v, d.v, 24) ||
+      if (d.kind == CG_CRANK) {   // the descriptor carries last bead, sin and cos where the chain kernel has i1 and its own sincos
+        if (r.rv_offset != d.i1 || r.mol != d.mol || r.i0 != d.i0 || memcmp(&r.s, &d.s, 8)) {
+          printf("step %d: crankshaft differs (first %d/%d last %d/%d angle %a/%a)\n", s, r.i0, d.i0, r.rv_offset, d.i1, r.s, d.s);
+          return 1;
+        }
+      } else if (r.mol != d.mol || r.kind != d.kind || r.i0 != d.i0 || memcmp(&r.s, &d.s, 8) || memcmp(r.v, d.v, 24) ||
           memcmp(&r.vlen, &d.vlen, 8)) {
         printf("step %d: descriptor differs (kind %d mol %d/%d i0 %d/%d s %a/%a)\n", s, d.kind, r.mol, d.mol, r.i0, d.i0, r.s, d.s);
         return 1;

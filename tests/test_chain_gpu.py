@@ -94,6 +94,51 @@ def test_chain_reproduces_reference_trace_spring(seed, cluster, batch):
     eng.close()
 
 
+@pytest.mark.parametrize("seed,cluster", [(1, 1), (2, 1), (1, 8), (2, 16)])
+def test_chain_with_crankshaft_moves_reproduces_reference_trace(seed, cluster):
+    """Molecule::Crankshaft (molecule.cc:239-265) inside the device-resident chain: the angle's sine and cosine come
+    from the device's sincos (<= 2 ulp from glibc's, which the reference used), so a crankshaft's trial coordinates
+    are compared at 1e-13 absolute instead of bit for bit, and once one has been accepted that molecule's later
+    coordinates inherit the difference; molecule, move kind and accept bit of all 400 steps must still be the
+    reference's, dE within 1e-10."""
+    r, s, eng = _engine("synth_crank")
+    ref = _trace_moves(replay.golden_short_trace("synth_crank", seed))
+    n = len(ref)
+    _configure(eng, r, cluster, keep_trials=True)
+    eng.chain_seed(seed)
+    want = s.xyz.copy()
+    rec, stop, ms = eng.chain_run(n)
+    assert len(rec) == n and stop == 0
+    n_crank, worst = 0, 0.0
+    touched = set()      # molecules whose coordinates have gone through an accepted crankshaft
+    for i in range(n):
+        kind, mol, dE_ref, acc_ref, trial, _ = ref[i]
+        assert (int(rec["kind"][i]), int(rec["mol"][i]), int(rec["accept"][i])) == (kind, mol, acc_ref), (i, rec[i], ref[i][:4])
+        got = eng.chain_trial_xyz(i, trial.shape[0])
+        if kind == 3 or mol in touched:
+            worst = max(worst, float(np.abs(got - trial).max()))
+            assert np.abs(got - trial).max() <= 1e-11, (i, kind, np.abs(got - trial).max())
+        else:
+            assert np.array_equal(got, trial), (i, kind, np.abs(got - trial).max())
+        n_crank += kind == 3
+        if dE_ref >= VLE:
+            assert rec["dE"][i] >= VLE
+        else:
+            assert replay.rel(rec["dE"][i], dE_ref) <= 1e-10, (i, kind, rec["dE"][i], dE_ref)
+        if acc_ref:
+            want[s.mol_first[mol]:s.mol_first[mol + 1]] = trial
+            if kind == 3:
+                touched.add(mol)
+    assert n_crank >= 60
+    assert np.abs(eng.positions() - want).max() <= 1e-11
+    print(f"synth_crank seed {seed} cluster {cluster}: {n_crank} crankshaft steps, max |trial - ref| on touched molecules {worst:.2e}")
+    eng.chain_check()
+    tot = eng.totals()
+    for k, v in zip(("pair", "ewald", "bond", "ext"), ref[-1][5]):
+        assert replay.rel(tot[k], v) <= 1e-9, (k, tot[k], v)
+    eng.close()
+
+
 def _cut_fixture(seed):
     z = np.load(os.path.join(replay.GOLDEN, "long", f"synth_cut_seed{seed}.npz"))
     return {k: z[k] for k in z.files}

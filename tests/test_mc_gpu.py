@@ -43,7 +43,8 @@ def _trace_moves(lines):
 
 
 @pytest.mark.parametrize("name,seed,batch", [("bulk_nvt", 1, 64), ("bulk_nvt", 2, 1000), ("confined_nvt", 1, 37),
-                                             ("confined_nvt", 2, 512), ("synth_spring", 1, 128), ("synth_spring", 2, 16)])
+                                             ("confined_nvt", 2, 512), ("synth_spring", 1, 128), ("synth_spring", 2, 16),
+                                             ("synth_crank", 1, 64), ("synth_crank", 2, 400)])
 def test_batched_chain_reproduces_reference_trace(name, seed, batch):
     r, s, eng = _engine(name)
     ref = _trace_moves(replay.golden_short_trace(name, seed))
@@ -70,7 +71,7 @@ def test_batched_chain_reproduces_reference_trace(name, seed, batch):
         assert replay.rel(tot[k], v) <= 1e-9, (k, tot[k], v)
 
 
-@pytest.mark.parametrize("name,seed", [("confined_nvt", 1), ("synth_spring", 1)])
+@pytest.mark.parametrize("name,seed", [("confined_nvt", 1), ("synth_spring", 1), ("synth_crank", 1), ("synth_crank", 2)])
 def test_device_built_trial_coordinates_are_bit_identical(name, seed):
     """One uploaded batch, read back step by step (pg_mc_trial_xyz) up to the first stop."""
     r, s, eng = _engine(name)
@@ -80,7 +81,8 @@ def test_device_built_trial_coordinates_are_bit_identical(name, seed):
     for m in ref:
         kind, d, rv = g.next()
         assert kind == m[0] and d.mol == m[1]
-        d.rv_offset = n_rows
+        if kind == 2:     # pivot rows of this step start here (a crankshaft keeps its last-bead index in rv_offset)
+            d.rv_offset = n_rows
         descs.append(d)
         rows.append(rv)
         n_rows += rv.shape[0]
@@ -91,7 +93,8 @@ def test_device_built_trial_coordinates_are_bit_identical(name, seed):
         kind, d, rv = g.next()
         if kind < 0:
             break
-        d.rv_offset = n_rows
+        if kind == 2:
+            d.rv_offset = n_rows
         descs.append(d)
         rows.append(rv)
         n_rows += rv.shape[0]
@@ -109,7 +112,7 @@ def test_device_built_trial_coordinates_are_bit_identical(name, seed):
             assert replay.rel(dE[i], dE_ref) <= 1e-10
 
 
-@pytest.mark.parametrize("name", ["bulk_nvt", "confined_nvt", "synth_spring"])
+@pytest.mark.parametrize("name", ["bulk_nvt", "confined_nvt", "synth_spring", "synth_crank"])
 def test_batched_path_equals_per_move_path(name):
     """Same seed through pg_delta_e/pg_commit (host-built trials) and through pg_mc_*: the same Markov chain."""
     n = 600

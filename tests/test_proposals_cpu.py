@@ -57,7 +57,10 @@ def _walk(name, seed, lines, r, s, max_steps=None):
         assert l - f == n
         mine = mcgen.apply(d, rv, xyz[f:l])
         assert np.array_equal(mine, trial), (name, seed, step, kind, np.abs(mine - trial).max())
-        assert moved.tolist() == ([1] + [0] * (n - 1) if kind == 0 else [1] * n)
+        if kind == 3:     # crankshaft: only the beads strictly between the axis beads (molecule.cc:251-253)
+            assert moved.tolist() == [int(d.i0 < k < d.rv_offset) for k in range(n)]
+        else:
+            assert moved.tolist() == ([1] + [0] * (n - 1) if kind == 0 else [1] * n)
         if dE >= VLE:
             assert accept == 0
             g.no_accept_draw()
@@ -73,12 +76,15 @@ def _walk(name, seed, lines, r, s, max_steps=None):
 
 
 @pytest.mark.parametrize("name,seed", [("bulk_nvt", 1), ("bulk_nvt", 2), ("confined_nvt", 1), ("confined_nvt", 2),
-                                       ("bulk_muvt", 1), ("confined_muvt", 2), ("synth_spring", 1), ("synth_spring", 2)])
+                                       ("bulk_muvt", 1), ("confined_muvt", 2), ("synth_spring", 1), ("synth_spring", 2),
+                                       ("synth_crank", 1), ("synth_crank", 2)])
 def test_generator_reproduces_reference_trial_coordinates(name, seed):
     r, s, _, _ = replay.load_golden(name)
     lines = replay.golden_short_trace(name, seed)
     n_moves, kinds = _walk(name, seed, lines, r, s)
     if not r.use_gc:
         assert n_moves >= 200 and {0, 2} <= kinds, (n_moves, kinds)
+    if name == "synth_crank":    # Molecule::Crankshaft (molecule.cc:239-265), Eigen's rotation order
+        assert {0, 1, 2, 3, 4} <= kinds
     if name == "synth_spring":   # spring bonds: Pivot / RandomReptation draw a bond length per step
         assert r.use_bond and {0, 1, 2, 4} <= kinds

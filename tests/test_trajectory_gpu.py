@@ -170,6 +170,29 @@ def test_chemical_potential_sampler_on_trajectory():
     assert abs(mu_got - mu_ref) <= 1e-6 * abs(mu_ref), (mu_got, mu_ref)
 
 
+@pytest.mark.parametrize("seed,env", [(1, {}), (2, {}), (1, {"PLUM_B200_CHAIN": "0"}), (2, {"PLUM_B200_BATCH": "0"})])
+def test_driver_with_crankshaft_moves_reproduces_the_reference(seed, env):
+    """bin/plum_gpu on tests/golden/examples/synth_crank (s1_prob_p_crankshaft 0.3): crankshaft steps run inside the
+    device-resident chain, inside descriptor batches (PLUM_B200_CHAIN=0) or move by move through the driver's own
+    Molecule::Crankshaft (PLUM_B200_BATCH=0) — every step's move kind, molecule and accept bit as plum_ref wrote
+    them, dE within 1e-10."""
+    assert replay.have_plum_gpu()
+    ref = [ln.split() for ln in replay.golden_short_trace("synth_crank", seed) if ln.startswith("T ")]
+    lines = replay.run_plum_ref(replay.golden_example_dir("synth_crank"), 400, seed, xyz=False, binary=replay.PLUM_GPU,
+                                extra_env=env)
+    got = [ln.split() for ln in lines if ln.startswith("T ")]
+    assert len(got) == len(ref) and sum(1 for t in ref if t[2] == "3") >= 60
+    for g, r_ in zip(got, ref):
+        assert g[1:4] == r_[1:4] and g[5] == r_[5], (g[:6], r_[:6])
+        a, b = replay.hx(g[4]), replay.hx(r_[4])
+        assert (a >= 1e8) == (b >= 1e8)
+        if b < 1e8:
+            assert abs(a - b) <= TOL * max(1.0, abs(b)), (g[:6], r_[:6])
+    for k in range(6, 10):
+        a, b = replay.hx(got[-1][k]), replay.hx(ref[-1][k])
+        assert abs(a - b) <= 1e-9 * max(1.0, abs(b))
+
+
 @pytest.mark.parametrize("name", ["bulk_nvt", "synth_spring"])
 def test_volume_perturbation_pressure_sampler_on_trajectory(name):
     """bin/plum_gpu with sampling every 10 steps: ForceField::CalcPressureVolScalingHSELSlit (façade ->
