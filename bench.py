@@ -330,8 +330,10 @@ def load_profile_summary():
         try:
             with open(f) as fh:
                 j = json.load(fh)
+            if "k_chain_fleet" in j:     # the whole fleet (one chain per SM) captured as ONE launch: device-wide counters
+                return os.path.basename(f), dict(j["k_chain_fleet"], section="k_chain_fleet")
             if "k_chain" in j:
-                return os.path.basename(f), j["k_chain"]
+                return os.path.basename(f), dict(j["k_chain"], section="k_chain")
         except Exception:
             continue
     return None, None
@@ -599,7 +601,8 @@ def run_ours(a):
             "achieved": ach, "frac": ach / (fp64_peak_gflops / 1e3),
             "achieved_note": "EXECUTED FP64 flop per step (2 x dfma + dadd + dmul thread instructions of the tracked ncu capture) x the "
                              "steps/s measured here with CUDA events",
-            "executed_fp64_flop_per_step": fl_step, "profile": "profiles/" + prof_file,
+            "executed_fp64_flop_per_step": fl_step, "profile": "profiles/" + prof_file, "profile_section": prof.get("section"),
+            "device_wide_pct_under_ncu": prof.get("device_wide_pct"),
             "traffic": prof.get("dram_bytes_per_step"),
             "traffic_note": "dram__bytes_read + dram__bytes_write per step from the same capture (one chain, cold caches): the working "
                             "set is L2-resident by design",

@@ -3,7 +3,11 @@
 executed FP64 work, warp instructions, L2 and DRAM bytes of the launch, and the same per Markov-chain step.
 bench.py reads the per-step figures for `roofline` (executed fraction, issue-slot fraction, L2 view).
 
-  python tools/ncu_chain_summary.py gpurun_out/prof_r02_kchain.ncu-rep <steps in the captured launch> profiles/r02_ncu_summary.json"""
+  python tools/ncu_chain_summary.py gpurun_out/prof_r02_kchain.ncu-rep <steps in the captured launch> profiles/r02_ncu_summary.json [section]
+
+`section` (default k_chain) names the entry; an existing output file is updated, so the single-chain capture (k_chain) and the
+capture of the whole fleet in one launch (k_chain_fleet: one chain per SM, device-wide issue / FP64-pipe / L2 percentages) share a file."""
+import os
 import csv
 import json
 import subprocess
@@ -27,6 +31,7 @@ def num(cell):
 
 def main():
     rep, steps, dst = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    section = sys.argv[4] if len(sys.argv) > 4 else "k_chain"
     launches = [r for r in raw_page(rep) if "k_chain" in r["Kernel Name"][1]]
     r = launches[-1]
     cyc = num(r["sm__cycles_elapsed.max"])
@@ -41,7 +46,14 @@ def main():
     dur = num(r["gpu__time_duration.sum"])
     grid = r["Grid Size"][1] if "Grid Size" in r else None
     block = r["Block Size"][1] if "Block Size" in r else None
-    out = {"k_chain": {
+    def pct(k):
+        return num(r[k]) if k in r else None
+    out = {}
+    if os.path.exists(dst):
+        with open(dst) as f:
+            out = json.load(f)
+    out[section] = {
+    "_": {
         "source": rep, "steps_in_launch": steps, "grid": grid, "block": block,
         "registers_per_thread": num(r["launch__registers_per_thread"]),
         "gpu_time_s": dur, "us_per_step_under_ncu": dur * 1e6 / steps,
@@ -51,11 +63,19 @@ def main():
         "dram_bytes": dram, "dram_bytes_per_step": dram / steps,
         "l2_bytes": l2, "l2_bytes_per_step": (l2 / steps) if l2 else None,
         "issue_active_pct": num(r["smsp__issue_active.avg.pct_of_peak_sustained_active"]) if "smsp__issue_active.avg.pct_of_peak_sustained_active" in r else None,
-        "note": "one chain (one CTA), workload S, `steps` Markov-chain steps in the captured launch; counters are launch totals "
-                "(per_cycle_elapsed x sm__cycles_elapsed.max for the FP64 thread-instruction counters)"}}
+        "device_wide_pct": {"sm_issue_active_of_elapsed": pct("sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
+                            "fp64_pipe_inst_of_active": pct("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                            "fp64_pipe_cycles_of_elapsed": pct("TPC.TriageCompute.sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
+                            "l2_throughput_of_elapsed": pct("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                            "l1tex_throughput_of_active": pct("l1tex__throughput.avg.pct_of_peak_sustained_active"),
+                            "dram_throughput_of_elapsed": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")},
+        "note": "workload S, `steps_in_launch` Markov-chain steps summed over the chains of the captured launch (one chain per CTA); "
+                "counters are launch totals (per_cycle_elapsed x sm__cycles_elapsed.max for the FP64 thread-instruction counters); "
+                "device_wide_pct are averages over all SMs / L2 slices of the device for that launch"}}
+    out[section] = out[section]["_"]
     with open(dst, "w") as f:
         json.dump(out, f, indent=1)
-    print(json.dumps(out["k_chain"]))
+    print(json.dumps(out[section]))
 
 
 if __name__ == "__main__":
