@@ -226,16 +226,36 @@ def run_example(args):
     t_init = float("inf")
     for _ in range(2):   # (the first start of a CUDA process on a box is slower: take the faster of two)
         t0 = time.perf_counter()
-        replay.run_plum_ref(d, base, 1, xyz=False, binary=binary, overrides=off, extra_env=extra_env)
+        replay.run_plum_ref(d, base, 1, xyz=False, binary=binary, overrides=off, extra_env=extra_env, trace=False)
         t_init = min(t_init, time.perf_counter() - t0)
+    err = []
+    prof_env = dict(extra_env or {})
+    if binary == replay.PLUM_GPU:
+        prof_env["PLUM_B200_PROFILE"] = "1"     # wall time inside each ABI entry point / GC attempt, printed at exit
     t0 = time.perf_counter()
-    lines = replay.run_plum_ref(d, base + steps, 1, xyz=False, binary=binary, overrides=off, extra_env=extra_env)
+    replay.run_plum_ref(d, base + steps, 1, xyz=False, binary=binary, overrides=off, extra_env=prof_env, stderr_to=err, trace=False)
     t_all = time.perf_counter() - t0
-    n_gc = sum(1 for ln in lines if ln.startswith("G ")) * steps // (base + steps)
-    n_t = sum(1 for ln in lines if ln.startswith("T ")) * steps // (base + steps)
+    # which steps were translational / grand-canonical: a traced run of the first `base` steps (not timed)
+    lines = replay.run_plum_ref(d, base, 1, xyz=False, binary=binary, overrides=off, extra_env=extra_env)
+    n_gc = sum(1 for ln in lines if ln.startswith("G ")) * steps // max(base, 1)
+    n_t = sum(1 for ln in lines if ln.startswith("T ")) * steps // max(base, 1)
     t_run = max(t_all - t_init, 1e-9)
-    return {"example": name, "steps": steps, "translational_steps": n_t, "gc_steps": n_gc, "startup_s": t_init, "run_s": t_run,
-            "steps_per_s": steps / t_run}
+    sites = {}
+    for ln in "".join(err).split("\n"):
+        if ln.startswith("plum_b200 profile: "):
+            t = ln.split()
+            sites[t[2]] = {"calls": int(t[4]), "total_s": float(t[6]), "us_per_call": float(t[8])}
+    out = {"example": name, "steps": steps, "translational_steps": n_t, "gc_steps": n_gc, "startup_s": t_init, "run_s": t_run,
+           "steps_per_s": steps / t_run}
+    if sites:
+        gc_s = sum(sites[k]["total_s"] for k in ("CBMCFChainInsertion", "CBMCFChainDeletion") if k in sites)
+        gc_n = sum(sites[k]["calls"] for k in ("CBMCFChainInsertion", "CBMCFChainDeletion") if k in sites)
+        out["facade_sites"] = sites      # of the (base + steps)-step run
+        if gc_n:
+            out["gc_attempts_per_s"] = gc_n / gc_s
+            out["gc_us_per_attempt"] = 1e6 * gc_s / gc_n
+        out["timing_note"] = "PLUM_TRACE off in the timed runs (a trace line reads the four totals every step); step kinds counted in a separate traced run"
+    return out
 
 
 def examples_block(binary, cores, extra_env=None, parallel=True, steps=EXAMPLE_STEPS):

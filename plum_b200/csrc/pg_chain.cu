@@ -13,8 +13,9 @@
 // within the real-space cutoff — the 22 000-bead benchmark system S) and replaces its stream-everything loop by spatial
 // structure that stays resident and is updated incrementally on accept:
 //
-//   LJ / WCA      a uniform cell grid (edge >= the largest LJ cutoff, <= 32^3 cells, 8 bead slots per cell + an overflow
-//                 list): a moved bead looks at 27 cells instead of at all N partners
+//   LJ / WCA      a uniform cell grid (edge >= the largest LJ cutoff, <= 64 cells per axis, 4..32 bead slots per cell
+//                 chosen when the grid is built + a chunked overflow list): a moved bead looks at 27 cells instead of
+//                 at all N partners
 //                 (pair set of potential_pair.cc:181-197, predicate r < rcut of potential_truncated_lj.cc:49-85)
 //   real space    a compact list of the charged beads (FP64 record + FP32 box fractions): FP32 pre-filter against the
 //                 real-space cutoff, exact FP64 separation for what passes, in-range configurations compacted into

@@ -864,11 +864,17 @@ int compute_totals(pg_engine* h, bool set_state, pg_totals* out) {
     int src = launch_sk_slice(h, 0, h->nk, S);
     if (src) return src;
   }
-  int n_tiles = (h->n + PG_TILE - 1) / PG_TILE;
+  // the N^2 triangle as (row tile) x (partner slice) CTAs: slices of PG_TILE partners, narrower for small systems so
+  // that the examples (a few hundred beads) still occupy the machine
+  const int n_rt = (h->n + PG_TILE - 1) / PG_TILE;
+  int pc = PG_TILE;
+  while (pc > 8 && (long long)n_rt * ((h->n + pc - 1) / pc) < 4LL * std::max(h->n_sm, 1)) pc >>= 1;
+  const int n_ct = (h->n + pc - 1) / pc;
+  const int n_tiles = n_rt * n_ct;
   int rc = ensure_partials(h, n_tiles);
   if (rc) return rc;
   if (n_tiles > 0) {
-    k_tot_pairs<<<n_tiles, PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->type, h->mol, h->n, h->d_partial);
+    k_tot_pairs<<<dim3((unsigned)n_rt, (unsigned)n_ct), PG_TILE, 0, h->stream>>>(h->P, h->xy, h->zq, h->type, h->mol, h->n, pc, h->d_partial);
     h->launches++;
     PG_CUDA(h, cudaGetLastError());
   }
@@ -2007,11 +2013,16 @@ int pg_vol_scaling_sample(pg_engine* h, int n_phantom, double dz, pg_vol_sample*
   memset(&A, 0, sizeof(A));
   A.xy = h->xy; A.zq = h->zq; A.type = h->type; A.mol = h->mol;
   A.n = n; A.n_mol = n_mol; A.phantom = n_phantom; A.dz = dz; A.nku = nku;
-  // one scratch block: Pz | mol_first | z_new | mol_part | row_part | k_part | kw | kl | out | grp
+  const int n_rt = (n + PG_TILE - 1) / PG_TILE;
+  int pc = PG_TILE;
+  while (pc > 8 && (long long)n_rt * ((n + pc - 1) / pc) < 4LL * std::max(h->n_sm, 1)) pc >>= 1;
+  const int n_ct = (n + pc - 1) / pc;
+  A.pc = pc; A.n_pair_part = n_rt * n_ct;
+  // one scratch block: Pz | mol_first | z_new | mol_part | pair_part | k_part | kw | kl | out | grp
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_P = take(sizeof(PgDev)), o_mf = take(sizeof(int) * (size_t)(n_mol + 1)), o_zn = take(sizeof(double) * (size_t)n),
-               o_mp = take(sizeof(double) * 4 * (size_t)n_mol), o_rp = take(sizeof(double) * 8 * (size_t)n),
+               o_mp = take(sizeof(double) * 4 * (size_t)n_mol), o_rp = take(sizeof(double) * 32 * (size_t)A.n_pair_part),
                o_kp = take(sizeof(double) * 16 * (size_t)(nku > 0 ? nku : 1)), o_kw = take(sizeof(double) * 2 * (size_t)(nku > 0 ? nku : 1)),
                o_kl = take(sizeof(int) * 4 * (size_t)(nku > 0 ? nku : 1)), o_out = take(sizeof(double) * 36), o_g = take((size_t)n);
   char* d = nullptr;
@@ -2024,11 +2035,11 @@ int pg_vol_scaling_sample(pg_engine* h, int n_phantom, double dz, pg_vol_sample*
   if (e == cudaSuccess) {
     A.Pz = reinterpret_cast<const PgDev*>(d + o_P); A.mol_first = reinterpret_cast<const int*>(d + o_mf);
     A.z_new = reinterpret_cast<double*>(d + o_zn); A.mol_part = reinterpret_cast<double*>(d + o_mp);
-    A.row_part = reinterpret_cast<double*>(d + o_rp); A.k_part = reinterpret_cast<double*>(d + o_kp);
+    A.pair_part = reinterpret_cast<double*>(d + o_rp); A.k_part = reinterpret_cast<double*>(d + o_kp);
     A.kw = reinterpret_cast<const double*>(d + o_kw); A.kl = reinterpret_cast<const int*>(d + o_kl);
     A.out = reinterpret_cast<double*>(d + o_out); A.grp = reinterpret_cast<unsigned char*>(d + o_g);
     k_vol_prep<<<(n_mol + 127) / 128, 128, 0, h->stream>>>(h->P, A);
-    k_vol_pairs<<<(n + PG_TILE - 1) / PG_TILE, PG_TILE, 0, h->stream>>>(h->P, A);
+    k_vol_pairs<<<dim3((unsigned)n_rt, (unsigned)n_ct), PG_TILE, 0, h->stream>>>(h->P, A);
     h->launches += 2;
     if (nku > 0) { k_vol_recip<<<(nku + 63) / 64, 64, 0, h->stream>>>(h->P, A); h->launches++; }
     k_vol_final<<<1, VS_FINAL_THREADS, 0, h->stream>>>(h->P, A);

@@ -419,15 +419,24 @@ __global__ void k_scatter_tail(double2* xy, double2* zq, int* type, int* mol, in
 
 // --------------------------------------------------------------- k_tot_pairs
 // All pairs i <= j: LJ (i < j) and Ewald real-space (i < j full, i == j self-image x0.5).
-// One "row" bead per thread, partner tiles staged in shared memory.
+// 2-D grid over the triangle: CTA (r, c) owns rows [r*PG_TILE, +PG_TILE) x partners [c*pc, +pc), one row bead per
+// thread, the partner slice staged in shared memory; CTAs entirely below the diagonal only write their zero.  The host
+// picks pc (<= PG_TILE) so that small systems still spread over the machine (potential_pair.cc:55-100 and
+// potential_ewald.cc EnergyInitialization are O(N^2) loops in the reference).
 __global__ void __launch_bounds__(PG_TILE) k_tot_pairs(const PgDev P, const double2* __restrict__ xy,
                                                        const double2* __restrict__ zq, const int* __restrict__ type,
-                                                       const int* __restrict__ mol, int n, double* partial) {
+                                                       const int* __restrict__ mol, int n, int pc, double* partial) {
   __shared__ double s_x[PG_TILE], s_y[PG_TILE], s_z[PG_TILE], s_q[PG_TILE];
   __shared__ int s_t[PG_TILE], s_m[PG_TILE];
   __shared__ double s_red[2 * 32];
   const int tid = threadIdx.x;
   const int i = blockIdx.x * PG_TILE + tid;
+  const int t0 = blockIdx.y * pc;
+  const size_t slot = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  if (t0 + pc <= blockIdx.x * PG_TILE || t0 >= n) {   // no partner j >= i in this slice
+    if (tid == 0) { partial[2 * slot] = 0.0; partial[2 * slot + 1] = 0.0; }
+    return;
+  }
   double ax = 0, ay = 0, az = 0, aq = 0;
   int at = 0, am = -1;
   if (i < n) {
@@ -435,35 +444,32 @@ __global__ void __launch_bounds__(PG_TILE) k_tot_pairs(const PgDev P, const doub
     ax = a.x; ay = a.y; az = c.x; aq = c.y; at = type[i]; am = mol[i];
   }
   double e_lj = 0.0, e_re = 0.0;
-  for (int t0 = blockIdx.x * PG_TILE; t0 < n; t0 += PG_TILE) {
-    __syncthreads();
+  const int cnt = min(pc, n - t0);
+  if (tid < cnt) {
     const int jl = t0 + tid;
-    if (jl < n) {
-      double2 a = xy[jl], c = zq[jl];
-      s_x[tid] = a.x; s_y[tid] = a.y; s_z[tid] = c.x; s_q[tid] = c.y; s_t[tid] = type[jl]; s_m[tid] = mol[jl];
-    }
-    __syncthreads();
-    if (i < n) {
-      const int cnt = min(PG_TILE, n - t0);
-      for (int jj = 0; jj < cnt; jj++) {
-        const int j = t0 + jj;
-        if (j < i) continue;
-        if (j > i) {
-          int do_lj = (P.pair_kind != 0);
-          if (P.pair_kind == 2 && j == i + 1 && s_m[jj] == am) do_lj = 0;
-          double lj, re;
-          pg_pair_both(P, ax, ay, az, aq, at, s_x[jj], s_y[jj], s_z[jj], s_q[jj], s_t[jj], do_lj, lj, re);
-          e_lj += lj; e_re += re;
-        } else if (P.use_ewald) {
-          double qq = aq * aq;
-          if (qq != 0) e_re += P.real_self_unit * qq;
-        }
+    double2 a = xy[jl], c = zq[jl];
+    s_x[tid] = a.x; s_y[tid] = a.y; s_z[tid] = c.x; s_q[tid] = c.y; s_t[tid] = type[jl]; s_m[tid] = mol[jl];
+  }
+  __syncthreads();
+  if (i < n) {
+    for (int jj = 0; jj < cnt; jj++) {
+      const int j = t0 + jj;
+      if (j < i) continue;
+      if (j > i) {
+        int do_lj = (P.pair_kind != 0);
+        if (P.pair_kind == 2 && j == i + 1 && s_m[jj] == am) do_lj = 0;
+        double lj, re;
+        pg_pair_both(P, ax, ay, az, aq, at, s_x[jj], s_y[jj], s_z[jj], s_q[jj], s_t[jj], do_lj, lj, re);
+        e_lj += lj; e_re += re;
+      } else if (P.use_ewald) {
+        double qq = aq * aq;
+        if (qq != 0) e_re += P.real_self_unit * qq;
       }
     }
   }
   double v[2] = {e_lj, e_re};
   block_sum<2>(v, s_red);
-  if (tid == 0) { partial[2 * blockIdx.x] = v[0]; partial[2 * blockIdx.x + 1] = v[1]; }
+  if (tid == 0) { partial[2 * slot] = v[0]; partial[2 * slot + 1] = v[1]; }
 }
 
 // ---------------------------------------------------------------- k_sk_slice

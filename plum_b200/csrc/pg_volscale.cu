@@ -21,8 +21,8 @@
 // The k sets of the two geometries may differ at the cutoff sphere; the host lists the union with a zero
 // weight where a vector is outside one of them.
 //
-// Four launches: k_vol_prep (one thread per molecule), k_vol_pairs (row bead per thread, partner tiles in
-// shared memory, as k_tot_pairs), k_vol_recip (one thread per k vector), k_vol_final (one CTA, fixed
+// Four launches: k_vol_prep (one thread per molecule), k_vol_pairs (row bead per thread, partner slices in
+// shared memory, the triangle tiled over the machine as k_tot_pairs), k_vol_recip (one thread per k vector), k_vol_final (one CTA, fixed
 // summation order).  A sampler, not the per-move path.
 #pragma once
 #include "pg_kernels.cuh"
@@ -37,7 +37,8 @@ struct PgVolArgs {
   double* z_new;             // [n] trial heights
   unsigned char* grp;        // [n] 0 cation, 1 anion, 2 polymer, 3 surface (first half), 4 surface (second half)
   double* mol_part;          // [n_mol][4] bond dU, wall dU, Mz old, Mz new
-  double* row_part;          // [n][8] el by partner species 0..3, hs by partner species 0..3
+  int pc, n_pair_part;       // partners per CTA slice; number of 32-value partials
+  double* pair_part;         // [n_pair_part][32] el[16] hs[16] of one CTA of k_vol_pairs
   // reciprocal space, union list of both geometries
   const int* kl;             // [nku][4]
   const double* kw;          // [nku][2] ek2 of the current / stretched box (0: vector not in that set)
@@ -92,13 +93,24 @@ __global__ void __launch_bounds__(128) k_vol_prep(const PgDev P, const PgVolArgs
 }
 
 // ---------------------------------------------------------------- k_vol_pairs
+// 2-D grid over the triangle like k_tot_pairs: CTA (r, c) owns rows [r*PG_TILE, +PG_TILE) x partners [c*pc, +pc).
+// Every thread keeps its row bead's sums by partner species; the CTA folds them into the 16 + 16 table entries in a
+// fixed order and writes one 32-value partial.
 __global__ void __launch_bounds__(PG_TILE) k_vol_pairs(const PgDev P, const PgVolArgs A) {
   __shared__ double s_x[PG_TILE], s_y[PG_TILE], s_z[PG_TILE], s_zn[PG_TILE], s_q[PG_TILE];
   __shared__ int s_t[PG_TILE], s_m[PG_TILE];
   __shared__ unsigned char s_g[PG_TILE];
+  __shared__ double s_val[PG_TILE][9];
+  __shared__ int s_ca[PG_TILE];
   const PgDev& Pz = *A.Pz;
-  const int tid = threadIdx.x, n = A.n;
+  const int tid = threadIdx.x, n = A.n, pc = A.pc;
   const int i = blockIdx.x * PG_TILE + tid;
+  const int t0 = blockIdx.y * pc;
+  double* slot = A.pair_part + 32 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+  if (t0 + pc <= blockIdx.x * PG_TILE || t0 >= n) {   // no partner j >= i in this slice
+    if (tid < 32) slot[tid] = 0.0;
+    return;
+  }
   double ax = 0, ay = 0, az = 0, azn = 0, aq = 0;
   int at = 0, am = -1, ag = 4;
   if (i < n) {
@@ -106,52 +118,61 @@ __global__ void __launch_bounds__(PG_TILE) k_vol_pairs(const PgDev P, const PgVo
     ax = a.x; ay = a.y; az = c.x; aq = c.y; azn = A.z_new[i]; at = A.type[i]; am = A.mol[i]; ag = A.grp[i];
   }
   double el[4] = {0, 0, 0, 0}, hs[4] = {0, 0, 0, 0};
-  for (int t0 = blockIdx.x * PG_TILE; t0 < n; t0 += PG_TILE) {
-    __syncthreads();
+  const int cnt = min(pc, n - t0);
+  if (tid < cnt) {
     const int jl = t0 + tid;
-    if (jl < n) {
-      const double2 a = A.xy[jl], c = A.zq[jl];
-      s_x[tid] = a.x; s_y[tid] = a.y; s_z[tid] = c.x; s_q[tid] = c.y; s_zn[tid] = A.z_new[jl];
-      s_t[tid] = A.type[jl]; s_m[tid] = A.mol[jl]; s_g[tid] = A.grp[jl];
-    }
-    __syncthreads();
-    if (i < n && ag != 4) {
-      const int cnt = min(PG_TILE, n - t0);
-      for (int jj = 0; jj < cnt; jj++) {
-        const int j = t0 + jj;
-        if (j < i) continue;
-        const int gj = s_g[jj];
-        // i >= phantom, or i on the first plate and k >= phantom / 2 (pressure.cc:264-265)
-        if (!(ag < 3 || gj != 3)) continue;
-        const int cb = gj < 3 ? gj : 3;
-        double d_el = 0.0, d_hs = 0.0;
-        if (j > i) {
-          const int mobile = (ag < 3 && gj < 3);
-          const int lj_new = (P.pair_kind != 0) && mobile;
-          int lj_old = lj_new;
-          // the stored energy of bonded hard-sphere neighbours is 0 (potential_pair.cc:64-67); PairEnergy is not
-          if (P.pair_kind == 2 && j == i + 1 && s_m[jj] == am) lj_old = 0;
-          double lj_o, re_o, lj_n, re_n;
-          pg_pair_both(P, ax, ay, az, aq, at, s_x[jj], s_y[jj], s_z[jj], s_q[jj], s_t[jj], lj_old, lj_o, re_o);
-          pg_pair_both(Pz, ax, ay, azn, aq, at, s_x[jj], s_y[jj], s_zn[jj], s_q[jj], s_t[jj], lj_new, lj_n, re_n);
-          d_el = re_n - re_o;
-          d_hs = lj_n - lj_o;
-        } else if (P.use_ewald) {
-          const double qq = aq * aq;
-          if (qq != 0) d_el = Pz.real_self_unit * qq - P.real_self_unit * qq;
-        }
+    const double2 a = A.xy[jl], c = A.zq[jl];
+    s_x[tid] = a.x; s_y[tid] = a.y; s_z[tid] = c.x; s_q[tid] = c.y; s_zn[tid] = A.z_new[jl];
+    s_t[tid] = A.type[jl]; s_m[tid] = A.mol[jl]; s_g[tid] = A.grp[jl];
+  }
+  __syncthreads();
+  if (i < n && ag != 4) {
+    for (int jj = 0; jj < cnt; jj++) {
+      const int j = t0 + jj;
+      if (j < i) continue;
+      const int gj = s_g[jj];
+      // i >= phantom, or i on the first plate and k >= phantom / 2 (pressure.cc:264-265)
+      if (!(ag < 3 || gj != 3)) continue;
+      const int cb = gj < 3 ? gj : 3;
+      double d_el = 0.0, d_hs = 0.0;
+      if (j > i) {
+        const int mobile = (ag < 3 && gj < 3);
+        const int lj_new = (P.pair_kind != 0) && mobile;
+        int lj_old = lj_new;
+        // the stored energy of bonded hard-sphere neighbours is 0 (potential_pair.cc:64-67); PairEnergy is not
+        if (P.pair_kind == 2 && j == i + 1 && s_m[jj] == am) lj_old = 0;
+        double lj_o, re_o, lj_n, re_n;
+        pg_pair_both(P, ax, ay, az, aq, at, s_x[jj], s_y[jj], s_z[jj], s_q[jj], s_t[jj], lj_old, lj_o, re_o);
+        pg_pair_both(Pz, ax, ay, azn, aq, at, s_x[jj], s_y[jj], s_zn[jj], s_q[jj], s_t[jj], lj_new, lj_n, re_n);
+        d_el = re_n - re_o;
+        d_hs = lj_n - lj_o;
+      } else if (P.use_ewald && ag < 3) {
+        const double qq = aq * aq;
+        if (qq != 0) d_el = Pz.real_self_unit * qq - P.real_self_unit * qq;
+      }
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          el[c] += (cb == c) ? d_el : 0.0;
-          hs[c] += (cb == c) ? d_hs : 0.0;
-        }
+      for (int c = 0; c < 4; c++) {
+        el[c] += (cb == c) ? d_el : 0.0;
+        hs[c] += (cb == c) ? d_hs : 0.0;
       }
     }
   }
-  if (i < n) {
-    double* o = A.row_part + 8 * (size_t)i;
 #pragma unroll
-    for (int c = 0; c < 4; c++) { o[c] = el[c]; o[4 + c] = hs[c]; }
+  for (int c = 0; c < 4; c++) { s_val[tid][c] = el[c]; s_val[tid][4 + c] = hs[c]; }
+  s_ca[tid] = ag < 3 ? ag : 3;
+  __syncthreads();
+  if (tid < 32) {
+    const int idx = tid & 15, pass = tid >> 4;   // table entry, el / hs
+    double sum = 0.0;
+    for (int rrow = 0; rrow < PG_TILE; rrow++) {
+      const int ca = s_ca[rrow];
+#pragma unroll
+      for (int cb = 0; cb < 4; cb++) {
+        const int e = (ca < cb ? ca : cb) * 4 + (ca > cb ? ca : cb);
+        if (e == idx) sum += s_val[rrow][4 * pass + cb];
+      }
+    }
+    slot[tid] = sum;
   }
 }
 
@@ -221,14 +242,9 @@ __global__ void __launch_bounds__(VS_FINAL_THREADS) k_vol_final(const PgDev P, c
   const PgDev& Pz = *A.Pz;
   for (int pass = 0; pass < 2; pass++) {   // 0: el, 1: hs
     for (int c = 0; c < 16; c++) s_acc[c][tid] = 0.0;
-    for (int i = tid; i < A.n; i += VS_FINAL_THREADS) {
-      const int g = A.grp[i];
-      const int ca = g < 3 ? g : 3;
-      const double* r = A.row_part + 8 * (size_t)i + 4 * pass;
-      for (int cb = 0; cb < 4; cb++) {
-        const int idx = (ca < cb ? ca : cb) * 4 + (ca > cb ? ca : cb);
-        s_acc[idx][tid] += r[cb];
-      }
+    for (int b = tid; b < A.n_pair_part; b += VS_FINAL_THREADS) {
+      const double* r = A.pair_part + 32 * (size_t)b + 16 * pass;
+      for (int c = 0; c < 16; c++) s_acc[c][tid] += r[c];
     }
     if (pass == 0 && P.use_ewald) {
       for (int k = tid; k < A.nku; k += VS_FINAL_THREADS)

@@ -41,9 +41,10 @@ namespace {
 double Uniform(mt19937& g) { return (double)g() / g.max(); }
 
 // PLUM_B200_PROFILE=1: wall time spent inside each ABI entry point, printed to stderr at exit.
-enum { kTDelta, kTCommit, kTTrials, kTInsert, kTDelete, kTTotals, kTWallForce, kTVolScale, kTSites };
+enum { kTDelta, kTCommit, kTTrials, kTInsert, kTDelete, kTTotals, kTWallForce, kTVolScale, kTGcInsert, kTGcDelete, kTBatch, kTSites };
 const char* const kSiteName[kTSites] = {"pg_delta_e", "pg_commit", "pg_trial_energies", "pg_insert_molecules",
-                                        "pg_delete_molecules", "pg_get_totals", "pg_wall_force", "pg_vol_scaling_sample"};
+                                        "pg_delete_molecules", "pg_get_totals", "pg_wall_force", "pg_vol_scaling_sample",
+                                        "CBMCFChainInsertion", "CBMCFChainDeletion", "TranslationalBatch"};
 bool prof_on = getenv("PLUM_B200_PROFILE") != NULL;
 double prof_s[kTSites];
 long prof_n[kTSites];
@@ -95,7 +96,7 @@ void MtImport(mt19937& g, const uint32_t* state, int pos) {
 }
 }  // namespace
 
-ForceField::ForceField() : vp_z(0), engine(NULL), pending_mol(-1), mc_state(NULL) {
+ForceField::ForceField() : vp_z(0), engine(NULL), tot_valid(false), pending_mol(-1), mc_state(NULL) {
   for (int i = 0; i < 12; i++) p_tensor[i] = 0;
   for (int i = 0; i < 20; i++) p_tensor2[i] = p_tensor3[i] = p_tensor_hs[i] = p_tensor_el[i] = 0;
 }
@@ -367,6 +368,7 @@ void ForceField::UploadSystem(vector<Molecule>& mols) {
     }
     first.push_back((int32_t)q.size());
   }
+  tot_valid = false;
   int rc = pg_upload_system(engine, (int)q.size(), xyz.data(), q.data(), type.data(), (int)mols.size(), first.data());
   if (rc) Fail("pg_upload_system", rc);
 }
@@ -417,6 +419,7 @@ void ForceField::Initialize(double beta_in, int npbc_in, double box_l_in[3], vec
 void ForceField::InitializeEnergy(vector<Molecule>& mols) {
   UploadSystem(mols);
   pg_totals t;
+  tot_valid = false;
   int rc = pg_init_energy(engine, &t);
   if (rc) Fail("pg_init_energy", rc);
   if (use_pair_pot) cout << "  Initialized pair potential." << endl;
@@ -460,6 +463,7 @@ void ForceField::FinalizeEnergies(vector<Molecule>& mols, bool accept, int moved
   (void)mols;
   if (pending_mol != moved_mol) return;   // EnergyDifference was skipped by the driver
   int rc;
+  tot_valid = false;
   { SiteTimer st_(kTCommit); rc = pg_commit(engine, accept ? 1 : 0); }
   if (rc) Fail("pg_commit", rc);
   pending_mol = -1;
@@ -485,6 +489,7 @@ void ForceField::SkDriftReset(int steps_done) {
   sk_steps += steps_done;
   if (sk_steps < every) return;
   sk_steps = 0;
+  tot_valid = false;
   int rc = pg_recompute_sk(engine, NULL);
   if (rc) Fail("pg_recompute_sk", rc);
 }
@@ -492,6 +497,7 @@ void ForceField::SkDriftReset(int steps_done) {
 int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, int max_steps, int first_step,
                                    double move_size, const double move_prob[5], int attempted[], int accepted[]) {
   if (max_steps <= 0) return 0;
+  SiteTimer whole_(kTBatch);
   if (!mc_state) mc_state = new McState();
   McState& S = *static_cast<McState*>(mc_state);
   // Where most steps end in an overlap (dE >= 1e8: dense systems, long pivots) a batch stops after a handful of
@@ -549,6 +555,7 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
         rc = pg_chain_set_rng(engine, state, pos);
         if (rc) Fail("pg_chain_set_rng", rc);
       }
+      tot_valid = false;
       rc = pg_chain_run(engine, max_steps, &n_done, &stop, S.steps.data(), NULL);
       if (rc) Fail("pg_chain_run", rc);
       rc = pg_chain_get_rng(engine, state, &pos);
@@ -598,6 +605,7 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
       { SiteTimer st_(kTDelta);
         rc = pg_mc_upload(engine, n_moves, b.moves.data(), (int)(b.rvec.size() / 4), b.rvec.data());
         if (rc) Fail("pg_mc_upload", rc);
+        tot_valid = false;
         rc = pg_mc_run(engine, 0, n_moves, S.dE.data(), S.acc.data(), &n_done, NULL); }
       if (rc) Fail("pg_mc_run", rc);
       stopped = n_done > 0 && S.dE[n_done - 1] >= kVeryLargeEnergy;
@@ -746,6 +754,7 @@ double ForceField::CBMCFGenTrialBeads(Bead& end_bead, vector<Molecule>& mols, in
 }
 
 bool ForceField::CBMCFChainInsertion(vector<Molecule>& mols, mt19937& rand_gen) {
+  SiteTimer whole_(kTGcInsert);   // the whole grand-canonical attempt, host and device (PLUM_B200_PROFILE=1)
   bool accept = false;
   double weight = 1.0;
   const bool charged = (gc_bead_charge != 0);
@@ -841,11 +850,13 @@ void ForceField::EnergyInitForAddedMolecule(vector<Molecule>& mols) {
     }
   }
   int rc;
+  tot_valid = false;
   { SiteTimer st_(kTInsert); rc = pg_insert_molecules(engine, added, lens.data(), xyz.data(), q.data(), type.data(), NULL); }
   if (rc) Fail("pg_insert_molecules", rc);
 }
 
 int ForceField::CBMCFChainDeletion(vector<Molecule>& mols, mt19937& rand_gen) {
+  SiteTimer whole_(kTGcDelete);
   UpdateMolCounts(mols);
   const bool charged = (gc_bead_charge != 0);
   const int k = cbmc_no_of_trials;
@@ -916,6 +927,7 @@ int ForceField::CBMCFChainDeletion(vector<Molecule>& mols, mt19937& rand_gen) {
     int counterion = 0;
     for (int i = 0; i < mols[delete_id].Size(); i++) counterion += (int)abs(round(mols[delete_id].bds[i].Charge()));
     int rc;
+    tot_valid = false;
     { SiteTimer st_(kTDelete); rc = pg_delete_molecules(engine, delete_id, delete_id + counterion, NULL); }
     if (rc) Fail("pg_delete_molecules", rc);
     return delete_id;
@@ -1085,34 +1097,23 @@ bool ForceField::UseAnglePot() { return use_angle_pot; }
 bool ForceField::UseDihedPot() { return use_dihed_pot; }
 bool ForceField::UseExtPot() { return use_ext_pot; }
 
-double ForceField::TotPairEnergy() {
-  pg_totals t;
-  int rc;
-  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
-  if (rc) Fail("pg_get_totals", rc);
-  return t.pair;
+// The four running totals come from one pg_get_totals per configuration: the driver asks for them one by one
+// (PrintStat, the trace hooks), the cache is dropped by every call that changes the resident state.
+const double* ForceField::Totals() {
+  if (!tot_valid) {
+    pg_totals t;
+    int rc;
+    { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
+    if (rc) Fail("pg_get_totals", rc);
+    tot_cache[0] = t.pair; tot_cache[1] = t.ewald; tot_cache[2] = t.bond; tot_cache[3] = t.ext;
+    tot_valid = true;
+  }
+  return tot_cache;
 }
-double ForceField::TotEwaldEnergy() {
-  pg_totals t;
-  int rc;
-  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
-  if (rc) Fail("pg_get_totals", rc);
-  return t.ewald;
-}
-double ForceField::TotBondEnergy() {
-  pg_totals t;
-  int rc;
-  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
-  if (rc) Fail("pg_get_totals", rc);
-  return t.bond;
-}
-double ForceField::TotExtEnergy() {
-  pg_totals t;
-  int rc;
-  { SiteTimer st_(kTTotals); rc = pg_get_totals(engine, &t); }
-  if (rc) Fail("pg_get_totals", rc);
-  return t.ext;
-}
+double ForceField::TotPairEnergy() { return Totals()[0]; }
+double ForceField::TotEwaldEnergy() { return Totals()[1]; }
+double ForceField::TotBondEnergy() { return Totals()[2]; }
+double ForceField::TotExtEnergy() { return Totals()[3]; }
 
 double ForceField::RigidBondLen() { return rigid_bond; }
 

@@ -77,6 +77,9 @@ class ForceField {
   map<string, double> wall_sigmas, wall_epsilons;
   // Device side.
   pg_engine* engine;
+  bool tot_valid;        // tot_cache holds the engine's running totals (one pg_get_totals per step at most)
+  double tot_cache[4];   // pair, ewald, bond, ext
+  const double* Totals();
   map<string, int> type_of;        // bead symbol -> dense type id
   vector<string> type_symbols;
   int pending_mol;                  // molecule of the trial awaiting FinalizeEnergies (-1: none)

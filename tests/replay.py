@@ -35,7 +35,8 @@ def have_plum_gpu() -> bool:
 
 
 def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, binary: str = None,
-                 overrides: dict = None, want_files=(), extra_env: dict = None) -> List[str]:
+                 overrides: dict = None, want_files=(), extra_env: dict = None, stderr_to: list = None,
+                 trace: bool = True) -> List[str]:
     """Run a driver binary (default: the reference, oracle/_ref/plum_ref; or bin/plum_gpu) on an example
     (inputs copied to a temp dir) and return its trace lines.  `overrides` replaces run.in values by key."""
     binary = binary or PLUM_REF
@@ -55,14 +56,24 @@ def run_plum_ref(example_dir: str, steps: int, seed: int, xyz: bool = True, bina
         for fn in ("input_crd.dat", "input_top.dat"):
             with open(os.path.join(example_dir, fn)) as fi, open(os.path.join(tmp, fn), "w") as fo:
                 fo.write(fi.read())
-        env = dict(os.environ, PLUM_SEED=str(seed), PLUM_TRACE=os.path.join(tmp, "trace.txt"))
+        env = dict(os.environ, PLUM_SEED=str(seed))
+        if trace:
+            env["PLUM_TRACE"] = os.path.join(tmp, "trace.txt")
+        else:
+            env.pop("PLUM_TRACE", None)      # timing runs: no per-step trace line (it reads the four totals every step)
         if xyz:
             env["PLUM_TRACE_XYZ"] = "1"
         env.update(extra_env or {})
         with open(os.path.join(tmp, "run.in")) as fin, open(os.path.join(tmp, "run.log"), "w") as fout:
-            subprocess.check_call([binary], stdin=fin, stdout=fout, cwd=tmp, env=env)
-        with open(os.path.join(tmp, "trace.txt")) as f:
-            lines = f.read().split("\n")
+            if stderr_to is None:
+                subprocess.check_call([binary], stdin=fin, stdout=fout, cwd=tmp, env=env)
+            else:     # the caller wants the binary's stderr (PLUM_B200_PROFILE=1 summary lines)
+                p = subprocess.run([binary], stdin=fin, stdout=fout, stderr=subprocess.PIPE, cwd=tmp, env=env, text=True, check=True)
+                stderr_to.append(p.stderr)
+        lines = []
+        if trace:
+            with open(os.path.join(tmp, "trace.txt")) as f:
+                lines = f.read().split("\n")
         if want_files:
             extra = {}
             for fn in want_files:

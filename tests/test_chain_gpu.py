@@ -277,6 +277,52 @@ def test_full_size_system_chain_equals_per_move(cluster):
         e.close()
 
 
+def test_full_size_chain_moves_against_the_oracle():
+    """The FAST path at N = 22 000 against the CPU oracle directly (not only against the per-move kernel): 400 steps of
+    the device-resident chain with the trial coordinates kept; every ion move and the first 24 chain moves (>= 200
+    moves in all) are re-evaluated by the oracle's pairwise restatement of ForceField::EnergyDifference on the
+    configuration the chain had in front of that step.  Prints plain-relative and max(1, |dE|)-scaled errors."""
+    from oracle.oracle_py import Oracle
+    from plum_b200 import synth
+    r, s, types, params = synth.load(cache_dir=os.path.join(replay.REPO, "gpurun_out", "cache"))
+    ids = types.ids(s.symbol)
+    eng = Engine(params, device=0, capacity_beads=s.n)
+    eng.upload(s.xyz, s.q, ids, s.mol_first)
+    eng.init_energy()
+    _configure(eng, r, 8, keep_trials=True)
+    eng.chain_seed(21)
+    n = 400
+    rec, stop, ms = eng.chain_run(n)
+    assert len(rec) == n and stop == 0
+    orc = Oracle(params)
+    pos = s.xyz.copy()
+    got, ref, n_chain_checked, kinds = [], [], 0, []
+    for i in range(n):
+        mol, kind, acc = int(rec["mol"][i]), int(rec["kind"][i]), int(rec["accept"][i])
+        if mol < 0:
+            continue
+        f, l = int(s.mol_first[mol]), int(s.mol_first[mol + 1])
+        trial = eng.chain_trial_xyz(i, l - f)
+        check = (kind == 0) or n_chain_checked < 24
+        if check:
+            orc.upload(pos, s.q, ids, s.mol_first)
+            mv = np.ones(l - f, dtype=np.uint8)
+            do = orc.delta_e(mol, trial, mv)
+            orc.commit(False)
+            got.append(float(rec["dE"][i])); ref.append(do["dE"]); kinds.append(kind)
+            n_chain_checked += kind != 0
+        if acc:
+            pos[f:l] = trial
+    got, ref = np.array(got), np.array(ref)
+    assert len(got) >= 200 and n_chain_checked == 24
+    assert np.array_equal(got >= VLE, ref >= VLE)
+    plain, scaled = _errors(got, ref)
+    print(f"S chain vs oracle: {len(got)} moves ({n_chain_checked} chain moves) max |ddE| / |dE| = {plain:.3e}, / max(1, |dE|) = {scaled:.3e}")
+    assert scaled <= 1e-10
+    assert np.array_equal(eng.positions(), pos)
+    eng.close()
+
+
 def test_many_replicas_in_one_launch_walk_their_own_chains():
     """pg_chain_run_multi: 6 replicas with different seeds in one launch == each of them run alone."""
     r, s, types, params = replay.load_golden("synth_cut")

@@ -2,7 +2,9 @@
 """Exercises every kernel of the path once or twice so that one ncu pass can capture them all:
    S (22 000 beads): init (k_tot_pairs, k_sk_slice, k_sk_reduce, k_tot_final), k_move<true> ion + chain,
                      k_trials (30 trials), k_delta insert / delete (8-bead chain + 8 ions), k_commit, k_propose (two 24-step batches)
-   bulk_nvt / confined_nvt (reference examples): k_move<false> ion + chain (multi-image path), k_wall_force.
+                     k_chain (40 steps, cluster 1 and 8), k_sk_block / k_sk_finish / k_sk_energy (full S(k) recompute), k_vol_* (pressure sample)
+   bulk_nvt / confined_nvt (reference examples): init (k_tot_pairs on a few hundred beads), k_move<false> ion + chain (multi-image path),
+                     k_wall_force, k_vol_* on bulk_nvt.
 Run:  ncu --set full --clock-control none --import-source on -k regex:'k_' -o gpurun_out/prof_<tag>_all python tools/profile_kernels.py   (tools/round_evidence.sh does it and keeps the raw-metric CSV)
 """
 import os, sys
@@ -36,7 +38,8 @@ for rep in range(2):
         kind, d, rv = g.next()
         if kind < 0:
             continue
-        d.rv_offset = n_rows
+        if kind == 2:
+            d.rv_offset = n_rows
         descs.append(d); rows.append(rv); n_rows += rv.shape[0]
     eng.mc_upload(descs, np.concatenate(rows) if n_rows else None)
     eng.mc_run(0, len(descs))
@@ -55,6 +58,17 @@ for rep in range(2):
     eng.insert_molecules([8] + [1] * 8, new_xyz, np.array([-1.0] * 8 + [1.0] * 8), np.full(16, tP, dtype=np.int32))
     eng.delete_molecules(s.n_mol, s.n_mol + 8)
 eng.totals()
+# round 2: the device-resident chain (k_chain, 40 steps, one CTA and a cluster of 8), the full S(k) recompute
+# (k_sk_block / k_sk_finish / k_sk_energy) and one volume-perturbation pressure sample (k_vol_*)
+bl, vary = mcgen.bond_settings(r)
+for cluster in (1, 8):
+    eng.chain_configure(r.phantom, r.move_size, r.move_prob, bl, vary_bond=vary, cluster=cluster)
+    eng.chain_seed(3)
+    for rep in range(2):
+        eng.chain_run(40)
+for rep in range(2):
+    eng.recompute_sk()
+    eng.vol_scaling_sample(0)
 eng.close()
 
 for name in ("bulk_nvt", "confined_nvt"):
@@ -71,5 +85,8 @@ for name in ("bulk_nvt", "confined_nvt"):
     if r.phantom:
         for rep in range(2):
             eng.wall_force(r.phantom)
+    else:
+        for rep in range(2):
+            eng.vol_scaling_sample(0)
     eng.close()
 print("profile_kernels done")

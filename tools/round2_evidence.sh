@@ -22,3 +22,7 @@ timeout -k 10 900 python bench.py > gpurun_out/${tag}_bench_n1.json 2> gpurun_ou
 timeout -k 10 900 python bench.py --impl reference > gpurun_out/${tag}_bench_ref_n1.json 2> gpurun_out/${tag}_bench_ref_n1.err; tail -c 400 gpurun_out/${tag}_bench_ref_n1.json
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --moves-per-step 128 --no-cpu-baseline --no-single --no-recompute --no-examples --replicas-per-gpu 16 > gpurun_out/${tag}_launches_bench.log 2>&1
+# every kernel of the path once or twice (tools/profile_kernels.py) -> per-kernel rows
+timeout -k 10 1200 ncu --set full --clock-control none -k regex:k_ -f -o /tmp/prof_${tag}_all python tools/profile_kernels.py > gpurun_out/${tag}_ncu_all.log 2>&1
+ncu -i /tmp/prof_${tag}_all.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_all_raw.csv 2>/dev/null
+python tools/kernels_summary.py gpurun_out/prof_${tag}_all_raw.csv gpurun_out/${tag}_kernels.json | tail -40
