@@ -724,7 +724,8 @@ def run_ours(a):
                     "ms_per_step": main["t_e2e"] * 1e3 / K,
                     "caller": f"native C++ caller (plum_b200/host/mc_bench.cc pb_run_chain), ONE host thread per GPU driving {R} chains: per batch of "
                               f"{a.batch} steps pg_chain_set_rng (std::mt19937 state down), pg_chain_run_multi (one launch), pg_chain_steps (log up), "
-                              f"pg_chain_get_rng, pg_download_positions (accepted coordinates up, as ForceField::TranslationalBatch does)"},
+                              f"pg_chain_get_rng, pg_download_positions (accepted coordinates up, as ForceField::TranslationalBatch does); = pg_chain_run_multi_io, "
+                              f"whose host-side repacking of the coordinates (56 B per bead) uses up to 8 worker threads"},
             "gpu_launches": int(main["launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
             "resident_matches_e2e": main["same"], "accept_ratio": main["accept"],
             "wall_ms_per_step_resident": main["wall_res"] * 1e3 / K,

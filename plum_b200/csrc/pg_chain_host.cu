@@ -538,11 +538,29 @@ int pg_chain_run_multi_io(pg_engine** hs, int n, int max_steps, uint32_t* rng_io
     if (n_done) n_done[i] = out[0];
     memcpy(rng_io + (size_t)i * 625, base, 625 * sizeof(uint32_t));
     if (steps && out[0] > 0) memcpy(steps + (size_t)i * max_steps, base + rng_b + out_b, sizeof(PgChainRec) * (size_t)out[0]);
-    if (xyz && xyz[i]) {
-      const double2* hxy = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b);
-      const double2* hzq = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b + pos_b);
-      double* dst = xyz[i];
-      for (int b = 0; b < nb; b++) { dst[3 * b] = hxy[b].x; dst[3 * b + 1] = hxy[b].y; dst[3 * b + 2] = hzq[b].x; }
+  }
+  if (xyz) {
+    // (x, y | z, q) pairs -> the caller's [n][3] arrays: memory-bound host work (56 B per bead), spread over a few
+    // threads when a whole fleet comes back at once
+    auto unpack = [&](int i0, int i1) {
+      for (int i = i0; i < i1; i++) {
+        if (!xyz[i]) continue;
+        const char* base = c.h_pin + per * (size_t)i;
+        const double2* hxy = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b);
+        const double2* hzq = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b + pos_b);
+        double* dst = xyz[i];
+        for (int b = 0; b < nb; b++) { dst[3 * b] = hxy[b].x; dst[3 * b + 1] = hxy[b].y; dst[3 * b + 2] = hzq[b].x; }
+      }
+    };
+    int T = 1;
+    if ((long long)n * nb >= 1000000) T = (int)std::min<unsigned>(std::min<unsigned>(8u, (unsigned)n), std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (T <= 1) {
+      unpack(0, n);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 1; t < T; t++) th.emplace_back(unpack, (int)((long long)n * t / T), (int)((long long)n * (t + 1) / T));
+      unpack(0, (int)((long long)n / T));
+      for (auto& x : th) x.join();
     }
   }
   return PG_OK;
