@@ -48,6 +48,8 @@ const char* const kSiteName[kTSites] = {"pg_delta_e", "pg_commit", "pg_trial_ene
 bool prof_on = getenv("PLUM_B200_PROFILE") != NULL;
 double prof_s[kTSites];
 long prof_n[kTSites];
+timespec prof_t_run;          // end of InitializeEnergy: everything behind it is the driver's run loop
+bool prof_run_started = false;
 struct SiteTimer {
   int site;
   timespec t0;
@@ -102,6 +104,12 @@ ForceField::ForceField() : vp_z(0), engine(NULL), tot_valid(false), pending_mol(
 }
 
 ForceField::~ForceField() {
+  if (prof_on && prof_run_started) {
+    timespec t1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double w = (t1.tv_sec - prof_t_run.tv_sec) + 1e-9 * (t1.tv_nsec - prof_t_run.tv_nsec);
+    cerr << "plum_b200 profile: run_wall calls 1 total " << w << " s, " << 1e6 * w << " us/call" << endl;
+  }
   if (prof_on)
     for (int i = 0; i < kTSites; i++)
       if (prof_n[i])
@@ -437,6 +445,7 @@ void ForceField::InitializeEnergy(vector<Molecule>& mols) {
   for (int i = 0; i < cbmc_no_of_trials; i++)
     cbmc_trial_beads.push_back(Bead(gc_bead_symbol, -1, -1, gc_chain_len ? -gc_chain_chg[0] : 0.0, 0, 0, 0));
   cbmc_trial_weights.assign(cbmc_no_of_trials, 0.0);
+  if (prof_on && !prof_run_started) { clock_gettime(CLOCK_MONOTONIC, &prof_t_run); prof_run_started = true; }
 }
 
 // ------------------------------------------------------------------ per move
