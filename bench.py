@@ -9,7 +9,7 @@ One *step* = MOVES_PER_STEP sequential Metropolis steps (move mix 0.5 ion transl
 0.1 reptation) of EVERY replica of the GPU.  Replicas are independent Markov chains (own engine, own random stream);
 there is no communication: scaling "weak", `value` is the aggregate over all ranks.
 
-  value   THROUGHPUT mode: `replicas_per_gpu` chains per GPU (default one per SM, one CTA each), all of them in ONE launch
+  value   THROUGHPUT mode: `replicas_per_gpu` chains per GPU (default two per SM, one CTA each: the 448-thread build of k_chain at 2 CTAs per SM), all of them in ONE launch
           of the device-resident chain kernel k_chain per step (pg_chain_run_multi); generator state, coordinates, S(k),
           cell grid already resident; CUDA-event time of the launches.  The rate ONE Markov chain sees is in
           `single_chain` (a 16-CTA cluster per chain), next to `value`, for both pivot modes.
@@ -360,7 +360,7 @@ def load_profile_summary():
         try:
             with open(f) as fh:
                 j = json.load(fh)
-            if "k_chain_fleet" in j:     # the whole fleet (one chain per SM) captured as ONE launch: device-wide counters
+            if "k_chain_fleet" in j:     # the whole fleet (two chains per SM) captured as ONE launch: device-wide counters
                 return os.path.basename(f), dict(j["k_chain_fleet"], section="k_chain_fleet")
             if "k_chain" in j:
                 return os.path.basename(f), dict(j["k_chain"], section="k_chain")
@@ -405,7 +405,7 @@ def run_ours(a):
 
     M, K, W = a.moves_per_step, a.steps, a.warmup
     n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else n_sm
+    R_auto = a.replicas_per_gpu if a.replicas_per_gpu > 0 else 2 * n_sm   # two chains per SM: the 448-thread build of k_chain
     r, sysm, types, params = synth.load(cache_dir=os.path.join(REPO, "gpurun_out", "cache"))
     ids = types.ids(sysm.symbol)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -759,7 +759,7 @@ def main():
     ap.add_argument("--no-recompute", action="store_true", help="skip the k-sharded full S(k) recompute timing")
     ap.add_argument("--no-examples", action="store_true", help="skip the four reference examples")
     ap.add_argument("--no-plum-ref", action="store_true", help="reference arm: skip the real plum_ref binary's legs")
-    ap.add_argument("--replicas-per-gpu", type=int, default=0, help="independent Markov chains per GPU; 0 = one per SM")
+    ap.add_argument("--replicas-per-gpu", type=int, default=0, help="independent Markov chains per GPU; 0 = two per SM")
     ap.add_argument("--cluster", type=int, default=1, help="CTAs per chain in throughput mode")
     ap.add_argument("--single-cluster", type=int, default=16, help="CTAs per chain in the single-chain measurement")
     ap.add_argument("--pivot-mode", type=int, default=0, help="0: pivot arms in the reference's operation order; 1: prefix sums")

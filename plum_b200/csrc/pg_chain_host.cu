@@ -22,11 +22,13 @@ void chain_free(pg_engine* h) {
 int chain_kernel_setup(pg_engine* h, int cluster) {
   static bool smem_done = false, np_done = false;
   if (!smem_done) {
-    PG_CUDA(h, cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem)));
+    PG_CUDA(h, cudaFuncSetAttribute(k_chain512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem512)));
+    PG_CUDA(h, cudaFuncSetAttribute(k_chain448, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem448)));
+    PG_CUDA(h, cudaFuncSetAttribute(k_chain448, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM
     smem_done = true;
   }
   if (cluster > 8 && !np_done) {
-    PG_CUDA(h, cudaFuncSetAttribute(k_chain, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    PG_CUDA(h, cudaFuncSetAttribute(k_chain512, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     np_done = true;
   }
   return PG_OK;
@@ -262,24 +264,37 @@ int chain_prepare(pg_engine* h, int max_steps) {
   rc = chain_reserve_io(h, std::max(max_steps, 1));
   if (rc) return rc;
   const int nk = h->P.use_ewald ? h->nk : 0;
-  if (((nk + c.cluster - 1) / c.cluster + CH_THREADS - 1) / CH_THREADS > CH_KPT) { h->err = "chain: too many k vectors per CTA (raise the cluster size)"; return PG_ERR_CAPACITY; }
+  if (((nk + c.cluster - 1) / c.cluster + 448 - 1) / 448 > CH_KPT) { h->err = "chain: too many k vectors per CTA (raise the cluster size)"; return PG_ERR_CAPACITY; }
   if ((c.kmax[0] + c.kmax[1] + c.kmax[2] + 3) > CH_TAB) { h->err = "chain: k table does not fit"; return PG_ERR_CAPACITY; }
   return chain_kernel_setup(h, c.cluster);
 }
 
+// Which build of k_chain a launch takes (pg_chain.cu): clusters and fleets of at most one chain per SM run the
+// 512-thread kernel (shortest step); more chains than SMs run the 448-thread kernel, two CTAs per SM.
+// PLUM_B200_CHAIN_THREADS=448 / 512 forces one of them for single-CTA chains (tests, A/B measurements).
+int chain_threads_for(const pg_engine* lead, int n_chains, int cluster) {
+  if (cluster > 1) return 512;
+  const char* env = getenv("PLUM_B200_CHAIN_THREADS");   // read per launch: tests switch it between chains
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 448 || forced == 512) return forced;
+  return (n_chains > std::max(1, lead->n_sm)) ? 448 : 512;
+}
+
 int chain_launch(pg_engine* lead, const PgChainArgs* d_args, int n_chains, int cluster) {
+  const int threads = chain_threads_for(lead, n_chains, cluster);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(n_chains * cluster), 1, 1);
-  cfg.blockDim = dim3(CH_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = sizeof(ChSmem);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = (threads == 448) ? sizeof(ChSmem448) : sizeof(ChSmem512);
   cfg.stream = lead->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PG_CUDA(lead, cudaLaunchKernelEx(&cfg, k_chain, d_args));
+  if (threads == 448) PG_CUDA(lead, cudaLaunchKernelEx(&cfg, k_chain448, d_args));
+  else PG_CUDA(lead, cudaLaunchKernelEx(&cfg, k_chain512, d_args));
   lead->launches++;
   return PG_OK;
 }

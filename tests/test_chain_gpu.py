@@ -144,6 +144,23 @@ def _cut_fixture(seed):
     return {k: z[k] for k in z.files}
 
 
+@pytest.fixture
+def fleet_kernel(monkeypatch):
+    """Single-CTA chains through the 448-thread, two-CTAs-per-SM build of k_chain (what fleets of more chains than SMs run)."""
+    monkeypatch.setenv("PLUM_B200_CHAIN_THREADS", "448")
+
+
+@pytest.mark.parametrize("seed,pivot_mode", [(1, 0), (2, 0), (2, 1)])
+def test_fleet_build_of_the_chain_kernel_reproduces_reference_on_the_cut(fleet_kernel, seed, pivot_mode):
+    test_chain_reproduces_reference_on_the_1320_bead_cut(seed, 1, pivot_mode)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_fleet_build_of_the_chain_kernel_reproduces_spring_and_crankshaft_traces(fleet_kernel, seed):
+    test_chain_reproduces_reference_trace_spring(seed, 1, 37 if seed == 2 else 400)
+    test_chain_with_crankshaft_moves_reproduces_reference_trace(seed, 1)
+
+
 @pytest.mark.parametrize("seed,cluster,pivot_mode", [(1, 1, 0), (2, 8, 0), (1, 4, 0), (2, 1, 1), (1, 8, 1)])
 def test_chain_reproduces_reference_on_the_1320_bead_cut(seed, cluster, pivot_mode):
     """plum_ref itself, 2000 steps on 12 x 100-bead chains + 120 ions in S's box (same alpha, cutoffs and K = 3574).

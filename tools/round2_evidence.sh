@@ -10,10 +10,10 @@ cd "$(dirname "$0")/.."
 timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:k_chain -s 1 -c 1 -f -o gpurun_out/prof_${tag}_kchain \
     python tools/chain_probe.py --system S --steps 300 --clusters 1 > gpurun_out/${tag}_ncu.log 2>&1
 python tools/ncu_chain_summary.py gpurun_out/prof_${tag}_kchain.ncu-rep 300 gpurun_out/${tag}_ncu_summary.json | head -c 400
-# the whole fleet (one chain per SM) is ONE launch: its capture gives device-wide issue / FP64-pipe / L2 percentages
+# the whole fleet (two chains per SM, the 448-thread build) is ONE launch: its capture gives device-wide issue / FP64-pipe / L2 percentages
 timeout -k 10 900 ncu --set full --clock-control none -k regex:k_chain -s 1 -c 1 -f -o gpurun_out/prof_${tag}_kchain_fleet \
-    python tools/chain_probe.py --system S --steps 100 --clusters "" --replicas 148 > gpurun_out/${tag}_ncu_fleet.log 2>&1
-python tools/ncu_chain_summary.py gpurun_out/prof_${tag}_kchain_fleet.ncu-rep 14800 gpurun_out/${tag}_ncu_summary.json k_chain_fleet | tail -c 600
+    python tools/chain_probe.py --system S --steps 100 --clusters "" --replicas 296 > gpurun_out/${tag}_ncu_fleet.log 2>&1
+python tools/ncu_chain_summary.py gpurun_out/prof_${tag}_kchain_fleet.ncu-rep 29600 gpurun_out/${tag}_ncu_summary.json k_chain_fleet | tail -c 600
 cp gpurun_out/${tag}_ncu_summary.json profiles/${tag}_ncu_summary.json
 timeout -k 10 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/${tag}_pytest_gpu.txt
 cat gpurun_out/${tag}_pytest_gpu.txt
