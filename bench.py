@@ -581,7 +581,7 @@ def run_ours(a):
     single = None
     if not a.no_single:
         single = {}
-        for pm in (0, 1):
+        for pm in (0, 2, 1):
             sc = chain_legs(1, a.single_cluster, pm, a.batch)
             single[f"pivot_mode_{pm}"] = {
                 "value": float(K * M) / sc["dev_s"], "e2e": float(K * M) / sc["t_e2e"], "us_per_step": sc["dev_s"] * 1e6 / (K * M),
@@ -603,7 +603,9 @@ def run_ours(a):
         single["cluster_ctas"] = a.single_cluster
         single["note"] = ("ONE Markov chain per GPU (what a single Plum run sees), a cluster of CTAs sharing the chain; pivot_mode 0 builds "
                           "pivot arms in the reference's operation order (trial coordinates bit-identical to the reference's, one "
-                          "dependent step per bead), pivot_mode 1 as a prefix sum (coordinates equal to ~1e-13)")
+                          "dependent step per bead), pivot_mode 1 as a prefix sum (coordinates equal to ~1e-13), pivot_mode 2 evaluates the energy "
+                          "change from the prefix-sum arms while two warps build the exact ones, which are what gets committed "
+                          "(bit-identical coordinates, dE equal to ~1e-13 relative); the throughput legs run config.pivot_mode")
 
     # ---------------- roofline of the dominant kernel (k_chain): executed work from the tracked ncu capture
     peaks = {}
@@ -762,7 +764,7 @@ def main():
     ap.add_argument("--replicas-per-gpu", type=int, default=0, help="independent Markov chains per GPU; 0 = two per SM")
     ap.add_argument("--cluster", type=int, default=1, help="CTAs per chain in throughput mode")
     ap.add_argument("--single-cluster", type=int, default=16, help="CTAs per chain in the single-chain measurement")
-    ap.add_argument("--pivot-mode", type=int, default=0, help="0: pivot arms in the reference's operation order; 1: prefix sums")
+    ap.add_argument("--pivot-mode", type=int, default=2, help="0: pivot arms in the reference's operation order; 1: prefix sums; 2: exact arms committed, energies from prefix-sum arms")
     ap.add_argument("--batch", type=int, default=MOVES_PER_STEP, help="steps per host round trip in the e2e leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

@@ -272,7 +272,11 @@ typedef struct pg_chain_config {
   int32_t keep_trials;    /* tests: keep every step's trial coordinates (pg_chain_trial_xyz)             */
   int32_t pivot_mode;     /* 0: Molecule::Pivot in the reference's operation order (trial coordinates bit-identical
                              to the reference's; one dependent step per bead of an arm); 1: the same arm as a prefix
-                             sum of independent bond vectors (coordinates equal to a few ulp, not bit for bit)  */
+                             sum of independent bond vectors (coordinates equal to a few ulp, not bit for bit);
+                             2: both — the energy change is evaluated from the prefix-sum coordinates while two warps
+                             build the exact arm, and the exact coordinates are what an accepted move commits (and
+                             what pg_chain_trial_xyz returns): bit-identical trajectories at the speed of mode 1, dE
+                             equal to mode 0's to ~1e-13 relative                                            */
   double move_size;       /* s1_MC_move_size                                                             */
   double bond_len;        /* RigidBondLen() or EqBondLen() (simulation.cc:288-296)                       */
   double move_prob[5];    /* bead, COM, pivot, crankshaft, reptation (simulation.cc:46-50)               */

@@ -81,7 +81,7 @@ struct PgChainArgs {
   PgState* state;
   int* out;                 // [4] steps done, stop kind, error, overflow high-water
   int max_steps;
-  int exact_pivot;
+  int pivot_mode;           // 0 exact arms, 1 prefix-sum arms, 2 exact arms for the state + prefix-sum arms for the energies
   int specialize;           // clusters: run the four phases of the energy change on disjoint warp groups
   int pad2_;
   // instrumentation (tools/chain_probe.py): per-phase clock64 sums of thread 0 of rank 0 [5 kinds][CH_NPHASE], and a

@@ -55,7 +55,7 @@ __device__ __forceinline__ void ch_bound_box(const ChSmem& sm, int n_e, int lane
 // rest of the arm is dragged along.  The dependency bead -> bead is sequential by construction; every lane computes it
 // redundantly, the dragged coordinates live in registers (lane l owns arm positions l + 1, l + 33, ...), so the only
 // traffic per step is three shuffles that are off the critical path.
-template <int DIR>
+template <int DIR, bool TO_ROWS>
 __device__ __forceinline__ void ch_pivot_arm(ChSmem& sm, int p, int glen, double msr, int lane) {
   const int La = DIR > 0 ? glen - 1 - p : p;
   const int rowbase = DIR > 0 ? 0 : glen - 1 - p;
@@ -101,7 +101,12 @@ __device__ __forceinline__ void ch_pivot_arm(ChSmem& sm, int p, int glen, double
 #pragma unroll
   for (int j = 0; j < NB; j++) {
     const int t = 32 * j + lane + 1;
-    if (t <= La) { const int i = p + DIR * t; sm.trl[0][i] = ox[j]; sm.trl[1][i] = oy[j]; sm.trl[2][i] = oz[j]; }
+    if (t <= La) {
+      // TO_ROWS (pivot_mode 2): sm.trl holds the prefix-sum coordinates the energy phases are reading right now; the exact
+      // ones go where this arm's rows were (every row has been consumed by now) and are copied over behind the decision
+      if (TO_ROWS) sm.rv[rowbase + t - 1] = make_double4(ox[j], oy[j], oz[j], 0.0);
+      else { const int i = p + DIR * t; sm.trl[0][i] = ox[j]; sm.trl[1][i] = oy[j]; sm.trl[2][i] = oz[j]; }
+    }
   }
 }
 
@@ -189,21 +194,13 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
   // intra-molecular pairs — run side by side on disjoint warp groups of every CTA, so a step costs the longest of them
   // instead of their sum.
   const bool spec = (G > 1) && A.specialize;
-  const int rW0 = 0, rWn = spec ? 4 : CH_WARPS;
-  const int qW0 = spec ? 4 : 0, qWn = spec ? 7 : CH_WARPS;
-  const int cW0 = spec ? 11 : 0, cWn = spec ? 4 : CH_WARPS;
-  const int iW0 = spec ? 15 : 0, iWn = spec ? 1 : CH_WARPS;
-  const bool in_r = warp >= rW0 && warp < rW0 + rWn, in_q = warp >= qW0 && warp < qW0 + qWn;
-  const bool in_c = warp >= cW0 && warp < cW0 + cWn, in_i = warp >= iW0 && warp < iW0 + iWn;
-  const int rt = (warp - rW0) * 32 + lane, RT = rWn * 32;            // reciprocal space: thread of the CTA's k slice
-  const int gw = rank * qWn + (warp - qW0), GW = G * qWn;             // real space: warp over all charged partners
-  const int ct = (rank * cWn + (warp - cW0)) * 32 + lane, CT = G * cWn * 32;   // cell units
-  const int it = (rank * iWn + (warp - iW0)) * 32 + lane, IT = G * iWn * 32;   // intra-molecular pairs
+  // (role indices are set per step below: in a pivot_mode 2 step warps 0 and 1 are busy with the exact arms)
+  bool in_r, in_q, in_c, in_i;
+  int rt, RT, gw, GW, ct, CT, it, IT;
   unsigned k_lo, k_hi;
   mv_share((unsigned)nk, (unsigned)G, (unsigned)rank, k_lo, k_hi);
   const int nq_tot = P.use_ewald ? A.nq_tot : 0;
-  const int nkt = ((int)(k_hi - k_lo) + RT - 1) / RT;
-  if (((nk + G - 1) / G + RT - 1) / RT > CH_KPT && tid == 0) sm.err = CH_ERR_K;   // (the host checks first)
+  int nkt = 0;
   const int ne0 = A.kmax[0] + 1, ne1 = A.kmax[1] + 1, ne2 = A.kmax[2] + 1, ne = ne0 + ne1 + ne2;
   const int EC = CH_TAB / ne;
   if (EC < 1 && tid == 0) sm.err = CH_ERR_K;
@@ -220,7 +217,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
     __syncthreads();
     t_prev = clock64();
   }
-  const int skip = A.dbg_skip & 0xff, prof_rank = (A.dbg_skip >> 8) & 0xff, pivot_mode = A.exact_pivot ? 0 : 1;
+  const int skip = A.dbg_skip & 0xff, prof_rank = (A.dbg_skip >> 8) & 0xff, pivot_mode = A.pivot_mode;
   for (; step_i < A.max_steps; step_i++) {
     // ------------------------------------------------------------------ (1) the step's head: which move, which molecule
     if (warp == 0) {
@@ -256,6 +253,30 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
     const int g0 = sm.g0, glen = sm.glen;
     int ovf_hw = sm.ovf_hw;
     CH_STAMP(0);
+    // Warp roles of this step.  One CTA per chain: every warp takes its share of every phase in turn.  A cluster per
+    // chain: the four independent parts of the energy change run side by side on disjoint warp groups of every CTA.
+    // pivot_mode 2: warps 0 and 1 leave the pool (x0 = 2) — they build the exact arms while the others already evaluate
+    // the energy change from the prefix-sum coordinates.
+    int x0 = 0;
+    if (kind == CG_PIVOT && pivot_mode == 2 && !(skip & 32)) {
+      const int rt_threads = spec ? 64 : CH_THREADS - 64;
+      if (((int)(k_hi - k_lo) + rt_threads - 1) / rt_threads <= CH_KPT) x0 = 2;   // else: this step runs as pivot_mode 0
+    }
+    {
+      const int aW = CH_WARPS - x0;
+      const int rW0 = x0, rWn = spec ? 4 - x0 : aW;
+      const int qW0 = spec ? 4 : x0, qWn = spec ? 7 : aW;
+      const int cW0 = spec ? 11 : x0, cWn = spec ? 4 : aW;
+      const int iW0 = spec ? 15 : x0, iWn = spec ? 1 : aW;
+      in_r = warp >= rW0 && warp < rW0 + rWn; in_q = warp >= qW0 && warp < qW0 + qWn;
+      in_c = warp >= cW0 && warp < cW0 + cWn; in_i = warp >= iW0 && warp < iW0 + iWn;
+      rt = (warp - rW0) * 32 + lane; RT = rWn * 32;                      // reciprocal space: thread of the CTA's k slice
+      gw = rank * qWn + (warp - qW0); GW = G * qWn;                      // real space: warp over all charged partners
+      ct = (rank * cWn + (warp - cW0)) * 32 + lane; CT = G * cWn * 32;   // cell units
+      it = (rank * iWn + (warp - iW0)) * 32 + lane; IT = G * iWn * 32;   // intra-molecular pairs
+      nkt = ((int)(k_hi - k_lo) + RT - 1) / RT;
+    }
+    const int wtid = tid - 32 * x0, WT = CH_THREADS - 32 * x0;   // thread index / count among the warps that evaluate
 
     // ------------------------------------------------------------------ (2) the molecule's current coordinates
     for (int i = tid; i < glen; i += CH_THREADS) {
@@ -352,9 +373,9 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
         }
       } else if (!(skip & 32)) {   // CG_PIVOT: the two arms in two warps
         const int p = d.i0;
-        if (pivot_mode == 0) {
-          if (warp == 0 && p + 1 < glen) ch_pivot_arm<1>(sm, p, glen, d.s, lane);
-          else if (warp == 1 && p > 0) ch_pivot_arm<-1>(sm, p, glen, d.s, lane);
+        if (pivot_mode == 0 || (pivot_mode == 2 && !x0)) {
+          if (warp == 0 && p + 1 < glen) ch_pivot_arm<1, false>(sm, p, glen, d.s, lane);
+          else if (warp == 1 && p > 0) ch_pivot_arm<-1, false>(sm, p, glen, d.s, lane);
         } else {
           if (warp == 0 && p + 1 < glen) ch_pivot_arm_prefix<1>(sm, p, glen, d.s, lane);
           else if (warp == 1 && p > 0) ch_pivot_arm_prefix<-1>(sm, p, glen, d.s, lane);
@@ -375,19 +396,21 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
     }
     __syncthreads();
     CH_STAMP(2);
-    if (A.trial_log && rank == 0)
-      for (int i = tid; i < 3 * glen; i += CH_THREADS) {
-        const int g = i / 3, a = i - 3 * g;
-        A.trial_log[((size_t)step_i * A.trial_stride + g) * 3 + a] = sm.trl[a][g];
-      }
     const int nq = sm.nq;
-    for (int e = tid; e < 2 * nq; e += CH_THREADS) {
-      const int g = sm.qidx[e >> 1];
-      const double(*c)[CH_MAXLEN] = (e & 1) ? sm.cur : sm.trl;
-      sm.fe[e] = make_float4(mv_frac(c[0][g], iLx), mv_frac(c[1][g], iLy), mv_frac(c[2][g], iLz), 0.0f);
-      sm.sq[e] = (e & 1) ? -sm.gq[g] : sm.gq[g];
+    if (x0 && warp < x0) {
+      // pivot_mode 2: the exact arms (the reference's operation order) into the consumed rows, while the other warps go on
+      const int p = sm.step.i0;
+      if (warp == 0 && p + 1 < glen) ch_pivot_arm<1, true>(sm, p, glen, sm.step.s, lane);
+      else if (warp == 1 && p > 0) ch_pivot_arm<-1, true>(sm, p, glen, sm.step.s, lane);
+    } else {
+      for (int e = wtid; e < 2 * nq; e += WT) {
+        const int g = sm.qidx[e >> 1];
+        const double(*c)[CH_MAXLEN] = (e & 1) ? sm.cur : sm.trl;
+        sm.fe[e] = make_float4(mv_frac(c[0][g], iLx), mv_frac(c[1][g], iLy), mv_frac(c[2][g], iLz), 0.0f);
+        sm.sq[e] = (e & 1) ? -sm.gq[g] : sm.gq[g];
+      }
+      if (x0) asm volatile("bar.sync 2, %0;" ::"r"(WT)); else __syncthreads();
     }
-    __syncthreads();
 
     double acc_pair = 0.0, acc_real = 0.0, acc_rec = 0.0, acc_ov = 0.0, w_sum = 0.0, b_sum = 0.0, w_out = 0.0, acc_cnt = 0.0;
 
@@ -398,7 +421,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
       for (int i = 0; i < CH_KPT; i++) { dre[i] = 0.0; dim[i] = 0.0; }
       for (int c0 = 0; c0 < 2 * nq; c0 += EC) {
         const int ec = min(EC, 2 * nq - c0);
-        if (c0 > 0) { if (spec) asm volatile("bar.sync 1, %0;" ::"r"(RT)); else __syncthreads(); }   // the previous chunk's tables are still being read
+        if (c0 > 0) { if (spec || x0) asm volatile("bar.sync 1, %0;" ::"r"(RT)); else __syncthreads(); }   // the previous chunk's tables are still being read
         for (int t = rt; t < 3 * ec; t += RT) {
           const int el = t / 3, ax = t - 3 * el, e = c0 + el;
           const int g = sm.qidx[e >> 1];
@@ -417,7 +440,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
             row[l] = make_double2(cr, sr);
           }
         }
-        if (spec) asm volatile("bar.sync 1, %0;" ::"r"(RT)); else __syncthreads();
+        if (spec || x0) asm volatile("bar.sync 1, %0;" ::"r"(RT)); else __syncthreads();
 #pragma unroll
         for (int i = 0; i < CH_KPT; i++) {
           const int k = (int)k_lo + rt + i * RT;
@@ -656,6 +679,21 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MIN_CTAS) k_chain(const PgChain
     }
     __syncthreads();
     ch_mt_fix(sm.mt, tid);
+    if (x0 && (sm.accept || A.trial_log)) {
+      // pivot_mode 2: what becomes the state (and what the tests read back) are the exact arms, parked in the rows
+      const int p = sm.step.i0;
+      for (int i = tid; i < glen; i += CH_THREADS)
+        if (i != p) {
+          const double4 r = sm.rv[i > p ? i - p - 1 : glen - 2 - i];
+          sm.trl[0][i] = r.x; sm.trl[1][i] = r.y; sm.trl[2][i] = r.z;
+        }
+      __syncthreads();
+    }
+    if (A.trial_log && rank == 0)
+      for (int i = tid; i < 3 * glen; i += CH_THREADS) {
+        const int g = i / 3, a = i - 3 * g;
+        A.trial_log[((size_t)step_i * A.trial_stride + g) * 3 + a] = sm.trl[a][g];
+      }
     CH_STAMP(9);
 
     // ------------------------------------------------------------------ (12) FinalizeEnergies: an accepted move becomes the state

@@ -238,7 +238,7 @@ void chain_fill_args(pg_engine* h, int max_steps, PgChainArgs& A) {
   A.mt_io = c.d_mt; A.log = c.d_log;
   A.trial_log = c.want_trials ? c.d_trial_log : nullptr;
   A.trial_stride = c.max_len;
-  A.state = h->d_state; A.out = c.d_out; A.max_steps = max_steps; A.exact_pivot = (c.pivot_mode == 0) ? 1 : 0;
+  A.state = h->d_state; A.out = c.d_out; A.max_steps = max_steps; A.pivot_mode = c.pivot_mode;
   // side-by-side phases need the CTA's k slice to fit the four reciprocal-space warps
   {
     const int nkc = (A.nk + c.cluster - 1) / c.cluster;
@@ -333,7 +333,7 @@ int pg_chain_configure(pg_engine* h, const pg_chain_config* cfg) {
   c.cfg.bond_len = cfg->bond_len;
   for (int i = 0; i < 5; i++) c.cfg.prob[i] = cfg->move_prob[i];
   c.want_trials = cfg->keep_trials != 0;
-  if (cfg->pivot_mode != 0 && cfg->pivot_mode != 1) { h->err = "pg_chain_*: pivot_mode must be 0 or 1"; return PG_ERR_INVALID; }
+  if (cfg->pivot_mode < 0 || cfg->pivot_mode > 2) { h->err = "pg_chain_*: pivot_mode must be 0, 1 or 2"; return PG_ERR_INVALID; }
   c.pivot_mode = cfg->pivot_mode;
   c.configured = true;
   return PG_OK;

@@ -533,7 +533,7 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
   // ---- the device-resident chain: the generator itself goes to the device, nothing stops a stretch but a GC step.
   // Offered for single-image systems (pg_chain_configure says so otherwise); PLUM_B200_CHAIN=0
   // keeps the descriptor path below, PLUM_B200_CLUSTER sets the CTAs that share the chain (default 16),
-  // PLUM_B200_PIVOT_MODE=1 the prefix-sum pivot arms.
+  // PLUM_B200_PIVOT_MODE = 0 / 1 / 2 the way pivot arms are built (pg_chain_config.pivot_mode, default 2).
   if (S.chain != 0) {
     static const bool chain_off = [] { const char* e = getenv("PLUM_B200_CHAIN"); return e && e[0] == '0'; }();
     if (S.chain < 0 || S.n_mol_configured < 0) {
@@ -545,7 +545,7 @@ int ForceField::TranslationalBatch(vector<Molecule>& mols, mt19937& rand_gen, in
       const char* ec = getenv("PLUM_B200_CLUSTER");
       cc.cluster_ctas = ec ? atoi(ec) : 16;
       const char* ep = getenv("PLUM_B200_PIVOT_MODE");
-      cc.pivot_mode = (ep && ep[0] == '1') ? 1 : 0;
+      cc.pivot_mode = ep ? atoi(ep) : 2;   // default 2: exact arms for the state, prefix-sum arms for the energies
       cc.keep_trials = tx ? 1 : 0;
       cc.move_size = move_size;
       cc.bond_len = use_bond_pot ? bond_r0 : (use_bond_rigid ? rigid_bond : 0.0);

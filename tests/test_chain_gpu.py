@@ -150,7 +150,7 @@ def fleet_kernel(monkeypatch):
     monkeypatch.setenv("PLUM_B200_CHAIN_THREADS", "448")
 
 
-@pytest.mark.parametrize("seed,pivot_mode", [(1, 0), (2, 0), (2, 1)])
+@pytest.mark.parametrize("seed,pivot_mode", [(1, 0), (2, 0), (2, 1), (1, 2), (2, 2)])
 def test_fleet_build_of_the_chain_kernel_reproduces_reference_on_the_cut(fleet_kernel, seed, pivot_mode):
     test_chain_reproduces_reference_on_the_1320_bead_cut(seed, 1, pivot_mode)
 
@@ -161,11 +161,13 @@ def test_fleet_build_of_the_chain_kernel_reproduces_spring_and_crankshaft_traces
     test_chain_with_crankshaft_moves_reproduces_reference_trace(seed, 1)
 
 
-@pytest.mark.parametrize("seed,cluster,pivot_mode", [(1, 1, 0), (2, 8, 0), (1, 4, 0), (2, 1, 1), (1, 8, 1)])
+@pytest.mark.parametrize("seed,cluster,pivot_mode", [(1, 1, 0), (2, 8, 0), (1, 4, 0), (2, 1, 1), (1, 8, 1),
+                                                     (1, 1, 2), (2, 1, 2), (1, 16, 2), (2, 8, 2), (1, 2, 2)])
 def test_chain_reproduces_reference_on_the_1320_bead_cut(seed, cluster, pivot_mode):
     """plum_ref itself, 2000 steps on 12 x 100-bead chains + 120 ions in S's box (same alpha, cutoffs and K = 3574).
     pivot_mode 0: the reference's operation order, trial coordinates bit-identical; pivot_mode 1: pivot arms as prefix
-    sums, trial coordinates equal to 1e-11, everything else held to the same bars."""
+    sums, trial coordinates equal to 1e-11, everything else held to the same bars; pivot_mode 2: the energies from the
+    prefix-sum arms while two warps build the exact ones — trial (= committed) coordinates bit-identical again."""
     r, s, eng = _engine("synth_cut")
     fx = _cut_fixture(seed)
     n = len(fx["kind"])
@@ -177,11 +179,11 @@ def test_chain_reproduces_reference_on_the_1320_bead_cut(seed, cluster, pivot_mo
     for i in range(n_tr):
         trial = fx["trial_xyz"][fx["trial_off"][i]:fx["trial_off"][i + 1]]
         got = eng.chain_trial_xyz(i, trial.shape[0])
-        if pivot_mode == 0:
+        if pivot_mode != 1:
             assert np.array_equal(got, trial), (i, int(fx["kind"][i]), np.abs(got - trial).max())
         else:
             worst = max(worst, float(np.abs(got - trial).max()))
-    if pivot_mode:
+    if pivot_mode == 1:
         print(f"pivot_mode 1: max |trial - reference trial| over {n_tr} steps = {worst:.3e}")
         assert worst <= 1e-11
     rec2, stop, ms = eng.chain_run(n - n_tr)

@@ -222,7 +222,7 @@ def test_volume_perturbation_pressure_sampler_on_trajectory(name):
             assert abs(p[k] - w["p"][k]) <= 1e-6 * abs(w["p"][k]) + 1e-300, (step, k, p[k], w["p"][k])
 
 
-@pytest.mark.parametrize("seed,env", [(1, {}), (2, {"PLUM_B200_CLUSTER": "8"}), (1, {"PLUM_B200_PIVOT_MODE": "1"}),
+@pytest.mark.parametrize("seed,env", [(1, {}), (2, {"PLUM_B200_CLUSTER": "8"}), (1, {"PLUM_B200_PIVOT_MODE": "1"}), (2, {"PLUM_B200_PIVOT_MODE": "0"}),
                                       (2, {"PLUM_B200_CHAIN": "0", "PLUM_B200_BATCH": "2"}), (1, {"PLUM_B200_BATCH": "0"})])
 def test_driver_over_the_device_resident_chain_reproduces_the_reference_on_the_cut_of_S(seed, env):
     """bin/plum_gpu (the reference's unchanged driver + façade) on the 1320-bead cut of the benchmark system: the
