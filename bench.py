@@ -764,7 +764,7 @@ def main():
     ap.add_argument("--replicas-per-gpu", type=int, default=0, help="independent Markov chains per GPU; 0 = two per SM")
     ap.add_argument("--cluster", type=int, default=1, help="CTAs per chain in throughput mode")
     ap.add_argument("--single-cluster", type=int, default=16, help="CTAs per chain in the single-chain measurement")
-    ap.add_argument("--pivot-mode", type=int, default=2, help="0: pivot arms in the reference's operation order; 1: prefix sums; 2: exact arms committed, energies from prefix-sum arms")
+    ap.add_argument("--pivot-mode", type=int, default=0, help="throughput legs: 0 pivot arms in the reference's operation order (fastest bit-identical mode for a fleet: the other CTA of the SM hides the arm); 1 prefix sums; 2 exact arms committed, energies from prefix-sum arms (the single-chain default)")
     ap.add_argument("--batch", type=int, default=MOVES_PER_STEP, help="steps per host round trip in the e2e leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
