@@ -717,10 +717,11 @@ def run_ours(a):
                          f"(SURVEY.md §0.8)"}
 
     # bytes crossing PCIe per step in the e2e leg (per GPU): generator state + launch arguments down; step log, generator
-    # state, status words and the accepted coordinates (2 x double2 per bead) up — per batch and replica
+    # state (padded to 640 words), status words and the accepted coordinates (3 doubles per bead, gathered on the device)
+    # up — per batch and replica, in one copy
     nb = main["batches_per_step"]
     h2d = float(R * nb * (625 * 4 + 768))
-    d2h = float(R * (16 * M + nb * (625 * 4 + 16 + 32 * sysm.n)))
+    d2h = float(R * (16 * M + nb * (640 * 4 + 16 + ((24 * sysm.n + 15) // 16) * 16)))
     evals_total = sum_over_ranks(main["evals"])     # a collective: every rank takes part
     if rank == 0:
         line = {
@@ -736,8 +737,9 @@ def run_ours(a):
                     "ms_per_step": main["t_e2e"] * 1e3 / K,
                     "caller": f"native C++ caller (plum_b200/host/mc_bench.cc pb_run_chain), ONE host thread per GPU driving {R} chains: per batch of "
                               f"{a.batch} steps pg_chain_set_rng (std::mt19937 state down), pg_chain_run_multi (one launch), pg_chain_steps (log up), "
-                              f"pg_chain_get_rng, pg_download_positions (accepted coordinates up, as ForceField::TranslationalBatch does); = pg_chain_run_multi_io, "
-                              f"whose host-side repacking of the coordinates (56 B per bead) uses up to 8 worker threads"},
+                              f"pg_chain_get_rng, pg_download_positions (accepted coordinates up, as ForceField::TranslationalBatch does); = pg_chain_run_multi_io: "
+                              f"a pack kernel gathers logs / generators / coordinates of all chains, one copy brings them up, up to 8 worker "
+                              f"threads inside the call hand them to the caller's arrays"},
             "gpu_launches": int(main["launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
             "resident_matches_e2e": main["same"], "accept_ratio": main["accept"],
             "wall_ms_per_step_resident": main["wall_res"] * 1e3 / K,

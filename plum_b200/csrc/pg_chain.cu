@@ -254,6 +254,7 @@ struct PgChainHost {
   unsigned long long* d_prof = nullptr;   // instrumentation
   unsigned long long* d_counters = nullptr;
   char* h_pin = nullptr;                  // pinned staging of pg_chain_run_multi_io
+  char* d_pack = nullptr;                 // ... and its device image (k_chain_pack)
   size_t pin_cap = 0;
   int dbg_skip = 0;
 };

@@ -15,6 +15,7 @@ void chain_free(pg_engine* h) {
   cudaFree(c.d_cell_slots); cudaFree(c.d_ovf); cudaFree(c.d_ovf_n); cudaFree(c.d_bead_cell); cudaFree(c.d_bead_slot);
   cudaFree(c.d_qslot); cudaFree(c.d_qpos); cudaFree(c.d_qfrac);
   if (c.h_pin) cudaFreeHost(c.h_pin);
+  cudaFree(c.d_pack);
   cudaFree(c.d_mt); cudaFree(c.d_log); cudaFree(c.d_trial_log); cudaFree(c.d_out); cudaFree(c.d_args); cudaFree(c.d_prof); cudaFree(c.d_counters);
   c = PgChainHost();
 }
@@ -269,6 +270,27 @@ int chain_prepare(pg_engine* h, int max_steps) {
   return chain_kernel_setup(h, c.cluster);
 }
 
+// What a fleet hands back, gathered per chain into one block (pg_chain_run_multi_io): generator, status words, step
+// log, coordinates as [n_beads][3].  Grid (chains, 16), 256 threads.
+__global__ void __launch_bounds__(256) k_chain_pack(const PgChainArgs* __restrict__ args, char* __restrict__ stage, size_t per,
+                                                    int log_steps, int nb) {
+  const PgChainArgs& A = args[blockIdx.x];
+  char* dst = stage + per * (size_t)blockIdx.x;
+  const int t = blockIdx.y * 256 + threadIdx.x, T = gridDim.y * 256;
+  uint32_t* d_rng = reinterpret_cast<uint32_t*>(dst);
+  for (int w = t; w < 625; w += T) d_rng[w] = A.mt_io[w];
+  int* d_out = reinterpret_cast<int*>(dst + 640 * sizeof(uint32_t));
+  for (int w = t; w < 4; w += T) d_out[w] = A.out[w];
+  int4* d_log = reinterpret_cast<int4*>(dst + 640 * sizeof(uint32_t) + 16);
+  const int4* s_log = reinterpret_cast<const int4*>(A.log);
+  for (int w = t; w < log_steps; w += T) d_log[w] = s_log[w];
+  double* d_xyz = reinterpret_cast<double*>(dst + 640 * sizeof(uint32_t) + 16 + sizeof(PgChainRec) * (size_t)log_steps);
+  for (int b = t; b < nb; b += T) {
+    const double2 a = A.xy[b], c = A.zq[b];
+    d_xyz[3 * b] = a.x; d_xyz[3 * b + 1] = a.y; d_xyz[3 * b + 2] = c.x;
+  }
+}
+
 // Which build of k_chain a launch takes (pg_chain.cu): clusters and fleets of at most one chain per SM run the
 // 512-thread kernel (shortest step); more chains than SMs run the 448-thread kernel, two CTAs per SM.
 // PLUM_B200_CHAIN_THREADS=448 / 512 forces one of them for single-CTA chains (tests, A/B measurements).
@@ -495,14 +517,18 @@ int pg_chain_run_multi_io(pg_engine** hs, int n, int max_steps, uint32_t* rng_io
     if (rc) { if (hs[i] != lead) lead->err = hs[i]->err; return rc; }
   }
   PgChainHost& c = lead->ch;
-  // pinned staging: [n] x { rng 625 u32 (pad to 640) | out 4 int | log max_steps x 16 B | xy nb x 16 B | zq nb x 16 B }
+  // what comes back, per chain and in this order: rng 625 u32 (padded to 640) | out 4 int | log max_steps x 16 B |
+  // xyz nb x 24 B.  A small kernel gathers the pieces of all chains into one device block (k_chain_pack), ONE copy
+  // brings it into pinned memory, a few host threads hand it to the caller's arrays.
   const size_t rng_b = 640 * sizeof(uint32_t), out_b = 16, log_b = steps ? sizeof(PgChainRec) * (size_t)std::max(max_steps, 1) : 0;
-  const size_t pos_b = xyz ? sizeof(double2) * (size_t)std::max(nb, 1) : 0;
-  const size_t per = rng_b + out_b + log_b + 2 * pos_b;
+  const size_t pos_b = xyz ? ((sizeof(double) * 3 * (size_t)std::max(nb, 1) + 15) & ~(size_t)15) : 0;
+  const size_t per = rng_b + out_b + log_b + pos_b;
   if (per * (size_t)n > c.pin_cap) {
     if (c.h_pin) cudaFreeHost(c.h_pin);
-    c.h_pin = nullptr; c.pin_cap = 0;
+    cudaFree(c.d_pack);
+    c.h_pin = nullptr; c.d_pack = nullptr; c.pin_cap = 0;
     PG_CUDA(lead, cudaHostAlloc((void**)&c.h_pin, per * (size_t)n, cudaHostAllocDefault));
+    PG_CUDA(lead, cudaMalloc((void**)&c.d_pack, per * (size_t)n));
     c.pin_cap = per * (size_t)n;
   }
   if (c.args_cap < (size_t)n) {
@@ -526,17 +552,10 @@ int pg_chain_run_multi_io(pg_engine** hs, int n, int max_steps, uint32_t* rng_io
   int rc = chain_launch(lead, c.d_args, n, cluster);
   if (rc) return rc;
   PG_CUDA(lead, cudaEventRecord(lead->ev1, lead->stream));
-  for (int i = 0; i < n; i++) {
-    char* base = c.h_pin + per * (size_t)i;
-    PG_CUDA(lead, cudaMemcpyAsync(base, hs[i]->ch.d_mt, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, lead->stream));
-    PG_CUDA(lead, cudaMemcpyAsync(base + rng_b, hs[i]->ch.d_out, sizeof(int) * 4, cudaMemcpyDeviceToHost, lead->stream));
-    if (steps && max_steps > 0)
-      PG_CUDA(lead, cudaMemcpyAsync(base + rng_b + out_b, hs[i]->ch.d_log, sizeof(PgChainRec) * (size_t)max_steps, cudaMemcpyDeviceToHost, lead->stream));
-    if (xyz && nb > 0) {
-      PG_CUDA(lead, cudaMemcpyAsync(base + rng_b + out_b + log_b, hs[i]->xy, pos_b, cudaMemcpyDeviceToHost, lead->stream));
-      PG_CUDA(lead, cudaMemcpyAsync(base + rng_b + out_b + log_b + pos_b, hs[i]->zq, pos_b, cudaMemcpyDeviceToHost, lead->stream));
-    }
-  }
+  k_chain_pack<<<dim3((unsigned)n, 16), 256, 0, lead->stream>>>(c.d_args, c.d_pack, per, (int)(log_b / sizeof(PgChainRec)), xyz ? nb : 0);
+  lead->launches++;
+  PG_CUDA(lead, cudaGetLastError());
+  PG_CUDA(lead, cudaMemcpyAsync(c.h_pin, c.d_pack, per * (size_t)n, cudaMemcpyDeviceToHost, lead->stream));
   PG_CUDA(lead, cudaStreamSynchronize(lead->stream));
   if (elapsed_ms) PG_CUDA(lead, cudaEventElapsedTime(elapsed_ms, lead->ev0, lead->ev1));
   for (int i = 0; i < n; i++) {
@@ -551,32 +570,26 @@ int pg_chain_run_multi_io(pg_engine** hs, int n, int max_steps, uint32_t* rng_io
     }
     if (out[0] < 0 || out[0] > max_steps) { lead->err = "chain: inconsistent step count"; return PG_ERR_STATE; }
     if (n_done) n_done[i] = out[0];
-    memcpy(rng_io + (size_t)i * 625, base, 625 * sizeof(uint32_t));
-    if (steps && out[0] > 0) memcpy(steps + (size_t)i * max_steps, base + rng_b + out_b, sizeof(PgChainRec) * (size_t)out[0]);
   }
-  if (xyz) {
-    // (x, y | z, q) pairs -> the caller's [n][3] arrays: memory-bound host work (56 B per bead), spread over a few
-    // threads when a whole fleet comes back at once
-    auto unpack = [&](int i0, int i1) {
-      for (int i = i0; i < i1; i++) {
-        if (!xyz[i]) continue;
-        const char* base = c.h_pin + per * (size_t)i;
-        const double2* hxy = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b);
-        const double2* hzq = reinterpret_cast<const double2*>(base + rng_b + out_b + log_b + pos_b);
-        double* dst = xyz[i];
-        for (int b = 0; b < nb; b++) { dst[3 * b] = hxy[b].x; dst[3 * b + 1] = hxy[b].y; dst[3 * b + 2] = hzq[b].x; }
-      }
-    };
-    int T = 1;
-    if ((long long)n * nb >= 1000000) T = (int)std::min<unsigned>(std::min<unsigned>(8u, (unsigned)n), std::max(1u, std::thread::hardware_concurrency() / 2));
-    if (T <= 1) {
-      unpack(0, n);
-    } else {
-      std::vector<std::thread> th;
-      for (int t = 1; t < T; t++) th.emplace_back(unpack, (int)((long long)n * t / T), (int)((long long)n * (t + 1) / T));
-      unpack(0, (int)((long long)n / T));
-      for (auto& x : th) x.join();
+  // pinned block -> the caller's arrays: memory-bound host work, spread over a few threads when a whole fleet comes back
+  auto unpack = [&](int i0, int i1) {
+    for (int i = i0; i < i1; i++) {
+      const char* base = c.h_pin + per * (size_t)i;
+      const int done = reinterpret_cast<const int*>(base + rng_b)[0];
+      memcpy(rng_io + (size_t)i * 625, base, 625 * sizeof(uint32_t));
+      if (steps && done > 0) memcpy(steps + (size_t)i * max_steps, base + rng_b + out_b, sizeof(PgChainRec) * (size_t)done);
+      if (xyz && xyz[i]) memcpy(xyz[i], base + rng_b + out_b + log_b, sizeof(double) * 3 * (size_t)nb);
     }
+  };
+  int T = 1;
+  if (xyz && (long long)n * nb >= 1000000) T = (int)std::min<unsigned>(std::min<unsigned>(8u, (unsigned)n), std::max(1u, std::thread::hardware_concurrency() / 2));
+  if (T <= 1) {
+    unpack(0, n);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(unpack, (int)((long long)n * t / T), (int)((long long)n * (t + 1) / T));
+    unpack(0, (int)((long long)n / T));
+    for (auto& x : th) x.join();
   }
   return PG_OK;
 }
