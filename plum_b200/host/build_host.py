@@ -30,7 +30,7 @@ def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, f) for f in ("force_field.h", "force_field.cc", "driver_hooks.py", "build_host.py", "mc_propose.h")]
+    deps = [os.path.join(HERE, f) for f in ("force_field.h", "force_field.cc", "driver_hooks.py", "build_host.py", "mc_propose.h", "mt_state.h")]
     deps.append(os.path.join(REPO, "plum_b200", "csrc", "pg_propose_math.h"))
     deps.append(os.path.join(REPO, "include", "plum_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)

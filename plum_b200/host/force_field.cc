@@ -24,6 +24,7 @@
 #include "../utilities/misc.h"
 #include "plum_b200.h"
 #include "mc_propose.h"
+#include "mt_state.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -83,19 +84,8 @@ struct McState {
 };
 
 // std::mt19937 <-> 624 state words + position: the textual form operator<< / operator>> define.
-void MtExport(const mt19937& g, uint32_t* state, int* pos) {
-  std::stringstream ss;
-  ss << g;
-  for (int i = 0; i < 624; i++) { unsigned long v; ss >> v; state[i] = (uint32_t)v; }
-  unsigned long p; ss >> p;
-  *pos = (int)p;
-}
-void MtImport(mt19937& g, const uint32_t* state, int pos) {
-  std::stringstream ss;
-  for (int i = 0; i < 624; i++) ss << state[i] << ' ';
-  ss << pos;
-  ss >> g;
-}
+void MtExport(const mt19937& g, uint32_t* state, int* pos) { plum_mt::export_state(g, state, pos); }
+void MtImport(mt19937& g, const uint32_t* state, int pos) { plum_mt::import_state(g, state, pos); }
 }  // namespace
 
 ForceField::ForceField() : vp_z(0), engine(NULL), tot_valid(false), pending_mol(-1), mc_state(NULL) {

@@ -23,6 +23,7 @@
 
 #include "plum_b200.h"
 #include "mc_propose.h"
+#include "mt_state.h"
 
 namespace {
 
@@ -355,19 +356,8 @@ int pb_run_mc(void** ps, int n_ctx, int n_moves, int batch_moves, double* wall_s
 namespace {
 
 // std::mt19937 <-> (624 state words, position): the textual form operator<< / operator>> define.
-void mt_export(const std::mt19937& g, uint32_t* state, int* pos) {
-  std::stringstream ss;
-  ss << g;
-  for (int i = 0; i < 624; i++) { unsigned long v; ss >> v; state[i] = (uint32_t)v; }
-  unsigned long p; ss >> p;
-  *pos = (int)p;
-}
-void mt_import(std::mt19937& g, const uint32_t* state, int pos) {
-  std::stringstream ss;
-  for (int i = 0; i < 624; i++) ss << state[i] << ' ';
-  ss << pos;
-  ss >> g;
-}
+void mt_export(const std::mt19937& g, uint32_t* state, int* pos) { plum_mt::export_state(g, state, pos); }
+void mt_import(std::mt19937& g, const uint32_t* state, int pos) { plum_mt::import_state(g, state, pos); }
 
 int chain_configure(Ctx* c, int cluster, int keep_trials) {
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "mc_propose.h"
+#include "mt_state.h"
 #include "pg_chain_gen.h"
 
 static void load_mt(const std::mt19937& g, PgMt& m) {
@@ -30,6 +31,21 @@ int main(int argc, char** argv) {
   const int n_steps = argc > 2 ? atoi(argv[2]) : 20000;
   const int vary = argc > 3 ? atoi(argv[3]) : 0;
   const int gc_freq = argc > 4 ? atoi(argv[4]) : 0;
+  // host <-> device hand-over of the generator (plum_b200/host/mt_state.h): the byte-copy path, when its self-test
+  // accepts the library's layout, must agree with the text form and continue the same stream
+  {
+    std::mt19937 g(seed + 77u);
+    for (int i = 0; i < 1000; i++) (void)g();
+    uint32_t a[624], b[624]; int pa = 0, pb = 0;
+    plum_mt::slow_export(g, a, &pa);
+    plum_mt::export_state(g, b, &pb);
+    if (pa != pb || memcmp(a, b, sizeof(a))) { printf("mt_state: export differs from the text form\n"); return 1; }
+    std::mt19937 h1, h2;
+    plum_mt::slow_import(h1, a, pa);
+    plum_mt::import_state(h2, b, pb);
+    for (int i = 0; i < 2000; i++) { const auto x = g(); if (h1() != x || h2() != x) { printf("mt_state: import does not continue the stream\n"); return 1; } }
+    printf("mt_state fast path: %s\n", plum_mt::fast_ok() ? "on" : "off (text form)");
+  }
   // raw stream first
   {
     std::mt19937 g(seed);
