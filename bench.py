@@ -369,47 +369,6 @@ def load_profile_summary():
     return None, None
 
 
-def _cpulist(text):
-    out = []
-    for part in text.strip().split(","):
-        if not part:
-            continue
-        lo, _, hi = part.partition("-")
-        out += list(range(int(lo), int(hi or lo) + 1))
-    return out
-
-
-def rank_cores(local_rank, world, torch):
-    """Host cores for this rank: the cores of its GPU's NUMA node, shared evenly with the other local ranks on that node;
-    an even slice of all cores when sysfs has no NUMA information."""
-    allowed = sorted(os.sched_getaffinity(0))
-
-    def node_of(dev):
-        try:
-            pr = torch.cuda.get_device_properties(dev)
-            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-                return int(f.read().strip())
-        except Exception:
-            return -1
-    nodes = [node_of(d) for d in range(world)]
-    mine = nodes[local_rank]
-    if mine >= 0:
-        try:
-            with open(f"/sys/devices/system/node/node{mine}/cpulist") as f:
-                cores = [c for c in _cpulist(f.read()) if c in set(allowed)]
-            peers = [d for d in range(world) if nodes[d] == mine]
-            per = max(1, len(cores) // len(peers))
-            k = peers.index(local_rank)
-            sl = cores[k * per:(k + 1) * per]
-            if sl:
-                return sl
-        except Exception:
-            pass
-    per = max(1, len(allowed) // world)
-    return allowed[local_rank * per:(local_rank + 1) * per] or allowed
-
-
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -419,16 +378,6 @@ def run_ours(a):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
-    host_cores = None
-    if world > 1:
-        # a slice of the host cores per rank, on the NUMA node of the rank's GPU when sysfs tells it (before the first CUDA
-        # context, so that the pinned staging memory is first-touched there): with 8 ranks roaming over both sockets the
-        # end-to-end leg lost 13 %
-        try:
-            host_cores = rank_cores(local_rank, world, torch)
-            os.sched_setaffinity(0, set(host_cores))
-        except Exception:
-            host_cores = None
     torch.cuda.set_device(local_rank)
     if world > 1:
         import datetime
@@ -782,8 +731,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD, "moves_per_step": M, "replicas_per_gpu": R, "cluster_ctas_per_chain": main["cluster"],
                        "pivot_mode": main["pivot_mode"],
                        "mode": f"throughput: {R} independent Markov chains per GPU, all in one k_chain launch per step; the rate of ONE chain is in single_chain",
-                       "l2": "flushed between steps (256 MiB fill); within a step each chain's working set stays L2-resident by design (north_star)",
-                       "host_cores_per_rank": (len(host_cores) if host_cores else None)},
+                       "l2": "flushed between steps (256 MiB fill); within a step each chain's working set stays L2-resident by design (north_star)"},
             "pair_dE_evals_per_s": evals_total / main["dev_s"],
             "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": main["t_e2e"] * 1e3 / K,
