@@ -268,6 +268,20 @@ def run_example(args):
     return out
 
 
+def run_example_own_frequencies(name, steps):
+    """bin/plum_gpu on one example with the example's OWN sampling / print frequencies (SURVEY.md §8d asks for both):
+    Sample(), the pressure samplers and the writers run as shipped; timed by the binary's own run-loop clock."""
+    replay = _replay()
+    err = []
+    replay.run_plum_ref(os.path.join(replay.GOLDEN, "examples", name), steps, 1, xyz=False, binary=replay.PLUM_GPU,
+                        extra_env={"PLUM_B200_PROFILE": "1"}, stderr_to=err, trace=False)
+    for ln in "".join(err).split("\n"):
+        if ln.startswith("plum_b200 profile: run_wall "):
+            w = float(ln.split()[6])
+            return {"steps": steps, "run_s": w, "steps_per_s": steps / w}
+    return {"error": "no run_wall line"}
+
+
 def examples_block(binary, cores, extra_env=None, parallel=True, steps=EXAMPLE_STEPS):
     replay = _replay()
     if not os.path.exists(binary):
@@ -670,6 +684,12 @@ def run_ours(a):
     if rank == 0 and not a.no_examples:
         replay = _replay()
         examples = examples_block(replay.PLUM_GPU, None, parallel=False, steps=EXAMPLE_STEPS_GPU)
+        for name in EXAMPLES:     # the same examples with their own sampling / output frequencies
+            try:
+                if isinstance(examples.get(name), dict):
+                    examples[name]["own_frequencies"] = run_example_own_frequencies(name, EXAMPLE_STEPS_GPU)
+            except Exception as e:   # noqa: BLE001
+                examples[name]["own_frequencies"] = {"error": repr(e)}
 
     # ---------------- k-sharded full S(k) recompute
     recompute = None
