@@ -395,8 +395,8 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import datetime
-        # a rank that dies must take the job down in minutes, not after NCCL's default 10 min watchdog
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
+        # (NCCL's default watchdog time: rank 0 alone runs the CPU baseline legs, the others wait in the next collective)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=600))
 
     def barrier():
         if world > 1:
@@ -681,7 +681,7 @@ def run_ours(a):
 
     # ---------------- examples through the unchanged driver
     examples = None
-    if rank == 0 and not a.no_examples:
+    if rank == 0 and world == 1 and not a.no_examples:   # (multi-GPU runs: the other ranks would sit in a collective meanwhile)
         replay = _replay()
         examples = examples_block(replay.PLUM_GPU, None, parallel=False, steps=EXAMPLE_STEPS_GPU)
         for name in EXAMPLES:     # the same examples with their own sampling / output frequencies
