@@ -107,6 +107,25 @@ def test_oracle_vol_scaling_matches_reference_accumulators(name):
         assert avg.p[5] != 0.0
 
 
+def test_oracle_vol_scaling_is_linear_in_the_stretch():
+    """Size-independent property of the volume-perturbation sample: for a stretch this small the energy change is the
+    first-order response, so doubling dz doubles every table entry (to the relative size of the stretch itself), and the
+    bookkeeping fields do not depend on dz."""
+    r, s, types, params = replay.load_golden("bulk_nvt")
+    o = Oracle(params)
+    o.upload(s.xyz, s.q, types.ids(s.symbol), s.mol_first)
+    o.init_energy()
+    a, b = o.vol_scaling_sample(r.phantom, 1e-5), o.vol_scaling_sample(r.phantom, 2e-5)
+    assert a["n_free"] == b["n_free"] == s.n_mol - r.phantom
+    for k in ("el", "hs"):
+        nz = np.abs(a[k]) > 0
+        assert np.array_equal(nz, np.abs(b[k]) > 0)     # (no WCA pair is inside its cutoff in the start configuration: hs may be empty)
+        assert k == "hs" or nz.any()
+        assert np.all(np.abs(b[k][nz] / a[k][nz] - 2.0) <= 1e-3), (k, a[k], b[k])
+    assert abs(b["dU"] / a["dU"] - 2.0) <= 1e-3
+    assert abs(a["dU"] - (a["el"].sum() + a["hs"].sum() + a["bond"] + a["dipole"])) <= 1e-12 * max(1.0, abs(a["dU"]))
+
+
 def test_ewald_setup_matches_reference_logs():
     """Cutoffs / k tables as echoed by the reference."""
     expect = {
