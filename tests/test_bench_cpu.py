@@ -48,3 +48,17 @@ def test_profile_summary_feeds_the_roofline():
     assert name and name.startswith("r") and prof
     for key in ("executed_fp64_flop_per_step", "warp_instructions_per_step", "dram_bytes_per_step", "steps_in_launch"):
         assert prof[key] > 0
+
+
+def test_tracked_ncu_summary_carries_what_the_roofline_reads():
+    """`roofline` of the bench line takes its executed-work counters from the newest profiles/r*_ncu_summary.json: the file
+    must be there, carry the fleet capture (the launch shape the bench times) and every per-step figure bench.py reads,
+    with plausible magnitudes — so that the fraction cannot silently lose its counters or go stale in shape."""
+    name, prof = bench.load_profile_summary()
+    assert name is not None and name.startswith("r") and prof["section"] == "k_chain_fleet"
+    for key in ("executed_fp64_flop_per_step", "warp_instructions_per_step", "l2_bytes_per_step", "dram_bytes_per_step"):
+        assert prof[key] > 0, key
+    assert 1e5 < prof["executed_fp64_flop_per_step"] < 1e7 and 1e4 < prof["warp_instructions_per_step"] < 1e7
+    assert prof["steps_in_launch"] >= 100 and "device_wide_pct" in prof
+    # executed FP64 cannot be below what had to be computed by more than the share of launches that end in an overlap
+    assert prof["executed_fp64_flop_per_step"] > 0.5e6
